@@ -1,0 +1,993 @@
+// Pi-0 control-step engine: weight repacking, workspace, the kernel schedule of one
+// `infer_action` call (reference: third_party/open_pi_zero/src/model/vla/pizero.py:473-547)
+// and its CUDA-graph replay, behind the C ABI of include/blurr_pi0.h.
+#include "../../include/blurr_pi0.h"
+
+#include "common.cuh"
+#include "gemm_tc.h"
+#include "kernels.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+using namespace blurr;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(BLURR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// repack kernels
+// ---------------------------------------------------------------------------
+enum RowMap { MAP_OFFSET = 0, MAP_GATE = 1, MAP_UP = 2 };
+__global__ void repack_rows_kernel(const bf16* __restrict__ src, int rows, int cols, int src_ld,
+                                   bf16* __restrict__ dst, int dst_ld, int mode, int row_off) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<size_t>(rows) * cols) return;
+    const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx - static_cast<size_t>(r) * cols);
+    int dr;
+    if (mode == MAP_OFFSET) dr = r + row_off;
+    else dr = (r / 64) * 128 + (mode == MAP_UP ? 64 : 0) + (r % 64);
+    dst[static_cast<size_t>(dr) * dst_ld + c] = src[static_cast<size_t>(r) * src_ld + c];
+}
+
+struct StageArgs {
+    const int64_t* ids; const int64_t* vpos; const int64_t* ppos; const int64_t* apos;
+    const bf16* proprios; const bf16* noise;
+    const bf16* mask_itp; long long itp_bs, itp_rs;
+    const bf16* mask_act; long long act_bs, act_rs;
+    int64_t* d_ids; int64_t* d_vpos; int64_t* d_ppos; int64_t* d_apos;
+    bf16* d_proprios; bf16* d_action; bf16* d_mask_itp; bf16* d_mask_act;
+    int n_ids, n_ppos, n_apos, n_prop, n_noise, itp_dim, act_rows, act_cols, batch;
+};
+// Copies the per-call inputs into the engine's static buffers (the CUDA graph reads those).
+__global__ void stage_inputs_kernel(const StageArgs a) {
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < a.n_ids) { a.d_ids[i] = a.ids[i]; a.d_vpos[i] = a.vpos[i]; return; }
+    i -= a.n_ids;
+    if (i < a.n_ppos) { a.d_ppos[i] = a.ppos[i]; return; }
+    i -= a.n_ppos;
+    if (i < a.n_apos) { a.d_apos[i] = a.apos[i]; return; }
+    i -= a.n_apos;
+    if (i < a.n_prop) { a.d_proprios[i] = a.proprios[i]; return; }
+    i -= a.n_prop;
+    if (i < a.n_noise) { a.d_action[i] = a.noise[i]; return; }
+    i -= a.n_noise;
+    const long long itp_per = static_cast<long long>(a.itp_dim) * a.itp_dim;
+    if (i < itp_per * a.batch) {
+        const long long b = i / itp_per, rem = i - b * itp_per;
+        const long long r = rem / a.itp_dim, c = rem - r * a.itp_dim;
+        a.d_mask_itp[i] = a.mask_itp[b * a.itp_bs + r * a.itp_rs + c];
+        return;
+    }
+    i -= itp_per * a.batch;
+    const long long act_per = static_cast<long long>(a.act_rows) * a.act_cols;
+    if (i < act_per * a.batch) {
+        const long long b = i / act_per, rem = i - b * act_per;
+        const long long r = rem / a.act_cols, c = rem - r * a.act_cols;
+        a.d_mask_act[i] = a.mask_act[b * a.act_bs + r * a.act_rs + c];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// engine state
+// ---------------------------------------------------------------------------
+struct Lin {
+    bf16* w = nullptr;
+    int Nw = 0, K = 0, ld = 0;     // padded rows, padded cols (= row stride)
+    bf16* bias = nullptr;          // [Nw] zero padded, or nullptr
+};
+struct VisionLayer {
+    Lin qkv, out, fc1, fc2;
+    bf16 *ln1w, *ln1b, *ln2w, *ln2b;
+};
+struct MixLayer {
+    Lin qkv, o, gu, down;
+    bf16 *in_ln, *post_ln;
+};
+struct MixtureW {
+    std::string name;
+    int hidden = 0, inter = 0;
+    std::vector<MixLayer> layers;
+    bf16* final_norm = nullptr;
+    float inv_freq[128];
+    bool have_inv_freq = false;
+    float *cos_t = nullptr, *sin_t = nullptr;
+};
+struct TapBuf { void* ptr; size_t bytes; };
+
+static constexpr int kNumPos = 1024;     // RoPE table rows (position ids 0..1023)
+static constexpr int kNumSMs = 148;
+
+struct blurr_pi0 {
+    blurr_pi0_config cfg;
+    int device = 0, max_batch = 0;
+    std::vector<void*> allocs;
+    size_t weight_bytes = 0;
+    // weights
+    bf16* embed = nullptr;
+    Lin patch; bf16* pos_emb = nullptr;
+    std::vector<VisionLayer> vlayers;
+    bf16 *post_ln_w = nullptr, *post_ln_b = nullptr;
+    Lin proj;
+    MixtureW mix[3];               // 0 vlm, 1 proprio, 2 action
+    bf16 *ae1_w = nullptr, *ae1_b = nullptr; Lin ae2, ae3;
+    bf16 *pe_w = nullptr, *pe_b = nullptr;
+    bf16 *dec_w = nullptr, *dec_b = nullptr;
+    std::set<std::string> expected, seen;
+    bool finalized = false;
+    // time table
+    bf16* time_table = nullptr; int time_steps = 0;
+    // static inputs
+    int64_t *d_ids, *d_vpos, *d_ppos, *d_apos;
+    bf16 *d_proprios, *d_action, *d_mask_itp, *d_mask_act, *d_out;
+    // activations
+    bf16 *patches, *xs, *xn, *sqkv, *sattn, *shmid, *imgfeat;
+    bf16 *E, *En, *Qv, *AOv, *H;
+    bf16 *Ep, *Epn, *Qp, *AOp, *Hp;
+    bf16 *Ea, *Ean, *Qa, *AOa, *Ha, *X2, *A1;
+    bf16 *kcache, *vcache;
+    float* ws = nullptr; size_t ws_floats = 0;
+    int* d_err = nullptr;
+    // options / bookkeeping
+    bool use_graph = true, debug = false;
+    int64_t launches = 0;
+    std::map<std::string, TapBuf> taps;
+    struct GraphEntry { cudaGraph_t graph; cudaGraphExec_t exec; int64_t launches; };
+    std::map<long long, GraphEntry> graphs;
+    // derived sizes
+    int T_img, n_itp, n_total;    // 256, 277, 281
+};
+
+static void* dalloc(blurr_pi0* h, size_t bytes, bool is_weight = false) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, bytes);
+    h->allocs.push_back(p);
+    if (is_weight) h->weight_bytes += bytes;
+    return p;
+}
+static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool alloc_lin(blurr_pi0* h, Lin& L, int N, int K, bool bias) {
+    L.Nw = pad_to(N, 128);
+    L.K = pad_to(K, 64);
+    L.ld = L.K;
+    L.w = static_cast<bf16*>(dalloc(h, static_cast<size_t>(L.Nw) * L.ld * 2, true));
+    if (!L.w) return false;
+    if (bias) {
+        L.bias = static_cast<bf16*>(dalloc(h, static_cast<size_t>(L.Nw) * 2, true));
+        if (!L.bias) return false;
+    }
+    return true;
+}
+static bf16* alloc_vec(blurr_pi0* h, int n, bool weight = true) {
+    return static_cast<bf16*>(dalloc(h, static_cast<size_t>(n) * 2, weight));
+}
+
+static const char* kMixNames[3] = {"vlm", "proprio", "action"};
+static const char* kVT = "vision_tower.vision_model.";
+
+static void build_expected(blurr_pi0* h) {
+    auto& e = h->expected;
+    e.insert("embed_tokens.weight");
+    e.insert(std::string(kVT) + "embeddings.patch_embedding.weight");
+    e.insert(std::string(kVT) + "embeddings.patch_embedding.bias");
+    e.insert(std::string(kVT) + "embeddings.position_embedding.weight");
+    for (int l = 0; l < h->cfg.vision_layers; ++l) {
+        const std::string p = std::string(kVT) + "encoder.layers." + std::to_string(l) + ".";
+        for (const char* n : {"q_proj", "k_proj", "v_proj", "out_proj"})
+            for (const char* s : {"weight", "bias"}) e.insert(p + "self_attn." + n + "." + s);
+        for (const char* n : {"layer_norm1", "layer_norm2", "mlp.fc1", "mlp.fc2"})
+            for (const char* s : {"weight", "bias"}) e.insert(p + n + "." + s);
+    }
+    e.insert(std::string(kVT) + "post_layernorm.weight");
+    e.insert(std::string(kVT) + "post_layernorm.bias");
+    e.insert("multi_modal_projector.linear.weight");
+    e.insert("multi_modal_projector.linear.bias");
+    for (int m = 0; m < 3; ++m) {
+        for (int l = 0; l < h->cfg.joint_layers; ++l) {
+            const std::string p = std::string("joint_model.mixtures.") + kMixNames[m] + ".layers." +
+                                  std::to_string(l) + ".";
+            for (const char* n : {"self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
+                                  "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj", "input_layernorm",
+                                  "post_attention_layernorm"})
+                e.insert(p + n + ".weight");
+        }
+        if (m > 0) e.insert(std::string("joint_model.mixtures.") + kMixNames[m] + ".norm.weight");
+    }
+    for (const char* n : {"action_encoder.linear_1", "action_encoder.linear_2", "action_encoder.linear_3",
+                          "proprio_encoder", "action_decoder"})
+        for (const char* s : {"weight", "bias"}) e.insert(std::string(n) + "." + s);
+}
+
+static int validate_cfg(const blurr_pi0_config& c) {
+    if (c.abi_version != BLURR_ABI_VERSION) return fail(BLURR_ERR_INVALID, "config abi_version mismatch");
+    if (c.head_dim != 256 || c.num_kv_heads != 1)
+        return fail(BLURR_ERR_INVALID, "joint attention kernels are built for head_dim 256, 1 KV head (MQA)");
+    if (c.vision_hidden % c.vision_heads != 0 || c.vision_hidden / c.vision_heads > 80 ||
+        (c.vision_hidden / c.vision_heads) % 8 != 0)
+        return fail(BLURR_ERR_INVALID, "SigLIP head_dim must be a multiple of 8 and <= 80");
+    if (c.patch_size != 14 || c.image_size != 224 || c.num_image_tokens != 256)
+        return fail(BLURR_ERR_INVALID, "patch-embed kernel is built for 224x224 images, 14x14 patches");
+    if (c.vision_hidden % 128 || c.vlm_hidden % 128 || c.expert_hidden % 128 || c.vlm_intermediate % 64 ||
+        c.expert_intermediate % 64 || (c.num_heads * c.head_dim) % 128)
+        return fail(BLURR_ERR_INVALID, "hidden sizes must be multiples of 128 (intermediate: 64)");
+    if (c.proprio_dim > 8 || c.action_dim > 8 || c.proprio_dim < 1 || c.action_dim < 1)
+        return fail(BLURR_ERR_INVALID, "proprio_dim/action_dim must be in 1..8");
+    if (c.vision_layers < 1 || c.joint_layers < 1 || c.num_inference_steps < 1)
+        return fail(BLURR_ERR_INVALID, "layer counts / num_inference_steps must be >= 1");
+    if (c.max_image_text_tokens < c.num_image_tokens || c.num_action_tokens < 1 || c.num_proprio_tokens < 1)
+        return fail(BLURR_ERR_INVALID, "bad sequence layout");
+    if (c.max_image_text_tokens + c.num_proprio_tokens + c.num_action_tokens > 512)
+        return fail(BLURR_ERR_INVALID, "sequence longer than 512 tokens is not supported");
+    return 0;
+}
+
+extern "C" int blurr_abi_version(void) { return BLURR_ABI_VERSION; }
+extern "C" const char* blurr_last_error(void) { return g_err.c_str(); }
+
+extern "C" void blurr_pi0_destroy(blurr_pi0_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : h->graphs) {
+        cudaGraphExecDestroy(kv.second.exec);
+        cudaGraphDestroy(kv.second.graph);
+    }
+    for (auto& kv : h->taps) cudaFree(kv.second.ptr);
+    for (void* p : h->allocs) cudaFree(p);
+    gemm_forget_tensor_maps();
+    delete h;
+}
+
+extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max_batch, blurr_pi0_t** out) {
+    if (!cfg || !out || max_batch < 1) return fail(BLURR_ERR_INVALID, "blurr_pi0_create: bad arguments");
+    if (int r = validate_cfg(*cfg)) return r;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BLURR_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(BLURR_ERR_INVALID, "bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(BLURR_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major) +
+                                        std::to_string(prop.minor) + ", kernels are built for sm_100a only");
+    blurr_pi0* h = new blurr_pi0();
+    h->cfg = *cfg;
+    h->device = device;
+    h->max_batch = max_batch;
+    const auto& c = h->cfg;
+    h->T_img = c.num_image_tokens;
+    h->n_itp = c.max_image_text_tokens + c.num_proprio_tokens;
+    h->n_total = h->n_itp + c.num_action_tokens;
+    bool ok = true;
+    // ---- weights ----
+    h->embed = static_cast<bf16*>(dalloc(h, static_cast<size_t>(c.vocab_size) * c.vlm_hidden * 2));
+    ok &= h->embed != nullptr;
+    ok &= alloc_lin(h, h->patch, c.vision_hidden, 3 * c.patch_size * c.patch_size, true);
+    h->pos_emb = alloc_vec(h, c.num_image_tokens * c.vision_hidden);
+    h->vlayers.resize(c.vision_layers);
+    for (auto& L : h->vlayers) {
+        ok &= alloc_lin(h, L.qkv, 3 * c.vision_hidden, c.vision_hidden, true);
+        ok &= alloc_lin(h, L.out, c.vision_hidden, c.vision_hidden, true);
+        ok &= alloc_lin(h, L.fc1, c.vision_intermediate, c.vision_hidden, true);
+        ok &= alloc_lin(h, L.fc2, c.vision_hidden, pad_to(c.vision_intermediate, 128), true);
+        L.ln1w = alloc_vec(h, c.vision_hidden); L.ln1b = alloc_vec(h, c.vision_hidden);
+        L.ln2w = alloc_vec(h, c.vision_hidden); L.ln2b = alloc_vec(h, c.vision_hidden);
+        ok &= L.ln1w && L.ln1b && L.ln2w && L.ln2b;
+    }
+    h->post_ln_w = alloc_vec(h, c.vision_hidden);
+    h->post_ln_b = alloc_vec(h, c.vision_hidden);
+    ok &= alloc_lin(h, h->proj, c.vlm_hidden, c.vision_hidden, true);
+    const int qkv_rows = (c.num_heads + 2) * c.head_dim;
+    for (int m = 0; m < 3; ++m) {
+        MixtureW& M = h->mix[m];
+        M.name = kMixNames[m];
+        M.hidden = (m == 0) ? c.vlm_hidden : c.expert_hidden;
+        M.inter = (m == 0) ? c.vlm_intermediate : c.expert_intermediate;
+        M.layers.resize(c.joint_layers);
+        for (auto& L : M.layers) {
+            ok &= alloc_lin(h, L.qkv, qkv_rows, M.hidden, false);
+            ok &= alloc_lin(h, L.o, M.hidden, c.num_heads * c.head_dim, false);
+            ok &= alloc_lin(h, L.gu, 2 * M.inter, M.hidden, false);
+            ok &= alloc_lin(h, L.down, M.hidden, M.inter, false);
+            L.in_ln = alloc_vec(h, M.hidden);
+            L.post_ln = alloc_vec(h, M.hidden);
+            ok &= L.in_ln && L.post_ln;
+        }
+        if (m > 0) { M.final_norm = alloc_vec(h, M.hidden); ok &= M.final_norm != nullptr; }
+        M.cos_t = static_cast<float*>(dalloc(h, static_cast<size_t>(kNumPos) * 128 * 4));
+        M.sin_t = static_cast<float*>(dalloc(h, static_cast<size_t>(kNumPos) * 128 * 4));
+        ok &= M.cos_t && M.sin_t;
+    }
+    h->ae1_w = alloc_vec(h, c.expert_hidden * c.action_dim); h->ae1_b = alloc_vec(h, c.expert_hidden);
+    ok &= alloc_lin(h, h->ae2, c.expert_hidden, 2 * c.expert_hidden, true);
+    ok &= alloc_lin(h, h->ae3, c.expert_hidden, c.expert_hidden, true);
+    h->pe_w = alloc_vec(h, c.expert_hidden * c.proprio_dim); h->pe_b = alloc_vec(h, c.expert_hidden);
+    h->dec_w = alloc_vec(h, c.action_dim * c.expert_hidden); h->dec_b = alloc_vec(h, c.action_dim);
+    // ---- static inputs / activations ----
+    const size_t B = max_batch;
+    const size_t Tv = B * c.num_image_tokens, Tt = B * c.max_image_text_tokens;
+    const size_t Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens;
+    auto bufb = [&](size_t elems) { return static_cast<bf16*>(dalloc(h, elems * 2)); };
+    h->d_ids = static_cast<int64_t*>(dalloc(h, Tt * 8));
+    h->d_vpos = static_cast<int64_t*>(dalloc(h, Tt * 8));
+    h->d_ppos = static_cast<int64_t*>(dalloc(h, Tp * 8));
+    h->d_apos = static_cast<int64_t*>(dalloc(h, Ta * 8));
+    h->d_proprios = bufb(Tp * c.proprio_dim);
+    h->d_action = bufb(Ta * c.action_dim);
+    h->d_out = bufb(Ta * c.action_dim);
+    h->d_mask_itp = bufb(B * h->n_itp * h->n_itp);
+    h->d_mask_act = bufb(B * c.num_action_tokens * h->n_total);
+    h->patches = bufb(Tv * h->patch.K);
+    h->xs = bufb(Tv * c.vision_hidden); h->xn = bufb(Tv * c.vision_hidden);
+    h->sqkv = bufb(Tv * 3 * c.vision_hidden); h->sattn = bufb(Tv * c.vision_hidden);
+    h->shmid = bufb(Tv * h->vlayers[0].fc1.Nw); h->imgfeat = bufb(Tv * c.vlm_hidden);
+    const int qw = c.num_heads * c.head_dim;
+    h->E = bufb(Tt * c.vlm_hidden); h->En = bufb(Tt * c.vlm_hidden);
+    h->Qv = bufb(Tt * qw); h->AOv = bufb(Tt * qw); h->H = bufb(Tt * c.vlm_intermediate);
+    h->Ep = bufb(Tp * c.expert_hidden); h->Epn = bufb(Tp * c.expert_hidden);
+    h->Qp = bufb(Tp * qw); h->AOp = bufb(Tp * qw); h->Hp = bufb(Tp * c.expert_intermediate);
+    h->Ea = bufb(Ta * c.expert_hidden); h->Ean = bufb(Ta * c.expert_hidden);
+    h->Qa = bufb(Ta * qw); h->AOa = bufb(Ta * qw); h->Ha = bufb(Ta * c.expert_intermediate);
+    h->X2 = bufb(Ta * 2 * c.expert_hidden); h->A1 = bufb(Ta * c.expert_hidden);
+    const size_t cache_elems = static_cast<size_t>(c.joint_layers) * B * h->n_total * c.head_dim;
+    h->kcache = bufb(cache_elems); h->vcache = bufb(cache_elems);
+    // split-K workspace: at most ~kNumSMs CTAs of 128 x (tokens per CTA) fp32 for small T, or one
+    // full [T][Nw] slab for large T (see pick_splitk)
+    size_t ws = 0;
+    {
+        const size_t maxNw = std::max<size_t>(qkv_rows, std::max<size_t>(c.vlm_hidden, 3 * c.vision_hidden));
+        const size_t maxT = std::max(Tt, Tv);
+        ws = std::max<size_t>(maxT * maxNw, static_cast<size_t>(kNumSMs + 20) * 128 * 512);
+        ws = std::max<size_t>(ws, 16 * maxT * c.expert_hidden);
+    }
+    h->ws_floats = ws;
+    h->ws = static_cast<float*>(dalloc(h, ws * 4));
+    h->d_err = static_cast<int*>(dalloc(h, 16));
+    ok &= h->ws && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
+    if (!ok) {
+        blurr_pi0_destroy(h);
+        return fail(BLURR_ERR_CUDA, "blurr_pi0_create: device allocation failed");
+    }
+    build_expected(h);
+    *out = h;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------
+static int repack(const bf16* src, int rows, int cols, int src_ld, bf16* dst, int dst_ld, int mode, int row_off) {
+    const size_t total = static_cast<size_t>(rows) * cols;
+    repack_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(src, rows, cols, src_ld, dst, dst_ld,
+                                                                            mode, row_off);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BLURR_ERR_CUDA, std::string("repack: ") + cudaGetErrorString(e));
+    return 0;
+}
+static bool shape_is(const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
+    if (ndim != static_cast<int>(want.size())) return false;
+    int i = 0;
+    for (int64_t w : want) if (shape[i++] != w) return false;
+    return true;
+}
+static int bad_shape(const std::string& key) { return fail(BLURR_ERR_INVALID, "unexpected shape for " + key); }
+
+static bool starts_with(const std::string& s, const std::string& p) { return s.compare(0, p.size(), p) == 0; }
+
+extern "C" int blurr_pi0_set_weight(blurr_pi0_t* h, const char* key_c, const void* dev_ptr,
+                                    const int64_t* shape, int ndim, int dtype) {
+    if (!h || !key_c || !dev_ptr || !shape) return fail(BLURR_ERR_INVALID, "set_weight: null argument");
+    if (dtype != BLURR_BF16)
+        return fail(BLURR_ERR_INVALID, "set_weight: only bf16 weights are supported (cast the model with .to(torch.bfloat16))");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const std::string key(key_c);
+    if (!h->expected.count(key)) return fail(BLURR_ERR_INVALID, "set_weight: unknown state_dict key " + key);
+    const auto& c = h->cfg;
+    const bf16* src = static_cast<const bf16*>(dev_ptr);
+    const int VH = c.vision_hidden, VI = c.vision_intermediate;
+    int rc = 0;
+    auto vec = [&](bf16* dst, int64_t n) -> int {
+        if (!shape_is(shape, ndim, {n})) return bad_shape(key);
+        return repack(src, 1, static_cast<int>(n), static_cast<int>(n), dst, static_cast<int>(n), MAP_OFFSET, 0);
+    };
+    auto mat = [&](Lin& L, int64_t rows, int64_t cols, int mode, int row_off) -> int {
+        if (!shape_is(shape, ndim, {rows, cols})) return bad_shape(key);
+        return repack(src, static_cast<int>(rows), static_cast<int>(cols), static_cast<int>(cols), L.w, L.ld, mode, row_off);
+    };
+    auto bias_rows = [&](Lin& L, int64_t n, int off) -> int {
+        if (!shape_is(shape, ndim, {n})) return bad_shape(key);
+        return repack(src, 1, static_cast<int>(n), static_cast<int>(n), L.bias + off, L.Nw, MAP_OFFSET, 0);
+    };
+
+    if (key == "embed_tokens.weight") {
+        if (!shape_is(shape, ndim, {c.vocab_size, c.vlm_hidden})) return bad_shape(key);
+        CUDA_TRY(cudaMemcpyAsync(h->embed, src, static_cast<size_t>(c.vocab_size) * c.vlm_hidden * 2,
+                                 cudaMemcpyDeviceToDevice, 0));
+    } else if (starts_with(key, kVT)) {
+        const std::string k = key.substr(strlen(kVT));
+        if (k == "embeddings.patch_embedding.weight") {
+            if (!shape_is(shape, ndim, {VH, 3, c.patch_size, c.patch_size})) return bad_shape(key);
+            const int kc = 3 * c.patch_size * c.patch_size;
+            rc = repack(src, VH, kc, kc, h->patch.w, h->patch.ld, MAP_OFFSET, 0);
+        } else if (k == "embeddings.patch_embedding.bias") rc = bias_rows(h->patch, VH, 0);
+        else if (k == "embeddings.position_embedding.weight") {
+            if (!shape_is(shape, ndim, {c.num_image_tokens, VH})) return bad_shape(key);
+            rc = repack(src, c.num_image_tokens, VH, VH, h->pos_emb, VH, MAP_OFFSET, 0);
+        } else if (k == "post_layernorm.weight") rc = vec(h->post_ln_w, VH);
+        else if (k == "post_layernorm.bias") rc = vec(h->post_ln_b, VH);
+        else {
+            int l = -1; char rest[128] = {0};
+            if (sscanf(k.c_str(), "encoder.layers.%d.%127s", &l, rest) != 2 || l < 0 || l >= c.vision_layers)
+                return fail(BLURR_ERR_INVALID, "set_weight: cannot parse " + key);
+            VisionLayer& L = h->vlayers[l];
+            const std::string r(rest);
+            if (r == "self_attn.q_proj.weight") rc = mat(L.qkv, VH, VH, MAP_OFFSET, 0);
+            else if (r == "self_attn.k_proj.weight") rc = mat(L.qkv, VH, VH, MAP_OFFSET, VH);
+            else if (r == "self_attn.v_proj.weight") rc = mat(L.qkv, VH, VH, MAP_OFFSET, 2 * VH);
+            else if (r == "self_attn.q_proj.bias") rc = bias_rows(L.qkv, VH, 0);
+            else if (r == "self_attn.k_proj.bias") rc = bias_rows(L.qkv, VH, VH);
+            else if (r == "self_attn.v_proj.bias") rc = bias_rows(L.qkv, VH, 2 * VH);
+            else if (r == "self_attn.out_proj.weight") rc = mat(L.out, VH, VH, MAP_OFFSET, 0);
+            else if (r == "self_attn.out_proj.bias") rc = bias_rows(L.out, VH, 0);
+            else if (r == "layer_norm1.weight") rc = vec(L.ln1w, VH);
+            else if (r == "layer_norm1.bias") rc = vec(L.ln1b, VH);
+            else if (r == "layer_norm2.weight") rc = vec(L.ln2w, VH);
+            else if (r == "layer_norm2.bias") rc = vec(L.ln2b, VH);
+            else if (r == "mlp.fc1.weight") rc = mat(L.fc1, VI, VH, MAP_OFFSET, 0);
+            else if (r == "mlp.fc1.bias") rc = bias_rows(L.fc1, VI, 0);
+            else if (r == "mlp.fc2.weight") rc = mat(L.fc2, VH, VI, MAP_OFFSET, 0);
+            else if (r == "mlp.fc2.bias") rc = bias_rows(L.fc2, VH, 0);
+            else return fail(BLURR_ERR_INVALID, "set_weight: cannot parse " + key);
+        }
+    } else if (key == "multi_modal_projector.linear.weight") rc = mat(h->proj, c.vlm_hidden, VH, MAP_OFFSET, 0);
+    else if (key == "multi_modal_projector.linear.bias") rc = bias_rows(h->proj, c.vlm_hidden, 0);
+    else if (starts_with(key, "joint_model.mixtures.")) {
+        char mname[16] = {0}; int l = -1; char rest[128] = {0};
+        const char* s = key.c_str() + strlen("joint_model.mixtures.");
+        int m = -1;
+        for (int i = 0; i < 3; ++i)
+            if (starts_with(s, std::string(kMixNames[i]) + ".")) m = i;
+        if (m < 0) return fail(BLURR_ERR_INVALID, "set_weight: cannot parse " + key);
+        (void)mname;
+        MixtureW& M = h->mix[m];
+        const std::string tail(s + strlen(kMixNames[m]) + 1);
+        const int Hd = M.hidden, I = M.inter, QW = c.num_heads * c.head_dim, D = c.head_dim;
+        if (tail == "norm.weight") rc = vec(M.final_norm, Hd);
+        else {
+            if (sscanf(tail.c_str(), "layers.%d.%127s", &l, rest) != 2 || l < 0 || l >= c.joint_layers)
+                return fail(BLURR_ERR_INVALID, "set_weight: cannot parse " + key);
+            MixLayer& L = M.layers[l];
+            const std::string r(rest);
+            if (r == "self_attn.q_proj.weight") rc = mat(L.qkv, QW, Hd, MAP_OFFSET, 0);
+            else if (r == "self_attn.k_proj.weight") rc = mat(L.qkv, D, Hd, MAP_OFFSET, QW);
+            else if (r == "self_attn.v_proj.weight") rc = mat(L.qkv, D, Hd, MAP_OFFSET, QW + D);
+            else if (r == "self_attn.o_proj.weight") rc = mat(L.o, Hd, QW, MAP_OFFSET, 0);
+            else if (r == "mlp.gate_proj.weight") rc = mat(L.gu, I, Hd, MAP_GATE, 0);
+            else if (r == "mlp.up_proj.weight") rc = mat(L.gu, I, Hd, MAP_UP, 0);
+            else if (r == "mlp.down_proj.weight") rc = mat(L.down, Hd, I, MAP_OFFSET, 0);
+            else if (r == "input_layernorm.weight") rc = vec(L.in_ln, Hd);
+            else if (r == "post_attention_layernorm.weight") rc = vec(L.post_ln, Hd);
+            else return fail(BLURR_ERR_INVALID, "set_weight: cannot parse " + key);
+        }
+    } else if (key == "action_encoder.linear_1.weight") {
+        if (!shape_is(shape, ndim, {c.expert_hidden, c.action_dim})) return bad_shape(key);
+        rc = repack(src, c.expert_hidden, c.action_dim, c.action_dim, h->ae1_w, c.action_dim, MAP_OFFSET, 0);
+    } else if (key == "action_encoder.linear_1.bias") rc = vec(h->ae1_b, c.expert_hidden);
+    else if (key == "action_encoder.linear_2.weight") rc = mat(h->ae2, c.expert_hidden, 2 * c.expert_hidden, MAP_OFFSET, 0);
+    else if (key == "action_encoder.linear_2.bias") rc = bias_rows(h->ae2, c.expert_hidden, 0);
+    else if (key == "action_encoder.linear_3.weight") rc = mat(h->ae3, c.expert_hidden, c.expert_hidden, MAP_OFFSET, 0);
+    else if (key == "action_encoder.linear_3.bias") rc = bias_rows(h->ae3, c.expert_hidden, 0);
+    else if (key == "proprio_encoder.weight") {
+        if (!shape_is(shape, ndim, {c.expert_hidden, c.proprio_dim})) return bad_shape(key);
+        rc = repack(src, c.expert_hidden, c.proprio_dim, c.proprio_dim, h->pe_w, c.proprio_dim, MAP_OFFSET, 0);
+    } else if (key == "proprio_encoder.bias") rc = vec(h->pe_b, c.expert_hidden);
+    else if (key == "action_decoder.weight") {
+        if (!shape_is(shape, ndim, {c.action_dim, c.expert_hidden})) return bad_shape(key);
+        rc = repack(src, c.action_dim, c.expert_hidden, c.expert_hidden, h->dec_w, c.expert_hidden, MAP_OFFSET, 0);
+    } else if (key == "action_decoder.bias") rc = vec(h->dec_b, c.action_dim);
+    else return fail(BLURR_ERR_INVALID, "set_weight: unhandled key " + key);
+    if (rc) return rc;
+    h->seen.insert(key);
+    h->finalized = false;
+    return 0;
+}
+
+extern "C" int blurr_pi0_set_rope_inv_freq(blurr_pi0_t* h, const char* mixture, const float* inv, int n) {
+    if (!h || !mixture || !inv || n != 128) return fail(BLURR_ERR_INVALID, "set_rope_inv_freq: need 128 values");
+    for (int m = 0; m < 3; ++m)
+        if (h->mix[m].name == mixture) {
+            memcpy(h->mix[m].inv_freq, inv, 128 * sizeof(float));
+            h->mix[m].have_inv_freq = true;
+            h->finalized = false;
+            return 0;
+        }
+    return fail(BLURR_ERR_INVALID, std::string("unknown mixture ") + mixture);
+}
+
+extern "C" int blurr_pi0_set_time_table(blurr_pi0_t* h, const void* dev_table, int num_steps) {
+    if (!h || !dev_table || num_steps < 1) return fail(BLURR_ERR_INVALID, "set_time_table: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (num_steps > h->time_steps) {
+        h->time_table = static_cast<bf16*>(dalloc(h, static_cast<size_t>(num_steps) * h->cfg.expert_hidden * 2));
+        if (!h->time_table) return fail(BLURR_ERR_CUDA, "set_time_table: allocation failed");
+    }
+    h->time_steps = num_steps;
+    CUDA_TRY(cudaMemcpy(h->time_table, dev_table, static_cast<size_t>(num_steps) * h->cfg.expert_hidden * 2,
+                        cudaMemcpyDeviceToDevice));
+    // a different step count changes the captured schedule
+    for (auto& kv : h->graphs) {
+        cudaGraphExecDestroy(kv.second.exec);
+        cudaGraphDestroy(kv.second.graph);
+    }
+    h->graphs.clear();
+    return 0;
+}
+
+extern "C" int blurr_pi0_finalize_weights(blurr_pi0_t* h) {
+    if (!h) return fail(BLURR_ERR_INVALID, "finalize: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (const auto& k : h->expected)
+        if (!h->seen.count(k)) return fail(BLURR_ERR_STATE, "finalize: missing weight " + k);
+    for (int m = 0; m < 3; ++m) {
+        MixtureW& M = h->mix[m];
+        if (!M.have_inv_freq) return fail(BLURR_ERR_STATE, "finalize: missing RoPE inv_freq for " + M.name);
+        float* d_inv = static_cast<float*>(dalloc(h, 128 * 4));
+        if (!d_inv) return fail(BLURR_ERR_CUDA, "finalize: allocation failed");
+        CUDA_TRY(cudaMemcpy(d_inv, M.inv_freq, 128 * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(launch_rope_table(0, d_inv, kNumPos, M.cos_t, M.sin_t));
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    h->finalized = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// the schedule
+// ---------------------------------------------------------------------------
+struct Run {
+    blurr_pi0* h;
+    cudaStream_t st;
+    int rc = 0;
+    void launched(cudaError_t e, const char* what) {
+        ++h->launches;
+        if (e != cudaSuccess && rc == 0) rc = fail(BLURR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    }
+    // split-K so that about one CTA per SM is in flight (each CTA owns ~all of an SM's smem)
+    int pick_splitk(int T, int Nw, int K) const {
+        GemmPlan p = gemm_make_plan(T, Nw, K, 1, EPI_PARTIAL, 0);
+        if (!p.valid) return 1;
+        const int ctas = p.grid_x * p.grid_y;
+        int s = kNumSMs / ctas;
+        if (s < 1) s = 1;
+        const int max_by_k = p.kb_total / 2 > 0 ? p.kb_total / 2 : 1;
+        if (s > max_by_k) s = max_by_k;
+        if (s > 16) s = 16;
+        while (s > 1 && static_cast<size_t>(s) * T * Nw > h->ws_floats) --s;
+        return s;
+    }
+    // returns split-K slices used
+    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true) {
+        if (rc) return 1;
+        GemmCall c{};
+        c.W = L.w; c.Nw = L.Nw; c.K = L.K; c.ldw = L.ld;
+        c.X = X; c.T = T; c.ldx = L.K;
+        c.epi = epi;
+        c.splitk = (epi == EPI_PARTIAL) ? pick_splitk(T, L.Nw, L.K) : 1;
+        c.bias = bias ? L.bias : nullptr;
+        c.out = out; c.ldo = ldo; c.partial = h->ws; c.bn_override = 0;
+        if (epi == EPI_PARTIAL && static_cast<size_t>(c.splitk) * T * L.Nw > h->ws_floats) {
+            rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
+            return 1;
+        }
+        std::string err;
+        int s = gemm_launch(st, c, &err);
+        ++h->launches;
+        if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 1; }
+        return s;
+    }
+    void consumer(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
+                  float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
+                  bf16* xn_out, bool use_partial = true) {
+        if (rc) return;
+        ConsumerArgs a{};
+        a.partial = use_partial ? h->ws : nullptr; a.splitk = splitk; a.T = T; a.N = N; a.ldp = ldp;
+        a.bias = bias; a.add_mode = add_mode; a.res = res; a.ldr = ldr;
+        a.pos = h->pos_emb; a.pos_rows = h->cfg.num_image_tokens; a.out_scale = out_scale;
+        a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
+        a.xn_out = xn_out; a.ldn = N;
+        launched(launch_consumer(st, a), "consumer");
+    }
+    void tap(const std::string& name, const void* src, size_t bytes) {
+        if (!h->debug || rc) return;
+        auto it = h->taps.find(name);
+        if (it == h->taps.end() || it->second.bytes != bytes) {
+            if (it != h->taps.end()) cudaFree(it->second.ptr);
+            void* p = nullptr;
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { rc = fail(BLURR_ERR_CUDA, "tap allocation failed"); return; }
+            h->taps[name] = TapBuf{p, bytes};
+            it = h->taps.find(name);
+        }
+        cudaMemcpyAsync(it->second.ptr, src, bytes, cudaMemcpyDeviceToDevice, st);
+    }
+};
+
+// SigLIP + projector + embedding merge (pizero.py:433-471; siglip.py)
+static void run_vision(Run& R, int B) {
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    const int Tv = B * c.num_image_tokens, VH = c.vision_hidden;
+    const float eps = c.layer_norm_eps;
+    int s = R.gemm(h->patch, h->patches, Tv, EPI_PARTIAL, nullptr, 0);
+    R.consumer(s, Tv, VH, h->patch.Nw, h->patch.bias, ADD_POSEMB, nullptr, 0, 1.0f, h->xs, NORM_LAYERNORM,
+               h->vlayers[0].ln1w, h->vlayers[0].ln1b, eps, h->xn);
+    R.tap("siglip.embeddings", h->xs, static_cast<size_t>(Tv) * VH * 2);
+    for (int l = 0; l < c.vision_layers; ++l) {
+        VisionLayer& L = h->vlayers[l];
+        R.gemm(L.qkv, h->xn, Tv, EPI_STORE, h->sqkv, 3 * VH);
+        R.launched(launch_siglip_attention(R.st, h->sqkv, 3 * VH, B, c.num_image_tokens, c.vision_heads, VH,
+                                           h->sattn, VH), "siglip_attention");
+        s = R.gemm(L.out, h->sattn, Tv, EPI_PARTIAL, nullptr, 0);
+        R.consumer(s, Tv, VH, L.out.Nw, L.out.bias, ADD_RESIDUAL, h->xs, VH, 1.0f, h->xs, NORM_LAYERNORM, L.ln2w,
+                   L.ln2b, eps, h->xn);
+        R.gemm(L.fc1, h->xn, Tv, EPI_GELU, h->shmid, L.fc1.Nw);
+        s = R.gemm(L.fc2, h->shmid, Tv, EPI_PARTIAL, nullptr, 0);
+        const bool last = (l == c.vision_layers - 1);
+        const bf16* nw = last ? h->post_ln_w : h->vlayers[l + 1].ln1w;
+        const bf16* nb = last ? h->post_ln_b : h->vlayers[l + 1].ln1b;
+        R.consumer(s, Tv, VH, L.fc2.Nw, L.fc2.bias, ADD_RESIDUAL, h->xs, VH, 1.0f, h->xs, NORM_LAYERNORM, nw, nb,
+                   eps, h->xn);
+        R.tap("siglip.layer" + std::to_string(l), h->xs, static_cast<size_t>(Tv) * VH * 2);
+    }
+    R.tap("siglip.post_layernorm", h->xn, static_cast<size_t>(Tv) * VH * 2);
+    R.gemm(h->proj, h->xn, Tv, EPI_STORE, h->imgfeat, c.vlm_hidden);
+    R.tap("projector", h->imgfeat, static_cast<size_t>(Tv) * c.vlm_hidden * 2);
+    // image_features / (hidden ** 0.5): ATen multiplies by the fp32 reciprocal of the Python scalar;
+    // normalizer: torch.tensor(hidden ** 0.5, dtype=bf16)
+    const float inv_div = 1.0f / static_cast<float>(std::sqrt(static_cast<double>(c.vlm_hidden)));
+    const float normalizer = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.vlm_hidden)))));
+    R.launched(launch_embed_merge(R.st, h->d_ids, B, c.max_image_text_tokens, h->embed, c.vocab_size, h->imgfeat,
+                                  c.num_image_tokens, c.vlm_hidden, c.image_token_index, c.pad_token_id, inv_div,
+                                  normalizer, h->E, h->d_err), "embed_merge");
+    R.tap("merged_embeds", h->E, static_cast<size_t>(B) * c.max_image_text_tokens * c.vlm_hidden * 2);
+}
+
+struct StreamBufs {
+    bf16 *x, *xn, *q, *ao, *hmid;
+    int tokens_per_sample, slot_base, q_row_offset;
+    const int64_t* pos;
+};
+
+// One mixture's share of a joint layer (joint_model.py:24-129): QKV+RoPE+cache, attention,
+// o_proj + residual + post-norm, GeGLU MLP + residual + next norm.
+static void layer_qkv(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only) {
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    MixtureW& M = h->mix[m];
+    MixLayer& L = M.layers[l];
+    const int T = B * sb.tokens_per_sample;
+    const int QW = c.num_heads * c.head_dim;
+    Lin qkv = L.qkv;
+    if (kv_only) {                      // last layer of vlm/proprio: only K and V are needed
+        qkv.w = L.qkv.w + static_cast<size_t>(QW) * L.qkv.ld;
+        qkv.Nw = L.qkv.Nw - QW;
+    }
+    const int s = R.gemm(qkv, sb.xn, T, EPI_PARTIAL, nullptr, 0, false);
+    if (R.rc) return;
+    RopeKvArgs a{};
+    a.partial = h->ws; a.splitk = s; a.T = T; a.ldp = qkv.Nw;
+    a.n_heads = kv_only ? 0 : c.num_heads;
+    a.tokens_per_sample = sb.tokens_per_sample; a.position_ids = sb.pos;
+    a.cos_table = M.cos_t; a.sin_table = M.sin_t; a.n_pos = kNumPos;
+    a.q_out = kv_only ? nullptr : sb.q;
+    const size_t layer_off = static_cast<size_t>(l) * h->max_batch * h->n_total * c.head_dim;
+    a.k_cache = h->kcache + layer_off; a.v_cache = h->vcache + layer_off;
+    a.n_slots = h->n_total; a.slot_base = sb.slot_base;
+    R.launched(launch_rope_kv(R.st, a), "rope_kv");
+}
+
+static void layer_attn(Run& R, int l, const StreamBufs& sb, int B, int n_keys, const bf16* mask, long long mbs,
+                       long long mrs, bool fewq) {
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    if (R.rc) return;
+    JointAttnArgs a{};
+    a.q = sb.q; a.q_per_sample = sb.tokens_per_sample; a.q_row_offset = sb.q_row_offset;
+    const size_t layer_off = static_cast<size_t>(l) * h->max_batch * h->n_total * c.head_dim;
+    a.k_cache = h->kcache + layer_off; a.v_cache = h->vcache + layer_off;
+    a.n_slots = h->n_total; a.n_keys = n_keys;
+    a.mask = mask; a.mask_bstride = mbs; a.mask_rstride = mrs;
+    a.batch = B; a.n_heads = c.num_heads; a.out = sb.ao;
+    if (fewq) R.launched(launch_joint_attention_fewq(R.st, a), "attention_fewq");
+    else R.launched(launch_joint_attention_prefill(R.st, a), "attention_prefill");
+}
+
+static void layer_post(Run& R, int m, int l, const StreamBufs& sb, int B, const bf16* next_norm) {
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    MixtureW& M = h->mix[m];
+    MixLayer& L = M.layers[l];
+    const int T = B * sb.tokens_per_sample;
+    int s = R.gemm(L.o, sb.ao, T, EPI_PARTIAL, nullptr, 0, false);
+    R.consumer(s, T, M.hidden, L.o.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x, NORM_RMS_GEMMA, L.post_ln,
+               nullptr, c.rms_norm_eps, sb.xn);
+    R.gemm(L.gu, sb.xn, T, EPI_GEGLU, sb.hmid, M.inter, false);
+    s = R.gemm(L.down, sb.hmid, T, EPI_PARTIAL, nullptr, 0, false);
+    R.consumer(s, T, M.hidden, L.down.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
+               next_norm ? NORM_RMS_GEMMA : NORM_NONE, next_norm, nullptr, c.rms_norm_eps, next_norm ? sb.xn : nullptr);
+}
+
+static void run_step(Run& R, int B, int steps) {
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    const int L = c.joint_layers;
+    run_vision(R, B);
+    // proprio_encoder (pizero.py:493) and `*= sqrt(1024)` (joint_model.py:358-365)
+    const int Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens;
+    const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
+    R.launched(launch_small_k_linear(R.st, h->d_proprios, Tp, c.proprio_dim, h->pe_w, h->pe_b, c.expert_hidden,
+                                     expert_norm, h->Ep, c.expert_hidden, 0, nullptr, 0), "proprio_encoder");
+
+    StreamBufs sv{h->E, h->En, h->Qv, h->AOv, h->H, c.max_image_text_tokens, 0, 0, h->d_vpos};
+    StreamBufs sp{h->Ep, h->Epn, h->Qp, h->AOp, h->Hp, c.num_proprio_tokens, c.max_image_text_tokens,
+                  c.max_image_text_tokens, h->d_ppos};
+    StreamBufs sa{h->Ea, h->Ean, h->Qa, h->AOa, h->Ha, c.num_action_tokens, h->n_itp, 0, h->d_apos};
+    const int Tt = B * c.max_image_text_tokens;
+
+    // ---- prefill: vlm + proprio into the KV cache (pizero.py:496-508) ----
+    R.consumer(1, Tt, c.vlm_hidden, 0, nullptr, ADD_NONE, h->E, c.vlm_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
+               h->mix[0].layers[0].in_ln, nullptr, c.rms_norm_eps, h->En, false);
+    R.consumer(1, Tp, c.expert_hidden, 0, nullptr, ADD_NONE, h->Ep, c.expert_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
+               h->mix[1].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Epn, false);
+    const long long itp_bs = static_cast<long long>(h->n_itp) * h->n_itp, itp_rs = h->n_itp;
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        layer_qkv(R, 0, l, sv, B, last);
+        layer_qkv(R, 1, l, sp, B, last);
+        if (last) break;                 // final layer: vlm/proprio stop after caching K,V (joint_model.py:380-382)
+        layer_attn(R, l, sv, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, false);
+        layer_attn(R, l, sp, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, true);
+        const bool next_kv_only = (l + 1 == L - 1);
+        (void)next_kv_only;
+        layer_post(R, 0, l, sv, B, h->mix[0].layers[l + 1].in_ln);
+        layer_post(R, 1, l, sp, B, h->mix[1].layers[l + 1].in_ln);
+        R.tap("prefill.L" + std::to_string(l) + ".vlm", h->E, static_cast<size_t>(Tt) * c.vlm_hidden * 2);
+        R.tap("prefill.L" + std::to_string(l) + ".proprio", h->Ep, static_cast<size_t>(Tp) * c.expert_hidden * 2);
+    }
+
+    // ---- flow matching: Euler steps of the action expert over the cache (pizero.py:516-538) ----
+    const long long act_bs = static_cast<long long>(c.num_action_tokens) * h->n_total, act_rs = h->n_total;
+    const float dt = static_cast<float>(1.0 / static_cast<double>(steps));
+    for (int s = 0; s < steps; ++s) {
+        // ActionEncoder (vla/modules.py:39-53)
+        R.launched(launch_small_k_linear(R.st, h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f,
+                                         h->X2, 2 * c.expert_hidden, c.expert_hidden,
+                                         h->time_table + static_cast<size_t>(s) * c.expert_hidden, c.expert_hidden),
+                   "action_encoder.linear_1");
+        int k = R.gemm(h->ae2, h->X2, Ta, EPI_PARTIAL, nullptr, 0);
+        if (!R.rc)
+            R.launched(launch_bias_act(R.st, h->ws, k, Ta, c.expert_hidden, h->ae2.Nw, h->ae2.bias, ACT_SILU, 1.0f,
+                                       h->A1, c.expert_hidden), "action_encoder.silu");
+        k = R.gemm(h->ae3, h->A1, Ta, EPI_PARTIAL, nullptr, 0);
+        R.consumer(k, Ta, c.expert_hidden, h->ae3.Nw, h->ae3.bias, ADD_NONE, nullptr, 0, expert_norm, h->Ea,
+                   NORM_RMS_GEMMA, h->mix[2].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Ean);
+        R.tap("flow" + std::to_string(s) + ".action_embeds", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
+        for (int l = 0; l < L; ++l) {
+            layer_qkv(R, 2, l, sa, B, false);
+            layer_attn(R, l, sa, B, h->n_total, h->d_mask_act, act_bs, act_rs, true);
+            const bf16* next = (l + 1 < L) ? h->mix[2].layers[l + 1].in_ln : h->mix[2].final_norm;
+            layer_post(R, 2, l, sa, B, next);
+            R.tap("flow" + std::to_string(s) + ".L" + std::to_string(l) + ".action", h->Ea,
+                  static_cast<size_t>(Ta) * c.expert_hidden * 2);
+        }
+        bf16* vel_tap = nullptr;
+        if (h->debug) {
+            const std::string nm = "flow" + std::to_string(s) + ".velocity";
+            R.tap(nm, h->d_action, static_cast<size_t>(Ta) * c.action_dim * 2);   // allocates the slot
+            if (!R.rc) vel_tap = static_cast<bf16*>(h->taps[nm].ptr);
+        }
+        R.launched(launch_action_tail(R.st, h->Ean, Ta, c.expert_hidden, h->dec_w, h->dec_b, c.action_dim, dt,
+                                      h->d_action, vel_tap), "action_tail");
+    }
+    R.launched(launch_clamp_copy(R.st, h->d_action, h->d_out, Ta * c.action_dim, c.has_clip,
+                                 c.final_action_clip_value), "clamp");
+}
+
+extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const blurr_pi0_inputs* in,
+                                      void* actions_out) {
+    if (!h || !in || !actions_out) return fail(BLURR_ERR_INVALID, "infer_action: null argument");
+    if (!h->finalized) return fail(BLURR_ERR_STATE, "infer_action: call blurr_pi0_finalize_weights first");
+    if (batch < 1 || batch > h->max_batch) return fail(BLURR_ERR_INVALID, "infer_action: batch out of range");
+    const auto& c = h->cfg;
+    const int steps = c.num_inference_steps;
+    if (!h->time_table || h->time_steps != steps)
+        return fail(BLURR_ERR_STATE, "infer_action: time table missing or not matching num_inference_steps");
+    if (!in->input_ids || !in->pixel_values || !in->image_text_proprio_mask || !in->action_mask ||
+        !in->vlm_position_ids || !in->proprio_position_ids || !in->action_position_ids || !in->proprios || !in->noise)
+        return fail(BLURR_ERR_INVALID, "infer_action: null input tensor");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    h->launches = 0;
+
+    // stage the per-call inputs (outside the graph: their addresses change from call to call)
+    StageArgs sa{};
+    sa.ids = in->input_ids; sa.vpos = in->vlm_position_ids; sa.ppos = in->proprio_position_ids;
+    sa.apos = in->action_position_ids;
+    sa.proprios = static_cast<const bf16*>(in->proprios); sa.noise = static_cast<const bf16*>(in->noise);
+    sa.mask_itp = static_cast<const bf16*>(in->image_text_proprio_mask);
+    sa.itp_bs = in->itp_mask_bstride; sa.itp_rs = in->itp_mask_rstride;
+    sa.mask_act = static_cast<const bf16*>(in->action_mask);
+    sa.act_bs = in->action_mask_bstride; sa.act_rs = in->action_mask_rstride;
+    sa.d_ids = h->d_ids; sa.d_vpos = h->d_vpos; sa.d_ppos = h->d_ppos; sa.d_apos = h->d_apos;
+    sa.d_proprios = h->d_proprios; sa.d_action = h->d_action; sa.d_mask_itp = h->d_mask_itp;
+    sa.d_mask_act = h->d_mask_act;
+    sa.n_ids = batch * c.max_image_text_tokens; sa.n_ppos = batch * c.num_proprio_tokens;
+    sa.n_apos = batch * c.num_action_tokens; sa.n_prop = batch * c.num_proprio_tokens * c.proprio_dim;
+    sa.n_noise = batch * c.num_action_tokens * c.action_dim;
+    sa.itp_dim = h->n_itp; sa.act_rows = c.num_action_tokens; sa.act_cols = h->n_total; sa.batch = batch;
+    const long long total = static_cast<long long>(sa.n_ids) + sa.n_ppos + sa.n_apos + sa.n_prop + sa.n_noise +
+                            static_cast<long long>(batch) * h->n_itp * h->n_itp +
+                            static_cast<long long>(batch) * c.num_action_tokens * h->n_total;
+    stage_inputs_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(sa);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_im2col(st, static_cast<const bf16*>(in->pixel_values), in->pixel_strides[0], in->pixel_strides[1],
+                           in->pixel_strides[2], in->pixel_strides[3], batch, h->patches, h->patch.K));
+    int64_t pre_launches = 2;
+
+    Run R{h, st};
+    const bool graph = h->use_graph && !h->debug;
+    if (!graph) {
+        run_step(R, batch, steps);
+        if (R.rc) return R.rc;
+        h->launches += pre_launches;
+    } else {
+        const long long key = static_cast<long long>(batch) * 4096 + steps;
+        auto it = h->graphs.find(key);
+        if (it == h->graphs.end()) {
+            // warm run outside capture: first-use attribute setup and tensor-map creation
+            run_step(R, batch, steps);
+            if (R.rc) return R.rc;
+            CUDA_TRY(cudaStreamSynchronize(st));
+            h->launches = 0;
+            cudaStream_t cs;
+            CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            Run C{h, cs};
+            cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) { cudaStreamDestroy(cs); return fail(BLURR_ERR_CUDA, "graph capture begin failed"); }
+            run_step(C, batch, steps);
+            cudaGraph_t g = nullptr;
+            e = cudaStreamEndCapture(cs, &g);
+            cudaStreamDestroy(cs);
+            if (C.rc) { if (g) cudaGraphDestroy(g); return C.rc; }
+            if (e != cudaSuccess || !g) return fail(BLURR_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+            cudaGraphExec_t ex = nullptr;
+            e = cudaGraphInstantiate(&ex, g, 0);
+            if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(BLURR_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e)); }
+            blurr_pi0::GraphEntry ge{g, ex, h->launches};
+            it = h->graphs.emplace(key, ge).first;
+            // the warm run already produced this call's result from the staged inputs; replay
+            // anyway so the first call exercises the same path as every later one
+            CUDA_TRY(launch_im2col(st, static_cast<const bf16*>(in->pixel_values), in->pixel_strides[0],
+                                   in->pixel_strides[1], in->pixel_strides[2], in->pixel_strides[3], batch,
+                                   h->patches, h->patch.K));
+            stage_inputs_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(sa);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaGraphLaunch(it->second.exec, st));
+        h->launches = it->second.launches + pre_launches;
+    }
+    CUDA_TRY(cudaMemcpyAsync(actions_out, h->d_out,
+                             static_cast<size_t>(batch) * c.num_action_tokens * c.action_dim * 2,
+                             cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t value) {
+    if (!h || !name) return fail(BLURR_ERR_INVALID, "set_option: null argument");
+    const std::string n(name);
+    if (n == "use_cuda_graph") h->use_graph = value != 0;
+    else if (n == "debug_taps") h->debug = value != 0;
+    else if (n == "num_inference_steps") {
+        if (value < 1) return fail(BLURR_ERR_INVALID, "num_inference_steps must be >= 1");
+        h->cfg.num_inference_steps = static_cast<int>(value);
+    } else return fail(BLURR_ERR_INVALID, "unknown option " + n);
+    return 0;
+}
+
+extern "C" int blurr_pi0_check(blurr_pi0_t* h, void* cuda_stream) {
+    if (!h) return fail(BLURR_ERR_INVALID, "check: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    int flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag != 0) {
+        CUDA_TRY(cudaMemset(h->d_err, 0, sizeof(int)));
+        return fail(BLURR_ERR_INPUT, flag == 1 ? "more image tokens in input_ids than image features"
+                                               : "token id outside the embedding table");
+    }
+    return 0;
+}
+
+extern "C" int blurr_pi0_debug_tap(blurr_pi0_t* h, const char* name, void* dst, size_t dst_bytes, size_t* bytes_out) {
+    if (!h || !name) return fail(BLURR_ERR_INVALID, "debug_tap: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const std::string n(name);
+    const auto& c = h->cfg;
+    if (n == "k_cache" || n == "v_cache") {
+        // full-capacity layout [layers][max_batch][slots][head_dim]
+        const size_t bytes = static_cast<size_t>(c.joint_layers) * h->max_batch * h->n_total * c.head_dim * 2;
+        if (bytes_out) *bytes_out = bytes;
+        if (!dst) return 0;
+        if (dst_bytes < bytes) return fail(BLURR_ERR_INVALID, "debug_tap: destination too small");
+        CUDA_TRY(cudaMemcpy(dst, n == "k_cache" ? h->kcache : h->vcache, bytes, cudaMemcpyDeviceToDevice));
+        return 0;
+    }
+    auto it = h->taps.find(n);
+    if (it == h->taps.end()) return fail(BLURR_ERR_STATE, "debug_tap: no such tap (enable option debug_taps and run a step): " + n);
+    if (bytes_out) *bytes_out = it->second.bytes;
+    if (!dst) return 0;
+    if (dst_bytes < it->second.bytes) return fail(BLURR_ERR_INVALID, "debug_tap: destination too small");
+    CUDA_TRY(cudaMemcpy(dst, it->second.ptr, it->second.bytes, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+extern "C" int64_t blurr_pi0_last_launch_count(const blurr_pi0_t* h) { return h ? h->launches : 0; }
+extern "C" int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h) { return h ? static_cast<int64_t>(h->weight_bytes) : 0; }
+
+// ---------------------------------------------------------------------------
+// single-operator entry points
+// ---------------------------------------------------------------------------
+extern "C" int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
+                             int epi, int splitk, const void* bias, void* out, int ldo, float* partial) {
+    GemmCall c{};
+    c.W = static_cast<const bf16*>(W); c.Nw = N; c.K = K; c.ldw = ldw;
+    c.X = static_cast<const bf16*>(X); c.T = T; c.ldx = ldx; c.epi = epi; c.splitk = splitk;
+    c.bias = static_cast<const bf16*>(bias); c.out = static_cast<bf16*>(out); c.ldo = ldo; c.partial = partial;
+    c.bn_override = 0;
+    std::string err;
+    const int s = gemm_launch(static_cast<cudaStream_t>(cuda_stream), c, &err);
+    if (s < 0) return fail(BLURR_ERR_INVALID, err);
+    return s;
+}
+
+extern "C" int blurr_op_siglip_attention(void* cuda_stream, const void* qkv, int ld_qkv, int batch, int seq, int heads,
+                                         int hidden, void* out, int ld_out) {
+    CUDA_TRY(launch_siglip_attention(static_cast<cudaStream_t>(cuda_stream), static_cast<const bf16*>(qkv), ld_qkv,
+                                     batch, seq, heads, hidden, static_cast<bf16*>(out), ld_out));
+    return 0;
+}
+
+extern "C" int blurr_op_joint_attention(void* cuda_stream, int few_query, const void* q, int q_per_sample,
+                                        int q_row_offset, const void* k_cache, const void* v_cache, int n_slots,
+                                        int n_keys, const void* mask, int64_t mask_bstride, int64_t mask_rstride,
+                                        int batch, int n_heads, void* out) {
+    JointAttnArgs a{};
+    a.q = static_cast<const bf16*>(q); a.q_per_sample = q_per_sample; a.q_row_offset = q_row_offset;
+    a.k_cache = static_cast<const bf16*>(k_cache); a.v_cache = static_cast<const bf16*>(v_cache);
+    a.n_slots = n_slots; a.n_keys = n_keys; a.mask = static_cast<const bf16*>(mask);
+    a.mask_bstride = mask_bstride; a.mask_rstride = mask_rstride; a.batch = batch; a.n_heads = n_heads;
+    a.out = static_cast<bf16*>(out);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CUDA_TRY(few_query ? launch_joint_attention_fewq(st, a) : launch_joint_attention_prefill(st, a));
+    return 0;
+}

@@ -1,0 +1,382 @@
+// tcgen05 / TMEM / TMA bf16 GEMM for every Linear on the Pi-0 control-step path.
+//
+//   Y[t, n] = sum_k X[t, k] * W[n, k]        X: activations [T, K] (K contiguous)
+//                                            W: nn.Linear weight [N, K] (K contiguous)
+//
+// "Swap-AB" orientation: a CTA owns 128 *weight rows* (UMMA M = 128, TMEM lane = output
+// feature n) and up to NT chunks of BN <= 256 *tokens* (UMMA N = BN, TMEM column = token).
+// At batch 1 (T = 256 / 276 / 1 / 4) every weight byte is therefore streamed from HBM exactly
+// once by exactly one CTA, and the token dimension pads to a multiple of 16 instead of 128.
+// Both operands are K-major bf16 tiles of 64 elements (128 B) per row, written by TMA with
+// the 128-byte swizzle and consumed through UMMA shared-memory descriptors.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue phase 1 (TMEM -> registers -> smem tile
+// [token][n]); then all 8 warps run phase 2 (row-wise 16-byte vector epilogue + stores).
+//
+// Epilogues reproduce the reference's bf16 rounding points:
+//   EPI_STORE   : bf16(acc + bias)                                   (nn.Linear output)
+//   EPI_GELU    : bf16(gelu_tanh(bf16(acc + bias)))                  (SigLIP fc1, siglip.py:188-190)
+//   EPI_GEGLU   : bf16(bf16(gelu_tanh(bf16(gate))) * bf16(up))       (GemmaMLP, modules.py:93-95)
+//   EPI_PARTIAL : fp32 partial sums of one split-K slice -> workspace [z][t][n]; the consumer
+//                 kernels in norm_consumers.cu finish bias/residual/norm in a fixed order.
+#include "common.cuh"
+#include "gemm_tc.h"
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+namespace blurr {
+
+static constexpr int kBlockM = 128;     // weight rows per CTA (UMMA M)
+static constexpr int kBlockK = 64;      // bf16 elements per k-block (one 128-byte swizzle row)
+static constexpr int kTileABytes = kBlockM * kBlockK * 2;
+static constexpr int kGemmThreads = 256;
+
+struct GemmDev {
+    int T;            // valid token rows
+    int bn;           // tokens per UMMA chunk (multiple of 16, <= 256)
+    int nt;           // chunks per CTA (nt * bn <= 512 TMEM columns)
+    int stages;       // smem pipeline depth
+    int kb_total;     // ceil(K / 64)
+    int kb_per_split; // k-blocks per blockIdx.z
+    int tmem_cols;    // power of two >= nt * bn
+    int Nw;           // padded weight rows (multiple of 128)
+    const bf16* bias; // [Nw] or nullptr
+    bf16* out;        // bf16 output
+    int ldo;          // output row stride (elements)
+    float* partial;   // EPI_PARTIAL: [splitk][T][Nw] fp32
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+               const GemmDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tmem_full_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one_sync()) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 1 && elect_one_sync()) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n0 = blockIdx.x * kBlockM;          // first weight row of this CTA
+    const int t0 = blockIdx.y * p.nt * p.bn;      // first token row of this CTA
+    const int kb0 = blockIdx.z * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    const int nkb = kb1 - kb0;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
+            const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (i / p.stages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + s * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+                const int kcoord = (kb0 + i) * kBlockK;
+                tma_load_2d_hint(st, &tmap_w, &full_bar[s], kcoord, n0, pol_w);
+                for (int c = 0; c < p.nt; ++c)
+                    tma_load_2d_hint(st + kTileABytes + c * p.bn * (kBlockK * 2), &tmap_x,
+                                     &full_bar[s], kcoord, t0 + c * p.bn, pol_x);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (i / p.stages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                for (int c = 0; c < p.nt; ++c) {
+                    const uint64_t b_desc =
+                        make_smem_desc_sw128(a_addr + kTileABytes + c * p.bn * (kBlockK * 2));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in
+                        // the 16-byte-granular start-address field
+                        umma_bf16_ss(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                     (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
+            }
+            umma_commit(tmem_full_bar);       // accumulators complete
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue phase 1: TMEM -> registers -> smem tile [token][128 n] ----
+        const int w4 = warp - 4;               // TMEM lane quarter this warp may access
+        const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        float bias = 0.f;
+        if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
+        const int ntok = p.nt * p.bn;
+        for (int g = 0; g < ntok / 16; ++g) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+            tmem_ld_wait();
+            if (EPI == EPI_PARTIAL) {
+                float* tile = reinterpret_cast<float*>(smem);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tile[(g * 16 + i) * kBlockM + nl] = __uint_as_float(r[i]);
+            } else {
+                bf16* tile = reinterpret_cast<bf16*>(smem);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v = bf16_round(__uint_as_float(r[i]) + bias);
+                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+
+    // ---- epilogue phase 2: row-wise vector stores (all 256 threads) ----
+    {
+        const int ntok = p.nt * p.bn;
+        if (EPI == EPI_PARTIAL) {
+            const float4* tile = reinterpret_cast<const float4*>(smem);
+            float* dst = p.partial + static_cast<size_t>(blockIdx.z) * p.T * p.Nw;
+            for (int idx = threadIdx.x; idx < ntok * 32; idx += kGemmThreads) {
+                const int t = idx >> 5, ch = idx & 31;
+                if (t0 + t < p.T)
+                    *reinterpret_cast<float4*>(dst + static_cast<size_t>(t0 + t) * p.Nw + n0 + ch * 4) =
+                        tile[t * 32 + ch];
+            }
+        } else if (EPI == EPI_GEGLU) {
+            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
+            for (int idx = threadIdx.x; idx < ntok * 8; idx += kGemmThreads) {
+                const int t = idx >> 3, ch = idx & 7;
+                if (t0 + t >= p.T) continue;
+                const bf16x8 g = tile[t * 16 + ch];
+                const bf16x8 u = tile[t * 16 + 8 + ch];
+                bf16x8 o;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 gf = unpack_bf16x2(g.u[j]);
+                    const float2 uf = unpack_bf16x2(u.u[j]);
+                    const float a = bf16_round(gelu_tanh_f32(gf.x)) * uf.x;
+                    const float b = bf16_round(gelu_tanh_f32(gf.y)) * uf.y;
+                    o.u[j] = pack_bf16x2(a, b);
+                }
+                *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo +
+                                           blockIdx.x * (kBlockM / 2) + ch * 8) = o;
+            }
+        } else {
+            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
+            for (int idx = threadIdx.x; idx < ntok * 16; idx += kGemmThreads) {
+                const int t = idx >> 4, ch = idx & 15;
+                if (t0 + t < p.T)
+                    *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + n0 +
+                                               ch * 8) = tile[t * 16 + ch];
+            }
+        }
+    }
+
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
+// ---------------------------------------------------------------------------
+// host side: tensor-map cache + launcher
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+                cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void* ptr;
+    int rows, cols, ld, box_rows;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h = h * 1000003u ^ static_cast<size_t>(k.rows);
+        h = h * 1000003u ^ static_cast<size_t>(k.cols);
+        h = h * 1000003u ^ static_cast<size_t>(k.ld);
+        h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
+        return h;
+    }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+
+// 2D bf16 tensor [rows][cols] with row stride `ld` elements; box = {64 cols, box_rows}.
+static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out,
+                    std::string* err) {
+    TmapKey key{ptr, rows, cols, ld, box_rows};
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *out = it->second; return 0; }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return -1; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((static_cast<size_t>(ld) * 2) & 15)) {
+        *err = "TMA operand must be 16-byte aligned with a 16-byte-multiple row stride";
+        return -1;
+    }
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
+        return -1;
+    }
+    g_tmaps.emplace(key, m);
+    *out = m;
+    return 0;
+}
+
+void gemm_forget_tensor_maps() {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    g_tmaps.clear();
+}
+
+static int next_pow2_cols(int c) {
+    int v = 32;
+    while (v < c) v <<= 1;
+    return v;
+}
+
+static constexpr int kSmemBudget = 227 * 1024;
+
+GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override) {
+    GemmPlan pl{};
+    pl.valid = false;
+    if (Nw % kBlockM != 0 || T <= 0 || K <= 0) return pl;
+    // token chunking: up to 512 tokens per CTA as 1..2 UMMA-N chunks
+    int bn, nt;
+    if (bn_override > 0) {
+        bn = bn_override;
+        nt = (T > bn) ? 2 : 1;
+    } else {
+        const int t16 = (T + 15) / 16 * 16;
+        if (t16 <= 256) { bn = t16; nt = 1; }
+        else if (t16 <= 512) { bn = ((t16 / 2) + 15) / 16 * 16; nt = 2; }
+        else { bn = 256; nt = 1; }
+    }
+    pl.bn = bn;
+    pl.nt = nt;
+    pl.kb_total = (K + kBlockK - 1) / kBlockK;
+    if (splitk < 1) splitk = 1;
+    if (splitk > pl.kb_total) splitk = pl.kb_total;
+    pl.kb_per_split = (pl.kb_total + splitk - 1) / splitk;
+    pl.splitk = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;   // no empty slices
+    const int stage_bytes = kTileABytes + nt * bn * kBlockK * 2;
+    const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
+    int stages = (kSmemBudget - 1024 - 256) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages > pl.kb_per_split) stages = pl.kb_per_split > 0 ? pl.kb_per_split : 1;
+    // the epilogue tile aliases the pipeline buffers: keep enough bytes for it
+    while (stages * stage_bytes < tile_bytes) ++stages;
+    if (stages * stage_bytes + 1024 + 256 > kSmemBudget) return pl;
+    pl.stages = stages;
+    pl.smem_bytes = stages * stage_bytes + 1024 + 256;
+    pl.tmem_cols = next_pow2_cols(nt * bn);
+    if (pl.tmem_cols > 512) return pl;
+    pl.grid_x = Nw / kBlockM;
+    pl.grid_y = (T + nt * bn - 1) / (nt * bn);
+    pl.valid = true;
+    return pl;
+}
+
+template <int EPI>
+static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUtensorMap& tw,
+                              const CUtensorMap& tx, const GemmDev& d) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(pl.grid_x, pl.grid_y, pl.splitk);
+    gemm_tc_kernel<EPI><<<grid, kGemmThreads, pl.smem_bytes, stream>>>(tw, tx, d);
+    return cudaGetLastError();
+}
+
+int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
+    GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
+    if (!pl.valid) {
+        *err = "gemm_launch: unsupported shape T=" + std::to_string(c.T) + " Nw=" + std::to_string(c.Nw) +
+               " K=" + std::to_string(c.K);
+        return -1;
+    }
+    if (c.epi != EPI_PARTIAL && pl.splitk != 1) { *err = "gemm_launch: split-K needs EPI_PARTIAL"; return -1; }
+    CUtensorMap tw, tx;
+    if (get_tmap(c.W, c.Nw, c.K, c.ldw, kBlockM, &tw, err)) return -1;
+    if (get_tmap(c.X, c.T, c.K, c.ldx, pl.bn, &tx, err)) return -1;
+    GemmDev d{};
+    d.T = c.T; d.bn = pl.bn; d.nt = pl.nt; d.stages = pl.stages; d.kb_total = pl.kb_total;
+    d.kb_per_split = pl.kb_per_split; d.tmem_cols = pl.tmem_cols; d.Nw = c.Nw;
+    d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
+    cudaError_t e;
+    switch (c.epi) {
+        case EPI_STORE:   e = launch_epi<EPI_STORE>(stream, pl, tw, tx, d); break;
+        case EPI_GELU:    e = launch_epi<EPI_GELU>(stream, pl, tw, tx, d); break;
+        case EPI_GEGLU:   e = launch_epi<EPI_GEGLU>(stream, pl, tw, tx, d); break;
+        case EPI_PARTIAL: e = launch_epi<EPI_PARTIAL>(stream, pl, tw, tx, d); break;
+        default: *err = "gemm_launch: bad epilogue"; return -1;
+    }
+    if (e != cudaSuccess) { *err = std::string("gemm launch failed: ") + cudaGetErrorString(e); return -1; }
+    return pl.splitk;
+}
+
+}  // namespace blurr

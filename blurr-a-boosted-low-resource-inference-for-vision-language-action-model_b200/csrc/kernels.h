@@ -1,0 +1,118 @@
+// Launchers of the bandwidth-bound and attention kernels (norm_consumers.cu, attention.cu,
+// misc_kernels.cu).  All launchers are asynchronous on `stream` and return cudaGetLastError().
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace blurr {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------
+// norm_consumers.cu — finish a GEMM (split-K sum, bias, residual / position add) and apply
+// the following normalisation in one pass over the row.
+// ---------------------------------------------------------------------------
+enum AddMode { ADD_NONE = 0, ADD_RESIDUAL = 1, ADD_POSEMB = 2 };
+enum NormMode { NORM_NONE = 0, NORM_RMS_GEMMA = 1, NORM_LAYERNORM = 2 };
+
+struct ConsumerArgs {
+    const float* partial;   // [splitk][T][ldp] fp32 or nullptr (then x = res)
+    int splitk, T, N, ldp;
+    const bf16* bias;       // [N] or nullptr
+    int add_mode;
+    const bf16* res;        // [T][ldr]
+    int ldr;
+    const bf16* pos;        // [pos_rows][N]
+    int pos_rows;
+    float out_scale;        // applied as bf16(x * out_scale) after bias (1.0f = none)
+    bf16* x_out;            // [T][ldx] stream after the add (nullable)
+    int ldx;
+    int norm_mode;
+    const bf16* norm_w;
+    const bf16* norm_b;
+    float eps;
+    bf16* xn_out;           // [T][ldn] normalised output (nullable)
+    int ldn;
+};
+cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a);
+
+// Element-wise finish without a norm: out = act(bf16(sum + bias)) * scale
+enum ActMode { ACT_NONE = 0, ACT_SILU = 1 };
+cudaError_t launch_bias_act(cudaStream_t stream, const float* partial, int splitk, int T, int N, int ldp,
+                            const bf16* bias, int act, float scale, bf16* out, int ldo);
+
+// RoPE + KV-cache append: finishes the fused QKV GEMM for one mixture.
+struct RopeKvArgs {
+    const float* partial;   // [splitk][T][ldp], columns: q (n_heads*256) | k (256) | v (256)
+    int splitk, T, ldp;
+    int n_heads;            // 8
+    int tokens_per_sample;  // 276 / 1 / 4
+    const int64_t* position_ids;   // [B][tokens_per_sample]
+    const float* cos_table; // [n_pos][128]  (values already rounded to bf16)
+    const float* sin_table;
+    int n_pos;
+    bf16* q_out;            // [T][n_heads*256] (nullable: last-layer vlm/proprio need no query)
+    bf16* k_cache;          // layer base: [B][n_slots][256]
+    bf16* v_cache;
+    int n_slots, slot_base;
+};
+cudaError_t launch_rope_kv(cudaStream_t stream, const RopeKvArgs& a);
+
+// ---------------------------------------------------------------------------
+// attention.cu
+// ---------------------------------------------------------------------------
+// SigLIP MHA (siglip.py:133-152): qkv [T][3*hidden] with head_dim 72, no mask.
+cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
+                                    int n_heads, int hidden, bf16* out, int ld_out);
+
+// Gemma joint attention, many queries (prefill): soft-clamped, additive mask, MQA.
+struct JointAttnArgs {
+    const bf16* q;          // [B*q_per_sample][n_heads*256]
+    int q_per_sample;       // rows of this query segment per sample
+    int q_row_offset;       // row of the first query in the mask (0 vlm, 276 proprio, 0 action)
+    const bf16* k_cache;    // [B][n_slots][256]
+    const bf16* v_cache;
+    int n_slots, n_keys;    // keys 0..n_keys-1 are attended
+    const bf16* mask;       // additive mask element (b, row, col) at mask[b*mask_bstride + row*mask_rstride + col]
+    int64_t mask_bstride, mask_rstride;
+    int batch, n_heads;
+    bf16* out;              // [B*q_per_sample][n_heads*256]
+};
+cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& a);
+// Few queries per sample (proprio: 1, action: 4): bandwidth kernel over the KV cache.
+cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& a);
+
+// ---------------------------------------------------------------------------
+// misc_kernels.cu
+// ---------------------------------------------------------------------------
+// pixel_values [B][3][224][224] (arbitrary strides, bf16) -> patches [B*256][ldp] with column
+// c*196 + kh*14 + kw (the flattened Conv2d weight order); columns >= 588 untouched (zero).
+cudaError_t launch_im2col(cudaStream_t stream, const bf16* pixels, int64_t sb, int64_t sc, int64_t sh,
+                          int64_t sw, int batch, bf16* patches, int ldp);
+
+// Merge text embeddings and projected image features (pizero.py:452-470) and apply the
+// `embeds *= sqrt(hidden)` of JointModel.forward (joint_model.py:358-365).
+cudaError_t launch_embed_merge(cudaStream_t stream, const int64_t* input_ids, int batch, int seq,
+                               const bf16* embed_table, int64_t vocab, const bf16* img_feat, int n_img,
+                               int hidden, int64_t image_token, int64_t pad_token, float inv_div,
+                               float normalizer, bf16* out, int* err_flag);
+
+// y[t][col_off + n] = bf16(bf16(sum_k x[t][k] W[n][k] + b[n]) * scale), K <= 8 (proprio_encoder,
+// action_encoder.linear_1); optionally fills y[t][0..time_cols) with time_cond (the torch.cat).
+cudaError_t launch_small_k_linear(cudaStream_t stream, const bf16* x, int T, int K, const bf16* W,
+                                  const bf16* b, int N, float scale, bf16* y, int ldy, int col_off,
+                                  const bf16* time_row, int time_cols);
+
+// action_decoder + Euler update (pizero.py:536-537): a = bf16(a + bf16(dt * bf16(dot + b)))
+cudaError_t launch_action_tail(cudaStream_t stream, const bf16* xn, int T, int hidden, const bf16* W,
+                               const bf16* b, int action_dim, float dt, bf16* action, bf16* velocity_tap);
+
+cudaError_t launch_clamp_copy(cudaStream_t stream, const bf16* src, bf16* dst, int n, int do_clamp,
+                              float clip);
+
+cudaError_t launch_rope_table(cudaStream_t stream, const float* inv_freq, int n_pos, float* cos_t,
+                              float* sin_t);
+
+}  // namespace blurr

@@ -1,0 +1,171 @@
+/*
+ * blurr_pi0.h — C ABI of the B200-native Pi-0 control-step engine (libblurr_pi0.so).
+ *
+ * The reference (JijiKing-Sam/BLURR, vendored open-pi-zero) has no plugin / FFI interface:
+ * its seam for this path is the Python class
+ *     src.model.vla.pizero.PiZeroInference      third_party/open_pi_zero/src/model/vla/pizero.py:721-742
+ * whose `forward` is `PiZero.infer_action` (pizero.py:473-547).  This header is the boundary a
+ * replacement binds underneath that class: plain pointers and sizes, no torch types.  The
+ * Python mirror of the class (blurr_b200/pizero.py) calls it through ctypes; INTEGRATION.md
+ * shows the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative blurr_status on error; the message is
+ *     available from blurr_last_error() (thread-local);
+ *   - all `dev` pointers are device pointers on the handle's device, owned by the caller;
+ *     the handle owns repacked weights, workspace, KV cache and CUDA graphs;
+ *   - arithmetic dtype is bf16 storage / fp32 accumulate (the `--preset blurr` path);
+ *   - calls are asynchronous on the given stream unless stated; a handle is not thread-safe;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef BLURR_PI0_H_
+#define BLURR_PI0_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLURR_ABI_VERSION 1
+
+typedef enum blurr_status {
+    BLURR_OK = 0,
+    BLURR_ERR_INVALID = -1,   /* bad argument / unsupported shape                         */
+    BLURR_ERR_CUDA = -2,      /* CUDA runtime / driver error                              */
+    BLURR_ERR_STATE = -3,     /* call order (e.g. infer before finalize, missing weight)  */
+    BLURR_ERR_INPUT = -4      /* device-side input validation failed (token id range ...) */
+} blurr_status;
+
+typedef enum blurr_dtype { BLURR_BF16 = 1, BLURR_F32 = 0, BLURR_I64 = 2 } blurr_dtype;
+
+/* Model hyper-parameters: the values of third_party/open_pi_zero/config/eval/bridge.yaml:35-136
+ * that shape the computation (cfg.* names of pizero.py:35-120 in comments). */
+typedef struct blurr_pi0_config {
+    int32_t abi_version;            /* BLURR_ABI_VERSION                                  */
+    /* SigLIP (cfg.vision.config) */
+    int32_t vision_layers;          /* num_hidden_layers      27                          */
+    int32_t vision_hidden;          /* hidden_size            1152                        */
+    int32_t vision_intermediate;    /* intermediate_size      4304                        */
+    int32_t vision_heads;           /* num_attention_heads    16                          */
+    int32_t image_size;             /* 224                                                */
+    int32_t patch_size;             /* 14                                                 */
+    int32_t num_image_tokens;       /* 256                                                */
+    float   layer_norm_eps;         /* 1e-6                                               */
+    /* joint model (cfg.joint.config, cfg.mixture.*) */
+    int32_t joint_layers;           /* num_hidden_layers      18                          */
+    int32_t num_heads;              /* num_attention_heads    8                           */
+    int32_t num_kv_heads;           /* num_key_value_heads    1                           */
+    int32_t head_dim;               /* 256                                                */
+    int32_t vlm_hidden;             /* mixture.vlm.hidden_size        2048                */
+    int32_t vlm_intermediate;       /* mixture.vlm.intermediate_size  16384               */
+    int32_t expert_hidden;          /* mixture.{proprio,action}.hidden_size        1024   */
+    int32_t expert_intermediate;    /* mixture.{proprio,action}.intermediate_size  4096   */
+    float   rms_norm_eps;           /* 1e-6                                               */
+    /* sequence layout (pizero.py:44-51) */
+    int32_t max_image_text_tokens;  /* 276                                                */
+    int32_t num_proprio_tokens;     /* cond_steps      1                                  */
+    int32_t num_action_tokens;      /* horizon_steps   4                                  */
+    int32_t action_dim;             /* 7                                                  */
+    int32_t proprio_dim;            /* 7 (Bridge) / 8 (Fractal)                           */
+    /* tokens (bridge.yaml:94-96) */
+    int64_t vocab_size;             /* 257216                                             */
+    int64_t image_token_index;      /* 257152                                             */
+    int64_t pad_token_id;           /* 0                                                  */
+    /* flow matching (pizero.py:58,62) */
+    int32_t num_inference_steps;    /* 1 for --preset blurr, 10 baseline                  */
+    int32_t has_clip;               /* final_action_clip_value is not None                */
+    float   final_action_clip_value;
+} blurr_pi0_config;
+
+typedef struct blurr_pi0 blurr_pi0_t;   /* opaque: one per (device, max_batch) */
+
+/* Lifetime.  Replaces `PiZeroInference(cfg)` + `.to(device)` (benchmark_pi0.py:127-142). */
+int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max_batch, blurr_pi0_t** out);
+void blurr_pi0_destroy(blurr_pi0_t* h);
+
+/* Weights.  Replaces `load_state_dict` (benchmark_pi0.py:139): one call per state_dict entry,
+ * key spelled exactly as in the reference state_dict.  The tensor is
+ * copied and repacked (fused QKV, interleaved gate/up, K padding); dtype must be BLURR_BF16. */
+int blurr_pi0_set_weight(blurr_pi0_t* h, const char* state_dict_key, const void* dev_ptr,
+                         const int64_t* shape, int ndim, int dtype);
+/* RoPE inverse frequencies of one mixture ("vlm" | "proprio" | "action"), 128 fp32 values on the
+ * HOST, already rounded the way `model.to(dtype)` rounds the `inv_freq` buffer
+ * (paligemma/modules.py:41-45). */
+int blurr_pi0_set_rope_inv_freq(blurr_pi0_t* h, const char* mixture, const float* host_inv_freq, int n);
+/* time_cond rows for the flow steps, bf16 [num_steps][expert_hidden] on the device, computed by
+ * the caller with the reference's own ops (vla/modules.py:15-22; `t` accumulates in bf16). */
+int blurr_pi0_set_time_table(blurr_pi0_t* h, const void* dev_table, int num_steps);
+/* Checks every weight is present, builds RoPE tables.  Synchronous. */
+int blurr_pi0_finalize_weights(blurr_pi0_t* h);
+
+/* The control step.  Replaces `PiZeroInference.forward` = `PiZero.infer_action`
+ * (pizero.py:473-547, 721-742).  Shapes for batch B (Bridge sizes in brackets):
+ *   input_ids                int64 [B][max_image_text_tokens]            [B][276]
+ *   pixel_values             bf16  [B][3][H][W], element strides given    [B][3][224][224]
+ *   image_text_proprio_mask  bf16  additive, element (b,r,c) at mask[b*bstride + r*rstride + c],
+ *                                  r,c < max_image_text_tokens + num_proprio_tokens   [277x277]
+ *   action_mask              bf16  (b,r,c) likewise, r < num_action_tokens, c < total [4x281]
+ *   *_position_ids           int64 [B][276], [B][1], [B][4]
+ *   proprios                 bf16  [B][num_proprio_tokens][proprio_dim]
+ *   noise                    bf16  [B][num_action_tokens][action_dim] — the `torch.randn` draw of
+ *                                  pizero.py:511-513, made by the caller
+ *   actions_out              bf16  [B][num_action_tokens][action_dim]
+ * Fresh KV state per call, like the reference (pizero.py:487). */
+typedef struct blurr_pi0_inputs {
+    const int64_t* input_ids;
+    const void* pixel_values;
+    int64_t pixel_strides[4];            /* elements: batch, channel, row, column */
+    const void* image_text_proprio_mask;
+    int64_t itp_mask_bstride, itp_mask_rstride;
+    const void* action_mask;
+    int64_t action_mask_bstride, action_mask_rstride;
+    const int64_t* vlm_position_ids;
+    const int64_t* proprio_position_ids;
+    const int64_t* action_position_ids;
+    const void* proprios;
+    const void* noise;
+} blurr_pi0_inputs;
+
+int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const blurr_pi0_inputs* in,
+                           void* actions_out);
+
+/* Options: "use_cuda_graph" (default 1), "debug_taps" (default 0; implies eager launches),
+ * "num_inference_steps". */
+int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t value);
+/* Synchronises the stream and reports device-side input validation errors. */
+int blurr_pi0_check(blurr_pi0_t* h, void* cuda_stream);
+
+/* Debug / parity taps: copy a named internal buffer (bf16 unless noted) to `dst_dev`.
+ * Names: "k_cache" / "v_cache" [layers][B][slots][head_dim]; with option debug_taps=1 also
+ * "siglip.embeddings", "siglip.layer<l>", "siglip.post_layernorm", "projector",
+ * "merged_embeds", "prefill.L<l>.vlm", "prefill.L<l>.proprio", "flow<s>.L<l>.action",
+ * "flow<s>.velocity".  Returns the byte size of the buffer through *bytes_out when dst_dev is NULL. */
+int blurr_pi0_debug_tap(blurr_pi0_t* h, const char* name, void* dst_dev, size_t dst_bytes, size_t* bytes_out);
+
+/* Kernel launches issued (or replayed) by the last blurr_pi0_infer_action call. */
+int64_t blurr_pi0_last_launch_count(const blurr_pi0_t* h);
+/* Bytes of repacked weights the step reads (the algorithmic-bytes numerator of the roofline). */
+int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h);
+
+const char* blurr_last_error(void);
+int blurr_abi_version(void);
+
+/* ---- single-operator entry points (same kernels, used by the per-kernel parity tests and
+ *      micro-benchmarks; synchronous on `cuda_stream` only with respect to errors) ---- */
+/* Y[T][N] = epilogue(X[T][K] @ W[N][K]^T); epi: 0 store(+bias) 1 gelu 2 geglu 3 partial(fp32 out,
+ * [splitk_used][T][N]); returns the number of split-K slices used (>=1) or a negative status. */
+int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
+                  int epi, int splitk, const void* bias, void* out, int ldo, float* partial);
+int blurr_op_siglip_attention(void* cuda_stream, const void* qkv, int ld_qkv, int batch, int seq, int heads,
+                              int hidden, void* out, int ld_out);
+int blurr_op_joint_attention(void* cuda_stream, int few_query, const void* q, int q_per_sample,
+                             int q_row_offset, const void* k_cache, const void* v_cache, int n_slots,
+                             int n_keys, const void* mask, int64_t mask_bstride, int64_t mask_rstride,
+                             int batch, int n_heads, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLURR_PI0_H_ */
