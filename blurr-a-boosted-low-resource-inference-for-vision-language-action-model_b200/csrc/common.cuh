@@ -100,13 +100,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees),
-// never as a hung GPU.  try_wait suspends in hardware, so the bound is generous in time.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+// Bounded wait: a protocol bug must never hang the GPU.  On expiry (~0.2 s of SM clocks) the
+// wait returns false; the caller records the failure in a device flag and unwinds, so the host
+// sees an error code instead of a hung or faulted device.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) { __trap(); }
+        if (clock64() - t0 > 400000000LL) return false;
     }
+    return true;
 }
 
 // ---------------------------------------------------------------------------

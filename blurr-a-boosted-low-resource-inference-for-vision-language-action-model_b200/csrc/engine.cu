@@ -918,6 +918,8 @@ extern "C" int blurr_pi0_check(blurr_pi0_t* h, void* cuda_stream) {
     if (!h) return fail(BLURR_ERR_INVALID, "check: null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    if (int tf = gemm_take_timeout_flag())
+        return fail(BLURR_ERR_CUDA, "a GEMM pipeline wait expired (role " + std::to_string(tf) + "): results are invalid");
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag != 0) {
@@ -967,6 +969,9 @@ extern "C" int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int
     std::string err;
     const int s = gemm_launch(static_cast<cudaStream_t>(cuda_stream), c, &err);
     if (s < 0) return fail(BLURR_ERR_INVALID, err);
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    if (int tf = gemm_take_timeout_flag())
+        return fail(BLURR_ERR_CUDA, "GEMM pipeline wait expired (role " + std::to_string(tf) + ")");
     return s;
 }
 

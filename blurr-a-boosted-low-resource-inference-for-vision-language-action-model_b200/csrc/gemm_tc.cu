@@ -49,6 +49,9 @@ struct GemmDev {
     float* partial;   // EPI_PARTIAL: [splitk][T][Nw] fp32
 };
 
+// Set (to 1 + role) when a pipeline wait expired; read by gemm_take_timeout_flag().
+__device__ int g_gemm_timeout_flag = 0;
+
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -99,7 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % p.stages;
                 const uint32_t ph = (i / p.stages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                if (!mbar_wait(&empty_bar[s], ph ^ 1)) { atomicExch(&g_gemm_timeout_flag, 1); break; }
                 uint8_t* st = smem + s * stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
                 const int kcoord = (kb0 + i) * kBlockK;
@@ -112,10 +115,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     } else if (warp == 1) {
         if (elect_one_sync()) {
             const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
+            bool ok = true;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % p.stages;
                 const uint32_t ph = (i / p.stages) & 1;
-                mbar_wait(&full_bar[s], ph);
+                if (!mbar_wait(&full_bar[s], ph)) { atomicExch(&g_gemm_timeout_flag, 2); ok = false; break; }
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                 const uint64_t a_desc = make_smem_desc_sw128(a_addr);
@@ -132,19 +136,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 }
                 umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
             }
-            umma_commit(tmem_full_bar);       // accumulators complete
+            if (ok) umma_commit(tmem_full_bar);   // accumulators complete
         }
     } else if (warp >= 4) {
         // ---- epilogue phase 1: TMEM -> registers -> smem tile [token][128 n] ----
         const int w4 = warp - 4;               // TMEM lane quarter this warp may access
         const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
-        mbar_wait(tmem_full_bar, 0);
+        const bool acc_ready = mbar_wait(tmem_full_bar, 0);
+        if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
         tcgen05_fence_after();
         float bias = 0.f;
         if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
         const int ntok = p.nt * p.bn;
-        for (int g = 0; g < ntok / 16; ++g) {
+        for (int g = 0; acc_ready && g < ntok / 16; ++g) {
             uint32_t r[16];
             tmem_ld_32x32b_x16(lane_addr + g * 16, r);
             tmem_ld_wait();
@@ -282,6 +287,16 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
     g_tmaps.emplace(key, m);
     *out = m;
     return 0;
+}
+
+int gemm_take_timeout_flag() {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_gemm_timeout_flag, sizeof(int)) != cudaSuccess) return -1;
+    if (v != 0) {
+        const int zero = 0;
+        cudaMemcpyToSymbol(g_gemm_timeout_flag, &zero, sizeof(int));
+    }
+    return v;
 }
 
 void gemm_forget_tensor_maps() {

@@ -39,6 +39,10 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
 // Returns the number of split-K slices actually used (>= 1), or -1 with *err set.
 int gemm_launch(cudaStream_t stream, const GemmCall& call, std::string* err);
 
+// Non-zero if a pipeline wait of a GEMM kernel expired since the last call (synchronises the
+// device through cudaMemcpyFromSymbol); clears the flag.
+int gemm_take_timeout_flag();
+
 // Tensor maps are cached by (pointer, shape); call when buffers are freed.
 void gemm_forget_tensor_maps();
 

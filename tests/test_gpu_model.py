@@ -1,0 +1,148 @@
+"""End-to-end parity of the CUDA control step (-m gpu) against the oracle (the reference's op
+sequence, `oracle/pi0_oracle.py`) run in bf16 on the same GPU: returned actions, per-layer
+activations, KV-cache contents and slot layout.  Tolerance from BASELINE.json's north_star:
+max-abs action error <= 1e-2 on the clamped output."""
+
+import pytest
+import torch
+
+from blurr_b200 import synth
+from blurr_b200.config import bridge_config, fractal_config, shrink_config
+from blurr_b200.pizero import PiZeroInference
+from oracle import pi0_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _setup(cfg, batch, stress=False, vary_text=True, seed=0):
+    sd = synth.synthetic_state_dict(cfg, seed, torch.bfloat16, stress=stress)
+    model = PiZeroInference.from_state_dict(cfg, sd, device=DEV)
+    sd_gpu = {k: v.to(DEV) for k, v in sd.items()}
+    inp = synth.synthetic_inputs(cfg, batch, dtype=torch.bfloat16, vary_text=vary_text, device=DEV)
+    return model, sd_gpu, inp
+
+
+def _oracle(sd, cfg, inp, taps=None, return_caches=False):
+    tap = None
+    if taps is not None:
+        def tap(name, t):
+            taps[name] = t.detach().clone()
+    with torch.inference_mode():
+        return O.infer_action(sd, cfg, inp["input_ids"], inp["pixel_values"].clone(),
+                              inp["image_text_proprio_mask"], inp["action_mask"], inp["vlm_position_ids"].to(DEV),
+                              inp["proprio_position_ids"].to(DEV), inp["action_position_ids"].to(DEV),
+                              inp["proprios"], noise=inp["noise"], tap=tap, return_caches=return_caches)
+
+
+def _run(model, inp):
+    with torch.inference_mode():
+        out = model(**synth.call_args(inp), noise=inp["noise"])
+    model._engine.check()
+    return out
+
+
+def _layer_report(model, cfg, taps, batch):
+    vc, jc = cfg.vision.config, cfg.joint.config
+    lines = []
+    names = ["siglip.embeddings"] + [f"siglip.layer{l}" for l in range(vc.num_hidden_layers)] + \
+            ["siglip.post_layernorm", "projector", "merged_embeds"]
+    names += [f"prefill.L{l}.{m}" for l in range(jc.num_hidden_layers - 1) for m in ("vlm", "proprio")]
+    for s in range(cfg.num_inference_steps):
+        names += [f"flow{s}.action_embeds"] + [f"flow{s}.L{l}.action" for l in range(jc.num_hidden_layers)]
+        names += [f"flow{s}.velocity"]
+    worst = 0.0
+    for n in names:
+        ref = taps[n].float().flatten()
+        got = model.debug_tap(n).float().flatten()
+        assert got.numel() == ref.numel(), (n, got.numel(), ref.numel())
+        err = (got - ref).abs().max().item()
+        rms = ref.pow(2).mean().sqrt().item()
+        rel = err / max(rms, 1e-6)
+        worst = max(worst, rel)
+        lines.append(f"  {n:28s} max_abs={err:.3e} ref_rms={rms:.3e} rel={rel:.3e}")
+    return lines, worst
+
+
+@pytest.mark.parametrize("stress", [False, True])
+def test_shrunk_model_layers_and_actions(stress):
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    cfg.final_action_clip_value = None          # un-clamped: nothing hides behind the clip
+    batch = 2
+    model, sd, inp = _setup(cfg, batch, stress=stress)
+    model.set_engine_options(debug_taps=True)
+    taps = {}
+    ref, caches = _oracle(sd, cfg, inp, taps, return_caches=True)
+    got = _run(model, inp)
+    lines, worst = _layer_report(model, cfg, taps, batch)
+    print(f"\nper-layer activation error (stress={stress}):\n" + "\n".join(lines))
+    # KV cache: slot i of the vlm block <-> position id i+1; proprio at slot 276 (bit-exact layout)
+    L, n_total = cfg.joint.config.num_hidden_layers, 281
+    kc = model.debug_tap("k_cache").view(L, model._engine.max_batch, n_total, 256)[:, :batch]
+    vcache = model.debug_tap("v_cache").view(L, model._engine.max_batch, n_total, 256)[:, :batch]
+    for l in range(L):
+        k_ref = torch.cat([caches["vlm"].key_cache[l], caches["proprio"].key_cache[l]], dim=2)[:, 0]
+        v_ref = torch.cat([caches["vlm"].value_cache[l], caches["proprio"].value_cache[l]], dim=2)[:, 0]
+        ek = (kc[l, :, :277].float() - k_ref.float()).abs().max().item()
+        ev = (vcache[l, :, :277].float() - v_ref.float()).abs().max().item()
+        print(f"  kv cache L{l}: k max_abs={ek:.3e} v max_abs={ev:.3e} (k rms {k_ref.float().pow(2).mean().sqrt():.3f})")
+        assert ek <= 0.25 and ev <= 0.25
+    err = (got.float() - ref.float()).abs().max().item()
+    print(f"actions (unclamped) max_abs={err:.3e}; ref range [{ref.min().item():.3f}, {ref.max().item():.3f}]")
+    assert torch.isfinite(got.float()).all()
+    assert worst <= 0.15
+    assert err <= (0.25 if stress else 5e-2)
+
+
+def test_shrunk_model_graph_equals_eager_and_is_deterministic():
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    model, sd, inp = _setup(cfg, 2)
+    model.set_engine_options(use_cuda_graph=False)
+    eager = _run(model, inp)
+    model.set_engine_options(use_cuda_graph=True)
+    g1 = _run(model, inp)          # captures
+    g2 = _run(model, inp)          # replays
+    assert torch.equal(eager, g1) and torch.equal(g1, g2)
+    assert model.last_launch_count > 0
+
+
+def test_shrunk_fractal_ten_steps():
+    """Config 3: proprio_dim 8, 10 Euler steps with bf16 `t` accumulation, same injected noise."""
+    cfg = shrink_config(fractal_config(10), 2, 3)
+    model, sd, inp = _setup(cfg, 1, vary_text=False)
+    ref = _oracle(sd, cfg, inp)
+    got = _run(model, inp)
+    err = (got.float() - ref.float()).abs().max().item()
+    print(f"fractal 10-step clamped actions max_abs={err:.3e}")
+    assert err <= 2e-2
+
+
+def test_naive_equals_cached():
+    cfg = shrink_config(bridge_config(2), 2, 3)
+    model, sd, inp = _setup(cfg, 2)
+    with torch.inference_mode():
+        a = model.infer_action(**synth.call_args(inp), noise=inp["noise"])
+        b = model.infer_action_naive(inp["input_ids"], inp["pixel_values"], inp["causal_mask"],
+                                     inp["vlm_position_ids"], inp["proprio_position_ids"],
+                                     inp["action_position_ids"], inp["proprios"], noise=inp["noise"])
+    assert torch.equal(a, b)
+
+
+def test_channels_last_pixels_and_default_noise():
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    model, sd, inp = _setup(cfg, 2)
+    a = _run(model, inp)
+    inp2 = dict(inp)
+    inp2["pixel_values"] = inp["pixel_values"].contiguous(memory_format=torch.channels_last)
+    b = _run(model, inp2)
+    assert torch.equal(a, b)
+    # without `noise` the wrapper draws it with the reference's own torch.randn call (pizero.py:511-513)
+    torch.manual_seed(7)
+    with torch.inference_mode():
+        c = model(**synth.call_args(inp))
+    torch.manual_seed(7)
+    nz = torch.randn((2, 4, 7), device=DEV, dtype=torch.bfloat16)
+    inp3 = dict(inp)
+    inp3["noise"] = nz
+    d = _run(model, inp3)
+    assert torch.equal(c, d)

@@ -1,0 +1,161 @@
+"""Per-kernel parity (-m gpu): each CUDA operator through its C-ABI entry point against a torch
+restatement of the reference op sequence (same rounding points) on the same device."""
+
+import math
+
+import pytest
+import torch
+
+from blurr_b200 import capi
+from helpers import bf16_ulp_err, op_gemm, op_joint_attention, op_siglip_attention, report
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+GEMM_SHAPES = [
+    # (T, N, K)   the Pi-0 shapes of SURVEY.md appendix B (padded to the kernel's granularity)
+    (256, 1152, 640), (256, 3456, 1152), (256, 4352, 1152), (256, 1152, 4352), (256, 2048, 1152),
+    (276, 2560, 2048), (276, 2048, 2048), (276, 2048, 16384),
+    (1, 2560, 1024), (4, 1024, 2048), (4, 1024, 4096), (4, 512, 1024),
+    (552, 2560, 2048), (1104, 1152, 1152), (16, 128, 64), (17, 256, 192),
+]
+
+
+@pytest.mark.parametrize("T,N,K", GEMM_SHAPES)
+def test_gemm_store_bias(T, N, K):
+    W = _rand((N, K), 1.0 / math.sqrt(K), 1)
+    X = _rand((T, K), 1.0, 2)
+    b = _rand((N,), 0.5, 3)
+    got = op_gemm(W, X, capi.EPI_STORE, bias=b)
+    ref = (X.float() @ W.float().t() + b.float()).to(torch.bfloat16)
+    print(report(f"gemm_store T={T} N={N} K={K}", got, ref))
+    assert bf16_ulp_err(got, ref) <= 1.01
+
+
+@pytest.mark.parametrize("T,N,K,S", [(276, 2048, 16384, 9), (276, 2560, 2048, 7), (256, 1152, 4352, 16),
+                                     (4, 1024, 4096, 16), (1, 2560, 1024, 6), (552, 2048, 2048, 3),
+                                     (276, 2048, 2048, 1)])
+def test_gemm_partial_splitk(T, N, K, S):
+    W = _rand((N, K), 1.0 / math.sqrt(K), 4)
+    X = _rand((T, K), 1.0, 5)
+    part = op_gemm(W, X, capi.EPI_PARTIAL, splitk=S)
+    assert 1 <= part.shape[0] <= S
+    got = part.sum(0)
+    ref = X.float() @ W.float().t()
+    err = (got - ref).abs().max().item()
+    print(f"gemm_partial T={T} N={N} K={K} S={part.shape[0]}: max_abs={err:.3e}")
+    assert err <= 2e-3
+
+
+@pytest.mark.parametrize("T,N,K", [(256, 4352, 1152), (17, 256, 192)])
+def test_gemm_gelu(T, N, K):
+    W = _rand((N, K), 1.0 / math.sqrt(K), 6)
+    X = _rand((T, K), 1.0, 7)
+    b = _rand((N,), 0.5, 8)
+    got = op_gemm(W, X, capi.EPI_GELU, bias=b)
+    h = (X.float() @ W.float().t() + b.float()).to(torch.bfloat16)
+    ref = torch.nn.functional.gelu(h, approximate="tanh")
+    print(report(f"gemm_gelu T={T} N={N} K={K}", got, ref))
+    assert bf16_ulp_err(got, ref) <= 2.01
+
+
+@pytest.mark.parametrize("T,I,K", [(276, 16384, 2048), (4, 4096, 1024), (17, 128, 192)])
+def test_gemm_geglu(T, I, K):
+    """Weight rows interleaved 64 gate / 64 up per 128-row tile (engine repack); output
+    bf16(bf16(gelu(bf16(gate))) * bf16(up)) (paligemma/modules.py:93-95)."""
+    Wg = _rand((I, K), 1.0 / math.sqrt(K), 9)
+    Wu = _rand((I, K), 1.0 / math.sqrt(K), 10)
+    X = _rand((T, K), 1.0, 11)
+    Wi = torch.empty((2 * I, K), device=DEV, dtype=torch.bfloat16)
+    Wi.view(I // 64, 2, 64, K)[:, 0] = Wg.view(I // 64, 64, K)
+    Wi.view(I // 64, 2, 64, K)[:, 1] = Wu.view(I // 64, 64, K)
+    got = op_gemm(Wi, X, capi.EPI_GEGLU)
+    gate = (X.float() @ Wg.float().t()).to(torch.bfloat16)
+    up = (X.float() @ Wu.float().t()).to(torch.bfloat16)
+    ref = torch.nn.functional.gelu(gate, approximate="tanh") * up
+    print(report(f"gemm_geglu T={T} I={I} K={K}", got, ref))
+    assert bf16_ulp_err(got, ref) <= 3.01
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_siglip_attention(batch):
+    """siglip.py:133-152: bf16 QK^T * scale, fp32 softmax -> bf16, PV."""
+    seq, heads, hidden = 256, 16, 1152
+    hd = hidden // heads
+    qkv = _rand((batch * seq, 3 * hidden), 1.0, 12)
+    got = op_siglip_attention(qkv, batch, seq, heads, hidden)
+    q, k, v = [t.view(batch, seq, heads, hd).transpose(1, 2) for t in qkv.view(batch, seq, 3 * hidden).split(hidden, -1)]
+    w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
+    w = torch.softmax(w, dim=-1, dtype=torch.float32).to(torch.bfloat16)
+    ref = torch.matmul(w, v).transpose(1, 2).contiguous().view(batch * seq, hidden)
+    print(report(f"siglip_attention B={batch}", got, ref))
+    assert (got.float() - ref.float()).abs().max().item() <= 0.03
+
+
+def _joint_ref(q, kc, vc, mask_rows, n_heads):
+    """joint_model.py:273-288 on [B, H, Q, 256] / [B, 1, KV, 256]."""
+    B = kc.shape[0]
+    qh = q.view(B, -1, n_heads, 256).transpose(1, 2)
+    k = kc[:, None].expand(B, n_heads, kc.shape[1], 256)
+    v = vc[:, None].expand(B, n_heads, vc.shape[1], 256)
+    w = torch.matmul(qh, k.transpose(2, 3)) / math.sqrt(256)
+    w = w / 50.0
+    w = torch.tanh(w)
+    w = w * 50.0
+    w = w + mask_rows[:, None]
+    w = torch.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+    o = torch.matmul(w, v)
+    return o.transpose(1, 2).contiguous().view(q.shape)
+
+
+def _block_mask(B, rows, cols, cnts, row0):
+    m = torch.full((B, rows, cols), torch.finfo(torch.bfloat16).min, dtype=torch.bfloat16, device=DEV)
+    for b, c in enumerate(cnts):
+        for r in range(rows):
+            gr = row0 + r
+            if gr < 276:
+                if gr < c:
+                    m[b, r, :c] = 0
+            else:
+                m[b, r, :c] = 0
+                m[b, r, 276:min(cols, 277)] = 0
+                if gr >= 277:
+                    m[b, r, 276:cols] = 0
+    return m
+
+
+@pytest.mark.parametrize("batch,scale", [(1, 1.0), (2, 6.0)])
+def test_joint_attention_prefill(batch, scale):
+    n_heads, n_keys, slots = 8, 277, 281
+    q = _rand((batch * 276, n_heads * 256), scale, 13)
+    kc = _rand((batch, slots, 256), scale, 14)
+    vc = _rand((batch, slots, 256), 1.0, 15)
+    mask = _block_mask(batch, 277, 277, [268, 261][:batch], 0)
+    got = op_joint_attention(False, q, 276, 0, kc, vc, n_keys, mask, batch, n_heads)
+    ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], mask[:, :276], n_heads)
+    print(report(f"joint_prefill B={batch} scale={scale}", got, ref))
+    assert (got.float() - ref.float()).abs().max().item() <= 0.05
+
+
+@pytest.mark.parametrize("qps,row0,n_keys", [(1, 276, 277), (4, 0, 281)])
+def test_joint_attention_fewq(qps, row0, n_keys):
+    batch, n_heads, slots = 2, 8, 281
+    q = _rand((batch * qps, n_heads * 256), 4.0, 16)
+    kc = _rand((batch, slots, 256), 4.0, 17)
+    vc = _rand((batch, slots, 256), 1.0, 18)
+    if qps == 1:
+        mask = _block_mask(batch, 277, 277, [268, 270], 0)      # proprio row = row 276 of the prefill mask
+        rows = mask[:, 276:277]
+    else:
+        mask = _block_mask(batch, 4, 281, [268, 270], 277)      # action mask rows
+        rows = mask
+    got = op_joint_attention(True, q, qps, row0, kc, vc, n_keys, mask, batch, n_heads)
+    ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], rows, n_heads)
+    print(report(f"joint_fewq qps={qps}", got, ref))
+    assert (got.float() - ref.float()).abs().max().item() <= 0.05
