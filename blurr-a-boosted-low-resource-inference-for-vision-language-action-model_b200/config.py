@@ -107,7 +107,12 @@ def _resolve_expr(root: Mapping, expr: str, depth: int) -> Any:
     return val
 
 
+_FLOAT_LIKE = re.compile(r"[-+]?(\d+\.?\d*|\.\d+)[eE][-+]?\d+")
+
+
 def _resolve_tree(root: Mapping, node: Any, depth: int = 0) -> Any:
+    if isinstance(node, str) and _FLOAT_LIKE.fullmatch(node.strip()):
+        return float(node)          # PyYAML (YAML 1.1) reads `1e-6` as a string; OmegaConf as a float
     if isinstance(node, Mapping):
         return AttrDict({k: _resolve_tree(root, v, depth) for k, v in node.items()})
     if isinstance(node, list):

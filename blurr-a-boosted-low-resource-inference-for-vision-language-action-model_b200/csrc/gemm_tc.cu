@@ -312,42 +312,60 @@ static int next_pow2_cols(int c) {
 
 static constexpr int kSmemBudget = 227 * 1024;
 
+static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out) {
+    const int stage_bytes = kTileABytes + nt * bn * kBlockK * 2;
+    const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
+    const int avail = kSmemBudget - 1024 - 256;
+    int stages = avail / stage_bytes;
+    if (stages < 1) return false;
+    if (stages > 8) stages = 8;
+    const int want = kb_per_split > 0 ? kb_per_split : 1;
+    if (stages > want) stages = want;
+    // the epilogue tile aliases the pipeline buffers: keep enough bytes for it
+    while (stages * stage_bytes < tile_bytes) ++stages;
+    if (stages * stage_bytes > avail) return false;
+    *stages_out = stages;
+    *smem_out = stages * stage_bytes + 1024 + 256;
+    return true;
+}
+
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override) {
     GemmPlan pl{};
     pl.valid = false;
     if (Nw % kBlockM != 0 || T <= 0 || K <= 0) return pl;
-    // token chunking: up to 512 tokens per CTA as 1..2 UMMA-N chunks
-    int bn, nt;
-    if (bn_override > 0) {
-        bn = bn_override;
-        nt = (T > bn) ? 2 : 1;
-    } else {
-        const int t16 = (T + 15) / 16 * 16;
-        if (t16 <= 256) { bn = t16; nt = 1; }
-        else if (t16 <= 512) { bn = ((t16 / 2) + 15) / 16 * 16; nt = 2; }
-        else { bn = 256; nt = 1; }
-    }
-    pl.bn = bn;
-    pl.nt = nt;
     pl.kb_total = (K + kBlockK - 1) / kBlockK;
     if (splitk < 1) splitk = 1;
     if (splitk > pl.kb_total) splitk = pl.kb_total;
     pl.kb_per_split = (pl.kb_total + splitk - 1) / splitk;
     pl.splitk = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;   // no empty slices
-    const int stage_bytes = kTileABytes + nt * bn * kBlockK * 2;
-    const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
-    int stages = (kSmemBudget - 1024 - 256) / stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages > pl.kb_per_split) stages = pl.kb_per_split > 0 ? pl.kb_per_split : 1;
-    // the epilogue tile aliases the pipeline buffers: keep enough bytes for it
-    while (stages * stage_bytes < tile_bytes) ++stages;
-    if (stages * stage_bytes + 1024 + 256 > kSmemBudget) return pl;
-    pl.stages = stages;
-    pl.smem_bytes = stages * stage_bytes + 1024 + 256;
+    // Token chunking.  A chunk is one UMMA N (<= 256 tokens, multiple of 16).  Two chunks share a
+    // CTA (one pass over the weight tile for up to ~448 tokens) when a >= 3-stage pipeline and the
+    // epilogue tile still fit in shared memory; otherwise chunks go to blockIdx.y.
+    const int t16 = (T + 15) / 16 * 16;
+    int bn, nt, gy, stages = 0, smem = 0;
+    if (bn_override > 0) {
+        bn = bn_override; nt = 1; gy = (T + bn - 1) / bn;
+        if (!plan_fits(bn, nt, pl.kb_per_split, epi, &stages, &smem)) return pl;
+    } else if (t16 <= 256) {
+        bn = t16; nt = 1; gy = 1;
+        if (!plan_fits(bn, nt, pl.kb_per_split, epi, &stages, &smem)) return pl;
+    } else {
+        const int chunks = (t16 + 255) / 256;
+        bn = ((T + chunks - 1) / chunks + 15) / 16 * 16;
+        nt = 1; gy = chunks;
+        int st2 = 0, sm2 = 0;
+        if (chunks == 2 && plan_fits(bn, 2, pl.kb_per_split, epi, &st2, &sm2) &&
+            (st2 >= 3 || st2 >= pl.kb_per_split)) {
+            nt = 2; gy = 1; stages = st2; smem = sm2;
+        } else if (!plan_fits(bn, 1, pl.kb_per_split, epi, &stages, &smem)) {
+            return pl;
+        }
+    }
+    pl.bn = bn; pl.nt = nt; pl.stages = stages; pl.smem_bytes = smem;
     pl.tmem_cols = next_pow2_cols(nt * bn);
     if (pl.tmem_cols > 512) return pl;
     pl.grid_x = Nw / kBlockM;
-    pl.grid_y = (T + nt * bn - 1) / (nt * bn);
+    pl.grid_y = gy;
     pl.valid = true;
     return pl;
 }

@@ -278,8 +278,9 @@ class PiZero(nn.Module):
             elif isinstance(m, _SiglipEmbeddingsParams):
                 m.position_ids = torch.arange(m.position_embedding.num_embeddings, device="cpu").expand((1, -1))
         model.freeze_all_weights()
-        if dtype is not None:
-            model.to(dtype)
+        if dtype is None:   # the reference flow always ends with `model.to(dtype)`, which also
+            dtype = next(iter(state_dict.values())).dtype   # rounds the RoPE `inv_freq` buffers
+        model.to(dtype)
         if device is not None:
             model.to(device)
         model.eval()

@@ -52,8 +52,12 @@ def _layer_report(model, cfg, taps, batch):
         names += [f"flow{s}.action_embeds"] + [f"flow{s}.L{l}.action" for l in range(jc.num_hidden_layers)]
         names += [f"flow{s}.velocity"]
     worst = 0.0
+    # the engine's merged/encoded embeddings already carry JointModel's `*= sqrt(hidden)`
+    alias = {"merged_embeds": "prefill.embeds.vlm"}
+    for s in range(cfg.num_inference_steps):
+        alias[f"flow{s}.action_embeds"] = f"flow{s}.embeds.action"
     for n in names:
-        ref = taps[n].float().flatten()
+        ref = taps[alias.get(n, n)].float().flatten()
         got = model.debug_tap(n).float().flatten()
         assert got.numel() == ref.numel(), (n, got.numel(), ref.numel())
         err = (got - ref).abs().max().item()
@@ -64,18 +68,31 @@ def _layer_report(model, cfg, taps, batch):
     return lines, worst
 
 
-@pytest.mark.parametrize("stress", [False, True])
-def test_shrunk_model_layers_and_actions(stress):
+def _oracle_fp32(sd, cfg, inp, taps, return_caches=False):
+    """fp32 run of the same bf16 model (bf16-rounded weights and RoPE inv_freq): the tie-breaker
+    where bf16 runs legitimately diverge from each other."""
+    sd32 = {k: v.float() for k, v in sd.items()}
+    def tap(name, t):
+        taps[name] = t.detach().clone()
+    f = lambda t: t.float() if t.is_floating_point() else t
+    with torch.inference_mode():
+        return O.infer_action(sd32, cfg, inp["input_ids"], f(inp["pixel_values"]),
+                              f(inp["image_text_proprio_mask"]), f(inp["action_mask"]), inp["vlm_position_ids"],
+                              inp["proprio_position_ids"], inp["action_position_ids"], f(inp["proprios"]),
+                              noise=inp["noise"], tap=tap, return_caches=return_caches, rope_dtype=torch.bfloat16)
+
+
+def test_shrunk_model_layers_and_actions():
     cfg = shrink_config(bridge_config(1), 2, 3)
     cfg.final_action_clip_value = None          # un-clamped: nothing hides behind the clip
     batch = 2
-    model, sd, inp = _setup(cfg, batch, stress=stress)
+    model, sd, inp = _setup(cfg, batch)
     model.set_engine_options(debug_taps=True)
     taps = {}
     ref, caches = _oracle(sd, cfg, inp, taps, return_caches=True)
     got = _run(model, inp)
     lines, worst = _layer_report(model, cfg, taps, batch)
-    print(f"\nper-layer activation error (stress={stress}):\n" + "\n".join(lines))
+    print("\nper-layer activation error vs the bf16 reference op sequence on this GPU:\n" + "\n".join(lines))
     # KV cache: slot i of the vlm block <-> position id i+1; proprio at slot 276 (bit-exact layout)
     L, n_total = cfg.joint.config.num_hidden_layers, 281
     kc = model.debug_tap("k_cache").view(L, model._engine.max_batch, n_total, 256)[:, :batch]
@@ -86,12 +103,48 @@ def test_shrunk_model_layers_and_actions(stress):
         ek = (kc[l, :, :277].float() - k_ref.float()).abs().max().item()
         ev = (vcache[l, :, :277].float() - v_ref.float()).abs().max().item()
         print(f"  kv cache L{l}: k max_abs={ek:.3e} v max_abs={ev:.3e} (k rms {k_ref.float().pow(2).mean().sqrt():.3f})")
-        assert ek <= 0.25 and ev <= 0.25
+        assert ek <= 0.07 and ev <= 0.07
     err = (got.float() - ref.float()).abs().max().item()
     print(f"actions (unclamped) max_abs={err:.3e}; ref range [{ref.min().item():.3f}, {ref.max().item():.3f}]")
     assert torch.isfinite(got.float()).all()
-    assert worst <= 0.15
-    assert err <= (0.25 if stress else 5e-2)
+    assert worst <= 0.06
+    assert err <= 3.2e-2          # 2 bf16 ulp at |a| in [2, 4); the clamped tolerance is tested below
+    clamped = (got.float().clamp(-1, 1) - ref.float().clamp(-1, 1)).abs().max().item()
+    print(f"actions (clamped to +-1) max_abs={clamped:.3e}")
+    assert clamped <= 1e-2        # BASELINE.json north_star tolerance
+
+
+def test_shrunk_model_stress_weights_vs_fp32_tiebreak():
+    """q/k weights x8: logits x64, so the tanh soft-clamp, the mask and RoPE decide the output, and
+    two bf16 runs with different summation order legitimately diverge (a 1-ulp logit change at
+    |logit| ~ 32 is 0.25 -> 28 % in a softmax weight).  The check is therefore against the fp32 run
+    of the same model: our error must not exceed the bf16 reference's own error by more than 2x."""
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    cfg.final_action_clip_value = None
+    batch = 2
+    model, sd, inp = _setup(cfg, batch, stress=True)
+    model.set_engine_options(debug_taps=True)
+    taps16, taps32 = {}, {}
+    ref16 = _oracle(sd, cfg, inp, taps16)
+    ref32 = _oracle_fp32(sd, cfg, inp, taps32)
+    got = _run(model, inp)
+    jc = cfg.joint.config
+    names = [f"prefill.L{l}.{m}" for l in range(jc.num_hidden_layers - 1) for m in ("vlm", "proprio")]
+    names += [f"flow0.L{l}.action" for l in range(jc.num_hidden_layers)] + ["flow0.velocity"]
+    print("\nstress weights: error vs fp32 (ours | bf16 reference op sequence)")
+    for n in names:
+        hi = taps32[n].float().flatten()
+        e_ours = (model.debug_tap(n).float().flatten() - hi).abs()
+        e_ref = (taps16[n].float().flatten() - hi).abs()
+        print(f"  {n:24s} ours max={e_ours.max().item():.3e} mean={e_ours.mean().item():.3e} | "
+              f"ref max={e_ref.max().item():.3e} mean={e_ref.mean().item():.3e}")
+        assert e_ours.mean().item() <= 1.5 * e_ref.mean().item() + 1e-4, n
+        assert e_ours.max().item() <= 2.0 * e_ref.max().item() + 1e-3, n
+    e_ours = (got.float() - ref32).abs().max().item()
+    e_ref = (ref16.float() - ref32).abs().max().item()
+    print(f"actions vs fp32: ours {e_ours:.3e} | bf16 reference {e_ref:.3e}; ours vs bf16 ref "
+          f"{(got.float() - ref16.float()).abs().max().item():.3e}")
+    assert e_ours <= 2.0 * e_ref + 1e-3
 
 
 def test_shrunk_model_graph_equals_eager_and_is_deterministic():

@@ -1,0 +1,152 @@
+"""Host-side logic on CPU: config handling, mask builders, state_dict contract, C-ABI library
+loading and symbol table, loud failure without a GPU."""
+
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from blurr_b200 import capi, masks, synth
+from blurr_b200.config import (AttrDict, bridge_config, fractal_config, load_yaml_config, merge,
+                               shrink_config)
+from blurr_b200.pizero import PiZeroInference, sinusoidal_time_table
+from oracle import pi0_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = capi.load_library()
+    assert lib.blurr_abi_version() == capi.ABI_VERSION
+    header = open(os.path.join(ROOT, "include", "blurr_pi0.h")).read()
+    declared = set(re.findall(r"\b(blurr_[a-z0-9_]+)\s*\(", header))
+    declared -= {"blurr_status", "blurr_dtype"}
+    assert declared == set(capi.DECLARED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_config_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "blurr_pi0.h")).read()
+    body = header[header.index("typedef struct blurr_pi0_config {"):header.index("} blurr_pi0_config;")]
+    fields = re.findall(r"^\s+(?:int32_t|int64_t|float)\s+([a-z_0-9]+);", body, flags=re.M)
+    assert fields == [f[0] for f in capi.Pi0ConfigC._fields_]
+    body = header[header.index("typedef struct blurr_pi0_inputs {"):header.index("} blurr_pi0_inputs;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"([a-z_0-9]+)(?:\[4\])?\s*[;,]", body)
+    assert [f[0] for f in capi.Pi0InputsC._fields_] == names
+
+
+def test_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = capi.load_library()
+    cfg = shrink_config(bridge_config(1), 1, 1)
+    model = PiZeroInference.from_state_dict(cfg, synth.synthetic_state_dict(cfg, 0, torch.bfloat16))
+    h = ctypes.c_void_p()
+    rc = lib.blurr_pi0_create(ctypes.byref(model._config_c()), 0, 1, ctypes.byref(h))
+    assert rc < 0 and b"CUDA" in lib.blurr_last_error()
+    inp = synth.synthetic_inputs(cfg, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model(**synth.call_args(inp))
+
+
+def test_invalid_config_rejected():
+    lib = capi.load_library()
+    cfg = shrink_config(bridge_config(1), 1, 1)
+    model = PiZeroInference.from_state_dict(cfg, synth.synthetic_state_dict(cfg, 0, torch.bfloat16))
+    c = model._config_c()
+    c.head_dim = 128
+    h = ctypes.c_void_p()
+    assert lib.blurr_pi0_create(ctypes.byref(c), 0, 1, ctypes.byref(h)) == -1
+    assert b"head_dim" in lib.blurr_last_error()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mask_builder_matches_oracle(dtype):
+    cfg = bridge_config(1)
+    am = torch.zeros(5, 276, dtype=torch.long)
+    for b, n in enumerate([276, 268, 257, 256, 1]):      # full, typical, BOS only, image only, degenerate
+        am[b, :n] = 1
+    got = masks.build_causal_mask_and_position_ids(am, dtype, 276, 1, 4)
+    want = O.build_causal_mask_and_position_ids(cfg, am, dtype)
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype and torch.equal(a, b)
+    assert int((got[0][1] == 0).sum()) == 268 * 268 + 5 * 268 + 1 + 4 * 5
+    g1, g2 = masks.split_full_mask_into_submasks(got[0], 276, 1, 4)
+    w1, w2 = O.split_full_mask_into_submasks(cfg, want[0])
+    assert g1.shape == (5, 1, 277, 277) and g2.shape == (5, 1, 4, 281)
+    assert torch.equal(g1, w1) and torch.equal(g2, w2)
+    assert g1.data_ptr() == got[0].data_ptr()            # views, like the reference
+
+
+def test_state_dict_contract():
+    cfg = bridge_config(1)
+    spec = synth.state_dict_spec(cfg)
+    assert len(spec) == 938
+    total = sum(int(torch.Size(s).numel()) for _, s, _, _ in spec)
+    assert total == 3_549_565_687
+    with torch.device("meta"):
+        model = PiZeroInference(cfg)
+    sd = model.state_dict()
+    assert set(sd.keys()) == {k for k, _, _, _ in spec}
+    for k, shape, _, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    f = synth.state_dict_spec(fractal_config(10))
+    assert dict((k, s) for k, s, _, _ in f)["proprio_encoder.weight"] == (1024, 8)
+
+
+def test_time_table_matches_oracle_and_bf16_accumulation():
+    for steps in (1, 10):
+        cfg = bridge_config(steps)
+        for dtype in (torch.float32, torch.bfloat16):
+            got = sinusoidal_time_table(steps, 1024, 10000.0, "cpu", dtype)
+            want = O.time_cond_table(cfg, dtype)
+            assert torch.equal(got, want)
+    one = sinusoidal_time_table(1, 1024, 10000.0, "cpu", torch.bfloat16)
+    assert torch.equal(one[0, :512], torch.zeros(512, dtype=torch.bfloat16))     # t = 0: [0.., 1..]
+    assert torch.equal(one[0, 512:], torch.ones(512, dtype=torch.bfloat16))
+
+
+def test_config_helpers(tmp_path):
+    cfg = bridge_config(10)
+    assert cfg.mixture.vlm.hidden_size == 2048 and cfg.get("missing", 3) == 3
+    assert cfg.joint.config.mixture.action.cache is False
+    m = merge(cfg.joint.config, cfg.joint.config.mixture.action)      # joint_model.py:328-330
+    assert m.hidden_size == 1024 and m.num_hidden_layers == 18
+    y = tmp_path / "c.yaml"
+    y.write_text("a: 3\nb: ${a}\nmixture:\n  vlm:\n    h: ${b}\nname: x_${a}\nn: ${eval:'2 * 5'}\n")
+    loaded = load_yaml_config(str(y))
+    assert loaded.b == 3 and loaded.mixture.vlm.h == 3 and loaded.name == "x_3" and loaded.n == 10
+    ref_yaml = "/root/reference/third_party/open_pi_zero/config/eval/bridge.yaml"
+    if os.path.isfile(ref_yaml):
+        ref_cfg = load_yaml_config(ref_yaml)
+        for key in ("num_inference_steps", "final_action_clip_value", "cond_steps", "horizon_steps", "action_dim",
+                    "proprio_dim", "max_image_text_tokens", "image_token_index", "vocab_size", "pad_token_id",
+                    "time_max_period"):
+            assert ref_cfg[key] == cfg[key], key
+        assert ref_cfg.vision.config == cfg.vision.config
+        assert ref_cfg.joint.config.mixture == cfg.joint.config.mixture
+        for key in ("num_hidden_layers", "num_attention_heads", "num_key_value_heads", "head_dim", "rms_norm_eps"):
+            assert ref_cfg.joint.config[key] == cfg.joint.config[key]
+        step1 = load_yaml_config(ref_yaml.replace("bridge.yaml", "bridge_step1.yaml"))
+        assert step1.num_inference_steps == 1
+        fr = load_yaml_config(ref_yaml.replace("bridge.yaml", "fractal_coke.yaml"))
+        assert fr.proprio_dim == fractal_config().proprio_dim and fr.act_steps == 2
+
+
+def test_synthetic_inputs_layout():
+    cfg = bridge_config(1)
+    inp = synth.synthetic_inputs(cfg, 3, vary_text=True)
+    ids = inp["input_ids"]
+    assert ids.shape == (3, 276) and (ids[:, :256] == 257152).all() and (ids[:, 256] == 2).all()
+    cnt = inp["attention_mask"].sum(1)
+    for b in range(3):
+        assert ids[b, cnt[b] - 1] == 108 and (ids[b, cnt[b]:] == 0).all()
+    assert inp["pixel_values"].abs().max() <= 1.0
+    base = synth.synthetic_inputs(cfg, 1)
+    assert base["attention_mask"].sum().item() == 268
+    assert base["input_ids"][0, 257:267].tolist() == [179378, 5125, 195997, 211369, 93264, 178254, 3810, 17301,
+                                                      14683, 160681]

@@ -15,8 +15,8 @@ run() { # name, timeout, cmd...
   tail -n "${TAIL_LINES:-30}" "gpurun_out/$name.log" | tee -a gpurun_out/summary.txt
   if [ $rc -ne 0 ]; then echo "STOP after $name" | tee -a gpurun_out/summary.txt; exit 1; fi
 }
-run gemm_tiny 240 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -s -k "gemm_store_bias and 16-128-64"
-run gemm_store 300 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -s -k "gemm_store"
+[ -n "${SKIP_GEMM_STORE:-}" ] || run gemm_tiny 240 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -s -k "gemm_store_bias and 16-128-64"
+[ -n "${SKIP_GEMM_STORE:-}" ] || run gemm_store 300 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -s -k "gemm_store"
 run gemm_rest 300 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -s -k "gemm and not gemm_store"
 run attention 300 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -s -k "attention"
 TAIL_LINES=120 run model_shrunk 900 python -m pytest tests/test_gpu_model.py -m gpu -x -q -s
