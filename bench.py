@@ -1,0 +1,438 @@
+#!/usr/bin/env python3
+"""Benchmark of the Pi-0 Bridge control step (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle)
+
+A *step* is one control step: one `PiZeroInference.forward` (= `infer_action`, reference
+`src/model/vla/pizero.py:473-547`) per episode, producing a chunk of `horizon_steps` = 4 actions.
+
+Workload at every N: BASELINE.json configs[1] — Bridge config, bf16, batch 1 per GPU, 1 flow step
+(`--preset blurr`), random-init weights, synthetic inputs, a fresh image + proprio every control
+step of a 50-step episode; for N > 1 every rank runs its own independent episode (weights
+replicated, no data-path collective; one NCCL all_gather of the final actions), `"scaling":
+"weak"`.  `value` = actions/s over all ranks with inputs resident in HBM; `e2e` = the same through
+the public call with all 8 input tensors copied from pinned host memory and the actions read back
+every step (what `src/agent/eval.py:207-218,239` does).  The same line carries the bs=1 latency
+percentiles, the secondary batched-episode measurement (configs[3], 64 episodes per GPU), the
+roofline of the dominant kernel and the CPU baseline (the oracle on the box's host cores).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_WEIGHT_BYTES_STEP = 5_793_957_358          # bf16 weights one bs=1, S=1 step depends on
+ALG_FLOPS_STEP = 1.2373e12                     # SURVEY.md §8(d), per sample
+HORIZON = 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=1, help="episodes per GPU in the primary measurement")
+    ap.add_argument("--batched", type=int, default=64, help="episodes per GPU of the secondary measurement (0 = skip)")
+    ap.add_argument("--batched-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--flow-steps", type=int, default=1, help="num_inference_steps (1 = --preset blurr)")
+    ap.add_argument("--ring", type=int, default=50, help="distinct pre-staged control-step inputs (one episode)")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def pct(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    i = min(len(xs) - 1, max(0, int(round(q * (len(xs) - 1)))))
+    return xs[i]
+
+
+def make_ring(cfg, batch, n, device, seed, pinned=False):
+    """`n` control-step input sets: same instruction (input_ids / masks / positions), a fresh image,
+    proprio and flow noise per step."""
+    import torch
+    from blurr_b200 import synth
+    base = synth.synthetic_inputs(cfg, batch, seed=seed, dtype=torch.bfloat16, vary_text=batch > 1)
+    ring = []
+    g = torch.Generator().manual_seed(seed + 17)
+    for _ in range(n):
+        d = dict(base)
+        img = torch.randint(0, 256, base["pixel_values"].shape, dtype=torch.uint8, generator=g)
+        d["pixel_values"] = synth.process_images(img).to(torch.bfloat16)
+        d["proprios"] = (torch.rand(base["proprios"].shape, generator=g) * 2 - 1).to(torch.bfloat16)
+        d["noise"] = torch.randn(base["noise"].shape, generator=g).to(torch.bfloat16)
+        keys = list(synth.CALL_KEYS) + ["noise"]
+        if pinned:
+            ring.append({k: d[k].contiguous().pin_memory() for k in keys})
+        else:
+            ring.append({k: d[k].to(device) for k in keys})
+    return ring
+
+
+def run_ours(args):
+    import torch
+    from blurr_b200 import capi, synth
+    from blurr_b200.config import bridge_config
+    from blurr_b200.pizero import PiZeroInference
+
+    world, rank, local = dist_setup(args)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    peaks = measured_peaks()
+    cfg = bridge_config(args.flow_steps)
+    sd = synth.random_state_dict_on_device(cfg, dev, seed=0)
+    model = PiZeroInference.from_state_dict(cfg, sd, device=dev)
+    del sd
+    model.set_engine_options(reserve_batch=max(args.batch, args.batched))
+    K, W, B = args.steps, max(args.warmup, 3), args.batch
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- primary: device-resident inputs ----------------
+    ring = make_ring(cfg, B, min(args.ring, max(K, 1)), dev, seed=1234 + rank)
+    with torch.inference_mode():
+        for i in range(W):
+            r = ring[i % len(ring)]
+            out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+        model._engine.check()
+        launches_per_step = model.last_launch_count
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        evs[0].record()
+        for i in range(K):
+            r = ring[i % len(ring)]
+            out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+            evs[i + 1].record()
+        if world > 1:       # the one collective of the path: gather the final actions of every episode
+            import torch.distributed as dist
+            gathered = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(gathered, out)
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        barrier()
+        clocks = sampler.stop()
+        model._engine.check()
+    total_ms = max_over_ranks(evs[0].elapsed_time(end))
+    lat = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+    ms_per_step = total_ms / K
+    value = world * B * HORIZON * K / (total_ms / 1e3)
+
+    # ---------------- e2e: pinned host inputs, H2D + D2H inside the timed region ----------------
+    hring = make_ring(cfg, B, min(8, len(ring)), dev, seed=4321 + rank, pinned=True)
+    h2d = sum(t.numel() * t.element_size() for t in hring[0].values())
+    host_out = torch.empty((B, HORIZON, cfg.action_dim), dtype=torch.float32).pin_memory()
+    with torch.inference_mode():
+        def e2e_step(r):
+            d = {k: v.to(dev, non_blocking=True) for k, v in r.items()}
+            a = model(**{k: d[k] for k in synth.CALL_KEYS}, noise=d["noise"])
+            host_out.copy_(a.float(), non_blocking=False)        # `actions.float().cpu()` (eval.py:239)
+            return a
+        for i in range(W):
+            e2e_step(hring[i % len(hring)])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(hring[i % len(hring)])
+        torch.cuda.synchronize(dev)
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+    e2e_value = world * B * HORIZON * K / e2e_s
+    d2h = host_out.numel() * host_out.element_size()
+
+    line = {
+        "metric": "pi0_bridge_actions_per_sec", "value": value, "unit": "actions/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (random-init weights, random uint8 images, random proprio, injected flow noise)",
+        "config": {"workload": "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[1])",
+                   "episodes_per_gpu": B, "flow_steps": args.flow_steps, "actions_per_step": HORIZON,
+                   "parallelism": f"episode-sharded x{world}, weights replicated",
+                   "l2": "inputs larger than L2: each step streams 5.79 GB of weights (L2 is 126 MB)",
+                   "cuda_graph": True},
+        "latency_ms": {"p50": pct(lat, 0.5), "p90": pct(lat, 0.9), "mean": statistics.fmean(lat), "min": min(lat),
+                       "note": "per control step at this rank, CUDA events, device-resident inputs"},
+        "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3 / K},
+        "gpu_launches": int(launches_per_step) * K,
+        "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clocks,
+        "step_roofline": {
+            "hbm_time_ms": ALG_WEIGHT_BYTES_STEP / (peaks["hbm_gbs"] * 1e9) * 1e3,
+            "tensor_time_ms": ALG_FLOPS_STEP / (peaks["bf16_tflops"] * 1e12) * 1e3,
+            "frac_of_hbm_roofline": (ALG_WEIGHT_BYTES_STEP / (peaks["hbm_gbs"] * 1e9) * 1e3) / pct(lat, 0.5)
+            if B == 1 and args.flow_steps == 1 else None,
+            "peaks": peaks["source"]},
+    }
+
+    # ---------------- roofline of the dominant kernel (rank 0) ----------------
+    if rank == 0 and not args.no_roofline:
+        line["roofline"] = dominant_kernel_roofline(dev, peaks)
+    # ---------------- secondary: batched episodes (BASELINE.json configs[3]) ----------------
+    if args.batched > 0:
+        Bb, Kb = args.batched, args.batched_steps
+        bring = make_ring(cfg, Bb, 2, dev, seed=99 + rank)
+        with torch.inference_mode():
+            for i in range(3):
+                r = bring[i % 2]
+                out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+            model._engine.check()
+            bl = model.last_launch_count
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(Kb):
+                r = bring[i % 2]
+                out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+            if world > 1:
+                import torch.distributed as dist
+                gathered = [torch.empty_like(out) for _ in range(world)]
+                dist.all_gather(gathered, out)
+            e.record()
+            barrier()
+        bms = max_over_ranks(s.elapsed_time(e))
+        b_value = world * Bb * HORIZON * Kb / (bms / 1e3)
+        flops = ALG_FLOPS_STEP * Bb * Kb / (bms / 1e3) / 1e12
+        line["batched"] = {"workload": "bridge_bs64_per_gpu_episode_sharded (BASELINE.json configs[3])",
+                           "episodes_per_gpu": Bb, "steps": Kb, "actions_per_sec": b_value,
+                           "ms_per_step": bms / Kb, "gpu_launches_per_step": int(bl),
+                           "tensor_roofline": {"bound": "tensor", "achieved": flops, "peak": peaks["bf16_tflops_sustained"],
+                                               "unit": "TFLOP/s", "frac": flops / peaks["bf16_tflops_sustained"],
+                                               "note": "algorithmic FLOPs per GPU / step time, of " + peaks["source"] + " sustained cuBLAS bf16"}}
+    # ---------------- CPU baseline (rank 0, N = 1) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, model, warm=1, timed=2)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(dev, peaks):
+    """The Gemma gate/up GEMM + GeGLU (32768 x 2048 weights, 276 tokens): 46 % of the step's bytes.
+    Times the kernel through its C-ABI operator entry point on 4 rotating weight buffers (537 MB
+    > L2) with CUDA events on the launching stream."""
+    import ctypes as C
+    import torch
+    from blurr_b200 import capi
+    lib = capi.load_library()
+    N, Kd, T = 32768, 2048, 276
+    nbuf, iters = 4, 40
+    Ws = [torch.empty((N, Kd), device=dev, dtype=torch.bfloat16).uniform_(-0.02, 0.02) for _ in range(nbuf)]
+    X = torch.randn((T, Kd), device=dev, dtype=torch.bfloat16)
+    out = torch.empty((T, N // 2), device=dev, dtype=torch.bfloat16)
+    stream = torch.cuda.current_stream(dev)
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def launch(i):
+        return lib.blurr_op_gemm_async(sp, C.c_void_p(Ws[i % nbuf].data_ptr()), N, Kd, Kd, C.c_void_p(X.data_ptr()), T, Kd,
+                                 capi.EPI_GEGLU, 1, None, C.c_void_p(out.data_ptr()), N // 2, None)
+    for i in range(nbuf):
+        capi.check(launch(i))
+    torch.cuda.synchronize(dev)
+    times = []
+    pairs = []
+    for i in range(iters):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        capi.check(launch(i))
+        e.record(stream)
+        pairs.append((s, e))
+    torch.cuda.synchronize(dev)
+    times = [s.elapsed_time(e) for s, e in pairs]
+    ms = statistics.fmean(times)
+    alg_bytes = N * Kd * 2
+    achieved = alg_bytes / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "gemm_tc_kernel<EPI_GEGLU> (Gemma gate/up, 276 tokens)",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": None, "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "ms_min": min(times),
+            "note": "algorithmic bytes = the 32768x2048 bf16 weight tile stream; peak = " + peaks["source"] + " copy bandwidth"}
+
+
+def cpu_baseline(cfg, model, warm=1, timed=2, state_dict=None):
+    """The oracle (a port of the reference's op sequence, `oracle/pi0_oracle.py`) on the box's host
+    cores: fp32, bs=1, full-size model (BASELINE.json configs[0])."""
+    import torch
+    from blurr_b200 import synth
+    from oracle import pi0_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if state_dict is None:
+        state_dict = {k: v.detach().to("cpu", torch.float32) for k, v in model.state_dict().items()}
+    inp = synth.synthetic_inputs(cfg, 1, dtype=torch.float32)
+    ts = []
+    with torch.inference_mode():
+        for i in range(warm + timed):
+            t0 = time.perf_counter()
+            O.infer_action(state_dict, cfg, **synth.call_args(inp), noise=inp["noise"])
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                ts.append(dt)
+    sec = statistics.median(ts)
+    return {"value": HORIZON / sec, "unit": "actions/s", "cores": cores, "kind": "port",
+            "ms_per_step": sec * 1e3,
+            "sample": f"{timed} full-size Bridge control steps (bs=1, fp32, 1 flow step) after {warm} warm-up; "
+                      f"torch {torch.__version__} with {torch.get_num_threads()} threads"}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
+    pure Python/PyTorch and cannot travel to the GPU box, so its pinned restatement (the oracle)
+    is timed on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from blurr_b200 import synth
+    from blurr_b200.config import bridge_config
+    from oracle import pi0_oracle as O
+    cfg = bridge_config(args.flow_steps)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synthetic_state_dict(cfg, 0, torch.float32)
+    inp = synth.synthetic_inputs(cfg, 1, dtype=torch.float32)
+    W = max(1, min(args.warmup, 2))
+    budget_s = 150.0
+    ts = []
+    with torch.inference_mode():
+        for _ in range(W):
+            O.infer_action(sd, cfg, **synth.call_args(inp), noise=inp["noise"])
+        t_begin = time.perf_counter()
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            O.infer_action(sd, cfg, **synth.call_args(inp), noise=inp["noise"])
+            ts.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_begin > budget_s:
+                break
+    sec = statistics.fmean(ts)
+    value = HORIZON / sec
+    sample = (f"{len(ts)} of {args.steps} requested full-size Bridge control steps (bs=1, fp32, {args.flow_steps} flow "
+              f"step) after {W} warm-up, bounded to {budget_s:.0f} s; torch {torch.__version__}, {cores} threads")
+    line = {
+        "impl": "reference", "metric": "pi0_bridge_actions_per_sec", "value": value, "unit": "actions/s",
+        "n_gpus": args.gpus, "steps": len(ts), "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[1])",
+                   "episodes_per_gpu": 1, "flow_steps": args.flow_steps, "actions_per_step": HORIZON,
+                   "parallelism": "host CPU, rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": "actions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

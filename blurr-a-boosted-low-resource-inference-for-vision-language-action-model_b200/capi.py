@@ -84,6 +84,9 @@ _SIGNATURES = [
     ("blurr_op_gemm", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("blurr_op_gemm_async", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("blurr_op_siglip_attention", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     ("blurr_op_joint_attention", C.c_int,

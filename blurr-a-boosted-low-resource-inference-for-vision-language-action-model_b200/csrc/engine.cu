@@ -959,6 +959,20 @@ extern "C" int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h) { return h ? sta
 // ---------------------------------------------------------------------------
 // single-operator entry points
 // ---------------------------------------------------------------------------
+extern "C" int blurr_op_gemm_async(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T,
+                                   int ldx, int epi, int splitk, const void* bias, void* out, int ldo,
+                                   float* partial) {
+    GemmCall c{};
+    c.W = static_cast<const bf16*>(W); c.Nw = N; c.K = K; c.ldw = ldw;
+    c.X = static_cast<const bf16*>(X); c.T = T; c.ldx = ldx; c.epi = epi; c.splitk = splitk;
+    c.bias = static_cast<const bf16*>(bias); c.out = static_cast<bf16*>(out); c.ldo = ldo; c.partial = partial;
+    c.bn_override = 0;
+    std::string err;
+    const int s = gemm_launch(static_cast<cudaStream_t>(cuda_stream), c, &err);
+    if (s < 0) return fail(BLURR_ERR_INVALID, err);
+    return s;
+}
+
 extern "C" int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
                              int epi, int splitk, const void* bias, void* out, int ldo, float* partial) {
     GemmCall c{};

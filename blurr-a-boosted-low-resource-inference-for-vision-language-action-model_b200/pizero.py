@@ -262,6 +262,7 @@ class PiZero(nn.Module):
         object.__setattr__(self, "_weights_version", 0)
         object.__setattr__(self, "_debug_taps", False)
         object.__setattr__(self, "_use_cuda_graph", True)
+        object.__setattr__(self, "_reserve_batch", 1)
 
     @classmethod
     def from_state_dict(cls, cfg, state_dict: Dict[str, torch.Tensor], device=None, dtype=None):
@@ -334,7 +335,12 @@ class PiZero(nn.Module):
         self._bump()
         return out
 
-    def set_engine_options(self, *, debug_taps: Optional[bool] = None, use_cuda_graph: Optional[bool] = None):
+    def set_engine_options(self, *, debug_taps: Optional[bool] = None, use_cuda_graph: Optional[bool] = None,
+                           reserve_batch: Optional[int] = None):
+        """`reserve_batch`: size the engine's workspace for at least this many episodes up front (a
+        larger batch later re-creates the engine and re-uploads the weights)."""
+        if reserve_batch is not None:
+            object.__setattr__(self, "_reserve_batch", int(reserve_batch))
         if debug_taps is not None:
             object.__setattr__(self, "_debug_taps", bool(debug_taps))
         if use_cuda_graph is not None:
@@ -385,7 +391,7 @@ class PiZero(nn.Module):
             return eng
         if eng is not None:
             eng.close()
-        eng = _Engine(self, device, max_batch=max(batch, 1))
+        eng = _Engine(self, device, max_batch=max(batch, self._reserve_batch, 1))
         object.__setattr__(self, "_engine", eng)
         object.__setattr__(self, "_engine_key", key)
         return eng

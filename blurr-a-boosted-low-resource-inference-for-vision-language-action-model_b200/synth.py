@@ -189,3 +189,27 @@ CALL_KEYS = ("input_ids", "pixel_values", "image_text_proprio_mask", "action_mas
 
 def call_args(inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return {k: inputs[k] for k in CALL_KEYS}
+
+
+def random_state_dict_on_device(cfg, device, seed: int = 0, dtype: torch.dtype = torch.bfloat16
+                                ) -> Dict[str, torch.Tensor]:
+    """Same layout and distributions as `synthetic_state_dict`, drawn directly on `device` with
+    its own generator (seconds instead of a minute for 3.5 B parameters).  Used by `bench.py`,
+    where only the shapes and value ranges matter; parity tests use the CPU-seeded recipe."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+    for key, shape, kind, fan_in in state_dict_spec(cfg):
+        if kind == "uniform":
+            bound = 1.0 / math.sqrt(fan_in)
+            t = torch.empty(shape, device=device, dtype=torch.float32).uniform_(-bound, bound, generator=g)
+        elif kind in ("embedding", "embedding_pad0"):
+            t = torch.empty(shape, device=device, dtype=dtype).normal_(generator=g)
+            if kind == "embedding_pad0":
+                t[0].zero_()
+        elif kind == "ln_weight":
+            t = 1.0 + torch.empty(shape, device=device, dtype=torch.float32).uniform_(-0.1, 0.1, generator=g)
+        else:
+            t = torch.empty(shape, device=device, dtype=torch.float32).uniform_(-0.1, 0.1, generator=g)
+        out[key] = t.to(dtype)
+    return out

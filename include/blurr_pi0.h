@@ -158,6 +158,10 @@ int blurr_abi_version(void);
  * [splitk_used][T][N]); returns the number of split-K slices used (>=1) or a negative status. */
 int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
                   int epi, int splitk, const void* bias, void* out, int ldo, float* partial);
+/* Same launch without the trailing stream synchronisation / pipeline-timeout check (for timing
+ * loops); returns the split-K slice count or a negative status. */
+int blurr_op_gemm_async(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
+                        int epi, int splitk, const void* bias, void* out, int ldo, float* partial);
 int blurr_op_siglip_attention(void* cuda_stream, const void* qkv, int ld_qkv, int batch, int seq, int heads,
                               int hidden, void* out, int ld_out);
 int blurr_op_joint_attention(void* cuda_stream, int few_query, const void* q, int q_per_sample,
