@@ -17,11 +17,11 @@
 // ATen CUDA kernels do them (multiplication by the fp32 reciprocal).
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace blurr {
 
 static constexpr int kAttnThreads = 256;
-static constexpr int kBM = 64;   // query rows per CTA
 static constexpr int kBK = 64;   // keys per streamed block
 
 struct AttnMmaArgs {
@@ -37,47 +37,58 @@ struct AttnMmaArgs {
     const bf16* mask; long long mask_bstride, mask_rstride; int q_row_offset;
 };
 
-template <int HD_PAD>
-__device__ __forceinline__ void load_rows_async(bf16* dst, const bf16* src, int ld, int row0, int nrows_valid,
-                                                int hd) {
-    // dst: [64][HD_PAD + 8]; 16-byte chunks; rows >= nrows_valid and columns >= hd are zero-filled
-    constexpr int CH = HD_PAD / 8;
-    for (int idx = threadIdx.x; idx < kBK * CH; idx += kAttnThreads) {
+// dst: [nrows][LDS]; 16-byte chunks; rows >= nrows_valid and columns >= hd are zero-filled
+template <int LDS, int CH>
+__device__ __forceinline__ void load_rows_async(bf16* dst, const bf16* src, int ld, int row0, int nrows,
+                                                int nrows_valid, int hd) {
+    for (int idx = threadIdx.x; idx < nrows * CH; idx += kAttnThreads) {
         const int r = idx / CH, c = idx - r * CH;
         const bool valid = (row0 + r < nrows_valid) && (c * 8 < hd);
         const bf16* g = valid ? (src + static_cast<size_t>(row0 + r) * ld + c * 8) : src;
-        cp_async_16(dst + r * (HD_PAD + 8) + c * 8, g, valid);
+        cp_async_16(dst + r * LDS + c * 8, g, valid);
     }
 }
 
-template <int HD_PAD, bool GEMMA>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMmaArgs a) {
-    constexpr int LDS = HD_PAD + 8;            // smem row stride of Q/K/V tiles (elements)
+// BM query rows per CTA; 8 warps = (BM/16) row groups x WC column groups.
+template <int HD_PAD, int BM, bool GEMMA>
+__global__ void __launch_bounds__(kAttnThreads) attn_mma_kernel(const AttnMmaArgs a) {
+    constexpr int WR = BM / 16;                 // row groups
+    constexpr int WC = 8 / WR;                  // column groups
+    constexpr int KPW = kBK / WC;               // keys per column group per streamed block (16 or 32)
+    constexpr int NT_S = KPW / 8;               // logit n-tiles per warp per block
+    constexpr int NT_ALL = HD_PAD / 8;          // output n-tiles over the head dim
+    constexpr int NT_PV = (NT_ALL + WC - 1) / WC;
+    constexpr int NP_PV = (NT_PV + 1) / 2;
+    constexpr int CH = HD_PAD / 8;              // 16-byte chunks per row that carry data
+    constexpr int LDS_MIN = WC * NP_PV * 16 > HD_PAD ? WC * NP_PV * 16 : HD_PAD;
+    constexpr int LDS = LDS_MIN + 8;            // smem row stride (elements), conflict-free for ldmatrix
     extern __shared__ __align__(16) uint8_t smem_attn[];
     const int nkb = (a.n_keys + kBK - 1) / kBK;
-    const int ldl = nkb * kBK + 8;             // logit row stride (elements)
+    const int ldl = nkb * kBK + 8;              // logit row stride (elements)
     bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
-    bf16* KVs = Qs + kBM * LDS;                // 2 buffers
-    bf16* Ls = KVs + 2 * kBK * LDS;            // [64][ldl]
+    bf16* KVs = Qs + BM * LDS;                  // 2 buffers
+    bf16* Ls = KVs + 2 * kBK * LDS;             // [BM][ldl]
 
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wr = warp & 3, wc = warp >> 2;
-    const int q_row0 = qt * kBM;
+    const int wr = warp % WR, wc = warp / WR;
+    const int q_row0 = qt * BM;
 
     const bf16* qbase = a.q + static_cast<size_t>(b) * a.q_per_sample * a.ldq + a.q_col0 + h * a.head_stride_q;
     const bf16* kbase = a.k + static_cast<size_t>(b) * a.kv_per_sample * a.ldk + a.k_col0 + h * a.head_stride_kv;
     const bf16* vbase = a.v + static_cast<size_t>(b) * a.kv_per_sample * a.ldv + a.v_col0 + h * a.head_stride_kv;
 
-    load_rows_async<HD_PAD>(Qs, qbase, a.ldq, q_row0, a.q_per_sample, a.hd);
-    load_rows_async<HD_PAD>(KVs, kbase, a.ldk, 0, a.n_keys, a.hd);
+    pdl_wait();
+    pdl_trigger();
+    load_rows_async<LDS, CH>(Qs, qbase, a.ldq, q_row0, BM, a.q_per_sample, a.hd);
+    load_rows_async<LDS, CH>(KVs, kbase, a.ldk, 0, kBK, a.n_keys, a.hd);
     cp_async_commit();
 
     // ---------------- phase S: logits = chain(Q K^T) -> Ls (bf16) ----------------
     for (int kb = 0; kb < nkb; ++kb) {
         bf16* Kcur = KVs + (kb & 1) * kBK * LDS;
         if (kb + 1 < nkb) {
-            load_rows_async<HD_PAD>(KVs + ((kb + 1) & 1) * kBK * LDS, kbase, a.ldk, (kb + 1) * kBK, a.n_keys, a.hd);
+            load_rows_async<LDS, CH>(KVs + ((kb + 1) & 1) * kBK * LDS, kbase, a.ldk, (kb + 1) * kBK, kBK, a.n_keys, a.hd);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -85,9 +96,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
         }
         __syncthreads();
 
-        float acc[4][4];
+        float acc[NT_S][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < NT_S; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
@@ -96,10 +107,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
             uint32_t af[4];
             ldmatrix_x4(af, smem_u32(Qs + (wr * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
 #pragma unroll
-            for (int np = 0; np < 2; ++np) {
+            for (int np = 0; np < NT_S / 2; ++np) {
                 uint32_t bfr[4];
                 const int mi = lane >> 3;
-                const int key = wc * 32 + np * 16 + (mi >> 1) * 8 + (lane & 7);
+                const int key = wc * KPW + np * 16 + (mi >> 1) * 8 + (lane & 7);
                 ldmatrix_x4(bfr, smem_u32(Kcur + key * LDS + kk * 16 + (mi & 1) * 8));
                 mma_bf16_16816(acc[np * 2 + 0], af, bfr[0], bfr[1]);
                 mma_bf16_16816(acc[np * 2 + 1], af, bfr[2], bfr[3]);
@@ -107,11 +118,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
         }
         // epilogue of this key block: rounding chain, write bf16 logits
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT_S; ++nt) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int r = wr * 16 + (lane >> 2) + half * 8;
-                const int kcol = kb * kBK + wc * 32 + nt * 8 + (lane & 3) * 2;
+                const int kcol = kb * kBK + wc * KPW + nt * 8 + (lane & 3) * 2;
                 float s0 = bf16_round(acc[nt][half * 2 + 0]);
                 float s1 = bf16_round(acc[nt][half * 2 + 1]);
                 if (GEMMA) {
@@ -142,12 +153,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
     }
 
     // prefetch V block 0 while the softmax runs
-    load_rows_async<HD_PAD>(KVs, vbase, a.ldv, 0, a.n_keys, a.hd);
+    load_rows_async<LDS, CH>(KVs, vbase, a.ldv, 0, kBK, a.n_keys, a.hd);
     cp_async_commit();
 
     // ---------------- softmax: fp32 over bf16 logits, result bf16 in place ----------------
-    for (int rr = 0; rr < kBM / 8; ++rr) {
-        bf16* lrow = Ls + (warp * (kBM / 8) + rr) * ldl;
+    for (int rr = 0; rr < BM / 8; ++rr) {
+        bf16* lrow = Ls + (warp * (BM / 8) + rr) * ldl;
         float m = -INFINITY;
         for (int c = lane; c < a.n_keys; c += 32) m = fmaxf(m, bf2f(lrow[c]));
         m = warp_max(m);
@@ -163,19 +174,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
     __syncthreads();
 
     // ---------------- phase PV ----------------
-    constexpr int DHALF = HD_PAD / 2;          // dims per column-warp
-    constexpr int NTILES = DHALF / 8;          // 16 (HD 256) or 5 (HD 80)
-    constexpr int NPAIRS = (NTILES + 1) / 2;
-    float oacc[NPAIRS * 2][4];
+    float oacc[NP_PV * 2][4];
 #pragma unroll
-    for (int i = 0; i < NPAIRS * 2; ++i)
+    for (int i = 0; i < NP_PV * 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+    const int nt0 = wc * NT_PV;                 // first output n-tile of this column group
 
     for (int kb = 0; kb < nkb; ++kb) {
         bf16* Vcur = KVs + (kb & 1) * kBK * LDS;
         if (kb + 1 < nkb) {
-            load_rows_async<HD_PAD>(KVs + ((kb + 1) & 1) * kBK * LDS, vbase, a.ldv, (kb + 1) * kBK, a.n_keys, a.hd);
+            load_rows_async<LDS, CH>(KVs + ((kb + 1) & 1) * kBK * LDS, vbase, a.ldv, (kb + 1) * kBK, kBK, a.n_keys, a.hd);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -187,14 +196,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
             uint32_t af[4];
             ldmatrix_x4(af, smem_u32(Ls + (wr * 16 + (lane & 15)) * ldl + kb * kBK + kk * 16 + (lane >> 4) * 8));
 #pragma unroll
-            for (int np = 0; np < NPAIRS; ++np) {
+            for (int np = 0; np < NP_PV; ++np) {
+                if ((nt0 + np * 2) >= NT_ALL) continue;          // column group past the head dim
                 uint32_t bfr[4];
                 const int mi = lane >> 3;
                 const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
-                const int dim = wc * DHALF + np * 16 + (mi >> 1) * 8;
+                const int dim = (nt0 + np * 2) * 8 + (mi >> 1) * 8;
                 ldmatrix_x4_trans(bfr, smem_u32(Vcur + key * LDS + dim));
                 mma_bf16_16816(oacc[np * 2 + 0], af, bfr[0], bfr[1]);
-                if (np * 2 + 1 < NTILES) mma_bf16_16816(oacc[np * 2 + 1], af, bfr[2], bfr[3]);
+                if (np * 2 + 1 < NT_PV && nt0 + np * 2 + 1 < NT_ALL)
+                    mma_bf16_16816(oacc[np * 2 + 1], af, bfr[2], bfr[3]);
             }
         }
         __syncthreads();
@@ -203,11 +214,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
     // ---------------- store ----------------
     bf16* obase = a.out + static_cast<size_t>(b) * a.q_per_sample * a.ldo + a.o_col0 + h * a.head_stride_q;
 #pragma unroll
-    for (int nt = 0; nt < NTILES; ++nt) {
+    for (int nt = 0; nt < NT_PV; ++nt) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int r = q_row0 + wr * 16 + (lane >> 2) + half * 8;
-            const int dim = wc * DHALF + nt * 8 + (lane & 3) * 2;
+            const int dim = (nt0 + nt) * 8 + (lane & 3) * 2;
             if (r < a.q_per_sample && dim < a.hd)
                 *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(r) * a.ldo + dim) =
                     pack_bf16x2(oacc[nt][half * 2 + 0], oacc[nt][half * 2 + 1]);
@@ -215,11 +226,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_mma_kernel(const AttnMma
     }
 }
 
-template <int HD_PAD>
+template <int HD_PAD, int BM>
 static size_t attn_smem_bytes(int n_keys) {
+    constexpr int WC = 8 / (BM / 16);
+    constexpr int NT_PV = (HD_PAD / 8 + WC - 1) / WC;
+    constexpr int NP_PV = (NT_PV + 1) / 2;
+    constexpr int LDS_MIN = WC * NP_PV * 16 > HD_PAD ? WC * NP_PV * 16 : HD_PAD;
+    constexpr int LDS = LDS_MIN + 8;
     const int nkb = (n_keys + kBK - 1) / kBK;
-    return static_cast<size_t>(kBM + 2 * kBK) * (HD_PAD + 8) * 2 + static_cast<size_t>(kBM) * (nkb * kBK + 8) * 2;
+    return static_cast<size_t>(BM + 2 * kBK) * LDS * 2 + static_cast<size_t>(BM) * (nkb * kBK + 8) * 2;
 }
+
+static constexpr int kAttnBM = 32;
 
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
                                     int n_heads, int hidden, bf16* out, int ld_out) {
@@ -231,24 +249,20 @@ cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld
     a.v = qkv; a.ldv = ld_qkv; a.v_col0 = 2 * hidden;
     a.out = out; a.ldo = ld_out; a.o_col0 = 0;
     a.hd = hd; a.head_stride_q = hd; a.head_stride_kv = hd; a.n_keys = seq;
-    a.scale = 1.0f / sqrtf(static_cast<float>(hd));
-    {   // Python: head_dim ** -0.5 evaluated in double, then used as an fp32 scalar operand
-        const double s = pow(static_cast<double>(hd), -0.5);
-        a.scale = static_cast<float>(s);
-    }
+    // Python: head_dim ** -0.5 evaluated in double, then used as an fp32 scalar operand
+    a.scale = static_cast<float>(pow(static_cast<double>(hd), -0.5));
     a.mask = nullptr;
-    const size_t smem = attn_smem_bytes<80>(seq);
+    const size_t smem = attn_smem_bytes<80, kAttnBM>(seq);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<80, false>,
+        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<80, kAttnBM, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    dim3 grid((seq + kBM - 1) / kBM, n_heads, batch);
-    attn_mma_kernel<80, false><<<grid, kAttnThreads, smem, stream>>>(a);
-    return cudaGetLastError();
+    dim3 grid((seq + kAttnBM - 1) / kAttnBM, n_heads, batch);
+    return launch_kernel(attn_mma_kernel<80, kAttnBM, false>, grid, dim3(kAttnThreads), smem, stream, a);
 }
 
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& j) {
@@ -261,53 +275,78 @@ cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnA
     a.scale = 0.f;
     a.mask = j.mask; a.mask_bstride = j.mask_bstride; a.mask_rstride = j.mask_rstride;
     a.q_row_offset = j.q_row_offset;
-    const size_t smem = attn_smem_bytes<256>(j.n_keys);
+    const size_t smem = attn_smem_bytes<256, kAttnBM>(j.n_keys);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<256, true>,
+        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<256, kAttnBM, true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    dim3 grid((j.q_per_sample + kBM - 1) / kBM, j.n_heads, j.batch);
-    attn_mma_kernel<256, true><<<grid, kAttnThreads, smem, stream>>>(a);
-    return cudaGetLastError();
+    dim3 grid((j.q_per_sample + kAttnBM - 1) / kAttnBM, j.n_heads, j.batch);
+    return launch_kernel(attn_mma_kernel<256, kAttnBM, true>, grid, dim3(kAttnThreads), smem, stream, a);
 }
 
 // ---------------------------------------------------------------------------
-// few-query attention over the KV cache: one CTA per (head, query, sample)
+// few-query attention over the KV cache: one CTA per (head, query, sample); the 8 warps split
+// the keys, 4 keys in flight per warp (16-byte K/V loads per lane, shuffle reductions).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_fewq_kernel(const JointAttnArgs a) {
-    extern __shared__ float fq_smem[];       // q[256] | logits[n_keys]
+    extern __shared__ float fq_smem[];       // logits[n_keys_pad] | partial_out[8][256]
     __shared__ float red[8];
-    float* qf = fq_smem;
-    float* lg = fq_smem + 256;
+    const int n_pad = (a.n_keys + 3) & ~3;
+    float* lg = fq_smem;
+    float* po = fq_smem + n_pad;
     const int h = blockIdx.x, qi = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ldq = a.n_heads * 256;
     const size_t qrow = static_cast<size_t>(b) * a.q_per_sample + qi;
-    qf[tid] = bf2f(a.q[qrow * ldq + h * 256 + tid]);
-    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
 
     const bf16* kc = a.k_cache + static_cast<size_t>(b) * a.n_slots * 256;
     const bf16* vc = a.v_cache + static_cast<size_t>(b) * a.n_slots * 256;
     const bf16* mrow = a.mask + static_cast<size_t>(b) * a.mask_bstride +
                        static_cast<size_t>(a.q_row_offset + qi) * a.mask_rstride;
     float qreg[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qreg[i] = qf[lane * 8 + i];
-    for (int k = warp; k < a.n_keys; k += 8) {
-        const bf16x8 kv = *reinterpret_cast<const bf16x8*>(kc + static_cast<size_t>(k) * 256 + lane * 8);
-        float dot = 0.f;
+    {
+        const bf16x8 qv = *reinterpret_cast<const bf16x8*>(a.q + qrow * ldq + h * 256 + lane * 8);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack_bf16x2(kv.u[i]);
-            dot += qreg[2 * i] * f.x + qreg[2 * i + 1] * f.y;
+            const float2 f = unpack_bf16x2(qv.u[i]);
+            qreg[2 * i] = f.x; qreg[2 * i + 1] = f.y;
         }
-        dot = warp_sum(dot);
-        if (lane == 0) {
-            float s = bf16_round(dot);
+    }
+    // ---- logits: warp w owns keys [w*kpw, (w+1)*kpw), 4 at a time ----
+    const int kpw = ((a.n_keys + 7) / 8 + 3) & ~3;
+    const int k_begin = warp * kpw, k_end = min(k_begin + kpw, a.n_keys);
+    for (int k0 = k_begin; k0 < k_end; k0 += 4) {
+        bf16x8 kv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = min(k0 + j, a.n_keys - 1);
+            kv[j] = *reinterpret_cast<const bf16x8*>(kc + static_cast<size_t>(k) * 256 + lane * 8);
+        }
+        float dot[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(kv[j].u[i]);
+                d += qreg[2 * i] * f.x + qreg[2 * i + 1] * f.y;
+            }
+            dot[j] = d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
+        }
+        if (lane < 4 && k0 + lane < k_end) {
+            const int k = k0 + lane;
+            float s = bf16_round(lane == 0 ? dot[0] : lane == 1 ? dot[1] : lane == 2 ? dot[2] : dot[3]);
             s = bf16_round(s * 0.0625f);
             s = bf16_round(s * (1.0f / 50.0f));
             s = bf16_round(tanhf(s));
@@ -317,7 +356,7 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(const JointAttnArgs a) {
         }
     }
     __syncthreads();
-    // softmax (fp32) -> bf16 probabilities
+    // ---- softmax (fp32) -> bf16 probabilities ----
     float m = -INFINITY;
     for (int k = tid; k < a.n_keys; k += 256) m = fmaxf(m, lg[k]);
     m = warp_max(m);
@@ -338,24 +377,42 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(const JointAttnArgs a) {
     __syncthreads();
     for (int k = tid; k < a.n_keys; k += 256) lg[k] = bf16_round(expf(lg[k] - m) / sum);
     __syncthreads();
-    // out[d] = sum_k P[k] V[k][d]
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    int k = 0;
-    for (; k + 3 < a.n_keys; k += 4) {
-        acc0 += lg[k] * bf2f(vc[static_cast<size_t>(k) * 256 + tid]);
-        acc1 += lg[k + 1] * bf2f(vc[static_cast<size_t>(k + 1) * 256 + tid]);
-        acc2 += lg[k + 2] * bf2f(vc[static_cast<size_t>(k + 2) * 256 + tid]);
-        acc3 += lg[k + 3] * bf2f(vc[static_cast<size_t>(k + 3) * 256 + tid]);
+    // ---- out = P V: warp w accumulates its keys for all 256 dims (8 per lane) ----
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k0 = k_begin; k0 < k_end; k0 += 4) {
+        bf16x8 vv[4];
+        float pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = min(k0 + j, a.n_keys - 1);
+            vv[j] = *reinterpret_cast<const bf16x8*>(vc + static_cast<size_t>(k) * 256 + lane * 8);
+            pk[j] = (k0 + j < k_end) ? lg[k] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(vv[j].u[i]);
+                acc[2 * i] += pk[j] * f.x;
+                acc[2 * i + 1] += pk[j] * f.y;
+            }
+        }
     }
-    for (; k < a.n_keys; ++k) acc0 += lg[k] * bf2f(vc[static_cast<size_t>(k) * 256 + tid]);
-    a.out[qrow * ldq + h * 256 + tid] = f2bf((acc0 + acc1) + (acc2 + acc3));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) po[warp * 256 + lane * 8 + i] = acc[i];
+    __syncthreads();
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += po[w * 256 + tid];
+    a.out[qrow * ldq + h * 256 + tid] = f2bf(o);
 }
 
 cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& a) {
     dim3 grid(a.n_heads, a.q_per_sample, a.batch);
-    const size_t smem = (256 + a.n_keys) * sizeof(float);
-    attn_fewq_kernel<<<grid, 256, smem, stream>>>(a);
-    return cudaGetLastError();
+    const size_t smem = (((a.n_keys + 3) & ~3) + 8 * 256) * sizeof(float);
+    return launch_kernel(attn_fewq_kernel, grid, dim3(256), smem, stream, a);
 }
 
 }  // namespace blurr

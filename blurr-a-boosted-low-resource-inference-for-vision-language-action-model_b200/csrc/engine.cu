@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "gemm_tc.h"
 #include "kernels.h"
+#include "launch.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -907,6 +908,14 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
     else if (n == "debug_taps") h->debug = value != 0;
+    else if (n == "use_pdl") {                 // programmatic dependent launch (process-wide)
+        pdl_set_enabled(value != 0);
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
     else if (n == "num_inference_steps") {
         if (value < 1) return fail(BLURR_ERR_INVALID, "num_inference_steps must be >= 1");
         h->cfg.num_inference_steps = static_cast<int>(value);

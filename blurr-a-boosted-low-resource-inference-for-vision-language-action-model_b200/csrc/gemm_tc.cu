@@ -22,6 +22,7 @@
 //                 kernels in norm_consumers.cu finish bias/residual/norm in a fixed order.
 #include "common.cuh"
 #include "gemm_tc.h"
+#include "launch.cuh"
 
 #include <mutex>
 #include <string>
@@ -88,6 +89,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
+    // the previous kernel; its results are needed from here on
+    pdl_wait();
+    pdl_trigger();
 
     const int n0 = blockIdx.x * kBlockM;          // first weight row of this CTA
     const int t0 = blockIdx.y * p.nt * p.bn;      // first token row of this CTA
@@ -289,6 +294,10 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
     return 0;
 }
 
+static bool g_pdl_enabled = true;
+bool pdl_enabled() { return g_pdl_enabled; }
+void pdl_set_enabled(bool on) { g_pdl_enabled = on; }
+
 int gemm_take_timeout_flag() {
     int v = 0;
     if (cudaMemcpyFromSymbol(&v, g_gemm_timeout_flag, sizeof(int)) != cudaSuccess) return -1;
@@ -381,8 +390,8 @@ static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUt
         attr_set = true;
     }
     dim3 grid(pl.grid_x, pl.grid_y, pl.splitk);
-    gemm_tc_kernel<EPI><<<grid, kGemmThreads, pl.smem_bytes, stream>>>(tw, tx, d);
-    return cudaGetLastError();
+    return launch_kernel(gemm_tc_kernel<EPI>, grid, dim3(kGemmThreads), static_cast<size_t>(pl.smem_bytes), stream,
+                         tw, tx, d);
 }
 
 int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {

@@ -3,6 +3,7 @@
 // decoder + Euler update, and the final clamp.
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace blurr {
 
@@ -12,6 +13,8 @@ namespace blurr {
 __global__ void __launch_bounds__(128) im2col_kernel(const bf16* __restrict__ px, long long sb, long long sc,
                                                      long long sh, long long sw, bf16* __restrict__ patches,
                                                      int ldp) {
+    pdl_wait();
+    pdl_trigger();
     const int p = blockIdx.x;            // patch index within the image, row-major 16x16
     const int b = blockIdx.y;
     const int ph = p >> 4, pw = p & 15;
@@ -26,9 +29,8 @@ __global__ void __launch_bounds__(128) im2col_kernel(const bf16* __restrict__ px
 
 cudaError_t launch_im2col(cudaStream_t stream, const bf16* pixels, int64_t sb, int64_t sc, int64_t sh,
                           int64_t sw, int batch, bf16* patches, int ldp) {
-    dim3 grid(256, batch);
-    im2col_kernel<<<grid, 128, 0, stream>>>(pixels, sb, sc, sh, sw, patches, ldp);
-    return cudaGetLastError();
+    return launch_kernel(im2col_kernel, dim3(256, batch), dim3(128), 0, stream, pixels, sb, sc, sh, sw, patches,
+                         ldp);
 }
 
 // ---------------------------------------------------------------------------
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) embed_merge_kernel(const int64_t* __restr
                                                           float inv_div, float normalizer,
                                                           bf16* __restrict__ out, int* err_flag) {
     __shared__ int s_rank;
+    pdl_wait();
+    pdl_trigger();
     const int pos = blockIdx.x, b = blockIdx.y;
     const int64_t* row = ids + static_cast<size_t>(b) * seq;
     const long long id = row[pos];
@@ -85,10 +89,9 @@ cudaError_t launch_embed_merge(cudaStream_t stream, const int64_t* input_ids, in
                                const bf16* embed_table, int64_t vocab, const bf16* img_feat, int n_img,
                                int hidden, int64_t image_token, int64_t pad_token, float inv_div,
                                float normalizer, bf16* out, int* err_flag) {
-    dim3 grid(seq, batch);
-    embed_merge_kernel<<<grid, 256, 0, stream>>>(input_ids, seq, embed_table, vocab, img_feat, n_img, hidden,
-                                                 image_token, pad_token, inv_div, normalizer, out, err_flag);
-    return cudaGetLastError();
+    return launch_kernel(embed_merge_kernel, dim3(seq, batch), dim3(256), 0, stream, input_ids, seq, embed_table,
+                         vocab, img_feat, n_img, hidden, image_token, pad_token, inv_div, normalizer, out,
+                         err_flag);
 }
 
 // ---------------------------------------------------------------------------
@@ -99,6 +102,8 @@ __global__ void __launch_bounds__(256) small_k_linear_kernel(const bf16* __restr
                                                              const bf16* __restrict__ bias, int N, float scale,
                                                              bf16* __restrict__ y, int ldy, int col_off,
                                                              const bf16* __restrict__ time_row, int time_cols) {
+    pdl_wait();
+    pdl_trigger();
     const int t = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < N) {
@@ -116,10 +121,8 @@ cudaError_t launch_small_k_linear(cudaStream_t stream, const bf16* x, int T, int
                                   const bf16* b, int N, float scale, bf16* y, int ldy, int col_off,
                                   const bf16* time_row, int time_cols) {
     const int cols = N > time_cols ? N : time_cols;
-    dim3 grid((cols + 255) / 256, T);
-    small_k_linear_kernel<<<grid, 256, 0, stream>>>(x, T, K, W, b, N, scale, y, ldy, col_off, time_row,
-                                                    time_cols);
-    return cudaGetLastError();
+    return launch_kernel(small_k_linear_kernel, dim3((cols + 255) / 256, T), dim3(256), 0, stream, x, T, K, W, b, N,
+                         scale, y, ldy, col_off, time_row, time_cols);
 }
 
 // ---------------------------------------------------------------------------
@@ -131,6 +134,8 @@ __global__ void __launch_bounds__(256) action_tail_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ bias, int action_dim,
                                                           float dt, bf16* __restrict__ action,
                                                           bf16* __restrict__ vel_tap) {
+    pdl_wait();
+    pdl_trigger();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= T * action_dim) return;
@@ -150,13 +155,14 @@ __global__ void __launch_bounds__(256) action_tail_kernel(const bf16* __restrict
 cudaError_t launch_action_tail(cudaStream_t stream, const bf16* xn, int T, int hidden, const bf16* W,
                                const bf16* b, int action_dim, float dt, bf16* action, bf16* velocity_tap) {
     const int warps = T * action_dim;
-    action_tail_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(xn, T, hidden, W, b, action_dim, dt, action,
-                                                                     velocity_tap);
-    return cudaGetLastError();
+    return launch_kernel(action_tail_kernel, dim3((warps * 32 + 255) / 256), dim3(256), 0, stream, xn, T, hidden, W,
+                         b, action_dim, dt, action, velocity_tap);
 }
 
 __global__ void clamp_copy_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n, int do_clamp,
                                   float clip) {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float v = bf2f(src[i]);
@@ -166,8 +172,7 @@ __global__ void clamp_copy_kernel(const bf16* __restrict__ src, bf16* __restrict
 
 cudaError_t launch_clamp_copy(cudaStream_t stream, const bf16* src, bf16* dst, int n, int do_clamp,
                               float clip) {
-    clamp_copy_kernel<<<(n + 255) / 256, 256, 0, stream>>>(src, dst, n, do_clamp, clip);
-    return cudaGetLastError();
+    return launch_kernel(clamp_copy_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, src, dst, n, do_clamp, clip);
 }
 
 }  // namespace blurr

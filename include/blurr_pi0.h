@@ -132,6 +132,7 @@ int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const b
                            void* actions_out);
 
 /* Options: "use_cuda_graph" (default 1), "debug_taps" (default 0; implies eager launches),
+ * "use_pdl" (default 1: programmatic dependent launch between the step's kernels; process-wide),
  * "num_inference_steps". */
 int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t value);
 /* Synchronises the stream and reports device-side input validation errors. */
