@@ -329,7 +329,8 @@ def dominant_kernel_roofline(dev, peaks):
     sp = C.c_void_p(stream.cuda_stream)
 
     def launch(i):
-        return lib.blurr_op_gemm_async(sp, C.c_void_p(Ws[i % nbuf].data_ptr()), N, Kd, Kd, C.c_void_p(X.data_ptr()), T, Kd,
+        # ldw = 0: tile-packed weights, the layout the engine streams (random values: no packing pass needed)
+        return lib.blurr_op_gemm_async(sp, C.c_void_p(Ws[i % nbuf].data_ptr()), N, Kd, 0, C.c_void_p(X.data_ptr()), T, Kd,
                                  capi.EPI_GEGLU, 1, None, C.c_void_p(out.data_ptr()), N // 2, None)
     for i in range(nbuf):
         capi.check(launch(i))

@@ -37,15 +37,20 @@ static int fail(int code, const std::string& msg) {
 // repack kernels
 // ---------------------------------------------------------------------------
 enum RowMap { MAP_OFFSET = 0, MAP_GATE = 1, MAP_UP = 2 };
+// dst_ld > 0: row-major destination; dst_ld == 0: tile-packed GEMM weight layout with `kb_total`
+// 64-column blocks per row ([row/128][col/64][row%128][col%64], see gemm_tc.h).
 __global__ void repack_rows_kernel(const bf16* __restrict__ src, int rows, int cols, int src_ld,
-                                   bf16* __restrict__ dst, int dst_ld, int mode, int row_off) {
+                                   bf16* __restrict__ dst, int dst_ld, int mode, int row_off, int kb_total) {
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<size_t>(rows) * cols) return;
     const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx - static_cast<size_t>(r) * cols);
     int dr;
     if (mode == MAP_OFFSET) dr = r + row_off;
     else dr = (r / 64) * 128 + (mode == MAP_UP ? 64 : 0) + (r % 64);
-    dst[static_cast<size_t>(dr) * dst_ld + c] = src[static_cast<size_t>(r) * src_ld + c];
+    size_t di;
+    if (dst_ld > 0) di = static_cast<size_t>(dr) * dst_ld + c;
+    else di = ((static_cast<size_t>(dr / 128) * kb_total + c / 64) * 128 + dr % 128) * 64 + c % 64;
+    dst[di] = src[static_cast<size_t>(r) * src_ld + c];
 }
 
 struct StageArgs {
@@ -90,8 +95,8 @@ __global__ void stage_inputs_kernel(const StageArgs a) {
 // engine state
 // ---------------------------------------------------------------------------
 struct Lin {
-    bf16* w = nullptr;
-    int Nw = 0, K = 0, ld = 0;     // padded rows, padded cols (= row stride)
+    bf16* w = nullptr;             // tile-packed [Nw/128][K/64][128][64] (gemm_tc.h)
+    int Nw = 0, K = 0, ld = 0;     // padded rows, padded cols
     bf16* bias = nullptr;          // [Nw] zero padded, or nullptr
 };
 struct VisionLayer {
@@ -148,6 +153,7 @@ struct blurr_pi0 {
     int* d_err = nullptr;
     // options / bookkeeping
     bool use_graph = true, debug = false;
+    int stage_mask = 7;            // bit 0 vision, bit 1 prefill, bit 2 action flow (timing experiments)
     int64_t launches = 0;
     std::map<std::string, TapBuf> taps;
     struct GraphEntry { cudaGraph_t graph; cudaGraphExec_t exec; int64_t launches; };
@@ -378,10 +384,11 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
 // ---------------------------------------------------------------------------
 // weights
 // ---------------------------------------------------------------------------
-static int repack(const bf16* src, int rows, int cols, int src_ld, bf16* dst, int dst_ld, int mode, int row_off) {
+static int repack(const bf16* src, int rows, int cols, int src_ld, bf16* dst, int dst_ld, int mode, int row_off,
+                  int kb_total = 0) {
     const size_t total = static_cast<size_t>(rows) * cols;
     repack_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(src, rows, cols, src_ld, dst, dst_ld,
-                                                                            mode, row_off);
+                                                                            mode, row_off, kb_total);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BLURR_ERR_CUDA, std::string("repack: ") + cudaGetErrorString(e));
     return 0;
@@ -414,7 +421,8 @@ extern "C" int blurr_pi0_set_weight(blurr_pi0_t* h, const char* key_c, const voi
     };
     auto mat = [&](Lin& L, int64_t rows, int64_t cols, int mode, int row_off) -> int {
         if (!shape_is(shape, ndim, {rows, cols})) return bad_shape(key);
-        return repack(src, static_cast<int>(rows), static_cast<int>(cols), static_cast<int>(cols), L.w, L.ld, mode, row_off);
+        return repack(src, static_cast<int>(rows), static_cast<int>(cols), static_cast<int>(cols), L.w, 0, mode, row_off,
+                      L.K / 64);
     };
     auto bias_rows = [&](Lin& L, int64_t n, int off) -> int {
         if (!shape_is(shape, ndim, {n})) return bad_shape(key);
@@ -430,7 +438,7 @@ extern "C" int blurr_pi0_set_weight(blurr_pi0_t* h, const char* key_c, const voi
         if (k == "embeddings.patch_embedding.weight") {
             if (!shape_is(shape, ndim, {VH, 3, c.patch_size, c.patch_size})) return bad_shape(key);
             const int kc = 3 * c.patch_size * c.patch_size;
-            rc = repack(src, VH, kc, kc, h->patch.w, h->patch.ld, MAP_OFFSET, 0);
+            rc = repack(src, VH, kc, kc, h->patch.w, 0, MAP_OFFSET, 0, h->patch.K / 64);
         } else if (k == "embeddings.patch_embedding.bias") rc = bias_rows(h->patch, VH, 0);
         else if (k == "embeddings.position_embedding.weight") {
             if (!shape_is(shape, ndim, {c.num_image_tokens, VH})) return bad_shape(key);
@@ -591,7 +599,7 @@ struct Run {
     int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true) {
         if (rc) return 1;
         GemmCall c{};
-        c.W = L.w; c.Nw = L.Nw; c.K = L.K; c.ldw = L.ld;
+        c.W = L.w; c.Nw = L.Nw; c.K = L.K; c.ldw = L.ld; c.w_packed = 1;
         c.X = X; c.T = T; c.ldx = L.K;
         c.epi = epi;
         c.splitk = (epi == EPI_PARTIAL) ? pick_splitk(T, L.Nw, L.K) : 1;
@@ -690,7 +698,7 @@ static void layer_qkv(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv
     const int QW = c.num_heads * c.head_dim;
     Lin qkv = L.qkv;
     if (kv_only) {                      // last layer of vlm/proprio: only K and V are needed
-        qkv.w = L.qkv.w + static_cast<size_t>(QW) * L.qkv.ld;
+        qkv.w = L.qkv.w + static_cast<size_t>(QW) * L.qkv.K;    // tile-packed: whole 128-row tiles are contiguous
         qkv.Nw = L.qkv.Nw - QW;
     }
     const int s = R.gemm(qkv, sb.xn, T, EPI_PARTIAL, nullptr, 0, false);
@@ -742,7 +750,7 @@ static void run_step(Run& R, int B, int steps) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
     const int L = c.joint_layers;
-    run_vision(R, B);
+    if (h->stage_mask & 1) run_vision(R, B);
     // proprio_encoder (pizero.py:493) and `*= sqrt(1024)` (joint_model.py:358-365)
     const int Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens;
     const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
@@ -756,6 +764,7 @@ static void run_step(Run& R, int B, int steps) {
     const int Tt = B * c.max_image_text_tokens;
 
     // ---- prefill: vlm + proprio into the KV cache (pizero.py:496-508) ----
+    if (h->stage_mask & 2) {
     R.consumer(1, Tt, c.vlm_hidden, 0, nullptr, ADD_NONE, h->E, c.vlm_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
                h->mix[0].layers[0].in_ln, nullptr, c.rms_norm_eps, h->En, false);
     R.consumer(1, Tp, c.expert_hidden, 0, nullptr, ADD_NONE, h->Ep, c.expert_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
@@ -775,11 +784,12 @@ static void run_step(Run& R, int B, int steps) {
         R.tap("prefill.L" + std::to_string(l) + ".vlm", h->E, static_cast<size_t>(Tt) * c.vlm_hidden * 2);
         R.tap("prefill.L" + std::to_string(l) + ".proprio", h->Ep, static_cast<size_t>(Tp) * c.expert_hidden * 2);
     }
+    }
 
     // ---- flow matching: Euler steps of the action expert over the cache (pizero.py:516-538) ----
     const long long act_bs = static_cast<long long>(c.num_action_tokens) * h->n_total, act_rs = h->n_total;
     const float dt = static_cast<float>(1.0 / static_cast<double>(steps));
-    for (int s = 0; s < steps; ++s) {
+    for (int s = 0; s < ((h->stage_mask & 4) ? steps : 0); ++s) {
         // ActionEncoder (vla/modules.py:39-53)
         R.launched(launch_small_k_linear(R.st, h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f,
                                          h->X2, 2 * c.expert_hidden, c.expert_hidden,
@@ -908,6 +918,22 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
     else if (n == "debug_taps") h->debug = value != 0;
+    else if (n == "stage_mask") {              // timing experiments only: run a subset of the stages
+        h->stage_mask = static_cast<int>(value) & 7;
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
+    else if (n == "gemm_cluster_max") {        // activation-multicast cluster size cap (process-wide)
+        gemm_set_cluster_max(static_cast<int>(value));
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
     else if (n == "use_pdl") {                 // programmatic dependent launch (process-wide)
         pdl_set_enabled(value != 0);
         for (auto& kv : h->graphs) {
@@ -920,6 +946,15 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
         if (value < 1) return fail(BLURR_ERR_INVALID, "num_inference_steps must be >= 1");
         h->cfg.num_inference_steps = static_cast<int>(value);
     } else return fail(BLURR_ERR_INVALID, "unknown option " + n);
+    return 0;
+}
+
+extern "C" int blurr_set_global_option(const char* name, int64_t value) {
+    if (!name) return fail(BLURR_ERR_INVALID, "set_global_option: null name");
+    const std::string n(name);
+    if (n == "gemm_cluster_max") gemm_set_cluster_max(static_cast<int>(value));
+    else if (n == "use_pdl") pdl_set_enabled(value != 0);
+    else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
     return 0;
 }
 
@@ -968,11 +1003,20 @@ extern "C" int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h) { return h ? sta
 // ---------------------------------------------------------------------------
 // single-operator entry points
 // ---------------------------------------------------------------------------
+extern "C" int blurr_op_pack_weight(void* cuda_stream, const void* W, int N, int K, int ldw, void* packed) {
+    if (N % 128 || K % 64) return fail(BLURR_ERR_INVALID, "pack_weight: N must be a multiple of 128, K of 64");
+    const size_t total = static_cast<size_t>(N) * K;
+    repack_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        static_cast<const bf16*>(W), N, K, ldw, static_cast<bf16*>(packed), 0, MAP_OFFSET, 0, K / 64);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int blurr_op_gemm_async(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T,
                                    int ldx, int epi, int splitk, const void* bias, void* out, int ldo,
                                    float* partial) {
     GemmCall c{};
-    c.W = static_cast<const bf16*>(W); c.Nw = N; c.K = K; c.ldw = ldw;
+    c.W = static_cast<const bf16*>(W); c.Nw = N; c.K = K; c.ldw = ldw > 0 ? ldw : K; c.w_packed = ldw <= 0;
     c.X = static_cast<const bf16*>(X); c.T = T; c.ldx = ldx; c.epi = epi; c.splitk = splitk;
     c.bias = static_cast<const bf16*>(bias); c.out = static_cast<bf16*>(out); c.ldo = ldo; c.partial = partial;
     c.bn_override = 0;
@@ -985,7 +1029,7 @@ extern "C" int blurr_op_gemm_async(void* cuda_stream, const void* W, int N, int 
 extern "C" int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
                              int epi, int splitk, const void* bias, void* out, int ldo, float* partial) {
     GemmCall c{};
-    c.W = static_cast<const bf16*>(W); c.Nw = N; c.K = K; c.ldw = ldw;
+    c.W = static_cast<const bf16*>(W); c.Nw = N; c.K = K; c.ldw = ldw > 0 ? ldw : K; c.w_packed = ldw <= 0;
     c.X = static_cast<const bf16*>(X); c.T = T; c.ldx = ldx; c.epi = epi; c.splitk = splitk;
     c.bias = static_cast<const bf16*>(bias); c.out = static_cast<bf16*>(out); c.ldo = ldo; c.partial = partial;
     c.bn_override = 0;

@@ -48,6 +48,9 @@ struct GemmDev {
     bf16* out;        // bf16 output
     int ldo;          // output row stride (elements)
     float* partial;   // EPI_PARTIAL: [splitk][T][Nw] fp32
+    int w_packed;     // weights are tile-packed (see gemm_tc.h)
+    int cluster;      // CTAs (consecutive weight tiles) sharing one multicast activation tile
+    int slice_rows;   // activation rows each CTA of the cluster loads and multicasts
 };
 
 // Set (to 1 + role) when a pipeline wait expired; read by gemm_take_timeout_flag().
@@ -56,7 +59,7 @@ __device__ int g_gemm_timeout_flag = 0;
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-               const GemmDev p) {
+               const __grid_constant__ CUtensorMap tmap_xs, const GemmDev p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
@@ -71,12 +74,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
-        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(p.cluster > 1 ? &tmap_xs : &tmap_x);
     }
     if (warp == 1 && elect_one_sync()) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], static_cast<uint32_t>(p.cluster));   // every CTA of the cluster frees it
         }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
@@ -87,8 +90,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = (p.cluster > 1) ? cluster_ctarank() : 0u;
+    const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
     // the previous kernel; its results are needed from here on
     pdl_wait();
@@ -111,10 +117,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 uint8_t* st = smem + s * stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
                 const int kcoord = (kb0 + i) * kBlockK;
-                tma_load_2d_hint(st, &tmap_w, &full_bar[s], kcoord, n0, pol_w);
-                for (int c = 0; c < p.nt; ++c)
-                    tma_load_2d_hint(st + kTileABytes + c * p.bn * (kBlockK * 2), &tmap_x,
-                                     &full_bar[s], kcoord, t0 + c * p.bn, pol_x);
+                if (p.w_packed)   // tile (blockIdx.x, k-block) is a contiguous 128 x 64 block
+                    tma_load_2d_hint(st, &tmap_w, &full_bar[s], 0,
+                                     (static_cast<int>(blockIdx.x) * p.kb_total + kb0 + i) * kBlockM, pol_w);
+                else
+                    tma_load_2d_hint(st, &tmap_w, &full_bar[s], kcoord, n0, pol_w);
+                if (p.cluster > 1) {
+                    // this CTA's slice of the shared activation tile, delivered to every CTA of the cluster
+                    const int r0 = static_cast<int>(crank) * p.slice_rows;
+                    tma_load_2d_multicast_hint(st + kTileABytes + r0 * (kBlockK * 2), &tmap_xs, &full_bar[s],
+                                               kcoord, t0 + r0, cmask, pol_x);
+                } else {
+                    for (int c = 0; c < p.nt; ++c)
+                        tma_load_2d_hint(st + kTileABytes + c * p.bn * (kBlockK * 2), &tmap_x,
+                                         &full_bar[s], kcoord, t0 + c * p.bn, pol_x);
+                }
             }
         }
     } else if (warp == 1) {
@@ -139,7 +156,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                                      (i > 0 || k > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
+                // frees the smem stage (in every CTA of the cluster) once these MMAs retire
+                if (p.cluster > 1) umma_commit_multicast(&empty_bar[s], cmask);
+                else umma_commit(&empty_bar[s]);
             }
             if (ok) umma_commit(tmem_full_bar);   // accumulators complete
         }
@@ -219,6 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
 
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();      // no CTA exits while peers may still signal its barriers
     if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
@@ -321,6 +341,12 @@ static int next_pow2_cols(int c) {
 
 static constexpr int kSmemBudget = 227 * 1024;
 
+// Measured on B200 (tools/time_gemm.py, round 1): multicasting the activation tile across a cluster of
+// 2/4 CTAs is *slower* than unicast at every Pi-0 shape (the CTAs of a cluster advance in lock-step and
+// each SM still ingests the full tile), so it is off by default; the knob stays for experiments.
+static int g_cluster_max = 1;
+void gemm_set_cluster_max(int c) { g_cluster_max = c < 1 ? 1 : (c > 8 ? 8 : c); }
+
 static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out) {
     const int stage_bytes = kTileABytes + nt * bn * kBlockK * 2;
     const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
@@ -375,13 +401,22 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
     if (pl.tmem_cols > 512) return pl;
     pl.grid_x = Nw / kBlockM;
     pl.grid_y = gy;
+    // activation multicast: the CTAs of a cluster own consecutive weight tiles and share the
+    // token tile; each loads 1/C of it (a multiple of 8 rows keeps the 128B swizzle phase)
+    pl.cluster = 1;
+    if (g_cluster_max > 1 && nt * bn >= 64) {
+        for (int c = g_cluster_max; c > 1; c >>= 1) {
+            if (pl.grid_x % c == 0 && (nt * bn) % (8 * c) == 0) { pl.cluster = c; break; }
+        }
+    }
+    pl.slice_rows = nt * bn / pl.cluster;
     pl.valid = true;
     return pl;
 }
 
 template <int EPI>
 static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUtensorMap& tw,
-                              const CUtensorMap& tx, const GemmDev& d) {
+                              const CUtensorMap& tx, const CUtensorMap& txs, const GemmDev& d) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>,
@@ -390,8 +425,8 @@ static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUt
         attr_set = true;
     }
     dim3 grid(pl.grid_x, pl.grid_y, pl.splitk);
-    return launch_kernel(gemm_tc_kernel<EPI>, grid, dim3(kGemmThreads), static_cast<size_t>(pl.smem_bytes), stream,
-                         tw, tx, d);
+    return launch_kernel_cluster(gemm_tc_kernel<EPI>, grid, dim3(kGemmThreads), static_cast<size_t>(pl.smem_bytes),
+                                 stream, pl.cluster, tw, tx, txs, d);
 }
 
 int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
@@ -402,19 +437,29 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         return -1;
     }
     if (c.epi != EPI_PARTIAL && pl.splitk != 1) { *err = "gemm_launch: split-K needs EPI_PARTIAL"; return -1; }
-    CUtensorMap tw, tx;
-    if (get_tmap(c.W, c.Nw, c.K, c.ldw, kBlockM, &tw, err)) return -1;
+    CUtensorMap tw, tx, txs;
+    if (c.w_packed) {
+        if (get_tmap(c.W, c.Nw * pl.kb_total, kBlockK, kBlockK, kBlockM, &tw, err)) return -1;
+    } else {
+        if (get_tmap(c.W, c.Nw, c.K, c.ldw, kBlockM, &tw, err)) return -1;
+    }
     if (get_tmap(c.X, c.T, c.K, c.ldx, pl.bn, &tx, err)) return -1;
+    if (pl.cluster > 1) {
+        if (get_tmap(c.X, c.T, c.K, c.ldx, pl.slice_rows, &txs, err)) return -1;
+    } else {
+        txs = tx;
+    }
     GemmDev d{};
     d.T = c.T; d.bn = pl.bn; d.nt = pl.nt; d.stages = pl.stages; d.kb_total = pl.kb_total;
     d.kb_per_split = pl.kb_per_split; d.tmem_cols = pl.tmem_cols; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
+    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed;
     cudaError_t e;
     switch (c.epi) {
-        case EPI_STORE:   e = launch_epi<EPI_STORE>(stream, pl, tw, tx, d); break;
-        case EPI_GELU:    e = launch_epi<EPI_GELU>(stream, pl, tw, tx, d); break;
-        case EPI_GEGLU:   e = launch_epi<EPI_GEGLU>(stream, pl, tw, tx, d); break;
-        case EPI_PARTIAL: e = launch_epi<EPI_PARTIAL>(stream, pl, tw, tx, d); break;
+        case EPI_STORE:   e = launch_epi<EPI_STORE>(stream, pl, tw, tx, txs, d); break;
+        case EPI_GELU:    e = launch_epi<EPI_GELU>(stream, pl, tw, tx, txs, d); break;
+        case EPI_GEGLU:   e = launch_epi<EPI_GEGLU>(stream, pl, tw, tx, txs, d); break;
+        case EPI_PARTIAL: e = launch_epi<EPI_PARTIAL>(stream, pl, tw, tx, txs, d); break;
         default: *err = "gemm_launch: bad epilogue"; return -1;
     }
     if (e != cudaSuccess) { *err = std::string("gemm launch failed: ") + cudaGetErrorString(e); return -1; }

@@ -16,8 +16,12 @@ enum GemmEpilogue {
 };
 
 struct GemmCall {
-    const __nv_bfloat16* W;   // [Nw][K], row stride ldw
+    const __nv_bfloat16* W;   // row-major [Nw][K] (row stride ldw), or tile-packed (w_packed)
     int Nw, K, ldw;
+    // Tile-packed weights: [Nw/128][ceil(K/64)][128 rows][64 cols] — every 128x64 operand tile is one
+    // contiguous 16 KB block and a CTA's whole K-stream is contiguous, so HBM sees long sequential
+    // bursts instead of 128-byte reads at a K*2-byte stride (gemm_pack_weight_index()).
+    int w_packed;
     const __nv_bfloat16* X;   // [T][K], row stride ldx
     int T, ldx;
     int epi;
@@ -32,6 +36,7 @@ struct GemmCall {
 struct GemmPlan {
     bool valid;
     int bn, nt, stages, kb_total, kb_per_split, splitk, tmem_cols, smem_bytes, grid_x, grid_y;
+    int cluster, slice_rows;
 };
 
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override);
@@ -42,6 +47,15 @@ int gemm_launch(cudaStream_t stream, const GemmCall& call, std::string* err);
 // Non-zero if a pipeline wait of a GEMM kernel expired since the last call (synchronises the
 // device through cudaMemcpyFromSymbol); clears the flag.
 int gemm_take_timeout_flag();
+
+// Element offset of W[row][col] inside the tile-packed layout (K padded to a multiple of 64).
+inline size_t gemm_pack_weight_index(int row, int col, int K) {
+    const int kb_total = (K + 63) / 64;
+    return ((static_cast<size_t>(row / 128) * kb_total + col / 64) * 128 + row % 128) * 64 + col % 64;
+}
+
+// Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
+void gemm_set_cluster_max(int c);
 
 // Tensor maps are cached by (pointer, shape); call when buffers are freed.
 void gemm_forget_tensor_maps();

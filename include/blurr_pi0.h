@@ -150,12 +150,20 @@ int64_t blurr_pi0_last_launch_count(const blurr_pi0_t* h);
 /* Bytes of repacked weights the step reads (the algorithmic-bytes numerator of the roofline). */
 int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h);
 
+/* Process-wide tuning knobs (no handle): "gemm_cluster_max" (1/2/4/8, activation-multicast cluster
+ * size cap of the GEMM kernel), "use_pdl" (0/1). */
+int blurr_set_global_option(const char* name, int64_t value);
+
 const char* blurr_last_error(void);
 int blurr_abi_version(void);
 
 /* ---- single-operator entry points (same kernels, used by the per-kernel parity tests and
  *      micro-benchmarks; synchronous on `cuda_stream` only with respect to errors) ---- */
-/* Y[T][N] = epilogue(X[T][K] @ W[N][K]^T); epi: 0 store(+bias) 1 gelu 2 geglu 3 partial(fp32 out,
+/* Pack a row-major bf16 weight W[N][K] (N % 128 == 0, K % 64 == 0) into the tile-packed layout the
+ * engine streams from HBM: [N/128][K/64][128][64] (every 128x64 operand tile contiguous). */
+int blurr_op_pack_weight(void* cuda_stream, const void* W, int N, int K, int ldw, void* packed);
+/* W is row-major with row stride ldw > 0, or tile-packed when ldw == 0.
+ * Y[T][N] = epilogue(X[T][K] @ W[N][K]^T); epi: 0 store(+bias) 1 gelu 2 geglu 3 partial(fp32 out,
  * [splitk_used][T][N]); returns the number of split-K slices used (>=1) or a negative status. */
 int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
                   int epi, int splitk, const void* bias, void* out, int ldo, float* partial);

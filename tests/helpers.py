@@ -18,21 +18,35 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def op_gemm(W, X, epi, splitk=1, bias=None, out_cols=None):
-    """W [N][K], X [T][K] bf16 cuda.  Returns bf16 [T][out_cols] or fp32 partial [S][T][N]."""
+def pack_weight(W):
+    """Row-major [N][K] -> the engine's tile-packed layout, through the C-ABI operator."""
+    lib = capi.load_library()
+    N, K = W.shape
+    packed = torch.empty(N * K, device=W.device, dtype=torch.bfloat16)
+    capi.check(lib.blurr_op_pack_weight(stream_ptr(), _ptr(W), N, K, K, _ptr(packed)))
+    return packed
+
+
+def op_gemm(W, X, epi, splitk=1, bias=None, out_cols=None, packed=True):
+    """W [N][K], X [T][K] bf16 cuda.  Returns bf16 [T][out_cols] or fp32 partial [S][T][N].
+    `packed`: stream the weights from the tile-packed layout (what the engine does)."""
     lib = capi.load_library()
     N, K = W.shape
     T = X.shape[0]
     assert X.shape[1] == K and W.is_contiguous() and X.is_contiguous()
+    ldw = K
+    if packed:
+        W = pack_weight(W)
+        ldw = 0
     if epi == capi.EPI_PARTIAL:
         partial = torch.zeros((max(splitk, 1), T, N), device=W.device, dtype=torch.float32)
-        s = capi.check(lib.blurr_op_gemm(stream_ptr(), _ptr(W), N, K, K, _ptr(X), T, K, epi, splitk, None, None, 0,
+        s = capi.check(lib.blurr_op_gemm(stream_ptr(), _ptr(W), N, K, ldw, _ptr(X), T, K, epi, splitk, None, None, 0,
                                          _ptr(partial)))
         torch.cuda.synchronize()
         return partial.view(-1)[: s * T * N].view(s, T, N)
     cols = out_cols if out_cols is not None else (N // 2 if epi == capi.EPI_GEGLU else N)
     out = torch.zeros((T, cols), device=W.device, dtype=torch.bfloat16)
-    capi.check(lib.blurr_op_gemm(stream_ptr(), _ptr(W), N, K, K, _ptr(X), T, K, epi, 1, _ptr(bias), _ptr(out), cols,
+    capi.check(lib.blurr_op_gemm(stream_ptr(), _ptr(W), N, K, ldw, _ptr(X), T, K, epi, 1, _ptr(bias), _ptr(out), cols,
                                  None))
     torch.cuda.synchronize()
     return out

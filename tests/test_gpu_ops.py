@@ -38,6 +38,15 @@ def test_gemm_store_bias(T, N, K):
     assert bf16_ulp_err(got, ref) <= 1.01
 
 
+@pytest.mark.parametrize("T,N,K", [(276, 2560, 2048), (17, 256, 192), (4, 1024, 4096)])
+def test_gemm_row_major_weights(T, N, K):
+    """Same kernel fed from a plain row-major nn.Linear weight (no packing)."""
+    W = _rand((N, K), 1.0 / math.sqrt(K), 21)
+    X = _rand((T, K), 1.0, 22)
+    got = op_gemm(W, X, capi.EPI_STORE, packed=False)
+    assert torch.equal(got, op_gemm(W, X, capi.EPI_STORE, packed=True))
+
+
 @pytest.mark.parametrize("T,N,K,S", [(276, 2048, 16384, 9), (276, 2560, 2048, 7), (256, 1152, 4352, 16),
                                      (4, 1024, 4096, 16), (1, 2560, 1024, 6), (552, 2048, 2048, 3),
                                      (276, 2048, 2048, 1)])
