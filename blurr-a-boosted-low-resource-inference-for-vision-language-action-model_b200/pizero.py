@@ -385,9 +385,11 @@ class PiZero(nn.Module):
 
     def _ensure_engine(self, device: torch.device, batch: int) -> "_Engine":
         key = (device.index if device.index is not None else torch.cuda.current_device(),
-               self._weights_version, self.num_inference_steps)
+               self._weights_version)
         eng = self._engine
         if eng is not None and self._engine_key == key and eng.max_batch >= batch:
+            if eng.num_steps != self.num_inference_steps:     # cheap: new time table + schedule
+                eng.set_steps(self, self.num_inference_steps)
             return eng
         if eng is not None:
             eng.close()
@@ -470,6 +472,7 @@ class _Engine:
         self.max_batch = max_batch
         self.handle = C.c_void_p()
         self.model_dims = (model.num_action_tokens, model.action_dim)
+        self.num_steps = model.num_inference_steps
         cfg_c = model._config_c()
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         capi.check(self.lib.blurr_pi0_create(C.byref(cfg_c), dev_index, max_batch, C.byref(self.handle)))
@@ -504,6 +507,15 @@ class _Engine:
             capi.check(self.lib.blurr_pi0_set_time_table(self.handle, C.c_void_p(table.data_ptr()),
                                                          model.num_inference_steps))
             capi.check(self.lib.blurr_pi0_finalize_weights(self.handle))
+
+    def set_steps(self, model: "PiZero", steps: int):
+        """Change `num_inference_steps` without re-uploading weights."""
+        self.set_option("num_inference_steps", steps)
+        with torch.cuda.device(self.device):
+            table = sinusoidal_time_table(steps, model.action_hidden_size, model.time_max_period, self.device,
+                                          torch.bfloat16)
+            capi.check(self.lib.blurr_pi0_set_time_table(self.handle, C.c_void_p(table.data_ptr()), steps))
+        self.num_steps = steps
 
     def set_option(self, name: str, value: int):
         capi.check(self.lib.blurr_pi0_set_option(self.handle, name.encode(), int(value)))

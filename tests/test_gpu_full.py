@@ -1,0 +1,125 @@
+"""Full-size Pi-0 Bridge (27 SigLIP + 18 joint layers, 3.55 B parameters) on the GPU (-m gpu):
+the CUDA control step against the oracle's bf16 run on the same device (BASELINE.json north_star:
+max-abs action error <= 1e-2 on the clamped output, per-layer errors reported), the fp32 tie-break,
+episode-sharding invariance and the KV-cache slot layout."""
+
+import pytest
+import torch
+
+from blurr_b200 import dist as bdist
+from blurr_b200 import synth
+from blurr_b200.config import bridge_config
+from blurr_b200.pizero import PiZeroInference
+from oracle import pi0_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def full():
+    cfg = bridge_config(1)
+    cfg.final_action_clip_value = None
+    sd = synth.synthetic_state_dict(cfg, 0, torch.bfloat16)
+    model = PiZeroInference.from_state_dict(cfg, sd, device=DEV)
+    model.set_engine_options(reserve_batch=4)
+    sd_gpu = {k: v.to(DEV) for k, v in sd.items()}
+    yield cfg, model, sd_gpu
+    model.release_engine()
+
+
+def _oracle(sd, cfg, inp, dtype=torch.bfloat16, taps=None):
+    f = (lambda t: t.to(dtype) if t.is_floating_point() else t)
+    sdd = sd if dtype == torch.bfloat16 else {k: v.float() for k, v in sd.items()}
+    tap = None if taps is None else (lambda n, t: taps.__setitem__(n, t.detach().clone()))
+    with torch.inference_mode():
+        return O.infer_action(sdd, cfg, inp["input_ids"], f(inp["pixel_values"]).clone(),
+                              f(inp["image_text_proprio_mask"]), f(inp["action_mask"]), inp["vlm_position_ids"],
+                              inp["proprio_position_ids"], inp["action_position_ids"], f(inp["proprios"]),
+                              noise=inp["noise"], tap=tap, rope_dtype=torch.bfloat16)
+
+
+def test_full_model_actions_and_layers(full):
+    cfg, model, sd = full
+    inp = synth.synthetic_inputs(cfg, 1, dtype=torch.bfloat16, device=DEV)
+    taps = {}
+    ref = _oracle(sd, cfg, inp, taps=taps)
+    model.set_engine_options(debug_taps=True)
+    with torch.inference_mode():
+        got = model(**synth.call_args(inp), noise=inp["noise"])
+    model._engine.check()
+    alias = {"merged_embeds": "prefill.embeds.vlm", "flow0.action_embeds": "flow0.embeds.action"}
+    names = ["siglip.embeddings"] + [f"siglip.layer{l}" for l in range(27)] + ["siglip.post_layernorm", "projector",
+             "merged_embeds"] + [f"prefill.L{l}.{m}" for l in range(17) for m in ("vlm", "proprio")] + \
+            ["flow0.action_embeds"] + [f"flow0.L{l}.action" for l in range(18)] + ["flow0.velocity"]
+    print("\nper-layer activation error, full-size Bridge, ours vs bf16 reference op sequence (same GPU):")
+    worst = 0.0
+    for n in names:
+        r = taps[alias.get(n, n)].float().flatten()
+        g = model.debug_tap(n).float().flatten()
+        err = (g - r).abs().max().item()
+        rms = r.pow(2).mean().sqrt().item()
+        worst = max(worst, err / max(rms, 1e-6))
+        print(f"  {n:24s} max_abs={err:.3e} ref_rms={rms:.3e} rel={err / max(rms, 1e-6):.3e}")
+    model.set_engine_options(debug_taps=False)
+    err = (got.float() - ref.float()).abs().max().item()
+    clamped = (got.float().clamp(-1, 1) - ref.float().clamp(-1, 1)).abs().max().item()
+    ref32 = _oracle(sd, cfg, inp, dtype=torch.float32)
+    e_ours, e_ref = (got.float() - ref32).abs().max().item(), (ref.float() - ref32).abs().max().item()
+    print(f"actions: ours vs bf16-ref un-clamped {err:.3e}, clamped {clamped:.3e}; vs fp32: ours {e_ours:.3e}, "
+          f"bf16-ref {e_ref:.3e}; range [{ref.min().item():.2f}, {ref.max().item():.2f}]")
+    assert torch.isfinite(got.float()).all()
+    assert clamped <= 1e-2                      # north_star tolerance
+    assert e_ours <= e_ref + 1.6e-2             # no worse than the reference's own bf16 error (+1 ulp)
+    assert worst <= 0.1
+
+
+def test_full_model_sharding_invariance_and_kv_layout(full):
+    """Episodes are independent: any partition of the batch gives bit-identical actions
+    (what makes 1/2/4/8-GPU episode sharding exact); KV slot i <-> position id i+1."""
+    cfg, model, sd = full
+    inp = synth.synthetic_inputs(cfg, 4, dtype=torch.bfloat16, vary_text=True, device=DEV)
+    with torch.inference_mode():
+        whole = model(**synth.call_args(inp), noise=inp["noise"]).clone()
+        parts = []
+        for rank in range(2):
+            loc = bdist.shard_inputs(inp, 2, rank)
+            parts.append(model(**synth.call_args(loc), noise=loc["noise"]).clone())
+        singles = [model(**synth.call_args(bdist.shard_inputs(inp, 4, r)), noise=inp["noise"][r:r + 1]).clone()
+                   for r in range(4)]
+    model._engine.check()
+    assert torch.equal(whole, torch.cat(parts)) and torch.equal(whole, torch.cat(singles))
+    # KV cache of the last call (episode 3 alone): pad slots of the vlm block hold the pad rows'
+    # keys, proprio sits at slot 276, nothing is shifted by the shorter text
+    L = cfg.joint.config.num_hidden_layers
+    kc = model.debug_tap("k_cache").view(L, model._engine.max_batch, 281, 256)
+    ref_taps = {}
+    loc = bdist.shard_inputs(inp, 4, 3)
+    with torch.inference_mode():
+        _, caches = O.infer_action(sd, cfg, **synth.call_args(loc), noise=loc["noise"], return_caches=True)
+    for l in (0, L // 2, L - 1):
+        k_ref = torch.cat([caches["vlm"].key_cache[l], caches["proprio"].key_cache[l]], dim=2)[0, 0]
+        e = (kc[l, 0, :277].float() - k_ref.float()).abs()
+        print(f"  k_cache L{l}: max_abs={e.max().item():.3e} (ref rms {k_ref.float().pow(2).mean().sqrt():.3f})")
+        assert e.max().item() <= 0.13
+
+
+def test_full_model_ten_step_vs_single_step(full):
+    """BASELINE.json configs[2] on the Bridge weights: 10-step flow vs single step from the same
+    injected noise; ours must track the reference op sequence in both schedules."""
+    cfg, model, sd = full
+    inp = synth.synthetic_inputs(cfg, 1, dtype=torch.bfloat16, device=DEV)
+    out = {}
+    for steps in (10, 1):
+        cfg.num_inference_steps = steps
+        model.num_inference_steps = steps        # new time table + schedule, weights stay uploaded
+        with torch.inference_mode():
+            got = model(**synth.call_args(inp), noise=inp["noise"]).float()
+        ref = _oracle(sd, cfg, inp).float()
+        out[steps] = (got, ref)
+        print(f"steps={steps}: ours vs bf16-ref max_abs {((got - ref).abs().max().item()):.3e}")
+        assert (got.clamp(-1, 1) - ref.clamp(-1, 1)).abs().max().item() <= 2e-2
+    d_ours = (out[10][0] - out[1][0]).abs().max().item()
+    d_ref = (out[10][1] - out[1][1]).abs().max().item()
+    print(f"10-step vs 1-step action difference: ours {d_ours:.3e}, reference {d_ref:.3e}")
+    assert abs(d_ours - d_ref) <= 5e-2
