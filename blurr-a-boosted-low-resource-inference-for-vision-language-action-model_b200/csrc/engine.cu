@@ -7,6 +7,7 @@
 #include "gemm_tc.h"
 #include "kernels.h"
 #include "launch.cuh"
+#include "step_kernel.h"
 
 #include <cmath>
 #include <cstdio>
@@ -150,10 +151,14 @@ struct blurr_pi0 {
     bf16 *Ea, *Ean, *Qa, *AOa, *Ha, *X2, *A1;
     bf16 *kcache, *vcache;
     float* ws = nullptr; size_t ws_floats = 0;
+    float* ws2 = nullptr; size_t ws2_floats = 0;     // second split-K workspace: the proprio stream runs beside the VLM
     int* d_err = nullptr;
     // options / bookkeeping
     bool use_graph = true, debug = false;
     int stage_mask = 7;            // bit 0 vision, bit 1 prefill, bit 2 action flow (timing experiments)
+    bool use_step_kernel = true;   // one persistent cooperative kernel per step instead of a kernel graph
+    std::map<long long, StepProgram> programs;
+    int64_t step_ops = 0;
     int64_t launches = 0;
     std::map<std::string, TapBuf> taps;
     struct GraphEntry { cudaGraph_t graph; cudaGraphExec_t exec; int64_t launches; };
@@ -259,6 +264,7 @@ extern "C" void blurr_pi0_destroy(blurr_pi0_t* h) {
         cudaGraphExecDestroy(kv.second.exec);
         cudaGraphDestroy(kv.second.graph);
     }
+    for (auto& kv : h->programs) step_program_free(kv.second);
     for (auto& kv : h->taps) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
     gemm_forget_tensor_maps();
@@ -370,8 +376,10 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
     }
     h->ws_floats = ws;
     h->ws = static_cast<float*>(dalloc(h, ws * 4));
+    h->ws2_floats = std::max<size_t>(static_cast<size_t>(16) * Ta * (qkv_rows + 0), static_cast<size_t>(kNumSMs + 20) * 128 * 16);
+    h->ws2 = static_cast<float*>(dalloc(h, h->ws2_floats * 4));
     h->d_err = static_cast<int*>(dalloc(h, 16));
-    ok &= h->ws && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
+    ok &= h->ws && h->ws2 && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
     if (!ok) {
         blurr_pi0_destroy(h);
         return fail(BLURR_ERR_CUDA, "blurr_pi0_create: device allocation failed");
@@ -545,6 +553,8 @@ extern "C" int blurr_pi0_set_time_table(blurr_pi0_t* h, const void* dev_table, i
     CUDA_TRY(cudaMemcpy(h->time_table, dev_table, static_cast<size_t>(num_steps) * h->cfg.expert_hidden * 2,
                         cudaMemcpyDeviceToDevice));
     // a different step count changes the captured schedule
+    for (auto& kv : h->programs) step_program_free(kv.second);
+    h->programs.clear();
     for (auto& kv : h->graphs) {
         cudaGraphExecDestroy(kv.second.exec);
         cudaGraphDestroy(kv.second.graph);
@@ -578,12 +588,31 @@ struct Run {
     blurr_pi0* h;
     cudaStream_t st;
     int rc = 0;
+    StepProgram* rec = nullptr;      // non-null: record step-kernel ops instead of launching kernels
+    int group = 0, group_items = 0;
+
     void launched(cudaError_t e, const char* what) {
         ++h->launches;
         if (e != cudaSuccess && rc == 0) rc = fail(BLURR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     }
+    // ops recorded between group_begin/group_end are independent: one grid barrier after the last
+    void group_begin() { ++group; group_items = 0; }
+    void group_end() {
+        --group;
+        if (rec && !rec->ops.empty()) rec->ops.back().hot.barrier_after = 1;
+    }
+    StepOp& push(int type, int gx, int gy, int gz) {
+        rec->ops.emplace_back();
+        StepOp& op = rec->ops.back();
+        memset(&op, 0, sizeof(StepOp));
+        op.hot.type = type; op.hot.gx = gx; op.hot.gy = gy; op.hot.gz = gz;
+        op.hot.barrier_after = group > 0 ? 0 : 1;
+        op.hot.pad0 = group > 0 ? group_items % kNumSMs : 0;      // first CTA of this op inside a group
+        group_items += gx * gy * gz;
+        return op;
+    }
     // split-K so that about one CTA per SM is in flight (each CTA owns ~all of an SM's smem)
-    int pick_splitk(int T, int Nw, int K) const {
+    int pick_splitk(int T, int Nw, int K, size_t ws_floats) const {
         GemmPlan p = gemm_make_plan(T, Nw, K, 1, EPI_PARTIAL, 0);
         if (!p.valid) return 1;
         const int ctas = p.grid_x * p.grid_y;
@@ -592,43 +621,107 @@ struct Run {
         const int max_by_k = p.kb_total / 2 > 0 ? p.kb_total / 2 : 1;
         if (s > max_by_k) s = max_by_k;
         if (s > 16) s = 16;
-        while (s > 1 && static_cast<size_t>(s) * T * Nw > h->ws_floats) --s;
+        while (s > 1 && static_cast<size_t>(s) * T * Nw > ws_floats) --s;
         return s;
     }
-    // returns split-K slices used
-    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true) {
+    // returns split-K slices used; `alt` selects the second workspace
+    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, bool alt = false) {
         if (rc) return 1;
+        float* ws = alt ? h->ws2 : h->ws;
+        const size_t ws_floats = alt ? h->ws2_floats : h->ws_floats;
         GemmCall c{};
         c.W = L.w; c.Nw = L.Nw; c.K = L.K; c.ldw = L.ld; c.w_packed = 1;
         c.X = X; c.T = T; c.ldx = L.K;
         c.epi = epi;
-        c.splitk = (epi == EPI_PARTIAL) ? pick_splitk(T, L.Nw, L.K) : 1;
+        c.splitk = (epi == EPI_PARTIAL) ? pick_splitk(T, L.Nw, L.K, ws_floats) : 1;
         c.bias = bias ? L.bias : nullptr;
-        c.out = out; c.ldo = ldo; c.partial = h->ws; c.bn_override = 0;
-        if (epi == EPI_PARTIAL && static_cast<size_t>(c.splitk) * T * L.Nw > h->ws_floats) {
+        c.out = out; c.ldo = ldo; c.partial = ws; c.bn_override = 0;
+        if (epi == EPI_PARTIAL && static_cast<size_t>(c.splitk) * T * L.Nw > ws_floats) {
             rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
             return 1;
         }
         std::string err;
-        int s = gemm_launch(st, c, &err);
-        ++h->launches;
+        int s;
+        if (rec) {
+            GemmDev d; CUtensorMap tw, tx; int gx = 0, gy = 0;
+            s = gemm_make_step_op(c, &d, &tw, &tx, &gx, &gy, &err);
+            if (s >= 0) {
+                StepOp& op = push(OP_GEMM, gx, gy, s);
+                op.tmap_w = tw; op.tmap_x = tx; op.hot.epi = epi; op.hot.u.gemm = d;
+            }
+        } else {
+            s = gemm_launch(st, c, &err);
+            ++h->launches;
+        }
         if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 1; }
         return s;
     }
     void consumer(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
                   float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
-                  bf16* xn_out, bool use_partial = true) {
+                  bf16* xn_out, bool use_partial = true, bool alt = false) {
         if (rc) return;
         ConsumerArgs a{};
-        a.partial = use_partial ? h->ws : nullptr; a.splitk = splitk; a.T = T; a.N = N; a.ldp = ldp;
+        a.partial = use_partial ? (alt ? h->ws2 : h->ws) : nullptr; a.splitk = splitk; a.T = T; a.N = N; a.ldp = ldp;
         a.bias = bias; a.add_mode = add_mode; a.res = res; a.ldr = ldr;
         a.pos = h->pos_emb; a.pos_rows = h->cfg.num_image_tokens; a.out_scale = out_scale;
         a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
         a.xn_out = xn_out; a.ldn = N;
-        launched(launch_consumer(st, a), "consumer");
+        if (rec) push(OP_CONSUMER, T, 1, 1).hot.u.consumer = a;
+        else launched(launch_consumer(st, a), "consumer");
+    }
+    void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo) {
+        if (rc) return;
+        if (rec) {
+            BiasActArgs a{h->ws, splitk, T, N, ldp, bias, act, scale, out, ldo};
+            push(OP_BIAS_ACT, (T * (N >> 2) + 255) / 256, 1, 1).hot.u.bias_act = a;
+        } else launched(launch_bias_act(st, h->ws, splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act");
+    }
+    void rope(const RopeKvArgs& a) {
+        if (rc) return;
+        if (rec) push(OP_ROPE_KV, a.T, 1, 1).hot.u.rope = a;
+        else launched(launch_rope_kv(st, a), "rope_kv");
+    }
+    void attn_siglip(const bf16* qkv, int ld_qkv, int B, int seq, int heads, int hidden, bf16* out, int ld_out) {
+        if (rc) return;
+        if (rec) push(OP_ATTN_SIGLIP, (seq + kAttnTileRows - 1) / kAttnTileRows, heads, B).hot.u.attn =
+                     make_siglip_attn_args(qkv, ld_qkv, seq, heads, hidden, out, ld_out);
+        else launched(launch_siglip_attention(st, qkv, ld_qkv, B, seq, heads, hidden, out, ld_out), "siglip_attention");
+    }
+    void attn_joint(const JointAttnArgs& a, bool fewq) {
+        if (rc) return;
+        if (rec) {
+            if (fewq) push(OP_ATTN_FEWQ, a.n_heads, a.q_per_sample, a.batch).hot.u.fewq = a;
+            else push(OP_ATTN_PREFILL, (a.q_per_sample + kAttnTileRows - 1) / kAttnTileRows, a.n_heads, a.batch).hot.u.attn =
+                     make_prefill_attn_args(a);
+        } else if (fewq) launched(launch_joint_attention_fewq(st, a), "attention_fewq");
+        else launched(launch_joint_attention_prefill(st, a), "attention_prefill");
+    }
+    void embed_merge(const EmbedMergeArgs& a, int B) {
+        if (rc) return;
+        if (rec) push(OP_EMBED_MERGE, a.seq, B, 1).hot.u.embed = a;
+        else launched(launch_embed_merge(st, a.ids, B, a.seq, a.table, a.vocab, a.img, a.n_img, a.hidden, a.image_token,
+                                         a.pad_token, a.inv_div, a.normalizer, a.out, a.err_flag), "embed_merge");
+    }
+    void small_k(const SmallKArgs& a) {
+        if (rc) return;
+        const int cols = a.N > a.time_cols ? a.N : a.time_cols;
+        if (rec) push(OP_SMALL_K, (cols + 255) / 256, a.T, 1).hot.u.small_k = a;
+        else launched(launch_small_k_linear(st, a.x, a.T, a.K, a.W, a.bias, a.N, a.scale, a.y, a.ldy, a.col_off, a.time_row,
+                                            a.time_cols), "small_k_linear");
+    }
+    void action_tail(const ActionTailArgs& a) {
+        if (rc) return;
+        if (rec) push(OP_ACTION_TAIL, (a.T * a.action_dim * 32 + 255) / 256, 1, 1).hot.u.tail = a;
+        else launched(launch_action_tail(st, a.xn, a.T, a.hidden, a.W, a.bias, a.action_dim, a.dt, a.action, a.vel_tap),
+                      "action_tail");
+    }
+    void clamp(const ClampArgs& a) {
+        if (rc) return;
+        if (rec) push(OP_CLAMP, (a.n + 255) / 256, 1, 1).hot.u.clamp = a;
+        else launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip), "clamp");
     }
     void tap(const std::string& name, const void* src, size_t bytes) {
-        if (!h->debug || rc) return;
+        if (!h->debug || rc || rec) return;
         auto it = h->taps.find(name);
         if (it == h->taps.end() || it->second.bytes != bytes) {
             if (it != h->taps.end()) cudaFree(it->second.ptr);
@@ -654,8 +747,7 @@ static void run_vision(Run& R, int B) {
     for (int l = 0; l < c.vision_layers; ++l) {
         VisionLayer& L = h->vlayers[l];
         R.gemm(L.qkv, h->xn, Tv, EPI_STORE, h->sqkv, 3 * VH);
-        R.launched(launch_siglip_attention(R.st, h->sqkv, 3 * VH, B, c.num_image_tokens, c.vision_heads, VH,
-                                           h->sattn, VH), "siglip_attention");
+        R.attn_siglip(h->sqkv, 3 * VH, B, c.num_image_tokens, c.vision_heads, VH, h->sattn, VH);
         s = R.gemm(L.out, h->sattn, Tv, EPI_PARTIAL, nullptr, 0);
         R.consumer(s, Tv, VH, L.out.Nw, L.out.bias, ADD_RESIDUAL, h->xs, VH, 1.0f, h->xs, NORM_LAYERNORM, L.ln2w,
                    L.ln2b, eps, h->xn);
@@ -675,9 +767,9 @@ static void run_vision(Run& R, int B) {
     // normalizer: torch.tensor(hidden ** 0.5, dtype=bf16)
     const float inv_div = 1.0f / static_cast<float>(std::sqrt(static_cast<double>(c.vlm_hidden)));
     const float normalizer = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.vlm_hidden)))));
-    R.launched(launch_embed_merge(R.st, h->d_ids, B, c.max_image_text_tokens, h->embed, c.vocab_size, h->imgfeat,
-                                  c.num_image_tokens, c.vlm_hidden, c.image_token_index, c.pad_token_id, inv_div,
-                                  normalizer, h->E, h->d_err), "embed_merge");
+    EmbedMergeArgs em{h->d_ids, c.max_image_text_tokens, h->embed, c.vocab_size, h->imgfeat, c.num_image_tokens,
+                      c.vlm_hidden, c.image_token_index, c.pad_token_id, inv_div, normalizer, h->E, h->d_err};
+    R.embed_merge(em, B);
     R.tap("merged_embeds", h->E, static_cast<size_t>(B) * c.max_image_text_tokens * c.vlm_hidden * 2);
 }
 
@@ -687,24 +779,29 @@ struct StreamBufs {
     const int64_t* pos;
 };
 
-// One mixture's share of a joint layer (joint_model.py:24-129): QKV+RoPE+cache, attention,
-// o_proj + residual + post-norm, GeGLU MLP + residual + next norm.
-static void layer_qkv(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only) {
+// One mixture's share of a joint layer (joint_model.py:24-129), split into its dependent phases so
+// that the same phase of two independent streams (VLM and proprio) can share a grid barrier.
+static int phase_qkv_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, bool alt, Lin* used) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
-    MixtureW& M = h->mix[m];
-    MixLayer& L = M.layers[l];
-    const int T = B * sb.tokens_per_sample;
+    MixLayer& L = h->mix[m].layers[l];
     const int QW = c.num_heads * c.head_dim;
     Lin qkv = L.qkv;
     if (kv_only) {                      // last layer of vlm/proprio: only K and V are needed
         qkv.w = L.qkv.w + static_cast<size_t>(QW) * L.qkv.K;    // tile-packed: whole 128-row tiles are contiguous
         qkv.Nw = L.qkv.Nw - QW;
     }
-    const int s = R.gemm(qkv, sb.xn, T, EPI_PARTIAL, nullptr, 0, false);
+    *used = qkv;
+    return R.gemm(qkv, sb.xn, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
+}
+
+static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int s, const Lin& qkv, bool alt) {
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    MixtureW& M = h->mix[m];
     if (R.rc) return;
     RopeKvArgs a{};
-    a.partial = h->ws; a.splitk = s; a.T = T; a.ldp = qkv.Nw;
+    a.partial = alt ? h->ws2 : h->ws; a.splitk = s; a.T = B * sb.tokens_per_sample; a.ldp = qkv.Nw;
     a.n_heads = kv_only ? 0 : c.num_heads;
     a.tokens_per_sample = sb.tokens_per_sample; a.position_ids = sb.pos;
     a.cos_table = M.cos_t; a.sin_table = M.sin_t; a.n_pos = kNumPos;
@@ -712,10 +809,10 @@ static void layer_qkv(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv
     const size_t layer_off = static_cast<size_t>(l) * h->max_batch * h->n_total * c.head_dim;
     a.k_cache = h->kcache + layer_off; a.v_cache = h->vcache + layer_off;
     a.n_slots = h->n_total; a.slot_base = sb.slot_base;
-    R.launched(launch_rope_kv(R.st, a), "rope_kv");
+    R.rope(a);
 }
 
-static void layer_attn(Run& R, int l, const StreamBufs& sb, int B, int n_keys, const bf16* mask, long long mbs,
+static void phase_attn(Run& R, int l, const StreamBufs& sb, int B, int n_keys, const bf16* mask, long long mbs,
                        long long mrs, bool fewq) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
@@ -727,23 +824,31 @@ static void layer_attn(Run& R, int l, const StreamBufs& sb, int B, int n_keys, c
     a.n_slots = h->n_total; a.n_keys = n_keys;
     a.mask = mask; a.mask_bstride = mbs; a.mask_rstride = mrs;
     a.batch = B; a.n_heads = c.num_heads; a.out = sb.ao;
-    if (fewq) R.launched(launch_joint_attention_fewq(R.st, a), "attention_fewq");
-    else R.launched(launch_joint_attention_prefill(R.st, a), "attention_prefill");
+    R.attn_joint(a, fewq);
 }
 
-static void layer_post(Run& R, int m, int l, const StreamBufs& sb, int B, const bf16* next_norm) {
-    blurr_pi0* h = R.h;
-    const auto& c = h->cfg;
-    MixtureW& M = h->mix[m];
+static int phase_o_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, bool alt) {
+    return R.gemm(R.h->mix[m].layers[l].o, sb.ao, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
+}
+static void phase_post_attn(Run& R, int m, int l, const StreamBufs& sb, int B, int s, bool alt) {
+    MixtureW& M = R.h->mix[m];
     MixLayer& L = M.layers[l];
-    const int T = B * sb.tokens_per_sample;
-    int s = R.gemm(L.o, sb.ao, T, EPI_PARTIAL, nullptr, 0, false);
-    R.consumer(s, T, M.hidden, L.o.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x, NORM_RMS_GEMMA, L.post_ln,
-               nullptr, c.rms_norm_eps, sb.xn);
-    R.gemm(L.gu, sb.xn, T, EPI_GEGLU, sb.hmid, M.inter, false);
-    s = R.gemm(L.down, sb.hmid, T, EPI_PARTIAL, nullptr, 0, false);
-    R.consumer(s, T, M.hidden, L.down.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
-               next_norm ? NORM_RMS_GEMMA : NORM_NONE, next_norm, nullptr, c.rms_norm_eps, next_norm ? sb.xn : nullptr);
+    R.consumer(s, B * sb.tokens_per_sample, M.hidden, L.o.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
+               NORM_RMS_GEMMA, L.post_ln, nullptr, R.h->cfg.rms_norm_eps, sb.xn, true, alt);
+}
+static void phase_gate_up(Run& R, int m, int l, const StreamBufs& sb, int B) {
+    MixtureW& M = R.h->mix[m];
+    R.gemm(M.layers[l].gu, sb.xn, B * sb.tokens_per_sample, EPI_GEGLU, sb.hmid, M.inter, false);
+}
+static int phase_down(Run& R, int m, int l, const StreamBufs& sb, int B, bool alt) {
+    return R.gemm(R.h->mix[m].layers[l].down, sb.hmid, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
+}
+static void phase_post_mlp(Run& R, int m, int l, const StreamBufs& sb, int B, int s, const bf16* next_norm, bool alt) {
+    MixtureW& M = R.h->mix[m];
+    MixLayer& L = M.layers[l];
+    R.consumer(s, B * sb.tokens_per_sample, M.hidden, L.down.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
+               next_norm ? NORM_RMS_GEMMA : NORM_NONE, next_norm, nullptr, R.h->cfg.rms_norm_eps,
+               next_norm ? sb.xn : nullptr, true, alt);
 }
 
 static void run_step(Run& R, int B, int steps) {
@@ -754,8 +859,6 @@ static void run_step(Run& R, int B, int steps) {
     // proprio_encoder (pizero.py:493) and `*= sqrt(1024)` (joint_model.py:358-365)
     const int Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens;
     const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
-    R.launched(launch_small_k_linear(R.st, h->d_proprios, Tp, c.proprio_dim, h->pe_w, h->pe_b, c.expert_hidden,
-                                     expert_norm, h->Ep, c.expert_hidden, 0, nullptr, 0), "proprio_encoder");
 
     StreamBufs sv{h->E, h->En, h->Qv, h->AOv, h->H, c.max_image_text_tokens, 0, 0, h->d_vpos};
     StreamBufs sp{h->Ep, h->Epn, h->Qp, h->AOp, h->Hp, c.num_proprio_tokens, c.max_image_text_tokens,
@@ -765,25 +868,55 @@ static void run_step(Run& R, int B, int steps) {
 
     // ---- prefill: vlm + proprio into the KV cache (pizero.py:496-508) ----
     if (h->stage_mask & 2) {
-    R.consumer(1, Tt, c.vlm_hidden, 0, nullptr, ADD_NONE, h->E, c.vlm_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
-               h->mix[0].layers[0].in_ln, nullptr, c.rms_norm_eps, h->En, false);
-    R.consumer(1, Tp, c.expert_hidden, 0, nullptr, ADD_NONE, h->Ep, c.expert_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
-               h->mix[1].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Epn, false);
-    const long long itp_bs = static_cast<long long>(h->n_itp) * h->n_itp, itp_rs = h->n_itp;
-    for (int l = 0; l < L; ++l) {
-        const bool last = (l == L - 1);
-        layer_qkv(R, 0, l, sv, B, last);
-        layer_qkv(R, 1, l, sp, B, last);
-        if (last) break;                 // final layer: vlm/proprio stop after caching K,V (joint_model.py:380-382)
-        layer_attn(R, l, sv, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, false);
-        layer_attn(R, l, sp, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, true);
-        const bool next_kv_only = (l + 1 == L - 1);
-        (void)next_kv_only;
-        layer_post(R, 0, l, sv, B, h->mix[0].layers[l + 1].in_ln);
-        layer_post(R, 1, l, sp, B, h->mix[1].layers[l + 1].in_ln);
-        R.tap("prefill.L" + std::to_string(l) + ".vlm", h->E, static_cast<size_t>(Tt) * c.vlm_hidden * 2);
-        R.tap("prefill.L" + std::to_string(l) + ".proprio", h->Ep, static_cast<size_t>(Tp) * c.expert_hidden * 2);
-    }
+        SmallKArgs pe{h->d_proprios, Tp, c.proprio_dim, h->pe_w, h->pe_b, c.expert_hidden, expert_norm, h->Ep,
+                      c.expert_hidden, 0, nullptr, 0};
+        R.small_k(pe);
+        R.group_begin();
+        R.consumer(1, Tt, c.vlm_hidden, 0, nullptr, ADD_NONE, h->E, c.vlm_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
+                   h->mix[0].layers[0].in_ln, nullptr, c.rms_norm_eps, h->En, false);
+        R.consumer(1, Tp, c.expert_hidden, 0, nullptr, ADD_NONE, h->Ep, c.expert_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
+                   h->mix[1].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Epn, false);
+        R.group_end();
+        const long long itp_bs = static_cast<long long>(h->n_itp) * h->n_itp, itp_rs = h->n_itp;
+        for (int l = 0; l < L; ++l) {
+            const bool last = (l == L - 1);
+            Lin qv, qp;
+            R.group_begin();
+            const int s_v = phase_qkv_gemm(R, 0, l, sv, B, last, false, &qv);
+            const int s_p = phase_qkv_gemm(R, 1, l, sp, B, last, true, &qp);
+            R.group_end();
+            R.group_begin();
+            phase_rope(R, 0, l, sv, B, last, s_v, qv, false);
+            phase_rope(R, 1, l, sp, B, last, s_p, qp, true);
+            R.group_end();
+            if (last) break;             // final layer: vlm/proprio stop after caching K,V (joint_model.py:380-382)
+            R.group_begin();
+            phase_attn(R, l, sv, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, false);
+            phase_attn(R, l, sp, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, true);
+            R.group_end();
+            R.group_begin();
+            const int o_v = phase_o_gemm(R, 0, l, sv, B, false);
+            const int o_p = phase_o_gemm(R, 1, l, sp, B, true);
+            R.group_end();
+            R.group_begin();
+            phase_post_attn(R, 0, l, sv, B, o_v, false);
+            phase_post_attn(R, 1, l, sp, B, o_p, true);
+            R.group_end();
+            R.group_begin();
+            phase_gate_up(R, 0, l, sv, B);
+            phase_gate_up(R, 1, l, sp, B);
+            R.group_end();
+            R.group_begin();
+            const int d_v = phase_down(R, 0, l, sv, B, false);
+            const int d_p = phase_down(R, 1, l, sp, B, true);
+            R.group_end();
+            R.group_begin();
+            phase_post_mlp(R, 0, l, sv, B, d_v, h->mix[0].layers[l + 1].in_ln, false);
+            phase_post_mlp(R, 1, l, sp, B, d_p, h->mix[1].layers[l + 1].in_ln, true);
+            R.group_end();
+            R.tap("prefill.L" + std::to_string(l) + ".vlm", h->E, static_cast<size_t>(Tt) * c.vlm_hidden * 2);
+            R.tap("prefill.L" + std::to_string(l) + ".proprio", h->Ep, static_cast<size_t>(Tp) * c.expert_hidden * 2);
+        }
     }
 
     // ---- flow matching: Euler steps of the action expert over the cache (pizero.py:516-538) ----
@@ -791,37 +924,41 @@ static void run_step(Run& R, int B, int steps) {
     const float dt = static_cast<float>(1.0 / static_cast<double>(steps));
     for (int s = 0; s < ((h->stage_mask & 4) ? steps : 0); ++s) {
         // ActionEncoder (vla/modules.py:39-53)
-        R.launched(launch_small_k_linear(R.st, h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f,
-                                         h->X2, 2 * c.expert_hidden, c.expert_hidden,
-                                         h->time_table + static_cast<size_t>(s) * c.expert_hidden, c.expert_hidden),
-                   "action_encoder.linear_1");
+        SmallKArgs a1{h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f, h->X2,
+                      2 * c.expert_hidden, c.expert_hidden, h->time_table + static_cast<size_t>(s) * c.expert_hidden,
+                      c.expert_hidden};
+        R.small_k(a1);
         int k = R.gemm(h->ae2, h->X2, Ta, EPI_PARTIAL, nullptr, 0);
-        if (!R.rc)
-            R.launched(launch_bias_act(R.st, h->ws, k, Ta, c.expert_hidden, h->ae2.Nw, h->ae2.bias, ACT_SILU, 1.0f,
-                                       h->A1, c.expert_hidden), "action_encoder.silu");
+        R.bias_act(k, Ta, c.expert_hidden, h->ae2.Nw, h->ae2.bias, ACT_SILU, 1.0f, h->A1, c.expert_hidden);
         k = R.gemm(h->ae3, h->A1, Ta, EPI_PARTIAL, nullptr, 0);
         R.consumer(k, Ta, c.expert_hidden, h->ae3.Nw, h->ae3.bias, ADD_NONE, nullptr, 0, expert_norm, h->Ea,
                    NORM_RMS_GEMMA, h->mix[2].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Ean);
         R.tap("flow" + std::to_string(s) + ".action_embeds", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
         for (int l = 0; l < L; ++l) {
-            layer_qkv(R, 2, l, sa, B, false);
-            layer_attn(R, l, sa, B, h->n_total, h->d_mask_act, act_bs, act_rs, true);
+            Lin qa;
+            const int s_a = phase_qkv_gemm(R, 2, l, sa, B, false, false, &qa);
+            phase_rope(R, 2, l, sa, B, false, s_a, qa, false);
+            phase_attn(R, l, sa, B, h->n_total, h->d_mask_act, act_bs, act_rs, true);
+            const int o_a = phase_o_gemm(R, 2, l, sa, B, false);
+            phase_post_attn(R, 2, l, sa, B, o_a, false);
+            phase_gate_up(R, 2, l, sa, B);
+            const int d_a = phase_down(R, 2, l, sa, B, false);
             const bf16* next = (l + 1 < L) ? h->mix[2].layers[l + 1].in_ln : h->mix[2].final_norm;
-            layer_post(R, 2, l, sa, B, next);
+            phase_post_mlp(R, 2, l, sa, B, d_a, next, false);
             R.tap("flow" + std::to_string(s) + ".L" + std::to_string(l) + ".action", h->Ea,
                   static_cast<size_t>(Ta) * c.expert_hidden * 2);
         }
         bf16* vel_tap = nullptr;
-        if (h->debug) {
+        if (h->debug && !R.rec) {
             const std::string nm = "flow" + std::to_string(s) + ".velocity";
             R.tap(nm, h->d_action, static_cast<size_t>(Ta) * c.action_dim * 2);   // allocates the slot
             if (!R.rc) vel_tap = static_cast<bf16*>(h->taps[nm].ptr);
         }
-        R.launched(launch_action_tail(R.st, h->Ean, Ta, c.expert_hidden, h->dec_w, h->dec_b, c.action_dim, dt,
-                                      h->d_action, vel_tap), "action_tail");
+        ActionTailArgs at{h->Ean, Ta, c.expert_hidden, h->dec_w, h->dec_b, c.action_dim, dt, h->d_action, vel_tap};
+        R.action_tail(at);
     }
-    R.launched(launch_clamp_copy(R.st, h->d_action, h->d_out, Ta * c.action_dim, c.has_clip,
-                                 c.final_action_clip_value), "clamp");
+    ClampArgs cl{h->d_action, h->d_out, Ta * c.action_dim, c.has_clip, c.final_action_clip_value};
+    R.clamp(cl);
 }
 
 extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const blurr_pi0_inputs* in,
@@ -866,8 +1003,27 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
     int64_t pre_launches = 2;
 
     Run R{h, st};
+    const bool stepk = h->use_step_kernel && !h->debug;
     const bool graph = h->use_graph && !h->debug;
-    if (!graph) {
+    if (stepk) {
+        // one persistent cooperative kernel walks the whole schedule (step_kernel.h)
+        const long long key = static_cast<long long>(batch) * 4096 + steps;
+        auto it = h->programs.find(key);
+        if (it == h->programs.end()) {
+            StepProgram prog;
+            Run C{h, st};
+            C.rec = &prog;
+            run_step(C, batch, steps);
+            if (C.rc) return C.rc;
+            std::string err;
+            if (step_program_upload(prog, &err)) return fail(BLURR_ERR_CUDA, err);
+            it = h->programs.emplace(key, std::move(prog)).first;
+        }
+        std::string err;
+        if (step_program_launch(it->second, st, &err)) return fail(BLURR_ERR_CUDA, err);
+        h->step_ops = static_cast<int64_t>(it->second.ops.size());
+        h->launches = pre_launches + 1;
+    } else if (!graph) {
         run_step(R, batch, steps);
         if (R.rc) return R.rc;
         h->launches += pre_launches;
@@ -917,9 +1073,12 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     if (!h || !name) return fail(BLURR_ERR_INVALID, "set_option: null argument");
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
+    else if (n == "use_step_kernel") h->use_step_kernel = value != 0;
     else if (n == "debug_taps") h->debug = value != 0;
     else if (n == "stage_mask") {              // timing experiments only: run a subset of the stages
         h->stage_mask = static_cast<int>(value) & 7;
+        for (auto& kv : h->programs) step_program_free(kv.second);
+        h->programs.clear();
         for (auto& kv : h->graphs) {
             cudaGraphExecDestroy(kv.second.exec);
             cudaGraphDestroy(kv.second.graph);
@@ -964,6 +1123,10 @@ extern "C" int blurr_pi0_check(blurr_pi0_t* h, void* cuda_stream) {
     CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
     if (int tf = gemm_take_timeout_flag())
         return fail(BLURR_ERR_CUDA, "a GEMM pipeline wait expired (role " + std::to_string(tf) + "): results are invalid");
+    for (auto& kv : h->programs)
+        if (int e = step_program_take_error(kv.second))
+            return fail(BLURR_ERR_CUDA, "the persistent step kernel gave up waiting (code " + std::to_string(e) +
+                                            "): results are invalid");
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag != 0) {
@@ -998,6 +1161,7 @@ extern "C" int blurr_pi0_debug_tap(blurr_pi0_t* h, const char* name, void* dst, 
 }
 
 extern "C" int64_t blurr_pi0_last_launch_count(const blurr_pi0_t* h) { return h ? h->launches : 0; }
+extern "C" int64_t blurr_pi0_last_op_count(const blurr_pi0_t* h) { return h ? h->step_ops : 0; }
 extern "C" int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h) { return h ? static_cast<int64_t>(h->weight_bytes) : 0; }
 
 // ---------------------------------------------------------------------------

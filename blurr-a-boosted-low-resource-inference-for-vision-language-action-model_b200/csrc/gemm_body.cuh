@@ -1,0 +1,224 @@
+// Device body of the tcgen05 / TMEM / TMA GEMM (see gemm_tc.cu for the design notes), written so
+// that the same code serves a stand-alone launch (one tile per CTA) and the persistent step kernel
+// (many tiles and many GEMMs per CTA): the shared-memory ring, its mbarriers and the TMEM allocation
+// are set up once by the caller, and the barrier phase parities live in a per-thread `GemmPipe`
+// that persists across tiles.
+#pragma once
+
+#include "common.cuh"
+#include "gemm_tc.h"
+
+namespace blurr {
+
+static constexpr int kBlockM = 128;     // weight rows per CTA (UMMA M)
+static constexpr int kBlockK = 64;      // bf16 elements per k-block (one 128-byte swizzle row)
+static constexpr int kTileABytes = kBlockM * kBlockK * 2;
+static constexpr int kGemmThreads = 256;
+static constexpr int kMaxStages = 8;
+
+
+struct GemmShared {
+    uint8_t* ring;            // 1024-byte aligned pipeline buffers (also the epilogue tile)
+    uint64_t* full_bar;       // [kMaxStages]
+    uint64_t* empty_bar;      // [kMaxStages]
+    uint64_t* tmem_full_bar;  // [1]
+    uint32_t tmem_base;
+};
+// Phase parity to wait for next, one bit per barrier; only the thread that waits on a barrier
+// consults its bit, so every thread keeps its own copy.
+struct GemmPipe {
+    uint32_t full_bits = 0, empty_bits = 0, tmem_bit = 0;
+};
+
+// Set (to 1 + role) when a pipeline wait expired; read by gemm_take_timeout_flag().
+static __device__ int g_gemm_timeout_flag = 0;
+
+// One 128-row weight tile x (nt x bn tokens) x one split-K slice.  Called by all 256 threads.
+template <int EPI>
+__device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_x,
+                                          const CUtensorMap* tmap_xs, const GemmShared& sh, GemmPipe& st,
+                                          const int bx, const int by, const int bz, const uint32_t crank) {
+    uint8_t* smem = sh.ring;
+    const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tmem_base = sh.tmem_base;
+    const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
+
+    const int n0 = bx * kBlockM;                  // first weight row of this tile
+    const int t0 = by * p.nt * p.bn;              // first token row of this tile
+    const int kb0 = bz * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    const int nkb = kb1 - kb0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
+            const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                if (!mbar_wait(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
+                    atomicExch(&g_gemm_timeout_flag, 1);
+                    break;
+                }
+                st.empty_bits ^= (1u << s);
+                uint8_t* stg = smem + s * stage_bytes;
+                mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(stage_bytes));
+                const int kcoord = (kb0 + i) * kBlockK;
+                if (p.w_packed)   // tile (bx, k-block) is a contiguous 128 x 64 block
+                    tma_load_2d_hint(stg, tmap_w, &sh.full_bar[s], 0, (bx * p.kb_total + kb0 + i) * kBlockM, pol_w);
+                else
+                    tma_load_2d_hint(stg, tmap_w, &sh.full_bar[s], kcoord, n0, pol_w);
+                if (p.cluster > 1) {
+                    // this CTA's slice of the shared activation tile, delivered to every CTA of the cluster
+                    const int r0 = static_cast<int>(crank) * p.slice_rows;
+                    tma_load_2d_multicast_hint(stg + kTileABytes + r0 * (kBlockK * 2), tmap_xs, &sh.full_bar[s],
+                                               kcoord, t0 + r0, cmask, pol_x);
+                } else {
+                    for (int c = 0; c < p.nt; ++c)
+                        tma_load_2d_hint(stg + kTileABytes + c * p.bn * (kBlockK * 2), tmap_x, &sh.full_bar[s],
+                                         kcoord, t0 + c * p.bn, pol_x);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
+            bool ok = true;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                if (!mbar_wait(&sh.full_bar[s], (st.full_bits >> s) & 1u)) {
+                    atomicExch(&g_gemm_timeout_flag, 2);
+                    ok = false;
+                    break;
+                }
+                st.full_bits ^= (1u << s);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                for (int c = 0; c < p.nt; ++c) {
+                    const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes + c * p.bn * (kBlockK * 2));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the
+                        // 16-byte-granular start-address field
+                        umma_bf16_ss(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                     (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                // frees the smem stage (in every CTA of the cluster) once these MMAs retire
+                if (p.cluster > 1) umma_commit_multicast(&sh.empty_bar[s], cmask);
+                else umma_commit(&sh.empty_bar[s]);
+            }
+            if (ok) umma_commit(sh.tmem_full_bar);   // accumulators complete
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue phase 1: TMEM -> registers -> smem tile [token][128 n] ----
+        const int w4 = warp - 4;               // TMEM lane quarter this warp may access
+        const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
+        const bool acc_ready = mbar_wait(sh.tmem_full_bar, st.tmem_bit);
+        st.tmem_bit ^= 1u;
+        if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
+        tcgen05_fence_after();
+        float bias = 0.f;
+        if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
+        const int ntok = p.nt * p.bn;
+        for (int g = 0; acc_ready && g < ntok / 16; ++g) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+            tmem_ld_wait();
+            if (EPI == EPI_PARTIAL) {
+                float* tile = reinterpret_cast<float*>(smem);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tile[(g * 16 + i) * kBlockM + nl] = __uint_as_float(r[i]);
+            } else {
+                bf16* tile = reinterpret_cast<bf16*>(smem);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v = bf16_round(__uint_as_float(r[i]) + bias);
+                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+
+    // ---- epilogue phase 2: row-wise vector stores (all 256 threads) ----
+    {
+        const int ntok = p.nt * p.bn;
+        if (EPI == EPI_PARTIAL) {
+            const float4* tile = reinterpret_cast<const float4*>(smem);
+            float* dst = p.partial + static_cast<size_t>(bz) * p.T * p.Nw;
+            for (int idx = threadIdx.x; idx < ntok * 32; idx += kGemmThreads) {
+                const int t = idx >> 5, ch = idx & 31;
+                if (t0 + t < p.T)
+                    *reinterpret_cast<float4*>(dst + static_cast<size_t>(t0 + t) * p.Nw + n0 + ch * 4) =
+                        tile[t * 32 + ch];
+            }
+        } else if (EPI == EPI_GEGLU) {
+            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
+            for (int idx = threadIdx.x; idx < ntok * 8; idx += kGemmThreads) {
+                const int t = idx >> 3, ch = idx & 7;
+                if (t0 + t >= p.T) continue;
+                const bf16x8 g = tile[t * 16 + ch];
+                const bf16x8 u = tile[t * 16 + 8 + ch];
+                bf16x8 o;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 gf = unpack_bf16x2(g.u[j]);
+                    const float2 uf = unpack_bf16x2(u.u[j]);
+                    const float a = bf16_round(gelu_tanh_f32(gf.x)) * uf.x;
+                    const float b = bf16_round(gelu_tanh_f32(gf.y)) * uf.y;
+                    o.u[j] = pack_bf16x2(a, b);
+                }
+                *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + bx * (kBlockM / 2) +
+                                           ch * 8) = o;
+            }
+        } else {
+            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
+            for (int idx = threadIdx.x; idx < ntok * 16; idx += kGemmThreads) {
+                const int t = idx >> 4, ch = idx & 15;
+                if (t0 + t < p.T)
+                    *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + n0 + ch * 8) =
+                        tile[t * 16 + ch];
+            }
+        }
+    }
+    __syncthreads();     // the tile aliases the ring: it must be drained before the next tile's TMA writes
+}
+
+// Ring + barrier carve-up of a dynamic shared-memory block and one-time initialisation.
+// Returns the shared view; `smem_raw` needs ring_bytes + 1024 (alignment) + 256 (barriers).
+__device__ __forceinline__ GemmShared gemm_setup_shared(uint8_t* smem_raw, int ring_bytes, int empty_count,
+                                                        uint32_t tmem_cols, uint32_t* tmem_slot_out) {
+    GemmShared sh;
+    sh.ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    sh.full_bar = reinterpret_cast<uint64_t*>(sh.ring + ring_bytes);
+    sh.empty_bar = sh.full_bar + kMaxStages;
+    sh.tmem_full_bar = sh.empty_bar + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sh.tmem_full_bar + 1);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp == 1 && elect_one_sync()) {
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&sh.full_bar[i], 1);
+            mbar_init(&sh.empty_bar[i], static_cast<uint32_t>(empty_count));
+        }
+        mbar_init(sh.tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    sh.tmem_base = *tmem_slot;
+    *tmem_slot_out = sh.tmem_base;
+    return sh;
+}
+
+}  // namespace blurr

@@ -20,8 +20,7 @@
 //   EPI_GEGLU   : bf16(bf16(gelu_tanh(bf16(gate))) * bf16(up))       (GemmaMLP, modules.py:93-95)
 //   EPI_PARTIAL : fp32 partial sums of one split-K slice -> workspace [z][t][n]; the consumer
 //                 kernels in norm_consumers.cu finish bias/residual/norm in a fixed order.
-#include "common.cuh"
-#include "gemm_tc.h"
+#include "gemm_body.cuh"
 #include "launch.cuh"
 
 #include <mutex>
@@ -30,214 +29,28 @@
 
 namespace blurr {
 
-static constexpr int kBlockM = 128;     // weight rows per CTA (UMMA M)
-static constexpr int kBlockK = 64;      // bf16 elements per k-block (one 128-byte swizzle row)
-static constexpr int kTileABytes = kBlockM * kBlockK * 2;
-static constexpr int kGemmThreads = 256;
-
-struct GemmDev {
-    int T;            // valid token rows
-    int bn;           // tokens per UMMA chunk (multiple of 16, <= 256)
-    int nt;           // chunks per CTA (nt * bn <= 512 TMEM columns)
-    int stages;       // smem pipeline depth
-    int kb_total;     // ceil(K / 64)
-    int kb_per_split; // k-blocks per blockIdx.z
-    int tmem_cols;    // power of two >= nt * bn
-    int Nw;           // padded weight rows (multiple of 128)
-    const bf16* bias; // [Nw] or nullptr
-    bf16* out;        // bf16 output
-    int ldo;          // output row stride (elements)
-    float* partial;   // EPI_PARTIAL: [splitk][T][Nw] fp32
-    int w_packed;     // weights are tile-packed (see gemm_tc.h)
-    int cluster;      // CTAs (consecutive weight tiles) sharing one multicast activation tile
-    int slice_rows;   // activation rows each CTA of the cluster loads and multicasts
-};
-
-// Set (to 1 + role) when a pipeline wait expired; read by gemm_take_timeout_flag().
-__device__ int g_gemm_timeout_flag = 0;
-
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                const __grid_constant__ CUtensorMap tmap_xs, const GemmDev p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
-    const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
-    uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* tmem_full_bar = empty_bar + p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-    const int lane = threadIdx.x & 31;
-
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(p.cluster > 1 ? &tmap_xs : &tmap_x);
     }
-    if (warp == 1 && elect_one_sync()) {
-        for (int i = 0; i < p.stages; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], static_cast<uint32_t>(p.cluster));   // every CTA of the cluster frees it
-        }
-        mbar_init(tmem_full_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 2) {
-        tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-        tmem_relinquish();
-    }
-    tcgen05_fence_before();
-    __syncthreads();
+    const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
+    uint32_t tmem_base;
+    GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes, p.cluster,
+                                      static_cast<uint32_t>(p.tmem_cols), &tmem_base);
     if (p.cluster > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
     const uint32_t crank = (p.cluster > 1) ? cluster_ctarank() : 0u;
-    const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
     // the previous kernel; its results are needed from here on
     pdl_wait();
     pdl_trigger();
-
-    const int n0 = blockIdx.x * kBlockM;          // first weight row of this CTA
-    const int t0 = blockIdx.y * p.nt * p.bn;      // first token row of this CTA
-    const int kb0 = blockIdx.z * p.kb_per_split;
-    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-    const int nkb = kb1 - kb0;
-
-    if (warp == 0) {
-        if (elect_one_sync()) {
-            const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
-            const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (i / p.stages) & 1;
-                if (!mbar_wait(&empty_bar[s], ph ^ 1)) { atomicExch(&g_gemm_timeout_flag, 1); break; }
-                uint8_t* st = smem + s * stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
-                const int kcoord = (kb0 + i) * kBlockK;
-                if (p.w_packed)   // tile (blockIdx.x, k-block) is a contiguous 128 x 64 block
-                    tma_load_2d_hint(st, &tmap_w, &full_bar[s], 0,
-                                     (static_cast<int>(blockIdx.x) * p.kb_total + kb0 + i) * kBlockM, pol_w);
-                else
-                    tma_load_2d_hint(st, &tmap_w, &full_bar[s], kcoord, n0, pol_w);
-                if (p.cluster > 1) {
-                    // this CTA's slice of the shared activation tile, delivered to every CTA of the cluster
-                    const int r0 = static_cast<int>(crank) * p.slice_rows;
-                    tma_load_2d_multicast_hint(st + kTileABytes + r0 * (kBlockK * 2), &tmap_xs, &full_bar[s],
-                                               kcoord, t0 + r0, cmask, pol_x);
-                } else {
-                    for (int c = 0; c < p.nt; ++c)
-                        tma_load_2d_hint(st + kTileABytes + c * p.bn * (kBlockK * 2), &tmap_x,
-                                         &full_bar[s], kcoord, t0 + c * p.bn, pol_x);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one_sync()) {
-            const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
-            bool ok = true;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (i / p.stages) & 1;
-                if (!mbar_wait(&full_bar[s], ph)) { atomicExch(&g_gemm_timeout_flag, 2); ok = false; break; }
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-                for (int c = 0; c < p.nt; ++c) {
-                    const uint64_t b_desc =
-                        make_smem_desc_sw128(a_addr + kTileABytes + c * p.bn * (kBlockK * 2));
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in
-                        // the 16-byte-granular start-address field
-                        umma_bf16_ss(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                     (i > 0 || k > 0) ? 1u : 0u);
-                    }
-                }
-                // frees the smem stage (in every CTA of the cluster) once these MMAs retire
-                if (p.cluster > 1) umma_commit_multicast(&empty_bar[s], cmask);
-                else umma_commit(&empty_bar[s]);
-            }
-            if (ok) umma_commit(tmem_full_bar);   // accumulators complete
-        }
-    } else if (warp >= 4) {
-        // ---- epilogue phase 1: TMEM -> registers -> smem tile [token][128 n] ----
-        const int w4 = warp - 4;               // TMEM lane quarter this warp may access
-        const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
-        const bool acc_ready = mbar_wait(tmem_full_bar, 0);
-        if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
-        tcgen05_fence_after();
-        float bias = 0.f;
-        if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
-        const int ntok = p.nt * p.bn;
-        for (int g = 0; acc_ready && g < ntok / 16; ++g) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(lane_addr + g * 16, r);
-            tmem_ld_wait();
-            if (EPI == EPI_PARTIAL) {
-                float* tile = reinterpret_cast<float*>(smem);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) tile[(g * 16 + i) * kBlockM + nl] = __uint_as_float(r[i]);
-            } else {
-                bf16* tile = reinterpret_cast<bf16*>(smem);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float v = bf16_round(__uint_as_float(r[i]) + bias);
-                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
-                    tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
-                }
-            }
-        }
-        tcgen05_fence_before();
-    }
-    __syncthreads();
-
-    // ---- epilogue phase 2: row-wise vector stores (all 256 threads) ----
-    {
-        const int ntok = p.nt * p.bn;
-        if (EPI == EPI_PARTIAL) {
-            const float4* tile = reinterpret_cast<const float4*>(smem);
-            float* dst = p.partial + static_cast<size_t>(blockIdx.z) * p.T * p.Nw;
-            for (int idx = threadIdx.x; idx < ntok * 32; idx += kGemmThreads) {
-                const int t = idx >> 5, ch = idx & 31;
-                if (t0 + t < p.T)
-                    *reinterpret_cast<float4*>(dst + static_cast<size_t>(t0 + t) * p.Nw + n0 + ch * 4) =
-                        tile[t * 32 + ch];
-            }
-        } else if (EPI == EPI_GEGLU) {
-            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
-            for (int idx = threadIdx.x; idx < ntok * 8; idx += kGemmThreads) {
-                const int t = idx >> 3, ch = idx & 7;
-                if (t0 + t >= p.T) continue;
-                const bf16x8 g = tile[t * 16 + ch];
-                const bf16x8 u = tile[t * 16 + 8 + ch];
-                bf16x8 o;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 gf = unpack_bf16x2(g.u[j]);
-                    const float2 uf = unpack_bf16x2(u.u[j]);
-                    const float a = bf16_round(gelu_tanh_f32(gf.x)) * uf.x;
-                    const float b = bf16_round(gelu_tanh_f32(gf.y)) * uf.y;
-                    o.u[j] = pack_bf16x2(a, b);
-                }
-                *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo +
-                                           blockIdx.x * (kBlockM / 2) + ch * 8) = o;
-            }
-        } else {
-            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
-            for (int idx = threadIdx.x; idx < ntok * 16; idx += kGemmThreads) {
-                const int t = idx >> 4, ch = idx & 15;
-                if (t0 + t < p.T)
-                    *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + n0 +
-                                               ch * 8) = tile[t * 16 + ch];
-            }
-        }
-    }
-
-    __syncthreads();
+    GemmPipe st;
+    gemm_tile<EPI>(p, &tmap_w, &tmap_x, &tmap_xs, sh, st, blockIdx.x, blockIdx.y, blockIdx.z, crank);
     if (p.cluster > 1) cluster_sync_all();      // no CTA exits while peers may still signal its barriers
     if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
@@ -340,6 +153,7 @@ static int next_pow2_cols(int c) {
 }
 
 static constexpr int kSmemBudget = 227 * 1024;
+static constexpr int kRingBytes = 225 * 1024;   // pipeline ring (stand-alone kernel and step kernel alike)
 
 // Measured on B200 (tools/time_gemm.py, round 1): multicasting the activation tile across a cluster of
 // 2/4 CTAs is *slower* than unicast at every Pi-0 shape (the CTAs of a cluster advance in lock-step and
@@ -350,7 +164,7 @@ void gemm_set_cluster_max(int c) { g_cluster_max = c < 1 ? 1 : (c > 8 ? 8 : c); 
 static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out) {
     const int stage_bytes = kTileABytes + nt * bn * kBlockK * 2;
     const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
-    const int avail = kSmemBudget - 1024 - 256;
+    const int avail = kRingBytes;
     int stages = avail / stage_bytes;
     if (stages < 1) return false;
     if (stages > 8) stages = 8;
@@ -427,6 +241,29 @@ static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUt
     dim3 grid(pl.grid_x, pl.grid_y, pl.splitk);
     return launch_kernel_cluster(gemm_tc_kernel<EPI>, grid, dim3(kGemmThreads), static_cast<size_t>(pl.smem_bytes),
                                  stream, pl.cluster, tw, tx, txs, d);
+}
+
+int gemm_make_step_op(const GemmCall& c, GemmDev* d, CUtensorMap* tmap_w, CUtensorMap* tmap_x, int* grid_x,
+                      int* grid_y, std::string* err) {
+    const int saved = g_cluster_max;
+    g_cluster_max = 1;
+    GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
+    g_cluster_max = saved;
+    if (!pl.valid) { *err = "gemm_make_step_op: unsupported shape"; return -1; }
+    if (c.epi != EPI_PARTIAL && pl.splitk != 1) { *err = "gemm_make_step_op: split-K needs EPI_PARTIAL"; return -1; }
+    if (c.w_packed) {
+        if (get_tmap(c.W, c.Nw * pl.kb_total, kBlockK, kBlockK, kBlockM, tmap_w, err)) return -1;
+    } else {
+        if (get_tmap(c.W, c.Nw, c.K, c.ldw, kBlockM, tmap_w, err)) return -1;
+    }
+    if (get_tmap(c.X, c.T, c.K, c.ldx, pl.bn, tmap_x, err)) return -1;
+    *d = GemmDev{};
+    d->T = c.T; d->bn = pl.bn; d->nt = pl.nt; d->stages = pl.stages; d->kb_total = pl.kb_total;
+    d->kb_per_split = pl.kb_per_split; d->tmem_cols = pl.tmem_cols; d->Nw = c.Nw;
+    d->bias = c.bias; d->out = c.out; d->ldo = c.ldo; d->partial = c.partial;
+    d->cluster = 1; d->slice_rows = pl.nt * pl.bn; d->w_packed = c.w_packed;
+    *grid_x = pl.grid_x; *grid_y = pl.grid_y;
+    return pl.splitk;
 }
 
 int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {

@@ -1,6 +1,7 @@
 // Host interface of the tcgen05 GEMM (gemm_tc.cu).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -33,6 +34,25 @@ struct GemmCall {
     int bn_override;          // 0 = automatic token chunking
 };
 
+// Device-side parameters of one GEMM (filled from a GemmPlan by gemm_launch / gemm_make_step_op).
+struct GemmDev {
+    int T;            // valid token rows
+    int bn;           // tokens per UMMA chunk (multiple of 16, <= 256)
+    int nt;           // chunks per CTA (nt * bn <= 512 TMEM columns)
+    int stages;       // smem pipeline depth
+    int kb_total;     // ceil(K / 64)
+    int kb_per_split; // k-blocks per blockIdx.z
+    int tmem_cols;    // power of two >= nt * bn
+    int Nw;           // padded weight rows (multiple of 128)
+    const __nv_bfloat16* bias; // [Nw] or nullptr
+    __nv_bfloat16* out;        // bf16 output
+    int ldo;          // output row stride (elements)
+    float* partial;   // EPI_PARTIAL: [splitk][T][Nw] fp32
+    int w_packed;     // weights are tile-packed (see gemm_tc.h)
+    int cluster;      // CTAs (consecutive weight tiles) sharing one multicast activation tile
+    int slice_rows;   // activation rows each CTA of the cluster loads and multicasts
+};
+
 struct GemmPlan {
     bool valid;
     int bn, nt, stages, kb_total, kb_per_split, splitk, tmem_cols, smem_bytes, grid_x, grid_y;
@@ -40,6 +60,12 @@ struct GemmPlan {
 };
 
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override);
+
+// Fill the device parameters and the two TMA tensor maps of a GEMM without launching it (used by the
+// persistent step kernel, which runs GEMM tiles as work items).  Cluster multicast is not used there.
+// Returns the split-K slice count or -1.
+int gemm_make_step_op(const GemmCall& call, GemmDev* dev, CUtensorMap* tmap_w, CUtensorMap* tmap_x,
+                      int* grid_x, int* grid_y, std::string* err);
 
 // Returns the number of split-K slices actually used (>= 1), or -1 with *err set.
 int gemm_launch(cudaStream_t stream, const GemmCall& call, std::string* err);

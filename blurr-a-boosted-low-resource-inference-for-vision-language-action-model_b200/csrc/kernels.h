@@ -63,6 +63,20 @@ cudaError_t launch_rope_kv(cudaStream_t stream, const RopeKvArgs& a);
 // ---------------------------------------------------------------------------
 // attention.cu
 // ---------------------------------------------------------------------------
+// Arguments of the tiled (mma.sync) attention body, shared by SigLIP and the joint prefill.
+struct AttnMmaArgs {
+    const bf16* q; int ldq; int q_col0; int q_per_sample;
+    const bf16* k; int ldk; int k_col0; int kv_per_sample;
+    const bf16* v; int ldv; int v_col0;
+    bf16* out; int ldo; int o_col0;
+    int hd;            // real head dim (72 / 256)
+    int head_stride_q; // column step between query heads (hd)
+    int head_stride_kv;// column step between kv heads (0 for MQA)
+    int n_keys;
+    float scale;       // SigLIP: head_dim^-0.5
+    const bf16* mask; long long mask_bstride, mask_rstride; int q_row_offset;
+};
+
 // SigLIP MHA (siglip.py:133-152): qkv [T][3*hidden] with head_dim 72, no mask.
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
                                     int n_heads, int hidden, bf16* out, int ld_out);
@@ -81,6 +95,11 @@ struct JointAttnArgs {
     bf16* out;              // [B*q_per_sample][n_heads*256]
 };
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& a);
+// The AttnMmaArgs the two launchers above build (the step kernel runs the same bodies as work items).
+AttnMmaArgs make_siglip_attn_args(const bf16* qkv, int ld_qkv, int seq, int n_heads, int hidden, bf16* out,
+                                  int ld_out);
+AttnMmaArgs make_prefill_attn_args(const JointAttnArgs& a);
+static constexpr int kAttnTileRows = 32;     // query rows per attention work item
 // Few queries per sample (proprio: 1, action: 4): bandwidth kernel over the KV cache.
 cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& a);
 

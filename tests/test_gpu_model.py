@@ -150,13 +150,30 @@ def test_shrunk_model_stress_weights_vs_fp32_tiebreak():
 def test_shrunk_model_graph_equals_eager_and_is_deterministic():
     cfg = shrink_config(bridge_config(1), 2, 3)
     model, sd, inp = _setup(cfg, 2)
-    model.set_engine_options(use_cuda_graph=False)
+    model.set_engine_options(use_cuda_graph=False, use_step_kernel=False)
     eager = _run(model, inp)
     model.set_engine_options(use_cuda_graph=True)
     g1 = _run(model, inp)          # captures
     g2 = _run(model, inp)          # replays
     assert torch.equal(eager, g1) and torch.equal(g1, g2)
     assert model.last_launch_count > 0
+
+
+@pytest.mark.parametrize("batch,steps", [(1, 1), (2, 1), (3, 4)])
+def test_step_kernel_equals_per_op_kernels(batch, steps):
+    """The persistent cooperative step kernel runs the same device bodies as work items between grid
+    barriers: its actions and KV cache are bit-identical to the one-kernel-per-op path."""
+    cfg = shrink_config(bridge_config(steps), 2, 3)
+    model, sd, inp = _setup(cfg, batch)
+    model.set_engine_options(use_step_kernel=False)
+    ref = _run(model, inp)
+    k_ref = model.debug_tap("k_cache").clone()
+    model.set_engine_options(use_step_kernel=True)
+    a = _run(model, inp)
+    b = _run(model, inp)
+    assert model._engine.last_op_count() > 0 and model.last_launch_count <= 4
+    assert torch.equal(a, ref) and torch.equal(a, b)
+    assert torch.equal(model.debug_tap("k_cache"), k_ref)
 
 
 def test_shrunk_fractal_ten_steps():
