@@ -20,12 +20,12 @@
 
 namespace blurr {
 
-template <int HD_PAD, int BM, bool GEMMA>
+template <int HD_PAD, bool GEMMA>
 __global__ void __launch_bounds__(kAttnThreads) attn_mma_kernel(const AttnMmaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
     pdl_wait();
     pdl_trigger();
-    attn_mma_body<HD_PAD, BM, GEMMA>(a, smem_attn, blockIdx.x, blockIdx.y, blockIdx.z);
+    attn_mma_body<HD_PAD, GEMMA>(a, smem_attn, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 static constexpr int kAttnBM = kAttnTileRows;
@@ -58,53 +58,68 @@ AttnMmaArgs make_prefill_attn_args(const JointAttnArgs& j) {
     return a;
 }
 
-size_t siglip_attn_smem_bytes(int seq) { return attn_smem_bytes<80, kAttnBM>(seq); }
-size_t prefill_attn_smem_bytes(int n_keys) { return attn_smem_bytes<256, kAttnBM>(n_keys); }
+// Few queries per sample (proprio: 1, action: 4): the (head, query) pairs of a sample form the rows of
+// the same tensor-core tile kernel — all 8 query heads share the sample's single K/V head (MQA), so
+// K and V are read once per 16 pairs instead of once per head.
+AttnMmaArgs make_fewq_attn_args(const JointAttnArgs& j) {
+    AttnMmaArgs a = make_prefill_attn_args(j);
+    a.head_stride_q = 256;
+    a.mqa_nq = j.q_per_sample;
+    a.mqa_heads = j.n_heads;
+    return a;
+}
+
+static constexpr size_t kAttnSmemMax = 215 * 1024;
 
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
                                     int n_heads, int hidden, bf16* out, int ld_out) {
     const int hd = hidden / n_heads;
-    if (hd > 80) return cudaErrorInvalidValue;
+    if (hd > 80 || seq > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
     AttnMmaArgs a = make_siglip_attn_args(qkv, ld_qkv, seq, n_heads, hidden, out, ld_out);
-    const size_t smem = attn_smem_bytes<80, kAttnBM>(seq);
+    const size_t smem = attn_smem_bytes<80>(seq);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<80, kAttnBM, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<80, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttnSmemMax));
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > kAttnSmemMax) return cudaErrorInvalidValue;
     dim3 grid((seq + kAttnBM - 1) / kAttnBM, n_heads, batch);
-    return launch_kernel(attn_mma_kernel<80, kAttnBM, false>, grid, dim3(kAttnThreads), smem, stream, a);
+    return launch_kernel(attn_mma_kernel<80, false>, grid, dim3(kAttnThreads), smem, stream, a);
 }
 
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& j) {
+    if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
     AttnMmaArgs a = make_prefill_attn_args(j);
-    const size_t smem = attn_smem_bytes<256, kAttnBM>(j.n_keys);
+    const size_t smem = attn_smem_bytes<256>(j.n_keys);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<256, kAttnBM, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<256, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttnSmemMax));
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > kAttnSmemMax) return cudaErrorInvalidValue;
     dim3 grid((j.q_per_sample + kAttnBM - 1) / kAttnBM, j.n_heads, j.batch);
-    return launch_kernel(attn_mma_kernel<256, kAttnBM, true>, grid, dim3(kAttnThreads), smem, stream, a);
+    return launch_kernel(attn_mma_kernel<256, true>, grid, dim3(kAttnThreads), smem, stream, a);
 }
 
-__global__ void __launch_bounds__(256) attn_fewq_kernel(const JointAttnArgs a) {
-    extern __shared__ float fq_smem[];
-    pdl_wait();
-    pdl_trigger();
-    attn_fewq_body(a, fq_smem, blockIdx.x, blockIdx.y, blockIdx.z);
-}
-
-cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& a) {
-    dim3 grid(a.n_heads, a.q_per_sample, a.batch);
-    const size_t smem = (((a.n_keys + 3) & ~3) + 8 * 256) * sizeof(float);
-    return launch_kernel(attn_fewq_kernel, grid, dim3(256), smem, stream, a);
+cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& j) {
+    if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
+    AttnMmaArgs a = make_fewq_attn_args(j);
+    const size_t smem = attn_smem_bytes<256>(j.n_keys);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<256, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttnSmemMax));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (smem > kAttnSmemMax) return cudaErrorInvalidValue;
+    const int pairs = j.n_heads * j.q_per_sample;
+    dim3 grid((pairs + kAttnBM - 1) / kAttnBM, 1, j.batch);
+    return launch_kernel(attn_mma_kernel<256, true>, grid, dim3(kAttnThreads), smem, stream, a);
 }
 
 }  // namespace blurr

@@ -224,9 +224,21 @@ __device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t) {
 // ===========================================================================
 // attention
 // ===========================================================================
-static constexpr int kAttnThreads = 256;
-static constexpr int kBK = 64;   // keys per streamed block
+static constexpr int kAttnThreads = 256;   // 8 warps per attention tile
+static constexpr int kBK = 64;             // keys per streamed block
+static constexpr int kAttnMaxBlocks = 5;   // up to 320 keys resident in shared memory
 
+__device__ __forceinline__ void attn_bar_sync() { __syncthreads(); }
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
+    // cp.async.wait_group needs an immediate: wait until at most `pending` groups are in flight
+    if (pending <= 0) cp_async_wait<0>();
+    else if (pending == 1) cp_async_wait<1>();
+    else if (pending == 2) cp_async_wait<2>();
+    else if (pending == 3) cp_async_wait<3>();
+    else cp_async_wait<4>();
+}
 
 // dst: [nrows][LDS]; 16-byte chunks; rows >= nrows_valid and columns >= hd are zero-filled
 template <int LDS, int CH>
@@ -240,14 +252,17 @@ __device__ __forceinline__ void load_rows_async(bf16* dst, const bf16* src, int 
     }
 }
 
-// BM query rows per CTA; 8 warps = (BM/16) row groups x WC column groups.
-template <int HD_PAD, int BM, bool GEMMA>
+// One tile = 16 query rows of one (sample, head); 4 warps split the keys (logits) / the head dim
+// (output).  All K blocks are requested at once (one cp.async group per 64-key block) and consumed
+// as they land; the V blocks are requested into the same buffers as soon as the logits are done, so
+// their latency hides behind the softmax.
+template <int HD_PAD, bool GEMMA>
 __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* smem_attn, const int qt, const int h,
                                               const int b) {
-    constexpr int WR = BM / 16;                 // row groups
-    constexpr int WC = 8 / WR;                  // column groups
-    constexpr int KPW = kBK / WC;               // keys per column group per streamed block (16 or 32)
-    constexpr int NT_S = KPW / 8;               // logit n-tiles per warp per block
+    constexpr int BM = 16;
+    constexpr int WC = kAttnThreads / 32;       // column groups (all warps share the 16 rows)
+    constexpr int KPW = kBK / WC;               // keys per warp per block (16)
+    constexpr int NT_S = KPW / 8;               // logit n-tiles per warp per block (2)
     constexpr int NT_ALL = HD_PAD / 8;          // output n-tiles over the head dim
     constexpr int NT_PV = (NT_ALL + WC - 1) / WC;
     constexpr int NP_PV = (NT_PV + 1) / 2;
@@ -257,32 +272,42 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     const int nkb = (a.n_keys + kBK - 1) / kBK;
     const int ldl = nkb * kBK + 8;              // logit row stride (elements)
     bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
-    bf16* KVs = Qs + BM * LDS;                  // 2 buffers
-    bf16* Ls = KVs + 2 * kBK * LDS;             // [BM][ldl]
+    bf16* KVs = Qs + BM * LDS;                  // nkb buffers of [64][LDS]
+    bf16* Ls = KVs + nkb * kBK * LDS;           // [BM][ldl]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wr = warp % WR, wc = warp / WR;
+    const int wc = warp;
     const int q_row0 = qt * BM;
 
     const bf16* qbase = a.q + static_cast<size_t>(b) * a.q_per_sample * a.ldq + a.q_col0 + h * a.head_stride_q;
     const bf16* kbase = a.k + static_cast<size_t>(b) * a.kv_per_sample * a.ldk + a.k_col0 + h * a.head_stride_kv;
     const bf16* vbase = a.v + static_cast<size_t>(b) * a.kv_per_sample * a.ldv + a.v_col0 + h * a.head_stride_kv;
 
-    load_rows_async<LDS, CH>(Qs, qbase, a.ldq, q_row0, BM, a.q_per_sample, a.hd);
-    load_rows_async<LDS, CH>(KVs, kbase, a.ldk, 0, kBK, a.n_keys, a.hd);
-    cp_async_commit();
+    // query rows -> smem (zero-filled past the valid rows / head dim)
+    const int n_rows_valid = a.mqa_nq > 0 ? a.mqa_heads * a.mqa_nq : a.q_per_sample;
+    for (int idx = threadIdx.x; idx < BM * CH; idx += kAttnThreads) {
+        const int r = idx / CH, c = idx - r * CH;
+        const int row = q_row0 + r;
+        const bool valid = (row < n_rows_valid) && (c * 8 < a.hd);
+        const bf16* g = qbase;
+        if (valid) {
+            if (a.mqa_nq > 0)
+                g = a.q + (static_cast<size_t>(b) * a.mqa_nq + row % a.mqa_nq) * a.ldq + (row / a.mqa_nq) * a.head_stride_q + c * 8;
+            else
+                g = qbase + static_cast<size_t>(row) * a.ldq + c * 8;
+        }
+        cp_async_16(Qs + r * LDS + c * 8, g, valid);
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        load_rows_async<LDS, CH>(KVs + kb * kBK * LDS, kbase, a.ldk, kb * kBK, kBK, a.n_keys, a.hd);
+        cp_async_commit();
+    }
 
     // ---------------- phase S: logits = chain(Q K^T) -> Ls (bf16) ----------------
     for (int kb = 0; kb < nkb; ++kb) {
-        bf16* Kcur = KVs + (kb & 1) * kBK * LDS;
-        if (kb + 1 < nkb) {
-            load_rows_async<LDS, CH>(KVs + ((kb + 1) & 1) * kBK * LDS, kbase, a.ldk, (kb + 1) * kBK, kBK, a.n_keys, a.hd);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+        const bf16* Kcur = KVs + kb * kBK * LDS;
+        cp_async_wait_dyn<0>(nkb - 1 - kb);
+        attn_bar_sync();
 
         float acc[NT_S][4];
 #pragma unroll
@@ -293,15 +318,23 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
 #pragma unroll
         for (int kk = 0; kk < HD_PAD / 16; ++kk) {
             uint32_t af[4];
-            ldmatrix_x4(af, smem_u32(Qs + (wr * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+            ldmatrix_x4(af, smem_u32(Qs + (lane & 15) * LDS + kk * 16 + (lane >> 4) * 8));
+            if (NT_S == 1) {
+                // one 8-key n-tile per warp: matrices (keys, dims k0..7) and (keys, dims k8..15)
+                uint32_t bfr[2];
+                const int key = wc * KPW + (lane & 7);
+                ldmatrix_x2(bfr, smem_u32(Kcur + key * LDS + kk * 16 + ((lane >> 3) & 1) * 8));
+                mma_bf16_16816(acc[0], af, bfr[0], bfr[1]);
+            } else {
 #pragma unroll
-            for (int np = 0; np < NT_S / 2; ++np) {
-                uint32_t bfr[4];
-                const int mi = lane >> 3;
-                const int key = wc * KPW + np * 16 + (mi >> 1) * 8 + (lane & 7);
-                ldmatrix_x4(bfr, smem_u32(Kcur + key * LDS + kk * 16 + (mi & 1) * 8));
-                mma_bf16_16816(acc[np * 2 + 0], af, bfr[0], bfr[1]);
-                mma_bf16_16816(acc[np * 2 + 1], af, bfr[2], bfr[3]);
+                for (int np = 0; np < NT_S / 2; ++np) {
+                    uint32_t bfr[4];
+                    const int mi = lane >> 3;
+                    const int key = wc * KPW + np * 16 + (mi >> 1) * 8 + (lane & 7);
+                    ldmatrix_x4(bfr, smem_u32(Kcur + key * LDS + kk * 16 + (mi & 1) * 8));
+                    mma_bf16_16816(acc[np * 2 + 0], af, bfr[0], bfr[1]);
+                    mma_bf16_16816(acc[np * 2 + (NT_S > 1 ? 1 : 0)], af, bfr[2], bfr[3]);
+                }
             }
         }
         // epilogue of this key block: rounding chain, write bf16 logits
@@ -309,13 +342,13 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
         for (int nt = 0; nt < NT_S; ++nt) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int r = wr * 16 + (lane >> 2) + half * 8;
+                const int r = (lane >> 2) + half * 8;
                 const int kcol = kb * kBK + wc * KPW + nt * 8 + (lane & 3) * 2;
                 float s0 = bf16_round(acc[nt][half * 2 + 0]);
                 float s1 = bf16_round(acc[nt][half * 2 + 1]);
                 if (GEMMA) {
-                    s0 = bf16_round(s0 * 0.0625f);              // / sqrt(256)
-                    s1 = bf16_round(s1 * 0.0625f);
+                    s0 = s0 * 0.0625f;                           // / sqrt(256): exact, stays a bf16 value
+                    s1 = s1 * 0.0625f;
                     const float inv50 = 1.0f / 50.0f;            // ATen: a * (1 / b) for a scalar divisor
                     s0 = bf16_round(s0 * inv50);
                     s1 = bf16_round(s1 * inv50);
@@ -324,9 +357,10 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
                     s0 = bf16_round(s0 * 50.0f);
                     s1 = bf16_round(s1 * 50.0f);
                     const int qr = q_row0 + r;
-                    if (qr < a.q_per_sample) {
+                    if (qr < n_rows_valid) {
+                        const int mr = a.mqa_nq > 0 ? qr % a.mqa_nq : qr;
                         const bf16* mrow = a.mask + static_cast<size_t>(b) * a.mask_bstride +
-                                           static_cast<size_t>(a.q_row_offset + qr) * a.mask_rstride;
+                                           static_cast<size_t>(a.q_row_offset + mr) * a.mask_rstride;
                         if (kcol < a.n_keys) s0 = bf16_round(s0 + bf2f(mrow[kcol]));
                         if (kcol + 1 < a.n_keys) s1 = bf16_round(s1 + bf2f(mrow[kcol + 1]));
                     }
@@ -337,29 +371,42 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
                 *reinterpret_cast<uint32_t*>(Ls + r * ldl + kcol) = pack_bf16x2(s0, s1);
             }
         }
-        __syncthreads();   // all warps done with Kcur before it is overwritten; Ls visible
     }
+    attn_bar_sync();   // every warp is done with the K blocks; all logits are visible
 
-    // prefetch V block 0 while the softmax runs
-    load_rows_async<LDS, CH>(KVs, vbase, a.ldv, 0, kBK, a.n_keys, a.hd);
-    cp_async_commit();
+    // V blocks into the same buffers; the softmax below runs while they arrive
+    for (int kb = 0; kb < nkb; ++kb) {
+        load_rows_async<LDS, CH>(KVs + kb * kBK * LDS, vbase, a.ldv, kb * kBK, kBK, a.n_keys, a.hd);
+        cp_async_commit();
+    }
 
     // ---------------- softmax: fp32 over bf16 logits, result bf16 in place ----------------
-    for (int rr = 0; rr < BM / 8; ++rr) {
-        bf16* lrow = Ls + (warp * (BM / 8) + rr) * ldl;
+    for (int rr = 0; rr < BM / WC; ++rr) {
+        bf16* lrow = Ls + (warp * (BM / WC) + rr) * ldl;
+        constexpr int PER_LANE = kAttnMaxBlocks * kBK / 32;     // 10 logits per lane
+        float x[PER_LANE];
         float m = -INFINITY;
-        for (int c = lane; c < a.n_keys; c += 32) m = fmaxf(m, bf2f(lrow[c]));
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+            const int c = lane + i * 32;
+            x[i] = (c < a.n_keys) ? bf2f(lrow[c]) : -INFINITY;
+            m = fmaxf(m, x[i]);
+        }
         m = warp_max(m);
         float sum = 0.f;
-        for (int c = lane; c < a.n_keys; c += 32) sum += expf(bf2f(lrow[c]) - m);
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+            const int c = lane + i * 32;
+            x[i] = (c < a.n_keys) ? expf(x[i] - m) : 0.f;
+            sum += x[i];
+        }
         sum = warp_sum(sum);
-        for (int c = lane; c < nkb * kBK; c += 32) {
-            float p = 0.f;
-            if (c < a.n_keys) p = expf(bf2f(lrow[c]) - m) / sum;
-            lrow[c] = f2bf(p);
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+            const int c = lane + i * 32;
+            if (c < nkb * kBK) lrow[c] = f2bf(x[i] / sum);
         }
     }
-    __syncthreads();
 
     // ---------------- phase PV ----------------
     float oacc[NP_PV * 2][4];
@@ -367,25 +414,19 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     for (int i = 0; i < NP_PV * 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
-    const int nt0 = wc * NT_PV;                 // first output n-tile of this column group
+    const int nt0 = wc * NT_PV;                 // first output n-tile of this warp
 
     for (int kb = 0; kb < nkb; ++kb) {
-        bf16* Vcur = KVs + (kb & 1) * kBK * LDS;
-        if (kb + 1 < nkb) {
-            load_rows_async<LDS, CH>(KVs + ((kb + 1) & 1) * kBK * LDS, vbase, a.ldv, (kb + 1) * kBK, kBK, a.n_keys, a.hd);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+        const bf16* Vcur = KVs + kb * kBK * LDS;
+        cp_async_wait_dyn<0>(nkb - 1 - kb);
+        attn_bar_sync();                        // (kb == 0: also publishes the probabilities)
 #pragma unroll
         for (int kk = 0; kk < kBK / 16; ++kk) {
             uint32_t af[4];
-            ldmatrix_x4(af, smem_u32(Ls + (wr * 16 + (lane & 15)) * ldl + kb * kBK + kk * 16 + (lane >> 4) * 8));
+            ldmatrix_x4(af, smem_u32(Ls + (lane & 15) * ldl + kb * kBK + kk * 16 + (lane >> 4) * 8));
 #pragma unroll
             for (int np = 0; np < NP_PV; ++np) {
-                if ((nt0 + np * 2) >= NT_ALL) continue;          // column group past the head dim
+                if ((nt0 + np * 2) >= NT_ALL) continue;          // warp past the head dim
                 uint32_t bfr[4];
                 const int mi = lane >> 3;
                 const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
@@ -396,7 +437,6 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
                     mma_bf16_16816(oacc[np * 2 + 1], af, bfr[2], bfr[3]);
             }
         }
-        __syncthreads();
     }
 
     // ---------------- store ----------------
@@ -405,144 +445,29 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     for (int nt = 0; nt < NT_PV; ++nt) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int r = q_row0 + wr * 16 + (lane >> 2) + half * 8;
+            const int r = q_row0 + (lane >> 2) + half * 8;
             const int dim = (nt0 + nt) * 8 + (lane & 3) * 2;
-            if (r < a.q_per_sample && dim < a.hd)
-                *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(r) * a.ldo + dim) =
-                    pack_bf16x2(oacc[nt][half * 2 + 0], oacc[nt][half * 2 + 1]);
+            if (r < n_rows_valid && dim < a.hd) {
+                bf16* dst = (a.mqa_nq > 0)
+                    ? a.out + (static_cast<size_t>(b) * a.mqa_nq + r % a.mqa_nq) * a.ldo + (r / a.mqa_nq) * a.head_stride_q
+                    : obase + static_cast<size_t>(r) * a.ldo;
+                *reinterpret_cast<uint32_t*>(dst + dim) = pack_bf16x2(oacc[nt][half * 2 + 0], oacc[nt][half * 2 + 1]);
+            }
         }
     }
+    attn_bar_sync();   // shared memory is reused by the caller's next work item
 }
 
-template <int HD_PAD, int BM>
+template <int HD_PAD>
 inline size_t attn_smem_bytes(int n_keys) {
-    constexpr int WC = 8 / (BM / 16);
+    constexpr int WC = kAttnThreads / 32;
     constexpr int NT_PV = (HD_PAD / 8 + WC - 1) / WC;
     constexpr int NP_PV = (NT_PV + 1) / 2;
     constexpr int LDS_MIN = WC * NP_PV * 16 > HD_PAD ? WC * NP_PV * 16 : HD_PAD;
     constexpr int LDS = LDS_MIN + 8;
     const int nkb = (n_keys + kBK - 1) / kBK;
-    return static_cast<size_t>(BM + 2 * kBK) * LDS * 2 + static_cast<size_t>(BM) * (nkb * kBK + 8) * 2;
+    return static_cast<size_t>(16 + nkb * kBK) * LDS * 2 + static_cast<size_t>(16) * (nkb * kBK + 8) * 2;
 }
-
-// ---------------------------------------------------------------------------
-// few-query attention over the KV cache: one CTA per (head, query, sample); the 8 warps split
-// the keys, 4 keys in flight per warp (16-byte K/V loads per lane, shuffle reductions).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void attn_fewq_body(const JointAttnArgs& a, float* fq_smem, const int h, const int qi,
-                                               const int b) {
-    // fq_smem: logits[n_keys_pad] | partial_out[8][256]
-    __shared__ float red[8];
-    const int n_pad = (a.n_keys + 3) & ~3;
-    float* lg = fq_smem;
-    float* po = fq_smem + n_pad;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ldq = a.n_heads * 256;
-    const size_t qrow = static_cast<size_t>(b) * a.q_per_sample + qi;
-    const bf16* kc = a.k_cache + static_cast<size_t>(b) * a.n_slots * 256;
-    const bf16* vc = a.v_cache + static_cast<size_t>(b) * a.n_slots * 256;
-    const bf16* mrow = a.mask + static_cast<size_t>(b) * a.mask_bstride +
-                       static_cast<size_t>(a.q_row_offset + qi) * a.mask_rstride;
-    float qreg[8];
-    {
-        const bf16x8 qv = ldcg_bf16x8(a.q + qrow * ldq + h * 256 + lane * 8);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack_bf16x2(qv.u[i]);
-            qreg[2 * i] = f.x; qreg[2 * i + 1] = f.y;
-        }
-    }
-    // ---- logits: warp w owns keys [w*kpw, (w+1)*kpw), 4 at a time ----
-    const int kpw = ((a.n_keys + 7) / 8 + 3) & ~3;
-    const int k_begin = warp * kpw, k_end = min(k_begin + kpw, a.n_keys);
-    for (int k0 = k_begin; k0 < k_end; k0 += 4) {
-        bf16x8 kv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = min(k0 + j, a.n_keys - 1);
-            kv[j] = ldcg_bf16x8(kc + static_cast<size_t>(k) * 256 + lane * 8);
-        }
-        float dot[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float d = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(kv[j].u[i]);
-                d += qreg[2 * i] * f.x + qreg[2 * i + 1] * f.y;
-            }
-            dot[j] = d;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
-        }
-        if (lane < 4 && k0 + lane < k_end) {
-            const int k = k0 + lane;
-            float s = bf16_round(lane == 0 ? dot[0] : lane == 1 ? dot[1] : lane == 2 ? dot[2] : dot[3]);
-            s = bf16_round(s * 0.0625f);
-            s = bf16_round(s * (1.0f / 50.0f));
-            s = bf16_round(tanhf(s));
-            s = bf16_round(s * 50.0f);
-            s = bf16_round(s + bf2f(mrow[k]));
-            lg[k] = s;
-        }
-    }
-    __syncthreads();
-    // ---- softmax (fp32) -> bf16 probabilities ----
-    float m = -INFINITY;
-    for (int k = tid; k < a.n_keys; k += 256) m = fmaxf(m, lg[k]);
-    m = warp_max(m);
-    if (lane == 0) red[warp] = m;
-    __syncthreads();
-    m = red[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-    __syncthreads();
-    float sum = 0.f;
-    for (int k = tid; k < a.n_keys; k += 256) sum += expf(lg[k] - m);
-    sum = warp_sum(sum);
-    if (lane == 0) red[warp] = sum;
-    __syncthreads();
-    sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sum += red[i];
-    __syncthreads();
-    for (int k = tid; k < a.n_keys; k += 256) lg[k] = bf16_round(expf(lg[k] - m) / sum);
-    __syncthreads();
-    // ---- out = P V: warp w accumulates its keys for all 256 dims (8 per lane) ----
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int k0 = k_begin; k0 < k_end; k0 += 4) {
-        bf16x8 vv[4];
-        float pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = min(k0 + j, a.n_keys - 1);
-            vv[j] = ldcg_bf16x8(vc + static_cast<size_t>(k) * 256 + lane * 8);
-            pk[j] = (k0 + j < k_end) ? lg[k] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(vv[j].u[i]);
-                acc[2 * i] += pk[j] * f.x;
-                acc[2 * i + 1] += pk[j] * f.y;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) po[warp * 256 + lane * 8 + i] = acc[i];
-    __syncthreads();
-    float o = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) o += po[w * 256 + tid];
-    a.out[qrow * ldq + h * 256 + tid] = f2bf(o);
-}
-
 
 // ===========================================================================
 // small kernels at the edges of the step

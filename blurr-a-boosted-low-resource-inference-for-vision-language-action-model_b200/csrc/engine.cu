@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <set>
 #include <string>
@@ -156,7 +157,15 @@ struct blurr_pi0 {
     // options / bookkeeping
     bool use_graph = true, debug = false;
     int stage_mask = 7;            // bit 0 vision, bit 1 prefill, bit 2 action flow (timing experiments)
-    bool use_step_kernel = true;   // one persistent cooperative kernel per step instead of a kernel graph
+    // One persistent cooperative kernel per step instead of a kernel graph.  Measured slower on B200
+    // (round 1: 7.8 ms vs 6.7 ms at bs=1): the step is bound by per-SM operand ingest and per-op
+    // parallelism, not by launch latency, and resident CTAs cannot oversubscribe an SM the way many
+    // small kernels do.  Kept as an option; results are bit-identical.
+    bool use_step_kernel = false;
+    bool profile = false;          // eager launches bracketed by CUDA events, per-kernel-label totals
+    struct ProfEntry { int count = 0; double ms = 0.0; };
+    std::map<std::string, ProfEntry> prof;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending;
     std::map<long long, StepProgram> programs;
     int64_t step_ops = 0;
     int64_t launches = 0;
@@ -232,8 +241,8 @@ static void build_expected(blurr_pi0* h) {
 
 static int validate_cfg(const blurr_pi0_config& c) {
     if (c.abi_version != BLURR_ABI_VERSION) return fail(BLURR_ERR_INVALID, "config abi_version mismatch");
-    if (c.head_dim != 256 || c.num_kv_heads != 1)
-        return fail(BLURR_ERR_INVALID, "joint attention kernels are built for head_dim 256, 1 KV head (MQA)");
+    if (c.head_dim != 256 || c.num_kv_heads != 1 || c.num_heads != 8)
+        return fail(BLURR_ERR_INVALID, "joint attention kernels are built for head_dim 256, 8 query heads, 1 KV head (MQA)");
     if (c.vision_hidden % c.vision_heads != 0 || c.vision_hidden / c.vision_heads > 80 ||
         (c.vision_hidden / c.vision_heads) % 8 != 0)
         return fail(BLURR_ERR_INVALID, "SigLIP head_dim must be a multiple of 8 and <= 80");
@@ -591,6 +600,18 @@ struct Run {
     StepProgram* rec = nullptr;      // non-null: record step-kernel ops instead of launching kernels
     int group = 0, group_items = 0;
 
+    std::string label;               // profile mode: current phase label
+    void prof_begin(const char* what) {
+        if (!h->profile || rec) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        h->prof_pending.push_back({label.empty() ? std::string(what) : label + ":" + what, {a, b}});
+    }
+    void prof_end() {
+        if (!h->profile || rec || h->prof_pending.empty()) return;
+        cudaEventRecord(h->prof_pending.back().second.second, st);
+    }
     void launched(cudaError_t e, const char* what) {
         ++h->launches;
         if (e != cudaSuccess && rc == 0) rc = fail(BLURR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -650,7 +671,11 @@ struct Run {
                 op.tmap_w = tw; op.tmap_x = tx; op.hot.epi = epi; op.hot.u.gemm = d;
             }
         } else {
+            char nm[96];
+            snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", epi, T, L.Nw, L.K, c.splitk);
+            prof_begin(nm);
             s = gemm_launch(st, c, &err);
+            prof_end();
             ++h->launches;
         }
         if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 1; }
@@ -667,58 +692,59 @@ struct Run {
         a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
         a.xn_out = xn_out; a.ldn = N;
         if (rec) push(OP_CONSUMER, T, 1, 1).hot.u.consumer = a;
-        else launched(launch_consumer(st, a), "consumer");
+        else { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
     }
     void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo) {
         if (rc) return;
         if (rec) {
             BiasActArgs a{h->ws, splitk, T, N, ldp, bias, act, scale, out, ldo};
             push(OP_BIAS_ACT, (T * (N >> 2) + 255) / 256, 1, 1).hot.u.bias_act = a;
-        } else launched(launch_bias_act(st, h->ws, splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act");
+        } else { prof_begin("bias_act"); launched(launch_bias_act(st, h->ws, splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act"); prof_end(); }
     }
     void rope(const RopeKvArgs& a) {
         if (rc) return;
         if (rec) push(OP_ROPE_KV, a.T, 1, 1).hot.u.rope = a;
-        else launched(launch_rope_kv(st, a), "rope_kv");
+        else { char nm[64]; snprintf(nm, sizeof nm, "rope_kv[T%d]", a.T); prof_begin(nm); launched(launch_rope_kv(st, a), "rope_kv"); prof_end(); }
     }
     void attn_siglip(const bf16* qkv, int ld_qkv, int B, int seq, int heads, int hidden, bf16* out, int ld_out) {
         if (rc) return;
         if (rec) push(OP_ATTN_SIGLIP, (seq + kAttnTileRows - 1) / kAttnTileRows, heads, B).hot.u.attn =
                      make_siglip_attn_args(qkv, ld_qkv, seq, heads, hidden, out, ld_out);
-        else launched(launch_siglip_attention(st, qkv, ld_qkv, B, seq, heads, hidden, out, ld_out), "siglip_attention");
+        else { prof_begin("siglip_attention"); launched(launch_siglip_attention(st, qkv, ld_qkv, B, seq, heads, hidden, out, ld_out), "siglip_attention"); prof_end(); }
     }
     void attn_joint(const JointAttnArgs& a, bool fewq) {
         if (rc) return;
         if (rec) {
-            if (fewq) push(OP_ATTN_FEWQ, a.n_heads, a.q_per_sample, a.batch).hot.u.fewq = a;
+            if (fewq) push(OP_ATTN_FEWQ, (a.n_heads * a.q_per_sample + kAttnTileRows - 1) / kAttnTileRows, 1, a.batch).hot.u.attn =
+                          make_fewq_attn_args(a);
             else push(OP_ATTN_PREFILL, (a.q_per_sample + kAttnTileRows - 1) / kAttnTileRows, a.n_heads, a.batch).hot.u.attn =
                      make_prefill_attn_args(a);
-        } else if (fewq) launched(launch_joint_attention_fewq(st, a), "attention_fewq");
-        else launched(launch_joint_attention_prefill(st, a), "attention_prefill");
+        } else if (fewq) { char nm[64]; snprintf(nm, sizeof nm, "attention_fewq[q%d]", a.q_per_sample); prof_begin(nm); launched(launch_joint_attention_fewq(st, a), "attention_fewq"); prof_end(); }
+        else { prof_begin("attention_prefill"); launched(launch_joint_attention_prefill(st, a), "attention_prefill"); prof_end(); }
     }
     void embed_merge(const EmbedMergeArgs& a, int B) {
         if (rc) return;
         if (rec) push(OP_EMBED_MERGE, a.seq, B, 1).hot.u.embed = a;
-        else launched(launch_embed_merge(st, a.ids, B, a.seq, a.table, a.vocab, a.img, a.n_img, a.hidden, a.image_token,
-                                         a.pad_token, a.inv_div, a.normalizer, a.out, a.err_flag), "embed_merge");
+        else { prof_begin("embed_merge"); launched(launch_embed_merge(st, a.ids, B, a.seq, a.table, a.vocab, a.img, a.n_img, a.hidden, a.image_token,
+                                         a.pad_token, a.inv_div, a.normalizer, a.out, a.err_flag), "embed_merge"); prof_end(); }
     }
     void small_k(const SmallKArgs& a) {
         if (rc) return;
         const int cols = a.N > a.time_cols ? a.N : a.time_cols;
         if (rec) push(OP_SMALL_K, (cols + 255) / 256, a.T, 1).hot.u.small_k = a;
-        else launched(launch_small_k_linear(st, a.x, a.T, a.K, a.W, a.bias, a.N, a.scale, a.y, a.ldy, a.col_off, a.time_row,
-                                            a.time_cols), "small_k_linear");
+        else { prof_begin("small_k_linear"); launched(launch_small_k_linear(st, a.x, a.T, a.K, a.W, a.bias, a.N, a.scale, a.y, a.ldy, a.col_off, a.time_row,
+                                            a.time_cols), "small_k_linear"); prof_end(); }
     }
     void action_tail(const ActionTailArgs& a) {
         if (rc) return;
         if (rec) push(OP_ACTION_TAIL, (a.T * a.action_dim * 32 + 255) / 256, 1, 1).hot.u.tail = a;
-        else launched(launch_action_tail(st, a.xn, a.T, a.hidden, a.W, a.bias, a.action_dim, a.dt, a.action, a.vel_tap),
-                      "action_tail");
+        else { prof_begin("action_tail"); launched(launch_action_tail(st, a.xn, a.T, a.hidden, a.W, a.bias, a.action_dim, a.dt, a.action, a.vel_tap),
+                      "action_tail"); prof_end(); }
     }
     void clamp(const ClampArgs& a) {
         if (rc) return;
         if (rec) push(OP_CLAMP, (a.n + 255) / 256, 1, 1).hot.u.clamp = a;
-        else launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip), "clamp");
+        else { prof_begin("clamp"); launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip), "clamp"); prof_end(); }
     }
     void tap(const std::string& name, const void* src, size_t bytes) {
         if (!h->debug || rc || rec) return;
@@ -855,7 +881,9 @@ static void run_step(Run& R, int B, int steps) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
     const int L = c.joint_layers;
+    R.label = "siglip";
     if (h->stage_mask & 1) run_vision(R, B);
+    R.label = "prefill";
     // proprio_encoder (pizero.py:493) and `*= sqrt(1024)` (joint_model.py:358-365)
     const int Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens;
     const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
@@ -922,6 +950,7 @@ static void run_step(Run& R, int B, int steps) {
     // ---- flow matching: Euler steps of the action expert over the cache (pizero.py:516-538) ----
     const long long act_bs = static_cast<long long>(c.num_action_tokens) * h->n_total, act_rs = h->n_total;
     const float dt = static_cast<float>(1.0 / static_cast<double>(steps));
+    R.label = "action";
     for (int s = 0; s < ((h->stage_mask & 4) ? steps : 0); ++s) {
         // ActionEncoder (vla/modules.py:39-53)
         SmallKArgs a1{h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f, h->X2,
@@ -1003,8 +1032,8 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
     int64_t pre_launches = 2;
 
     Run R{h, st};
-    const bool stepk = h->use_step_kernel && !h->debug;
-    const bool graph = h->use_graph && !h->debug;
+    const bool stepk = h->use_step_kernel && !h->debug && !h->profile;
+    const bool graph = h->use_graph && !h->debug && !h->profile;
     if (stepk) {
         // one persistent cooperative kernel walks the whole schedule (step_kernel.h)
         const long long key = static_cast<long long>(batch) * 4096 + steps;
@@ -1027,6 +1056,17 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
         run_step(R, batch, steps);
         if (R.rc) return R.rc;
         h->launches += pre_launches;
+        if (h->profile) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            for (auto& p : h->prof_pending) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+                auto& e = h->prof[p.first];
+                e.count += 1; e.ms += ms;
+                cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second);
+            }
+            h->prof_pending.clear();
+        }
     } else {
         const long long key = static_cast<long long>(batch) * 4096 + steps;
         auto it = h->graphs.find(key);
@@ -1074,6 +1114,7 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
     else if (n == "use_step_kernel") h->use_step_kernel = value != 0;
+    else if (n == "profile") { h->profile = value != 0; if (value == 2) h->prof.clear(); }
     else if (n == "debug_taps") h->debug = value != 0;
     else if (n == "stage_mask") {              // timing experiments only: run a subset of the stages
         h->stage_mask = static_cast<int>(value) & 7;
@@ -1161,6 +1202,26 @@ extern "C" int blurr_pi0_debug_tap(blurr_pi0_t* h, const char* name, void* dst, 
 }
 
 extern "C" int64_t blurr_pi0_last_launch_count(const blurr_pi0_t* h) { return h ? h->launches : 0; }
+extern "C" int blurr_pi0_profile_report(blurr_pi0_t* h, char* buf, size_t buf_bytes) {
+    if (!h || !buf || buf_bytes == 0) return fail(BLURR_ERR_INVALID, "profile_report: bad arguments");
+    std::vector<std::pair<double, std::string>> rows;
+    double total = 0.0;
+    for (auto& kv : h->prof) { rows.push_back({kv.second.ms, kv.first}); total += kv.second.ms; }
+    std::sort(rows.begin(), rows.end(), [](const std::pair<double, std::string>& a, const std::pair<double, std::string>& b) { return a.first > b.first; });
+    std::string out;
+    char line[256];
+    snprintf(line, sizeof line, "total %.3f ms over %zu labels (eager launches, CUDA events, warm L2)\n", total, rows.size());
+    out += line;
+    for (auto& r : rows) {
+        const auto& e = h->prof[r.second];
+        snprintf(line, sizeof line, "%9.1f us %5.1f%% %5dx avg %7.2f us  %s\n", e.ms * 1e3, 100.0 * e.ms / (total > 0 ? total : 1),
+                 e.count, e.ms * 1e3 / e.count, r.second.c_str());
+        out += line;
+    }
+    snprintf(buf, buf_bytes, "%s", out.c_str());
+    return 0;
+}
+
 extern "C" int64_t blurr_pi0_last_op_count(const blurr_pi0_t* h) { return h ? h->step_ops : 0; }
 extern "C" int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h) { return h ? static_cast<int64_t>(h->weight_bytes) : 0; }
 

@@ -75,6 +75,9 @@ struct AttnMmaArgs {
     int n_keys;
     float scale;       // SigLIP: head_dim^-0.5
     const bf16* mask; long long mask_bstride, mask_rstride; int q_row_offset;
+    // MQA few-query mode (mqa_nq > 0): the tile's rows enumerate (head, query) pairs of one sample,
+    // pair p -> head p / mqa_nq, query p % mqa_nq; all pairs share the sample's single K/V head.
+    int mqa_nq, mqa_heads;
 };
 
 // SigLIP MHA (siglip.py:133-152): qkv [T][3*hidden] with head_dim 72, no mask.
@@ -99,7 +102,8 @@ cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnA
 AttnMmaArgs make_siglip_attn_args(const bf16* qkv, int ld_qkv, int seq, int n_heads, int hidden, bf16* out,
                                   int ld_out);
 AttnMmaArgs make_prefill_attn_args(const JointAttnArgs& a);
-static constexpr int kAttnTileRows = 32;     // query rows per attention work item
+AttnMmaArgs make_fewq_attn_args(const JointAttnArgs& a);
+static constexpr int kAttnTileRows = 16;     // query rows per attention work item
 // Few queries per sample (proprio: 1, action: 4): bandwidth kernel over the KV cache.
 cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& a);
 

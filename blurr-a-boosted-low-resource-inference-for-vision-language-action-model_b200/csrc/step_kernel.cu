@@ -40,6 +40,11 @@ __device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned target) {
     return s_ok != 0;
 }
 
+template <int HD_PAD, bool GEMMA>
+__device__ __forceinline__ void attn_step_tile(const AttnMmaArgs& a, uint8_t* smem, int bx, int by, int bz) {
+    attn_mma_body<HD_PAD, GEMMA>(a, smem, bx, by, bz);
+}
+
 __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepOp* __restrict__ ops, const int n_ops,
                                                                unsigned* sync) {
     extern __shared__ uint8_t smem_raw[];
@@ -88,9 +93,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepOp* __r
                     break;
                 }
                 case OP_ROPE_KV: rope_kv_body(hot.u.rope, bx); break;
-                case OP_ATTN_SIGLIP: attn_mma_body<80, kAttnTileRows, false>(hot.u.attn, sh.ring, bx, by, bz); break;
-                case OP_ATTN_PREFILL: attn_mma_body<256, kAttnTileRows, true>(hot.u.attn, sh.ring, bx, by, bz); break;
-                case OP_ATTN_FEWQ: attn_fewq_body(hot.u.fewq, reinterpret_cast<float*>(sh.ring), bx, by, bz); break;
+                case OP_ATTN_SIGLIP: attn_step_tile<80, false>(hot.u.attn, sh.ring, bx, by, bz); break;
+                case OP_ATTN_PREFILL: attn_step_tile<256, true>(hot.u.attn, sh.ring, bx, by, bz); break;
+                case OP_ATTN_FEWQ: attn_step_tile<256, true>(hot.u.attn, sh.ring, bx, by, bz); break;
                 case OP_EMBED_MERGE: {
                     const EmbedMergeArgs& a = hot.u.embed;
                     embed_merge_body(a.ids, a.seq, a.table, a.vocab, a.img, a.n_img, a.hidden, a.image_token, a.pad_token,

@@ -263,7 +263,7 @@ class PiZero(nn.Module):
         object.__setattr__(self, "_debug_taps", False)
         object.__setattr__(self, "_use_cuda_graph", True)
         object.__setattr__(self, "_reserve_batch", 1)
-        object.__setattr__(self, "_use_step_kernel", True)
+        object.__setattr__(self, "_use_step_kernel", False)
 
     @classmethod
     def from_state_dict(cls, cfg, state_dict: Dict[str, torch.Tensor], device=None, dtype=None):
@@ -582,6 +582,17 @@ class _Engine:
 
     def last_launch_count(self) -> int:
         return int(self.lib.blurr_pi0_last_launch_count(self.handle))
+
+    def profile(self, fn, iters: int = 3) -> str:
+        """Run `fn()` `iters` times with every kernel bracketed by CUDA events; returns the report."""
+        self.set_option("profile", 2)
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize(self.device)
+        self.set_option("profile", 0)
+        buf = C.create_string_buffer(1 << 16)
+        capi.check(self.lib.blurr_pi0_profile_report(self.handle, buf, len(buf)))
+        return buf.value.decode()
 
     def last_op_count(self) -> int:
         return int(self.lib.blurr_pi0_last_op_count(self.handle))

@@ -131,8 +131,8 @@ typedef struct blurr_pi0_inputs {
 int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const blurr_pi0_inputs* in,
                            void* actions_out);
 
-/* Options: "use_step_kernel" (default 1: the whole step runs as ONE persistent cooperative kernel
- * that walks a device-resident op list with grid barriers; 0: one kernel per op),
+/* Options: "use_step_kernel" (default 0; 1: the whole step runs as ONE persistent cooperative kernel
+ * that walks a device-resident op list with grid barriers — bit-identical, measured slower),
  * "use_cuda_graph" (default 1; replay of the per-op kernels as a CUDA graph when the step kernel is off), "debug_taps" (default 0; implies eager launches),
  * "use_pdl" (default 1: programmatic dependent launch between the step's kernels; process-wide),
  * "num_inference_steps". */
@@ -149,6 +149,9 @@ int blurr_pi0_debug_tap(blurr_pi0_t* h, const char* name, void* dst_dev, size_t 
 
 /* Kernel launches issued (or replayed) by the last blurr_pi0_infer_action call. */
 int64_t blurr_pi0_last_launch_count(const blurr_pi0_t* h);
+/* Option "profile" = 1: every kernel is launched eagerly and bracketed by CUDA events; the per-label
+ * totals accumulated since "profile" = 2 (reset) are written as text into `buf`. */
+int blurr_pi0_profile_report(blurr_pi0_t* h, char* buf, size_t buf_bytes);
 /* Ops the persistent step kernel executed in the last call (0 when it is off). */
 int64_t blurr_pi0_last_op_count(const blurr_pi0_t* h);
 /* Bytes of repacked weights the step reads (the algorithmic-bytes numerator of the roofline). */

@@ -172,6 +172,7 @@ def test_step_kernel_equals_per_op_kernels(batch, steps):
     a = _run(model, inp)
     b = _run(model, inp)
     assert model._engine.last_op_count() > 0 and model.last_launch_count <= 4
+    model.set_engine_options(use_step_kernel=False)
     assert torch.equal(a, ref) and torch.equal(a, b)
     assert torch.equal(model.debug_tap("k_cache"), k_ref)
 

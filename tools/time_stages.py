@@ -39,7 +39,15 @@ with torch.inference_mode():
 for name, mask in [("all", 7), ("vision only", 1), ("prefill only", 2), ("action only", 4), ("staging only", 0)]:
     model._engine.set_option("stage_mask", mask)
     ms, launches = timed(30 if B == 1 else 5)
-    print(f"B={B} {name:14s}: {ms:8.3f} ms  launches={launches}  ({1e3 * ms / max(launches, 1):.2f} us/launch)", flush=True)
+    ops = model._engine.last_op_count()
+    print(f"B={B} {name:14s}: {ms:8.3f} ms  launches={launches} ops={ops} ({1e3 * ms / max(ops, 1):.2f} us/op)", flush=True)
+model._engine.set_option("stage_mask", 7)
+print("--- per-op kernels (CUDA graph + PDL) instead of the persistent step kernel")
+model._engine.set_option("use_step_kernel", 0)
+for name, mask in [("all", 7), ("vision only", 1), ("prefill only", 2), ("action only", 4)]:
+    model._engine.set_option("stage_mask", mask)
+    ms, launches = timed(30 if B == 1 else 5)
+    print(f"B={B} {name:14s}: {ms:8.3f} ms  launches={launches}", flush=True)
 model._engine.set_option("stage_mask", 7)
 for opt, val in [("use_pdl", 0), ("use_cuda_graph", 0)]:
     model._engine.set_option(opt, val)
