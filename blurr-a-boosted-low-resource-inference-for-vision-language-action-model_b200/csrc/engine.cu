@@ -153,6 +153,14 @@ struct blurr_pi0 {
     bf16 *kcache, *vcache;
     float* ws = nullptr; size_t ws_floats = 0;
     float* ws2 = nullptr; size_t ws2_floats = 0;     // second split-K workspace: the proprio stream runs beside the VLM
+    float* ws3 = nullptr;                            // third: the action stream (same size as ws2)
+    // The proprio expert and the first flow step of the action expert run on their own streams,
+    // concurrently with the VLM prefill: layer l of either only needs layer l's K/V of the streams
+    // before it, so they pipeline one layer behind instead of adding ~290 kernels to the critical path.
+    bool use_streams = true;
+    cudaStream_t s_prop = nullptr, s_act = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_done_p = nullptr, ev_done_a = nullptr;
+    std::vector<cudaEvent_t> ev_v, ev_p;
     int* d_err = nullptr;
     // options / bookkeeping
     bool use_graph = true, debug = false;
@@ -274,6 +282,11 @@ extern "C" void blurr_pi0_destroy(blurr_pi0_t* h) {
         cudaGraphDestroy(kv.second.graph);
     }
     for (auto& kv : h->programs) step_program_free(kv.second);
+    for (cudaEvent_t e : h->ev_v) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_p) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_fork, h->ev_done_p, h->ev_done_a}) if (e) cudaEventDestroy(e);
+    if (h->s_prop) cudaStreamDestroy(h->s_prop);
+    if (h->s_act) cudaStreamDestroy(h->s_act);
     for (auto& kv : h->taps) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
     gemm_forget_tensor_maps();
@@ -387,8 +400,21 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
     h->ws = static_cast<float*>(dalloc(h, ws * 4));
     h->ws2_floats = std::max<size_t>(static_cast<size_t>(16) * Ta * (qkv_rows + 0), static_cast<size_t>(kNumSMs + 20) * 128 * 16);
     h->ws2 = static_cast<float*>(dalloc(h, h->ws2_floats * 4));
+    h->ws3 = static_cast<float*>(dalloc(h, h->ws2_floats * 4));
+    {
+        bool ev_ok = cudaStreamCreateWithFlags(&h->s_prop, cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaStreamCreateWithFlags(&h->s_act, cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&h->ev_done_p, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&h->ev_done_a, cudaEventDisableTiming) == cudaSuccess;
+        h->ev_v.resize(c.joint_layers); h->ev_p.resize(c.joint_layers);
+        for (int l = 0; l < c.joint_layers && ev_ok; ++l)
+            ev_ok = cudaEventCreateWithFlags(&h->ev_v[l], cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&h->ev_p[l], cudaEventDisableTiming) == cudaSuccess;
+        ok &= ev_ok;
+    }
     h->d_err = static_cast<int*>(dalloc(h, 16));
-    ok &= h->ws && h->ws2 && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
+    ok &= h->ws && h->ws2 && h->ws3 && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
     if (!ok) {
         blurr_pi0_destroy(h);
         return fail(BLURR_ERR_CUDA, "blurr_pi0_create: device allocation failed");
@@ -646,9 +672,20 @@ struct Run {
         return s;
     }
     // returns split-K slices used; `alt` selects the second workspace
-    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, bool alt = false) {
+    float* wsp(int alt) const { return alt == 0 ? h->ws : (alt == 1 ? h->ws2 : h->ws3); }
+    // streams: 0 = caller's stream (SigLIP, VLM), 1 = proprio expert, 2 = action expert
+    cudaStream_t s_main = nullptr;
+    bool multi = false;
+    void on(int which) { st = !multi ? s_main : (which == 0 ? s_main : (which == 1 ? h->s_prop : h->s_act)); }
+    void record(cudaEvent_t ev) {
+        if (multi && !rec && rc == 0 && cudaEventRecord(ev, st) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaEventRecord failed");
+    }
+    void wait(cudaEvent_t ev) {
+        if (multi && !rec && rc == 0 && cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaStreamWaitEvent failed");
+    }
+    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, int alt = 0) {
         if (rc) return 1;
-        float* ws = alt ? h->ws2 : h->ws;
+        float* ws = wsp(alt);
         const size_t ws_floats = alt ? h->ws2_floats : h->ws_floats;
         GemmCall c{};
         c.W = L.w; c.Nw = L.Nw; c.K = L.K; c.ldw = L.ld; c.w_packed = 1;
@@ -683,10 +720,10 @@ struct Run {
     }
     void consumer(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
                   float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
-                  bf16* xn_out, bool use_partial = true, bool alt = false) {
+                  bf16* xn_out, bool use_partial = true, int alt = 0) {
         if (rc) return;
         ConsumerArgs a{};
-        a.partial = use_partial ? (alt ? h->ws2 : h->ws) : nullptr; a.splitk = splitk; a.T = T; a.N = N; a.ldp = ldp;
+        a.partial = use_partial ? wsp(alt) : nullptr; a.splitk = splitk; a.T = T; a.N = N; a.ldp = ldp;
         a.bias = bias; a.add_mode = add_mode; a.res = res; a.ldr = ldr;
         a.pos = h->pos_emb; a.pos_rows = h->cfg.num_image_tokens; a.out_scale = out_scale;
         a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
@@ -694,12 +731,12 @@ struct Run {
         if (rec) push(OP_CONSUMER, T, 1, 1).hot.u.consumer = a;
         else { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
     }
-    void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo) {
+    void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo, int alt) {
         if (rc) return;
         if (rec) {
-            BiasActArgs a{h->ws, splitk, T, N, ldp, bias, act, scale, out, ldo};
+            BiasActArgs a{wsp(alt), splitk, T, N, ldp, bias, act, scale, out, ldo};
             push(OP_BIAS_ACT, (T * (N >> 2) + 255) / 256, 1, 1).hot.u.bias_act = a;
-        } else { prof_begin("bias_act"); launched(launch_bias_act(st, h->ws, splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act"); prof_end(); }
+        } else { prof_begin("bias_act"); launched(launch_bias_act(st, wsp(alt), splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act"); prof_end(); }
     }
     void rope(const RopeKvArgs& a) {
         if (rc) return;
@@ -807,7 +844,7 @@ struct StreamBufs {
 
 // One mixture's share of a joint layer (joint_model.py:24-129), split into its dependent phases so
 // that the same phase of two independent streams (VLM and proprio) can share a grid barrier.
-static int phase_qkv_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, bool alt, Lin* used) {
+static int phase_qkv_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt, Lin* used) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
     MixLayer& L = h->mix[m].layers[l];
@@ -821,13 +858,13 @@ static int phase_qkv_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, boo
     return R.gemm(qkv, sb.xn, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
 }
 
-static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int s, const Lin& qkv, bool alt) {
+static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int s, const Lin& qkv, int alt) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
     MixtureW& M = h->mix[m];
     if (R.rc) return;
     RopeKvArgs a{};
-    a.partial = alt ? h->ws2 : h->ws; a.splitk = s; a.T = B * sb.tokens_per_sample; a.ldp = qkv.Nw;
+    a.partial = R.wsp(alt); a.splitk = s; a.T = B * sb.tokens_per_sample; a.ldp = qkv.Nw;
     a.n_heads = kv_only ? 0 : c.num_heads;
     a.tokens_per_sample = sb.tokens_per_sample; a.position_ids = sb.pos;
     a.cos_table = M.cos_t; a.sin_table = M.sin_t; a.n_pos = kNumPos;
@@ -853,10 +890,10 @@ static void phase_attn(Run& R, int l, const StreamBufs& sb, int B, int n_keys, c
     R.attn_joint(a, fewq);
 }
 
-static int phase_o_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, bool alt) {
+static int phase_o_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, int alt) {
     return R.gemm(R.h->mix[m].layers[l].o, sb.ao, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
 }
-static void phase_post_attn(Run& R, int m, int l, const StreamBufs& sb, int B, int s, bool alt) {
+static void phase_post_attn(Run& R, int m, int l, const StreamBufs& sb, int B, int s, int alt) {
     MixtureW& M = R.h->mix[m];
     MixLayer& L = M.layers[l];
     R.consumer(s, B * sb.tokens_per_sample, M.hidden, L.o.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
@@ -866,10 +903,10 @@ static void phase_gate_up(Run& R, int m, int l, const StreamBufs& sb, int B) {
     MixtureW& M = R.h->mix[m];
     R.gemm(M.layers[l].gu, sb.xn, B * sb.tokens_per_sample, EPI_GEGLU, sb.hmid, M.inter, false);
 }
-static int phase_down(Run& R, int m, int l, const StreamBufs& sb, int B, bool alt) {
+static int phase_down(Run& R, int m, int l, const StreamBufs& sb, int B, int alt) {
     return R.gemm(R.h->mix[m].layers[l].down, sb.hmid, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
 }
-static void phase_post_mlp(Run& R, int m, int l, const StreamBufs& sb, int B, int s, const bf16* next_norm, bool alt) {
+static void phase_post_mlp(Run& R, int m, int l, const StreamBufs& sb, int B, int s, const bf16* next_norm, int alt) {
     MixtureW& M = R.h->mix[m];
     MixLayer& L = M.layers[l];
     R.consumer(s, B * sb.tokens_per_sample, M.hidden, L.down.Nw, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
@@ -877,114 +914,160 @@ static void phase_post_mlp(Run& R, int m, int l, const StreamBufs& sb, int B, in
                next_norm ? sb.xn : nullptr, true, alt);
 }
 
+// Layer l of one expert stream (mixture m, workspace `alt`), split at the point where it needs the
+// K/V of the streams before it.
+static void expert_layer_head(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt) {
+    Lin q;
+    const int s = phase_qkv_gemm(R, m, l, sb, B, kv_only, alt, &q);
+    phase_rope(R, m, l, sb, B, kv_only, s, q, alt);
+}
+static void expert_layer_tail(Run& R, int m, int l, const StreamBufs& sb, int B, int n_keys, const bf16* mask,
+                              long long mbs, long long mrs, const bf16* next_norm, int alt) {
+    phase_attn(R, l, sb, B, n_keys, mask, mbs, mrs, true);
+    const int o = phase_o_gemm(R, m, l, sb, B, alt);
+    phase_post_attn(R, m, l, sb, B, o, alt);
+    phase_gate_up(R, m, l, sb, B);
+    const int d = phase_down(R, m, l, sb, B, alt);
+    phase_post_mlp(R, m, l, sb, B, d, next_norm, alt);
+}
+
+static void action_encode(Run& R, int B, int s) {
+    // ActionEncoder (vla/modules.py:39-53) + `*= sqrt(1024)` + input norm of layer 0
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    const int Ta = B * c.num_action_tokens;
+    const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
+    SmallKArgs a1{h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f, h->X2,
+                  2 * c.expert_hidden, c.expert_hidden, h->time_table + static_cast<size_t>(s) * c.expert_hidden,
+                  c.expert_hidden};
+    R.small_k(a1);
+    int k = R.gemm(h->ae2, h->X2, Ta, EPI_PARTIAL, nullptr, 0, true, 2);
+    R.bias_act(k, Ta, c.expert_hidden, h->ae2.Nw, h->ae2.bias, ACT_SILU, 1.0f, h->A1, c.expert_hidden, 2);
+    k = R.gemm(h->ae3, h->A1, Ta, EPI_PARTIAL, nullptr, 0, true, 2);
+    R.consumer(k, Ta, c.expert_hidden, h->ae3.Nw, h->ae3.bias, ADD_NONE, nullptr, 0, expert_norm, h->Ea,
+               NORM_RMS_GEMMA, h->mix[2].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Ean, true, 2);
+    R.tap("flow" + std::to_string(s) + ".action_embeds", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
+}
+
+static void action_decode(Run& R, int B, int s, float dt) {
+    blurr_pi0* h = R.h;
+    const auto& c = h->cfg;
+    const int Ta = B * c.num_action_tokens;
+    bf16* vel_tap = nullptr;
+    if (h->debug && !R.rec) {
+        const std::string nm = "flow" + std::to_string(s) + ".velocity";
+        R.tap(nm, h->d_action, static_cast<size_t>(Ta) * c.action_dim * 2);   // allocates the slot
+        if (!R.rc) vel_tap = static_cast<bf16*>(h->taps[nm].ptr);
+    }
+    ActionTailArgs at{h->Ean, Ta, c.expert_hidden, h->dec_w, h->dec_b, c.action_dim, dt, h->d_action, vel_tap};
+    R.action_tail(at);
+}
+
 static void run_step(Run& R, int B, int steps) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
     const int L = c.joint_layers;
-    R.label = "siglip";
-    if (h->stage_mask & 1) run_vision(R, B);
-    R.label = "prefill";
-    // proprio_encoder (pizero.py:493) and `*= sqrt(1024)` (joint_model.py:358-365)
-    const int Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens;
+    const int Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens, Tt = B * c.max_image_text_tokens;
     const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
+    const bool do_prefill = (h->stage_mask & 2) != 0, do_action = (h->stage_mask & 4) != 0;
+    const float dt = static_cast<float>(1.0 / static_cast<double>(steps));
 
     StreamBufs sv{h->E, h->En, h->Qv, h->AOv, h->H, c.max_image_text_tokens, 0, 0, h->d_vpos};
     StreamBufs sp{h->Ep, h->Epn, h->Qp, h->AOp, h->Hp, c.num_proprio_tokens, c.max_image_text_tokens,
                   c.max_image_text_tokens, h->d_ppos};
     StreamBufs sa{h->Ea, h->Ean, h->Qa, h->AOa, h->Ha, c.num_action_tokens, h->n_itp, 0, h->d_apos};
-    const int Tt = B * c.max_image_text_tokens;
+    const long long itp_bs = static_cast<long long>(h->n_itp) * h->n_itp, itp_rs = h->n_itp;
+    const long long act_bs = static_cast<long long>(c.num_action_tokens) * h->n_total, act_rs = h->n_total;
 
-    // ---- prefill: vlm + proprio into the KV cache (pizero.py:496-508) ----
-    if (h->stage_mask & 2) {
+    // fork: the expert streams start once the inputs are staged
+    R.on(0);
+    R.record(h->ev_fork);
+    R.on(1); R.wait(h->ev_fork);
+    R.on(2); R.wait(h->ev_fork);
+
+    // ---- expert prologues (independent of the image) ----
+    if (do_prefill) {
+        R.on(1);
+        R.label = "prefill";
+        // proprio_encoder (pizero.py:493) and `*= sqrt(1024)` (joint_model.py:358-365)
         SmallKArgs pe{h->d_proprios, Tp, c.proprio_dim, h->pe_w, h->pe_b, c.expert_hidden, expert_norm, h->Ep,
                       c.expert_hidden, 0, nullptr, 0};
         R.small_k(pe);
-        R.group_begin();
-        R.consumer(1, Tt, c.vlm_hidden, 0, nullptr, ADD_NONE, h->E, c.vlm_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
-                   h->mix[0].layers[0].in_ln, nullptr, c.rms_norm_eps, h->En, false);
         R.consumer(1, Tp, c.expert_hidden, 0, nullptr, ADD_NONE, h->Ep, c.expert_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
                    h->mix[1].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Epn, false);
-        R.group_end();
-        const long long itp_bs = static_cast<long long>(h->n_itp) * h->n_itp, itp_rs = h->n_itp;
-        for (int l = 0; l < L; ++l) {
-            const bool last = (l == L - 1);
-            Lin qv, qp;
-            R.group_begin();
-            const int s_v = phase_qkv_gemm(R, 0, l, sv, B, last, false, &qv);
-            const int s_p = phase_qkv_gemm(R, 1, l, sp, B, last, true, &qp);
-            R.group_end();
-            R.group_begin();
-            phase_rope(R, 0, l, sv, B, last, s_v, qv, false);
-            phase_rope(R, 1, l, sp, B, last, s_p, qp, true);
-            R.group_end();
-            if (last) break;             // final layer: vlm/proprio stop after caching K,V (joint_model.py:380-382)
-            R.group_begin();
-            phase_attn(R, l, sv, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, false);
-            phase_attn(R, l, sp, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, true);
-            R.group_end();
-            R.group_begin();
-            const int o_v = phase_o_gemm(R, 0, l, sv, B, false);
-            const int o_p = phase_o_gemm(R, 1, l, sp, B, true);
-            R.group_end();
-            R.group_begin();
-            phase_post_attn(R, 0, l, sv, B, o_v, false);
-            phase_post_attn(R, 1, l, sp, B, o_p, true);
-            R.group_end();
-            R.group_begin();
-            phase_gate_up(R, 0, l, sv, B);
-            phase_gate_up(R, 1, l, sp, B);
-            R.group_end();
-            R.group_begin();
-            const int d_v = phase_down(R, 0, l, sv, B, false);
-            const int d_p = phase_down(R, 1, l, sp, B, true);
-            R.group_end();
-            R.group_begin();
-            phase_post_mlp(R, 0, l, sv, B, d_v, h->mix[0].layers[l + 1].in_ln, false);
-            phase_post_mlp(R, 1, l, sp, B, d_p, h->mix[1].layers[l + 1].in_ln, true);
-            R.group_end();
-            R.tap("prefill.L" + std::to_string(l) + ".vlm", h->E, static_cast<size_t>(Tt) * c.vlm_hidden * 2);
-            R.tap("prefill.L" + std::to_string(l) + ".proprio", h->Ep, static_cast<size_t>(Tp) * c.expert_hidden * 2);
-        }
+    }
+    if (do_action) {
+        R.on(2);
+        R.label = "action";
+        action_encode(R, B, 0);
     }
 
-    // ---- flow matching: Euler steps of the action expert over the cache (pizero.py:516-538) ----
-    const long long act_bs = static_cast<long long>(c.num_action_tokens) * h->n_total, act_rs = h->n_total;
-    const float dt = static_cast<float>(1.0 / static_cast<double>(steps));
-    R.label = "action";
-    for (int s = 0; s < ((h->stage_mask & 4) ? steps : 0); ++s) {
-        // ActionEncoder (vla/modules.py:39-53)
-        SmallKArgs a1{h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f, h->X2,
-                      2 * c.expert_hidden, c.expert_hidden, h->time_table + static_cast<size_t>(s) * c.expert_hidden,
-                      c.expert_hidden};
-        R.small_k(a1);
-        int k = R.gemm(h->ae2, h->X2, Ta, EPI_PARTIAL, nullptr, 0);
-        R.bias_act(k, Ta, c.expert_hidden, h->ae2.Nw, h->ae2.bias, ACT_SILU, 1.0f, h->A1, c.expert_hidden);
-        k = R.gemm(h->ae3, h->A1, Ta, EPI_PARTIAL, nullptr, 0);
-        R.consumer(k, Ta, c.expert_hidden, h->ae3.Nw, h->ae3.bias, ADD_NONE, nullptr, 0, expert_norm, h->Ea,
-                   NORM_RMS_GEMMA, h->mix[2].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Ean);
-        R.tap("flow" + std::to_string(s) + ".action_embeds", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
-        for (int l = 0; l < L; ++l) {
-            Lin qa;
-            const int s_a = phase_qkv_gemm(R, 2, l, sa, B, false, false, &qa);
-            phase_rope(R, 2, l, sa, B, false, s_a, qa, false);
-            phase_attn(R, l, sa, B, h->n_total, h->d_mask_act, act_bs, act_rs, true);
-            const int o_a = phase_o_gemm(R, 2, l, sa, B, false);
-            phase_post_attn(R, 2, l, sa, B, o_a, false);
-            phase_gate_up(R, 2, l, sa, B);
-            const int d_a = phase_down(R, 2, l, sa, B, false);
+    // ---- SigLIP + projector + merge (main stream) ----
+    R.on(0);
+    R.label = "siglip";
+    if (h->stage_mask & 1) run_vision(R, B);
+
+    // ---- joint layers: VLM (main), proprio and action flow step 0 one dependency behind ----
+    R.label = "prefill";
+    if (do_prefill)
+        R.consumer(1, Tt, c.vlm_hidden, 0, nullptr, ADD_NONE, h->E, c.vlm_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
+                   h->mix[0].layers[0].in_ln, nullptr, c.rms_norm_eps, h->En, false);
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        if (do_prefill) {
+            // VLM: K/V of layer l first (the experts wait for them), then the rest of the layer
+            R.on(0); R.label = "prefill";
+            {
+                Lin qv;
+                const int s_v = phase_qkv_gemm(R, 0, l, sv, B, last, 0, &qv);
+                phase_rope(R, 0, l, sv, B, last, s_v, qv, 0);
+                R.record(h->ev_v[l]);
+            }
+            R.on(1);
+            expert_layer_head(R, 1, l, sp, B, last, 1);
+            R.record(h->ev_p[l]);
+            if (!last) {
+                R.on(0);
+                phase_attn(R, l, sv, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, false);
+                const int o_v = phase_o_gemm(R, 0, l, sv, B, 0);
+                phase_post_attn(R, 0, l, sv, B, o_v, 0);
+                phase_gate_up(R, 0, l, sv, B);
+                const int d_v = phase_down(R, 0, l, sv, B, 0);
+                phase_post_mlp(R, 0, l, sv, B, d_v, h->mix[0].layers[l + 1].in_ln, 0);
+                R.tap("prefill.L" + std::to_string(l) + ".vlm", h->E, static_cast<size_t>(Tt) * c.vlm_hidden * 2);
+                R.on(1);
+                R.wait(h->ev_v[l]);          // the proprio query attends over the VLM keys of this layer
+                expert_layer_tail(R, 1, l, sp, B, h->n_itp, h->d_mask_itp, itp_bs, itp_rs, h->mix[1].layers[l + 1].in_ln, 1);
+                R.tap("prefill.L" + std::to_string(l) + ".proprio", h->Ep, static_cast<size_t>(Tp) * c.expert_hidden * 2);
+            }
+        }
+        if (do_action) {
+            R.on(2); R.label = "action";
+            expert_layer_head(R, 2, l, sa, B, false, 2);
+            if (do_prefill) { R.wait(h->ev_v[l]); R.wait(h->ev_p[l]); }
             const bf16* next = (l + 1 < L) ? h->mix[2].layers[l + 1].in_ln : h->mix[2].final_norm;
-            phase_post_mlp(R, 2, l, sa, B, d_a, next, false);
+            expert_layer_tail(R, 2, l, sa, B, h->n_total, h->d_mask_act, act_bs, act_rs, next, 2);
+            R.tap("flow0.L" + std::to_string(l) + ".action", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
+        }
+    }
+    if (do_action) { R.on(2); action_decode(R, B, 0, dt); }
+    // join
+    R.on(1); R.record(h->ev_done_p);
+    R.on(2); R.record(h->ev_done_a);
+    R.on(0); R.wait(h->ev_done_p); R.wait(h->ev_done_a);
+
+    // ---- remaining Euler steps of the flow (pizero.py:516-538): sequential over the finished cache ----
+    R.label = "action";
+    for (int s = 1; s < (do_action ? steps : 0); ++s) {
+        action_encode(R, B, s);
+        for (int l = 0; l < L; ++l) {
+            expert_layer_head(R, 2, l, sa, B, false, 2);
+            const bf16* next = (l + 1 < L) ? h->mix[2].layers[l + 1].in_ln : h->mix[2].final_norm;
+            expert_layer_tail(R, 2, l, sa, B, h->n_total, h->d_mask_act, act_bs, act_rs, next, 2);
             R.tap("flow" + std::to_string(s) + ".L" + std::to_string(l) + ".action", h->Ea,
                   static_cast<size_t>(Ta) * c.expert_hidden * 2);
         }
-        bf16* vel_tap = nullptr;
-        if (h->debug && !R.rec) {
-            const std::string nm = "flow" + std::to_string(s) + ".velocity";
-            R.tap(nm, h->d_action, static_cast<size_t>(Ta) * c.action_dim * 2);   // allocates the slot
-            if (!R.rc) vel_tap = static_cast<bf16*>(h->taps[nm].ptr);
-        }
-        ActionTailArgs at{h->Ean, Ta, c.expert_hidden, h->dec_w, h->dec_b, c.action_dim, dt, h->d_action, vel_tap};
-        R.action_tail(at);
+        action_decode(R, B, s, dt);
     }
     ClampArgs cl{h->d_action, h->d_out, Ta * c.action_dim, c.has_clip, c.final_action_clip_value};
     R.clamp(cl);
@@ -1032,6 +1115,8 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
     int64_t pre_launches = 2;
 
     Run R{h, st};
+    R.s_main = st;
+    R.multi = h->use_streams && !h->debug && !h->profile;
     const bool stepk = h->use_step_kernel && !h->debug && !h->profile;
     const bool graph = h->use_graph && !h->debug && !h->profile;
     if (stepk) {
@@ -1041,6 +1126,7 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
         if (it == h->programs.end()) {
             StepProgram prog;
             Run C{h, st};
+            C.s_main = st;
             C.rec = &prog;
             run_step(C, batch, steps);
             if (C.rc) return C.rc;
@@ -1079,6 +1165,8 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
             cudaStream_t cs;
             CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
             Run C{h, cs};
+            C.s_main = cs;
+            C.multi = R.multi;
             cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
             if (e != cudaSuccess) { cudaStreamDestroy(cs); return fail(BLURR_ERR_CUDA, "graph capture begin failed"); }
             run_step(C, batch, steps);
@@ -1114,6 +1202,14 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
     else if (n == "use_step_kernel") h->use_step_kernel = value != 0;
+    else if (n == "use_streams") {
+        h->use_streams = value != 0;
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
     else if (n == "profile") { h->profile = value != 0; if (value == 2) h->prof.clear(); }
     else if (n == "debug_taps") h->debug = value != 0;
     else if (n == "stage_mask") {              // timing experiments only: run a subset of the stages

@@ -159,6 +159,7 @@ static constexpr int kRingBytes = 225 * 1024;   // pipeline ring (stand-alone ke
 // 2/4 CTAs is *slower* than unicast at every Pi-0 shape (the CTAs of a cluster advance in lock-step and
 // each SM still ingests the full tile), so it is off by default; the knob stays for experiments.
 static int g_cluster_max = 1;
+static constexpr int kTargetCtas = 148;   // one CTA per SM of a B200
 void gemm_set_cluster_max(int c) { g_cluster_max = c < 1 ? 1 : (c > 8 ? 8 : c); }
 
 static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out) {
@@ -197,6 +198,19 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
         if (!plan_fits(bn, nt, pl.kb_per_split, epi, &stages, &smem)) return pl;
     } else if (t16 <= 256) {
         bn = t16; nt = 1; gy = 1;
+        // A GEMM whose epilogue needs complete sums cannot split K; when its weight tiles alone
+        // leave most SMs idle, split the *tokens* across CTAs instead: every CTA then ingests
+        // (128 + bn) rows per k-block instead of (128 + T), and ~all SMs pull operands in parallel
+        // (measured: the per-SM operand ingest rate, not HBM, bounds these small-N GEMMs).
+        const int gx = Nw / kBlockM;
+        if (epi != EPI_PARTIAL && gx * 2 <= kTargetCtas && t16 >= 64) {
+            int chunks = kTargetCtas / gx;
+            if (chunks > t16 / 32) chunks = t16 / 32;            // keep at least 32 tokens per CTA
+            if (chunks > 1) {
+                bn = ((T + chunks - 1) / chunks + 15) / 16 * 16;
+                gy = (T + bn - 1) / bn;
+            }
+        }
         if (!plan_fits(bn, nt, pl.kb_per_split, epi, &stages, &smem)) return pl;
     } else {
         const int chunks = (t16 + 255) / 256;
