@@ -1,6 +1,7 @@
 // Attention kernels of the Pi-0 path.
 //
-//  * attn_mma_kernel<HD_PAD, GEMMA>: "full-row" attention for the two many-query cases
+//  * attn_mma_kernel<HD_PAD, BM, GEMMA>: "full-row" attention, BM query rows per CTA (16 at batch 1,
+//    32/64 for batched episodes), for the many-query cases
 //      - SigLIP MHA, 16 heads x 256 tokens x head_dim 72 (siglip.py:133-152), no mask;
 //      - Gemma joint-attention prefill, 8 query heads sharing one KV head (MQA), 276 query rows
 //        x 277 keys x head_dim 256 with tanh soft-clamp and additive block mask
@@ -8,9 +9,9 @@
 //    The tiles are tiny (<= 64 x 320 logits), so they run on warp-level mma.sync (bf16, fp32
 //    accumulate) with ldmatrix-fed fragments; the whole logit row is kept in shared memory so
 //    the softmax is the reference's exact two-pass fp32 softmax over bf16-rounded logits.
-//  * attn_fewq_kernel: 1 (proprio) or 4 (action) query rows per sample over the KV cache
-//    (joint_model.py:164-170 "append_non_active"): a bandwidth kernel, coalesced 16-byte K
-//    loads + warp-shuffle dot products, coalesced V accumulation.
+//  * few-query mode of the same kernel: 1 (proprio) or 4 (action) query rows per sample over the
+//    KV cache (joint_model.py:164-170 "append_non_active"); the (head, query) pairs of a sample
+//    form the tile rows, so the sample's single K/V head is read once for all 8 query heads.
 //
 // Rounding points: QK^T -> bf16; every scale / tanh / mask op
 // -> bf16; softmax in fp32 -> bf16; PV -> bf16.  Divisions by Python scalars are done as the
@@ -20,15 +21,13 @@
 
 namespace blurr {
 
-template <int HD_PAD, bool GEMMA>
+template <int HD_PAD, int BM, bool GEMMA>
 __global__ void __launch_bounds__(kAttnThreads) attn_mma_kernel(const AttnMmaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
     pdl_wait();
     pdl_trigger();
-    attn_mma_body<HD_PAD, GEMMA>(a, smem_attn, blockIdx.x, blockIdx.y, blockIdx.z);
+    attn_mma_body<HD_PAD, BM, GEMMA>(a, smem_attn, blockIdx.x, blockIdx.y, blockIdx.z);
 }
-
-static constexpr int kAttnBM = kAttnTileRows;
 
 AttnMmaArgs make_siglip_attn_args(const bf16* qkv, int ld_qkv, int seq, int n_heads, int hidden, bf16* out,
                                   int ld_out) {
@@ -71,55 +70,56 @@ AttnMmaArgs make_fewq_attn_args(const JointAttnArgs& j) {
 
 static constexpr size_t kAttnSmemMax = 215 * 1024;
 
+template <int HD_PAD, int BM, bool GEMMA>
+static cudaError_t launch_attn(cudaStream_t stream, const AttnMmaArgs& a, int rows, int heads, int batch) {
+    const size_t smem = attn_smem_bytes<HD_PAD, BM>(a.n_keys);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<HD_PAD, BM, GEMMA>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttnSmemMax));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (smem > kAttnSmemMax) return cudaErrorInvalidValue;
+    dim3 grid((rows + BM - 1) / BM, heads, batch);
+    return launch_kernel(attn_mma_kernel<HD_PAD, BM, GEMMA>, grid, dim3(kAttnThreads), smem, stream, a);
+}
+
+// rows per tile: 16 while that already gives every SM a couple of tiles, larger tiles beyond
+int attn_tile_rows(int rows, int heads, int batch, int max_rows) {
+    const long tiles16 = static_cast<long>((rows + 15) / 16) * heads * batch;
+    if (tiles16 <= 2 * 148 || max_rows <= 16) return 16;
+    const long tiles32 = static_cast<long>((rows + 31) / 32) * heads * batch;
+    if (tiles32 <= 4 * 148 || max_rows <= 32) return 32;
+    return 64;
+}
+
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
                                     int n_heads, int hidden, bf16* out, int ld_out) {
     const int hd = hidden / n_heads;
     if (hd > 80 || seq > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
     AttnMmaArgs a = make_siglip_attn_args(qkv, ld_qkv, seq, n_heads, hidden, out, ld_out);
-    const size_t smem = attn_smem_bytes<80>(seq);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<80, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttnSmemMax));
-        if (e != cudaSuccess) return e;
-        attr = true;
+    switch (attn_tile_rows(seq, n_heads, batch, 64)) {
+        case 16: return launch_attn<80, 16, false>(stream, a, seq, n_heads, batch);
+        case 32: return launch_attn<80, 32, false>(stream, a, seq, n_heads, batch);
+        default: return launch_attn<80, 64, false>(stream, a, seq, n_heads, batch);
     }
-    if (smem > kAttnSmemMax) return cudaErrorInvalidValue;
-    dim3 grid((seq + kAttnBM - 1) / kAttnBM, n_heads, batch);
-    return launch_kernel(attn_mma_kernel<80, false>, grid, dim3(kAttnThreads), smem, stream, a);
 }
 
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& j) {
     if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
     AttnMmaArgs a = make_prefill_attn_args(j);
-    const size_t smem = attn_smem_bytes<256>(j.n_keys);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<256, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttnSmemMax));
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
-    if (smem > kAttnSmemMax) return cudaErrorInvalidValue;
-    dim3 grid((j.q_per_sample + kAttnBM - 1) / kAttnBM, j.n_heads, j.batch);
-    return launch_kernel(attn_mma_kernel<256, true>, grid, dim3(kAttnThreads), smem, stream, a);
+    if (attn_tile_rows(j.q_per_sample, j.n_heads, j.batch, 32) == 16)
+        return launch_attn<256, 16, true>(stream, a, j.q_per_sample, j.n_heads, j.batch);
+    return launch_attn<256, 32, true>(stream, a, j.q_per_sample, j.n_heads, j.batch);
 }
 
 cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& j) {
     if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
     AttnMmaArgs a = make_fewq_attn_args(j);
-    const size_t smem = attn_smem_bytes<256>(j.n_keys);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<256, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAttnSmemMax));
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
-    if (smem > kAttnSmemMax) return cudaErrorInvalidValue;
     const int pairs = j.n_heads * j.q_per_sample;
-    dim3 grid((pairs + kAttnBM - 1) / kAttnBM, 1, j.batch);
-    return launch_kernel(attn_mma_kernel<256, true>, grid, dim3(kAttnThreads), smem, stream, a);
+    if (attn_tile_rows(pairs, 1, j.batch, 32) == 16) return launch_attn<256, 16, true>(stream, a, pairs, 1, j.batch);
+    return launch_attn<256, 32, true>(stream, a, pairs, 1, j.batch);
 }
 
 }  // namespace blurr

@@ -256,13 +256,15 @@ __device__ __forceinline__ void load_rows_async(bf16* dst, const bf16* src, int 
 // (output).  All K blocks are requested at once (one cp.async group per 64-key block) and consumed
 // as they land; the V blocks are requested into the same buffers as soon as the logits are done, so
 // their latency hides behind the softmax.
-template <int HD_PAD, bool GEMMA>
+template <int HD_PAD, int BM, bool GEMMA>
 __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* smem_attn, const int qt, const int h,
                                               const int b) {
-    constexpr int BM = 16;
-    constexpr int WC = kAttnThreads / 32;       // column groups (all warps share the 16 rows)
-    constexpr int KPW = kBK / WC;               // keys per warp per block (16)
-    constexpr int NT_S = KPW / 8;               // logit n-tiles per warp per block (2)
+    // BM query rows per tile: 16 at batch 1 (most tiles, least latency), 32/64 for batched episodes
+    // (K/V of a head are re-read once per tile, so larger tiles cut the L2 -> SM traffic)
+    constexpr int WR = BM / 16;                 // row groups
+    constexpr int WC = (kAttnThreads / 32) / WR;   // column groups
+    constexpr int KPW = kBK / WC;               // keys per warp per block
+    constexpr int NT_S = KPW / 8;               // logit n-tiles per warp per block
     constexpr int NT_ALL = HD_PAD / 8;          // output n-tiles over the head dim
     constexpr int NT_PV = (NT_ALL + WC - 1) / WC;
     constexpr int NP_PV = (NT_PV + 1) / 2;
@@ -276,7 +278,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     bf16* Ls = KVs + nkb * kBK * LDS;           // [BM][ldl]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wc = warp;
+    const int wr = warp % WR, wc = warp / WR;
     const int q_row0 = qt * BM;
 
     const bf16* qbase = a.q + static_cast<size_t>(b) * a.q_per_sample * a.ldq + a.q_col0 + h * a.head_stride_q;
@@ -318,7 +320,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
 #pragma unroll
         for (int kk = 0; kk < HD_PAD / 16; ++kk) {
             uint32_t af[4];
-            ldmatrix_x4(af, smem_u32(Qs + (lane & 15) * LDS + kk * 16 + (lane >> 4) * 8));
+            ldmatrix_x4(af, smem_u32(Qs + (wr * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
             if (NT_S == 1) {
                 // one 8-key n-tile per warp: matrices (keys, dims k0..7) and (keys, dims k8..15)
                 uint32_t bfr[2];
@@ -342,7 +344,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
         for (int nt = 0; nt < NT_S; ++nt) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int r = (lane >> 2) + half * 8;
+                const int r = wr * 16 + (lane >> 2) + half * 8;
                 const int kcol = kb * kBK + wc * KPW + nt * 8 + (lane & 3) * 2;
                 float s0 = bf16_round(acc[nt][half * 2 + 0]);
                 float s1 = bf16_round(acc[nt][half * 2 + 1]);
@@ -381,8 +383,8 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     }
 
     // ---------------- softmax: fp32 over bf16 logits, result bf16 in place ----------------
-    for (int rr = 0; rr < BM / WC; ++rr) {
-        bf16* lrow = Ls + (warp * (BM / WC) + rr) * ldl;
+    for (int rr = 0; rr < BM / 8; ++rr) {
+        bf16* lrow = Ls + (warp * (BM / 8) + rr) * ldl;
         constexpr int PER_LANE = kAttnMaxBlocks * kBK / 32;     // 10 logits per lane
         float x[PER_LANE];
         float m = -INFINITY;
@@ -423,7 +425,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
 #pragma unroll
         for (int kk = 0; kk < kBK / 16; ++kk) {
             uint32_t af[4];
-            ldmatrix_x4(af, smem_u32(Ls + (lane & 15) * ldl + kb * kBK + kk * 16 + (lane >> 4) * 8));
+            ldmatrix_x4(af, smem_u32(Ls + (wr * 16 + (lane & 15)) * ldl + kb * kBK + kk * 16 + (lane >> 4) * 8));
 #pragma unroll
             for (int np = 0; np < NP_PV; ++np) {
                 if ((nt0 + np * 2) >= NT_ALL) continue;          // warp past the head dim
@@ -445,7 +447,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     for (int nt = 0; nt < NT_PV; ++nt) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int r = q_row0 + (lane >> 2) + half * 8;
+            const int r = q_row0 + wr * 16 + (lane >> 2) + half * 8;
             const int dim = (nt0 + nt) * 8 + (lane & 3) * 2;
             if (r < n_rows_valid && dim < a.hd) {
                 bf16* dst = (a.mqa_nq > 0)
@@ -458,15 +460,15 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     attn_bar_sync();   // shared memory is reused by the caller's next work item
 }
 
-template <int HD_PAD>
+template <int HD_PAD, int BM>
 inline size_t attn_smem_bytes(int n_keys) {
-    constexpr int WC = kAttnThreads / 32;
+    constexpr int WC = (kAttnThreads / 32) / (BM / 16);
     constexpr int NT_PV = (HD_PAD / 8 + WC - 1) / WC;
     constexpr int NP_PV = (NT_PV + 1) / 2;
     constexpr int LDS_MIN = WC * NP_PV * 16 > HD_PAD ? WC * NP_PV * 16 : HD_PAD;
     constexpr int LDS = LDS_MIN + 8;
     const int nkb = (n_keys + kBK - 1) / kBK;
-    return static_cast<size_t>(16 + nkb * kBK) * LDS * 2 + static_cast<size_t>(16) * (nkb * kBK + 8) * 2;
+    return static_cast<size_t>(BM + nkb * kBK) * LDS * 2 + static_cast<size_t>(BM) * (nkb * kBK + 8) * 2;
 }
 
 // ===========================================================================

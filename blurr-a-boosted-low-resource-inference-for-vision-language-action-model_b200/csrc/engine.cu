@@ -48,7 +48,7 @@ __global__ void repack_rows_kernel(const bf16* __restrict__ src, int rows, int c
     const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx - static_cast<size_t>(r) * cols);
     int dr;
     if (mode == MAP_OFFSET) dr = r + row_off;
-    else dr = (r / 64) * 128 + (mode == MAP_UP ? 64 : 0) + (r % 64);
+    else dr = 2 * r + (mode == MAP_UP ? 1 : 0);       // gate_j, up_j alternate: the GeGLU epilogue pairs adjacent rows
     size_t di;
     if (dst_ld > 0) di = static_cast<size_t>(dr) * dst_ld + c;
     else di = ((static_cast<size_t>(dr / 128) * kb_total + c / 64) * 128 + dr % 128) * 64 + c % 64;
@@ -1249,6 +1249,8 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     if (!name) return fail(BLURR_ERR_INVALID, "set_global_option: null name");
     const std::string n(name);
     if (n == "gemm_cluster_max") gemm_set_cluster_max(static_cast<int>(value));
+    else if (n == "gemm_use_2cta") gemm_set_use_2cta(static_cast<int>(value));
+    else if (n == "gemm_persistent") gemm_set_persistent(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
     else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
     return 0;

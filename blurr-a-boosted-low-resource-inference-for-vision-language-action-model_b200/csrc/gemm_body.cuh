@@ -33,6 +33,53 @@ struct GemmPipe {
 // Set (to 1 + role) when a pipeline wait expired; read by gemm_take_timeout_flag().
 static __device__ int g_gemm_timeout_flag = 0;
 
+// Epilogue phase 2: the [token][128] tile staged in shared memory -> global memory with 16-byte
+// row-wise stores (all 256 threads).
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, uint8_t* smem, const int bx, const int bz,
+                                                    const int n0, const int t0) {
+    {
+        const int ntok = p.nt * p.bn;
+        if (EPI == EPI_PARTIAL) {
+            const float4* tile = reinterpret_cast<const float4*>(smem);
+            float* dst = p.partial + static_cast<size_t>(bz) * p.T * p.Nw;
+            for (int idx = threadIdx.x; idx < ntok * 32; idx += kGemmThreads) {
+                const int t = idx >> 5, ch = idx & 31;
+                if (t0 + t < p.T)
+                    *reinterpret_cast<float4*>(dst + static_cast<size_t>(t0 + t) * p.Nw + n0 + ch * 4) =
+                        tile[t * 32 + ch];
+            }
+        } else if (EPI == EPI_GEGLU) {
+            // weight rows alternate gate_j, up_j: 16 consecutive tile columns give 8 outputs
+            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
+            for (int idx = threadIdx.x; idx < ntok * 8; idx += kGemmThreads) {
+                const int t = idx >> 3, ch = idx & 7;
+                if (t0 + t >= p.T) continue;
+                const bf16x8 lo = tile[t * 16 + 2 * ch];
+                const bf16x8 hi = tile[t * 16 + 2 * ch + 1];
+                bf16x8 o;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float2 a0 = unpack_bf16x2(lo.u[2 * j]), a1 = unpack_bf16x2(lo.u[2 * j + 1]);
+                    const float2 b0 = unpack_bf16x2(hi.u[2 * j]), b1 = unpack_bf16x2(hi.u[2 * j + 1]);
+                    o.u[j] = pack_bf16x2(bf16_round(gelu_tanh_f32(a0.x)) * a0.y, bf16_round(gelu_tanh_f32(a1.x)) * a1.y);
+                    o.u[2 + j] = pack_bf16x2(bf16_round(gelu_tanh_f32(b0.x)) * b0.y, bf16_round(gelu_tanh_f32(b1.x)) * b1.y);
+                }
+                *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + bx * (kBlockM / 2) +
+                                           ch * 8) = o;
+            }
+        } else {
+            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
+            for (int idx = threadIdx.x; idx < ntok * 16; idx += kGemmThreads) {
+                const int t = idx >> 4, ch = idx & 15;
+                if (t0 + t < p.T)
+                    *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + n0 + ch * 8) =
+                        tile[t * 16 + ch];
+            }
+        }
+    }
+}
+
 // One 128-row weight tile x (nt x bn tokens) x one split-K slice.  Called by all 256 threads.
 template <int EPI>
 __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_x,
@@ -146,54 +193,261 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
     }
     __syncthreads();
 
-    // ---- epilogue phase 2: row-wise vector stores (all 256 threads) ----
-    {
-        const int ntok = p.nt * p.bn;
-        if (EPI == EPI_PARTIAL) {
-            const float4* tile = reinterpret_cast<const float4*>(smem);
-            float* dst = p.partial + static_cast<size_t>(bz) * p.T * p.Nw;
-            for (int idx = threadIdx.x; idx < ntok * 32; idx += kGemmThreads) {
-                const int t = idx >> 5, ch = idx & 31;
-                if (t0 + t < p.T)
-                    *reinterpret_cast<float4*>(dst + static_cast<size_t>(t0 + t) * p.Nw + n0 + ch * 4) =
-                        tile[t * 32 + ch];
-            }
-        } else if (EPI == EPI_GEGLU) {
-            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
-            for (int idx = threadIdx.x; idx < ntok * 8; idx += kGemmThreads) {
-                const int t = idx >> 3, ch = idx & 7;
-                if (t0 + t >= p.T) continue;
-                const bf16x8 g = tile[t * 16 + ch];
-                const bf16x8 u = tile[t * 16 + 8 + ch];
-                bf16x8 o;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 gf = unpack_bf16x2(g.u[j]);
-                    const float2 uf = unpack_bf16x2(u.u[j]);
-                    const float a = bf16_round(gelu_tanh_f32(gf.x)) * uf.x;
-                    const float b = bf16_round(gelu_tanh_f32(gf.y)) * uf.y;
-                    o.u[j] = pack_bf16x2(a, b);
+    gemm_epilogue_store<EPI>(p, smem, bx, bz, n0, t0);
+    __syncthreads();     // the tile aliases the ring: it must be drained before the next tile's TMA writes
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant: the CTA walks tiles `first, first + stride, ...` of the (gx, gy, gz) tile grid.
+// The three roles run decoupled across tile boundaries: the TMA producer keeps filling free stages
+// with the NEXT tile's operands while the epilogue of the current tile drains TMEM, so HBM stays busy
+// through the prologue / epilogue bubbles that a one-tile-per-CTA launch pays once per wave (measured:
+// 3.4 TB/s instead of ~6 TB/s on the gate/up shape at any token count).  The epilogue goes TMEM ->
+// registers -> global memory directly (no shared-memory tile), so nothing ever aliases the ring.
+template <int EPI>
+__device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_x,
+                                                const GemmShared& sh, uint64_t* tmem_empty_bar, const int gx,
+                                                const int gy, const int gz, const int first, const int stride) {
+    uint8_t* smem = sh.ring;
+    const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tmem_base = sh.tmem_base;
+    const int n_tiles = gx * gy * gz;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
+            const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
+            uint32_t empty_bits = 0;
+            int s = 0;
+            for (int tile = first; tile < n_tiles; tile += stride) {
+                const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
+                const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
+                const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    if (!mbar_wait(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) {
+                        atomicExch(&g_gemm_timeout_flag, 1);
+                        return;
+                    }
+                    empty_bits ^= (1u << s);
+                    uint8_t* stg = smem + s * stage_bytes;
+                    mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(stage_bytes));
+                    if (p.w_packed)
+                        tma_load_2d_hint(stg, tmap_w, &sh.full_bar[s], 0, (bx * p.kb_total + kb) * kBlockM, pol_w);
+                    else
+                        tma_load_2d_hint(stg, tmap_w, &sh.full_bar[s], kb * kBlockK, n0, pol_w);
+                    for (int c = 0; c < p.nt; ++c)
+                        tma_load_2d_hint(stg + kTileABytes + c * p.bn * (kBlockK * 2), tmap_x, &sh.full_bar[s],
+                                         kb * kBlockK, t0 + c * p.bn, pol_x);
+                    s = (s + 1 == p.stages) ? 0 : s + 1;
                 }
-                *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + bx * (kBlockM / 2) +
-                                           ch * 8) = o;
-            }
-        } else {
-            const bf16x8* tile = reinterpret_cast<const bf16x8*>(smem);
-            for (int idx = threadIdx.x; idx < ntok * 16; idx += kGemmThreads) {
-                const int t = idx >> 4, ch = idx & 15;
-                if (t0 + t < p.T)
-                    *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + n0 + ch * 8) =
-                        tile[t * 16 + ch];
             }
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
+            uint32_t full_bits = 0, tmem_empty_bit = 0;
+            int s = 0;
+            for (int tile = first; tile < n_tiles; tile += stride) {
+                const int bz = tile / (gx * gy);
+                const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                // the epilogue must have drained the previous tile's accumulators
+                if (!mbar_wait(tmem_empty_bar, tmem_empty_bit ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 4); return; }
+                tmem_empty_bit ^= 1u;
+                tcgen05_fence_after();
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    if (!mbar_wait(&sh.full_bar[s], (full_bits >> s) & 1u)) { atomicExch(&g_gemm_timeout_flag, 2); return; }
+                    full_bits ^= (1u << s);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                    const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                    for (int c = 0; c < p.nt; ++c) {
+                        const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes + c * p.bn * (kBlockK * 2));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_ss(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                         (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&sh.empty_bar[s]);
+                    s = (s + 1 == p.stages) ? 0 : s + 1;
+                }
+                umma_commit(sh.tmem_full_bar);
+            }
+        }
+    } else if (warp >= 4) {
+        const int w4 = warp - 4;               // TMEM lane quarter this warp may access
+        const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
+        const int ntok = p.nt * p.bn;
+        uint32_t tmem_bit = 0;
+        for (int tile = first; tile < n_tiles; tile += stride) {
+            const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
+            const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
+            const bool ready = mbar_wait(sh.tmem_full_bar, tmem_bit);
+            tmem_bit ^= 1u;
+            if (!ready) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 3); return; }
+            tcgen05_fence_after();
+            float bias = 0.f;
+            if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
+            for (int g = 0; g < ntok / 16; ++g) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+                tmem_ld_wait();
+                const int tb = t0 + g * 16;
+                if (EPI == EPI_PARTIAL) {
+                    float* dst = p.partial + (static_cast<size_t>(bz) * p.T + tb) * p.Nw + n0 + nl;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (tb + i < p.T) dst[static_cast<size_t>(i) * p.Nw] = __uint_as_float(r[i]);
+                } else if (EPI == EPI_GEGLU) {
+                    // rows alternate gate_j (even lane) / up_j (odd lane): pair them with one shuffle
+                    bf16* dst = p.out + static_cast<size_t>(tb) * p.ldo + bx * (kBlockM / 2) + (nl >> 1);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float v = bf16_round(__uint_as_float(r[i]));
+                        const float up = __shfl_down_sync(0xffffffffu, v, 1);
+                        if ((lane & 1) == 0 && tb + i < p.T)
+                            dst[static_cast<size_t>(i) * p.ldo] = f2bf(bf16_round(gelu_tanh_f32(v)) * up);
+                    }
+                } else {
+                    bf16* dst = p.out + static_cast<size_t>(tb) * p.ldo + n0 + nl;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = bf16_round(__uint_as_float(r[i]) + bias);
+                        if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                        if (tb + i < p.T) dst[static_cast<size_t>(i) * p.ldo] = f2bf(v);
+                    }
+                }
+            }
+            // accumulators are in registers / memory: hand TMEM back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+        }
     }
-    __syncthreads();     // the tile aliases the ring: it must be drained before the next tile's TMA writes
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2).  The pair owns 256 weight rows (UMMA M = 256: this CTA's
+// 128 rows land in its own TMEM) and shares the token operand: each CTA loads only half of every
+// token chunk and the tensor cores read the other half from the peer SM's shared memory, so the
+// per-SM operand ingest per k-block drops from (128 + tokens) to (128 + tokens/2) rows — the quantity
+// that bounds these GEMMs at T = 256..276 (measured ~48 B/clk/SM).  TMA loads of both CTAs complete
+// on the leader's (even CTA) full barrier; the leader issues the MMAs and its commits arrive on the
+// barriers of both CTAs.
+template <int EPI>
+__device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_xh,
+                                               const GemmShared& sh, GemmPipe& st, const int bx, const int by,
+                                               const int bz, const uint32_t crank) {
+    uint8_t* smem = sh.ring;
+    const int half = p.bn / 2;                                       // token rows of a chunk held by one CTA
+    const int stage_bytes = kTileABytes + p.nt * half * (kBlockK * 2);   // per CTA
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tmem_base = sh.tmem_base;
+    const bool leader = (crank == 0);
+
+    const int n0 = bx * kBlockM;
+    const int t0 = by * p.nt * p.bn;
+    const int kb0 = bz * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    const int nkb = kb1 - kb0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol_w = make_policy_evict_first();
+            const uint64_t pol_x = make_policy_evict_last();
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                if (!mbar_wait(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
+                    atomicExch(&g_gemm_timeout_flag, 1);
+                    break;
+                }
+                st.empty_bits ^= (1u << s);
+                uint8_t* stg = smem + s * stage_bytes;
+                if (leader) mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+                const uint32_t bar = map_to_cta(&sh.full_bar[s], 0u);       // the leader's barrier
+                const int kcoord = (kb0 + i) * kBlockK;
+                if (p.w_packed)
+                    tma_load_2d_2sm_hint(stg, tmap_w, bar, 0, (bx * p.kb_total + kb0 + i) * kBlockM, pol_w);
+                else
+                    tma_load_2d_2sm_hint(stg, tmap_w, bar, kcoord, n0, pol_w);
+                for (int c = 0; c < p.nt; ++c)
+                    tma_load_2d_2sm_hint(stg + kTileABytes + c * half * (kBlockK * 2), tmap_xh, bar, kcoord,
+                                         t0 + c * p.bn + static_cast<int>(crank) * half, pol_x);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, static_cast<uint32_t>(p.bn));
+            bool ok = true;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                if (!mbar_wait(&sh.full_bar[s], (st.full_bits >> s) & 1u)) {
+                    atomicExch(&g_gemm_timeout_flag, 2);
+                    ok = false;
+                    break;
+                }
+                st.full_bits ^= (1u << s);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                for (int c = 0; c < p.nt; ++c) {
+                    const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes + c * half * (kBlockK * 2));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16_ss_2sm(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                         (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit_2sm(&sh.empty_bar[s]);      // frees stage s in both CTAs
+            }
+            if (ok) umma_commit_2sm(sh.tmem_full_bar);  // both epilogues may start
+        }
+    } else if (warp >= 4) {
+        const int w4 = warp - 4;
+        const int nl = w4 * 32 + lane;
+        const bool acc_ready = mbar_wait(sh.tmem_full_bar, st.tmem_bit);
+        st.tmem_bit ^= 1u;
+        if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
+        tcgen05_fence_after();
+        float bias = 0.f;
+        if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
+        const int ntok = p.nt * p.bn;
+        for (int g = 0; acc_ready && g < ntok / 16; ++g) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+            tmem_ld_wait();
+            if (EPI == EPI_PARTIAL) {
+                float* tile = reinterpret_cast<float*>(smem);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tile[(g * 16 + i) * kBlockM + nl] = __uint_as_float(r[i]);
+            } else {
+                bf16* tile = reinterpret_cast<bf16*>(smem);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v = bf16_round(__uint_as_float(r[i]) + bias);
+                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    // The epilogue tile aliases the ring: the peer's tensor cores may still be reading THIS CTA's B
+    // half until the pair's accumulators are complete.  Warps 4..7 only write after tmem_full, which
+    // the leader commits after every MMA of the tile — so the ring is free by then in both CTAs.
+    __syncthreads();
+    gemm_epilogue_store<EPI>(p, smem, bx, bz, n0, t0);
+    __syncthreads();
 }
 
 // Ring + barrier carve-up of a dynamic shared-memory block and one-time initialisation.
 // Returns the shared view; `smem_raw` needs ring_bytes + 1024 (alignment) + 256 (barriers).
 __device__ __forceinline__ GemmShared gemm_setup_shared(uint8_t* smem_raw, int ring_bytes, int empty_count,
-                                                        uint32_t tmem_cols, uint32_t* tmem_slot_out) {
+                                                        uint32_t tmem_cols, uint32_t* tmem_slot_out,
+                                                        bool two_sm = false) {
     GemmShared sh;
     sh.ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     sh.full_bar = reinterpret_cast<uint64_t*>(sh.ring + ring_bytes);
@@ -209,9 +463,10 @@ __device__ __forceinline__ GemmShared gemm_setup_shared(uint8_t* smem_raw, int r
         mbar_init(sh.tmem_full_bar, 1);
         fence_barrier_init();
     }
+    if (two_sm) cluster_sync_all();       // the pair allocates TMEM collectively: both CTAs are here
     if (warp == 2) {
-        tmem_alloc(tmem_slot, tmem_cols);
-        tmem_relinquish();
+        if (two_sm) { tmem_alloc_2sm(tmem_slot, tmem_cols); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
     }
     tcgen05_fence_before();
     __syncthreads();

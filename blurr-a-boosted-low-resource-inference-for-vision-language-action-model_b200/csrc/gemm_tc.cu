@@ -55,6 +55,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
+// Persistent 1-CTA kernel: at most one CTA per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                const GemmDev p, const int gx, const int gy, const int gz) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp == 0 && elect_one_sync()) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+    }
+    const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
+    uint32_t tmem_base;
+    GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes, 1, static_cast<uint32_t>(p.tmem_cols), &tmem_base);
+    uint64_t* tmem_empty_bar = sh.tmem_full_bar + 2;      // after tmem_full_bar and the TMEM slot word
+    if (threadIdx.x == 0) {
+        mbar_init(tmem_empty_bar, 4);                      // one arrive per epilogue warp
+        fence_barrier_init();
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    gemm_persistent<EPI>(p, &tmap_w, &tmap_x, sh, tmem_empty_bar, gx, gy, gz, blockIdx.x, gridDim.x);
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
+// CTA-pair (cta_group::2) variant: launched as clusters of 2 along the weight-tile dimension.
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_xh,
+                const GemmDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp == 0 && elect_one_sync()) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_xh);
+    }
+    const int stage_bytes = kTileABytes + p.nt * (p.bn / 2) * (kBlockK * 2);
+    uint32_t tmem_base;
+    GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes, 1, static_cast<uint32_t>(p.tmem_cols),
+                                      &tmem_base, true);
+    cluster_sync_all();                         // both CTAs' barriers exist before any remote signal
+    const uint32_t crank = cluster_ctarank();
+    pdl_wait();
+    pdl_trigger();
+    GemmPipe st;
+    gemm_tile_2cta<EPI>(p, &tmap_w, &tmap_xh, sh, st, blockIdx.x, blockIdx.y, blockIdx.z, crank);
+    tcgen05_fence_before();
+    cluster_sync_all();                         // the peer is done with this CTA's smem / TMEM / barriers
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
 // ---------------------------------------------------------------------------
 // host side: tensor-map cache + launcher
 // ---------------------------------------------------------------------------
@@ -162,8 +215,21 @@ static int g_cluster_max = 1;
 static constexpr int kTargetCtas = 148;   // one CTA per SM of a B200
 void gemm_set_cluster_max(int c) { g_cluster_max = c < 1 ? 1 : (c > 8 ? 8 : c); }
 
-static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out) {
-    const int stage_bytes = kTileABytes + nt * bn * kBlockK * 2;
+// Measured on B200 (round 1): CTA pairs are correct but not faster at batch 1 (61 vs 59 us on the gate/up
+// shape) — the loss there is per-tile fixed cost, which the persistent kernel removes; pairs help at
+// batch 64 (880 vs 818 TFLOP/s), so the knob stays.
+static int g_use_2cta = 0;
+void gemm_set_use_2cta(int on) { g_use_2cta = on ? 1 : 0; }
+// Persistent kernel: measured on B200 (round 1) it wins only while the epilogue is trivial (T = 16:
+// 33.5 vs 39.9 us on the gate/up shape); from T >= 64 its direct TMEM -> global epilogue (2-byte stores,
+// 4 warps) stalls the next tile's MMAs longer than the bubbles it removes (GeGLU, T = 276: 95 vs 59 us),
+// so it is used for few-token GEMMs only.
+static int g_persistent = 1;
+static constexpr int kPersistentMaxTokens = 32;
+void gemm_set_persistent(int on) { g_persistent = on ? 1 : 0; }
+
+static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out, int b_div = 1) {
+    const int stage_bytes = kTileABytes + nt * (bn / b_div) * kBlockK * 2;
     const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
     const int avail = kRingBytes;
     int stages = avail / stage_bytes;
@@ -238,8 +304,49 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
         }
     }
     pl.slice_rows = nt * bn / pl.cluster;
+    // CTA pairs (cta_group::2): consecutive weight tiles share the token operand, each CTA loads half
+    pl.two_cta = 0;
+    if (g_use_2cta && pl.cluster == 1 && pl.grid_x % 2 == 0 && nt * bn >= 64 && bn % 16 == 0) {
+        int st2 = 0, sm2 = 0;
+        if (plan_fits(bn, nt, pl.kb_per_split, epi, &st2, &sm2, 2)) {
+            pl.two_cta = 1;
+            pl.stages = st2;
+            pl.smem_bytes = sm2;
+        }
+    }
     pl.valid = true;
     return pl;
+}
+
+template <int EPI>
+static cudaError_t launch_epip(cudaStream_t stream, const GemmPlan& pl, const CUtensorMap& tw, const CUtensorMap& tx,
+                               const GemmDev& d) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = pl.grid_x * pl.grid_y * pl.splitk;
+    const int ctas = tiles < kTargetCtas ? tiles : kTargetCtas;
+    return launch_kernel(gemm_tcp_kernel<EPI>, dim3(ctas), dim3(kGemmThreads), static_cast<size_t>(pl.smem_bytes), stream,
+                         tw, tx, d, pl.grid_x, pl.grid_y, pl.splitk);
+}
+
+template <int EPI>
+static cudaError_t launch_epi2(cudaStream_t stream, const GemmPlan& pl, const CUtensorMap& tw, const CUtensorMap& txh,
+                               const GemmDev& d) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(pl.grid_x, pl.grid_y, pl.splitk);
+    return launch_kernel_cluster(gemm_tc2_kernel<EPI>, grid, dim3(kGemmThreads), static_cast<size_t>(pl.smem_bytes),
+                                 stream, 2, tw, txh, d);
 }
 
 template <int EPI>
@@ -259,10 +366,12 @@ static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUt
 
 int gemm_make_step_op(const GemmCall& c, GemmDev* d, CUtensorMap* tmap_w, CUtensorMap* tmap_x, int* grid_x,
                       int* grid_y, std::string* err) {
-    const int saved = g_cluster_max;
+    const int saved = g_cluster_max, saved2 = g_use_2cta;
     g_cluster_max = 1;
+    g_use_2cta = 0;
     GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
     g_cluster_max = saved;
+    g_use_2cta = saved2;
     if (!pl.valid) { *err = "gemm_make_step_op: unsupported shape"; return -1; }
     if (c.epi != EPI_PARTIAL && pl.splitk != 1) { *err = "gemm_make_step_op: split-K needs EPI_PARTIAL"; return -1; }
     if (c.w_packed) {
@@ -306,6 +415,30 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
     d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed;
     cudaError_t e;
+    if (pl.two_cta) {
+        CUtensorMap txh;
+        if (get_tmap(c.X, c.T, c.K, c.ldx, pl.bn / 2, &txh, err)) return -1;
+        switch (c.epi) {
+            case EPI_STORE:   e = launch_epi2<EPI_STORE>(stream, pl, tw, txh, d); break;
+            case EPI_GELU:    e = launch_epi2<EPI_GELU>(stream, pl, tw, txh, d); break;
+            case EPI_GEGLU:   e = launch_epi2<EPI_GEGLU>(stream, pl, tw, txh, d); break;
+            case EPI_PARTIAL: e = launch_epi2<EPI_PARTIAL>(stream, pl, tw, txh, d); break;
+            default: *err = "gemm_launch: bad epilogue"; return -1;
+        }
+        if (e != cudaSuccess) { *err = std::string("gemm (2-CTA) launch failed: ") + cudaGetErrorString(e); return -1; }
+        return pl.splitk;
+    }
+    if (g_persistent && pl.cluster == 1 && pl.nt * pl.bn <= kPersistentMaxTokens && c.epi != EPI_GEGLU) {
+        switch (c.epi) {
+            case EPI_STORE:   e = launch_epip<EPI_STORE>(stream, pl, tw, tx, d); break;
+            case EPI_GELU:    e = launch_epip<EPI_GELU>(stream, pl, tw, tx, d); break;
+            case EPI_GEGLU:   e = launch_epip<EPI_GEGLU>(stream, pl, tw, tx, d); break;
+            case EPI_PARTIAL: e = launch_epip<EPI_PARTIAL>(stream, pl, tw, tx, d); break;
+            default: *err = "gemm_launch: bad epilogue"; return -1;
+        }
+        if (e != cudaSuccess) { *err = std::string("gemm (persistent) launch failed: ") + cudaGetErrorString(e); return -1; }
+        return pl.splitk;
+    }
     switch (c.epi) {
         case EPI_STORE:   e = launch_epi<EPI_STORE>(stream, pl, tw, tx, txs, d); break;
         case EPI_GELU:    e = launch_epi<EPI_GELU>(stream, pl, tw, tx, txs, d); break;

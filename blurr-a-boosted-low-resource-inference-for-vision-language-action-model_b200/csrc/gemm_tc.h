@@ -57,6 +57,7 @@ struct GemmPlan {
     bool valid;
     int bn, nt, stages, kb_total, kb_per_split, splitk, tmem_cols, smem_bytes, grid_x, grid_y;
     int cluster, slice_rows;
+    int two_cta;       // launched as CTA pairs (tcgen05 cta_group::2)
 };
 
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override);
@@ -79,6 +80,11 @@ inline size_t gemm_pack_weight_index(int row, int col, int K) {
     const int kb_total = (K + 63) / 64;
     return ((static_cast<size_t>(row / 128) * kb_total + col / 64) * 128 + row % 128) * 64 + col % 64;
 }
+
+// CTA pairs (tcgen05 cta_group::2) for GEMMs with an even number of weight tiles and >= 64 tokens.
+void gemm_set_use_2cta(int on);
+// Persistent one-CTA-per-SM kernel with a direct TMEM -> global epilogue (default) vs one tile per CTA.
+void gemm_set_persistent(int on);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
 void gemm_set_cluster_max(int c);

@@ -103,7 +103,8 @@ AttnMmaArgs make_siglip_attn_args(const bf16* qkv, int ld_qkv, int seq, int n_he
                                   int ld_out);
 AttnMmaArgs make_prefill_attn_args(const JointAttnArgs& a);
 AttnMmaArgs make_fewq_attn_args(const JointAttnArgs& a);
-static constexpr int kAttnTileRows = 16;     // query rows per attention work item
+static constexpr int kAttnTileRows = 16;     // query rows per attention work item of the step kernel
+int attn_tile_rows(int rows, int heads, int batch, int max_rows);   // tile rows the launchers pick
 // Few queries per sample (proprio: 1, action: 4): bandwidth kernel over the KV cache.
 cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& a);
 

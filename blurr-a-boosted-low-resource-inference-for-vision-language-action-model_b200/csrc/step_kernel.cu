@@ -42,7 +42,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned target) {
 
 template <int HD_PAD, bool GEMMA>
 __device__ __forceinline__ void attn_step_tile(const AttnMmaArgs& a, uint8_t* smem, int bx, int by, int bz) {
-    attn_mma_body<HD_PAD, GEMMA>(a, smem, bx, by, bz);
+    attn_mma_body<HD_PAD, kAttnTileRows, GEMMA>(a, smem, bx, by, bz);
 }
 
 __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepOp* __restrict__ ops, const int n_ops,

@@ -79,14 +79,14 @@ def test_gemm_gelu(T, N, K):
 
 @pytest.mark.parametrize("T,I,K", [(276, 16384, 2048), (4, 4096, 1024), (17, 128, 192)])
 def test_gemm_geglu(T, I, K):
-    """Weight rows interleaved 64 gate / 64 up per 128-row tile (engine repack); output
+    """Weight rows alternate gate_j, up_j (engine repack); output
     bf16(bf16(gelu(bf16(gate))) * bf16(up)) (paligemma/modules.py:93-95)."""
     Wg = _rand((I, K), 1.0 / math.sqrt(K), 9)
     Wu = _rand((I, K), 1.0 / math.sqrt(K), 10)
     X = _rand((T, K), 1.0, 11)
     Wi = torch.empty((2 * I, K), device=DEV, dtype=torch.bfloat16)
-    Wi.view(I // 64, 2, 64, K)[:, 0] = Wg.view(I // 64, 64, K)
-    Wi.view(I // 64, 2, 64, K)[:, 1] = Wu.view(I // 64, 64, K)
+    Wi[0::2] = Wg
+    Wi[1::2] = Wu
     got = op_gemm(Wi, X, capi.EPI_GEGLU)
     gate = (X.float() @ Wg.float().t()).to(torch.bfloat16)
     up = (X.float() @ Wu.float().t()).to(torch.bfloat16)

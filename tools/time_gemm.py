@@ -28,9 +28,10 @@ SHAPES = [  # name, N, K, T, epi, splitk
 ]
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 # weights: tile-packed (ldw = 0; values are random so no packing pass is needed) vs row-major (ldw = K)
-CASES = [(int(a), m) for a in (sys.argv[1:] or ["1", "2", "4"]) for m in ("packed", "rowmajor")]
-for cmax, LDW_MODE in CASES:
-    capi.check(lib.blurr_set_global_option(b"gemm_cluster_max", cmax))
+CASES = [(int(a), "packed") for a in (sys.argv[1:] or ["1", "0"])]
+for use2, LDW_MODE in CASES:
+    cmax = use2
+    capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", use2))
     for name, N, K, T, epi, S in SHAPES:
         LDW = 0 if LDW_MODE == "packed" else K
         nbuf = max(2, min(6, int(600e6 // (N * K * 2)) + 1))
@@ -58,5 +59,5 @@ for cmax, LDW_MODE in CASES:
         ms = statistics.fmean(s.elapsed_time(e) for s, e in pairs)
         gbs = N * K * 2 / ms / 1e6
         tf = 2.0 * N * K * T / ms / 1e9
-        print(f"cluster_max={cmax} {LDW_MODE:8s} {name:18s} T={T:5d} N={N:5d} K={K:5d}: {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s weights  {tf:7.1f} TFLOP/s", flush=True)
+        print(f"2cta={cmax} {LDW_MODE:8s} {name:18s} T={T:5d} N={N:5d} K={K:5d}: {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s weights  {tf:7.1f} TFLOP/s", flush=True)
         del Ws, X, out, part
