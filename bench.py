@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -90,6 +90,13 @@ class ClockSampler:
                 self.lines.append(line.strip())
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this call are reported."""
+        self.first = len(self.lines)
+
+    def count(self):
+        return len(self.lines) - getattr(self, "first", 0)
 
     def stop(self):
         if self.proc is None:
@@ -101,7 +108,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in self.lines[getattr(self, "first", 0):]:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -192,14 +199,15 @@ def run_ours(args):
     # ---------------- primary: device-resident inputs ----------------
     ring = make_ring(cfg, B, min(args.ring, max(K, 1)), dev, seed=1234 + rank)
     with torch.inference_mode():
+        sampler = ClockSampler(local)
+        sampler.start()                     # nvidia-smi needs a few 100 ms to come up: start before warm-up
         for i in range(W):
             r = ring[i % len(ring)]
             out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
         model._engine.check()
         launches_per_step = model.last_launch_count
-        sampler = ClockSampler(local)
-        sampler.start()
         barrier()
+        sampler.mark()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         evs[0].record()
         for i in range(K):
@@ -213,7 +221,18 @@ def run_ours(args):
         end = torch.cuda.Event(enable_timing=True)
         end.record()
         barrier()
+        # a short timed region ends before nvidia-smi has sampled it a few times: keep the same load
+        # running (untimed) until there are enough samples of the clocks under this workload
+        tail_steps, t_tail = 0, time.perf_counter()
+        while sampler.proc is not None and sampler.count() < 6 and time.perf_counter() - t_tail < 3.0:
+            r = ring[tail_steps % len(ring)]
+            model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+            tail_steps += 1
+            if tail_steps % 8 == 0:
+                torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
         clocks = sampler.stop()
+        clocks["untimed_tail_steps"] = tail_steps
         model._engine.check()
     total_ms = max_over_ranks(evs[0].elapsed_time(end))
     lat = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
@@ -312,6 +331,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
+    committed `ncu --set full` capture (profiles/ncu_gateup_traffic.json); None when there is none."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_gateup_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def dominant_kernel_roofline(dev, peaks):
     """The Gemma gate/up GEMM + GeGLU (32768 x 2048 weights, 276 tokens): 46 % of the step's bytes.
     Times the kernel through its C-ABI operator entry point on 4 rotating weight buffers (537 MB
@@ -350,7 +380,7 @@ def dominant_kernel_roofline(dev, peaks):
     achieved = alg_bytes / (ms / 1e3) / 1e9
     return {"bound": "hbm", "kernel": "gemm_tc_kernel<EPI_GEGLU> (Gemma gate/up, 276 tokens)",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "ms_min": min(times),
+            "traffic": ncu_traffic_bytes(), "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "ms_min": min(times),
             "note": "algorithmic bytes = the 32768x2048 bf16 weight tile stream; peak = " + peaks["source"] + " copy bandwidth"}
 
 

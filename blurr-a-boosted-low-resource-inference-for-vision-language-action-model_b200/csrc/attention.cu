@@ -24,14 +24,18 @@ namespace blurr {
 template <int HD_PAD, int BM, bool GEMMA>
 __global__ void __launch_bounds__(kAttnThreads) attn_mma_kernel(const AttnMmaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
+    trace_stamp(a.trace, 0);
+    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
-    pdl_trigger();
+    trace_stamp(a.trace, 1);
     attn_mma_body<HD_PAD, BM, GEMMA>(a, smem_attn, blockIdx.x, blockIdx.y, blockIdx.z);
+    trace_stamp(a.trace, 2);
 }
 
 AttnMmaArgs make_siglip_attn_args(const bf16* qkv, int ld_qkv, int seq, int n_heads, int hidden, bf16* out,
                                   int ld_out) {
     AttnMmaArgs a{};
+    a.trace = nullptr;
     const int hd = hidden / n_heads;           // 72
     a.q = qkv; a.ldq = ld_qkv; a.q_col0 = 0; a.q_per_sample = seq;
     a.k = qkv; a.ldk = ld_qkv; a.k_col0 = hidden; a.kv_per_sample = seq;
@@ -54,6 +58,7 @@ AttnMmaArgs make_prefill_attn_args(const JointAttnArgs& j) {
     a.scale = 0.f;
     a.mask = j.mask; a.mask_bstride = j.mask_bstride; a.mask_rstride = j.mask_rstride;
     a.q_row_offset = j.q_row_offset;
+    a.trace = j.trace;
     return a;
 }
 
@@ -95,10 +100,11 @@ int attn_tile_rows(int rows, int heads, int batch, int max_rows) {
 }
 
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
-                                    int n_heads, int hidden, bf16* out, int ld_out) {
+                                    int n_heads, int hidden, bf16* out, int ld_out, unsigned long long* trace) {
     const int hd = hidden / n_heads;
     if (hd > 80 || seq > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
     AttnMmaArgs a = make_siglip_attn_args(qkv, ld_qkv, seq, n_heads, hidden, out, ld_out);
+    a.trace = trace;
     switch (attn_tile_rows(seq, n_heads, batch, 64)) {
         case 16: return launch_attn<80, 16, false>(stream, a, seq, n_heads, batch);
         case 32: return launch_attn<80, 32, false>(stream, a, seq, n_heads, batch);

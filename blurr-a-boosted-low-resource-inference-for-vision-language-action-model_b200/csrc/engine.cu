@@ -171,6 +171,12 @@ struct blurr_pi0 {
     // small kernels do.  Kept as an option; results are bit-identical.
     bool use_step_kernel = false;
     bool profile = false;          // eager launches bracketed by CUDA events, per-kernel-label totals
+    // in-graph timeline: kernels stamp %globaltimer into trace_buf (launch.cuh); slots are handed out
+    // while the step is issued / captured, so every graph replay rewrites the same slots
+    bool trace = false;
+    unsigned long long* trace_buf = nullptr;       // [kTraceMax][4]
+    std::vector<std::string> trace_labels;
+    std::vector<int> trace_streams;
     struct ProfEntry { int count = 0; double ms = 0.0; };
     std::map<std::string, ProfEntry> prof;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending;
@@ -289,6 +295,7 @@ extern "C" void blurr_pi0_destroy(blurr_pi0_t* h) {
     if (h->s_act) cudaStreamDestroy(h->s_act);
     for (auto& kv : h->taps) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->trace_buf) cudaFree(h->trace_buf);
     gemm_forget_tensor_maps();
     delete h;
 }
@@ -402,8 +409,13 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
     h->ws2 = static_cast<float*>(dalloc(h, h->ws2_floats * 4));
     h->ws3 = static_cast<float*>(dalloc(h, h->ws2_floats * 4));
     {
-        bool ev_ok = cudaStreamCreateWithFlags(&h->s_prop, cudaStreamNonBlocking) == cudaSuccess &&
-                     cudaStreamCreateWithFlags(&h->s_act, cudaStreamNonBlocking) == cudaSuccess &&
+        // the expert streams run at the lowest priority: when SMs free up, pending CTAs of the main
+        // (SigLIP / VLM) stream are placed first, so a 148-CTA VLM GEMM is not split into two waves by
+        // an expert kernel that happened to be launched a moment earlier
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        bool ev_ok = cudaStreamCreateWithPriority(&h->s_prop, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+                     cudaStreamCreateWithPriority(&h->s_act, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
                      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
                      cudaEventCreateWithFlags(&h->ev_done_p, cudaEventDisableTiming) == cudaSuccess &&
                      cudaEventCreateWithFlags(&h->ev_done_a, cudaEventDisableTiming) == cudaSuccess;
@@ -619,10 +631,20 @@ extern "C" int blurr_pi0_finalize_weights(blurr_pi0_t* h) {
 // ---------------------------------------------------------------------------
 // the schedule
 // ---------------------------------------------------------------------------
+static constexpr int kTraceMax = 4096;
+
 struct Run {
     blurr_pi0* h;
     cudaStream_t st;
     int rc = 0;
+    unsigned long long* trace_slot(const char* what) {
+        if (!h->trace || rec || h->trace_buf == nullptr) return nullptr;
+        const size_t idx = h->trace_labels.size();
+        if (idx >= static_cast<size_t>(kTraceMax)) return nullptr;
+        h->trace_labels.push_back(label.empty() ? std::string(what) : label + ":" + what);
+        h->trace_streams.push_back(st == s_main ? 0 : (st == h->s_prop ? 1 : 2));
+        return h->trace_buf + idx * 4;
+    }
     StepProgram* rec = nullptr;      // non-null: record step-kernel ops instead of launching kernels
     int group = 0, group_items = 0;
 
@@ -710,6 +732,7 @@ struct Run {
         } else {
             char nm[96];
             snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", epi, T, L.Nw, L.K, c.splitk);
+            c.trace = trace_slot(nm);
             prof_begin(nm);
             s = gemm_launch(st, c, &err);
             prof_end();
@@ -729,7 +752,7 @@ struct Run {
         a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
         a.xn_out = xn_out; a.ldn = N;
         if (rec) push(OP_CONSUMER, T, 1, 1).hot.u.consumer = a;
-        else { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
+        else { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
     }
     void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo, int alt) {
         if (rc) return;
@@ -738,26 +761,27 @@ struct Run {
             push(OP_BIAS_ACT, (T * (N >> 2) + 255) / 256, 1, 1).hot.u.bias_act = a;
         } else { prof_begin("bias_act"); launched(launch_bias_act(st, wsp(alt), splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act"); prof_end(); }
     }
-    void rope(const RopeKvArgs& a) {
+    void rope(RopeKvArgs a) {
         if (rc) return;
         if (rec) push(OP_ROPE_KV, a.T, 1, 1).hot.u.rope = a;
-        else { char nm[64]; snprintf(nm, sizeof nm, "rope_kv[T%d]", a.T); prof_begin(nm); launched(launch_rope_kv(st, a), "rope_kv"); prof_end(); }
+        else { char nm[64]; snprintf(nm, sizeof nm, "rope_kv[T%d]", a.T); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_rope_kv(st, a), "rope_kv"); prof_end(); }
     }
     void attn_siglip(const bf16* qkv, int ld_qkv, int B, int seq, int heads, int hidden, bf16* out, int ld_out) {
         if (rc) return;
         if (rec) push(OP_ATTN_SIGLIP, (seq + kAttnTileRows - 1) / kAttnTileRows, heads, B).hot.u.attn =
                      make_siglip_attn_args(qkv, ld_qkv, seq, heads, hidden, out, ld_out);
-        else { prof_begin("siglip_attention"); launched(launch_siglip_attention(st, qkv, ld_qkv, B, seq, heads, hidden, out, ld_out), "siglip_attention"); prof_end(); }
+        else { prof_begin("siglip_attention"); launched(launch_siglip_attention(st, qkv, ld_qkv, B, seq, heads, hidden, out, ld_out, trace_slot("siglip_attention")), "siglip_attention"); prof_end(); }
     }
-    void attn_joint(const JointAttnArgs& a, bool fewq) {
+    void attn_joint(JointAttnArgs a, bool fewq) {
         if (rc) return;
+        a.trace = nullptr;
         if (rec) {
             if (fewq) push(OP_ATTN_FEWQ, (a.n_heads * a.q_per_sample + kAttnTileRows - 1) / kAttnTileRows, 1, a.batch).hot.u.attn =
                           make_fewq_attn_args(a);
             else push(OP_ATTN_PREFILL, (a.q_per_sample + kAttnTileRows - 1) / kAttnTileRows, a.n_heads, a.batch).hot.u.attn =
                      make_prefill_attn_args(a);
-        } else if (fewq) { char nm[64]; snprintf(nm, sizeof nm, "attention_fewq[q%d]", a.q_per_sample); prof_begin(nm); launched(launch_joint_attention_fewq(st, a), "attention_fewq"); prof_end(); }
-        else { prof_begin("attention_prefill"); launched(launch_joint_attention_prefill(st, a), "attention_prefill"); prof_end(); }
+        } else if (fewq) { char nm[64]; snprintf(nm, sizeof nm, "attention_fewq[q%d]", a.q_per_sample); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_joint_attention_fewq(st, a), "attention_fewq"); prof_end(); }
+        else { a.trace = trace_slot("attention_prefill"); prof_begin("attention_prefill"); launched(launch_joint_attention_prefill(st, a), "attention_prefill"); prof_end(); }
     }
     void embed_merge(const EmbedMergeArgs& a, int B) {
         if (rc) return;
@@ -966,6 +990,13 @@ static void action_decode(Run& R, int B, int s, float dt) {
 static void run_step(Run& R, int B, int steps) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
+    if (h->trace && !R.rec && h->trace_buf != nullptr) {
+        // every issue / capture of the step hands out the same slot sequence; each replay re-arms it
+        h->trace_labels.clear();
+        h->trace_streams.clear();
+        if (cudaMemsetAsync(h->trace_buf, 0xFF, static_cast<size_t>(kTraceMax) * 4 * sizeof(unsigned long long), R.st) != cudaSuccess)
+            R.rc = fail(BLURR_ERR_CUDA, "trace buffer reset failed");
+    }
     const int L = c.joint_layers;
     const int Tp = B * c.num_proprio_tokens, Ta = B * c.num_action_tokens, Tt = B * c.max_image_text_tokens;
     const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
@@ -1163,7 +1194,10 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
             CUDA_TRY(cudaStreamSynchronize(st));
             h->launches = 0;
             cudaStream_t cs;
-            CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            // the captured kernel nodes inherit the capture stream's priority (highest: see s_prop / s_act)
+            CUDA_TRY(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, prio_hi));
             Run C{h, cs};
             C.s_main = cs;
             C.multi = R.multi;
@@ -1211,6 +1245,17 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
         h->graphs.clear();
     }
     else if (n == "profile") { h->profile = value != 0; if (value == 2) h->prof.clear(); }
+    else if (n == "trace") {                   // in-graph per-kernel timeline (blurr_pi0_trace_report)
+        if (value != 0 && h->trace_buf == nullptr &&
+            cudaMalloc(&h->trace_buf, static_cast<size_t>(kTraceMax) * 4 * sizeof(unsigned long long)) != cudaSuccess)
+            return fail(BLURR_ERR_CUDA, "trace buffer allocation failed");
+        h->trace = value != 0;
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
     else if (n == "debug_taps") h->debug = value != 0;
     else if (n == "stage_mask") {              // timing experiments only: run a subset of the stages
         h->stage_mask = static_cast<int>(value) & 7;
@@ -1251,6 +1296,7 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     if (n == "gemm_cluster_max") gemm_set_cluster_max(static_cast<int>(value));
     else if (n == "gemm_use_2cta") gemm_set_use_2cta(static_cast<int>(value));
     else if (n == "gemm_persistent") gemm_set_persistent(static_cast<int>(value));
+    else if (n == "gemm_max_stages") gemm_set_max_stages(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
     else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
     return 0;
@@ -1317,6 +1363,29 @@ extern "C" int blurr_pi0_profile_report(blurr_pi0_t* h, char* buf, size_t buf_by
         out += line;
     }
     snprintf(buf, buf_bytes, "%s", out.c_str());
+    return 0;
+}
+
+extern "C" int blurr_pi0_trace_report(blurr_pi0_t* h, char* buf, size_t buf_bytes) {
+    if (!h || !buf || buf_bytes == 0) return fail(BLURR_ERR_INVALID, "trace_report: bad arguments");
+    if (!h->trace || h->trace_buf == nullptr) return fail(BLURR_ERR_STATE, "trace_report: option trace is off");
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t n = h->trace_labels.size();
+    std::vector<unsigned long long> host(n * 4);
+    if (n) CUDA_TRY(cudaMemcpy(host.data(), h->trace_buf, n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < n; ++i) if (host[i * 4] < t0) t0 = host[i * 4];
+    std::string out = "# idx stream start_us waited_us end_us label   (globaltimer, relative to the first kernel start)\n";
+    char line[256];
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned long long s = host[i * 4], w = host[i * 4 + 1], e = ~host[i * 4 + 2];
+        if (s == ~0ull) continue;     // never ran (stage masked off)
+        snprintf(line, sizeof line, "%zu %d %.3f %.3f %.3f %s\n", i, h->trace_streams[i], (s - t0) * 1e-3,
+                 w == ~0ull ? -1.0 : (w - t0) * 1e-3, (e - t0) * 1e-3, h->trace_labels[i].c_str());
+        out += line;
+    }
+    if (out.size() + 1 > buf_bytes) return fail(BLURR_ERR_INVALID, "trace_report: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 

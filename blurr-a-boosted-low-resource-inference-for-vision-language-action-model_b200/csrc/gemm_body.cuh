@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.h"
+#include "launch.cuh"
 
 namespace blurr {
 
@@ -14,7 +15,7 @@ static constexpr int kBlockM = 128;     // weight rows per CTA (UMMA M)
 static constexpr int kBlockK = 64;      // bf16 elements per k-block (one 128-byte swizzle row)
 static constexpr int kTileABytes = kBlockM * kBlockK * 2;
 static constexpr int kGemmThreads = 256;
-static constexpr int kMaxStages = 8;
+static constexpr int kMaxStages = 12;
 
 
 struct GemmShared {
@@ -84,7 +85,8 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, uint8_t* s
 template <int EPI>
 __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_x,
                                           const CUtensorMap* tmap_xs, const GemmShared& sh, GemmPipe& st,
-                                          const int bx, const int by, const int bz, const uint32_t crank) {
+                                          const int bx, const int by, const int bz, const uint32_t crank,
+                                          const bool pdl = false) {
     uint8_t* smem = sh.ring;
     const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -102,7 +104,28 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
         if (lane == 0) {
             const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
             const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
-            for (int i = 0; i < nkb; ++i) {
+            // Launched with PDL: the weights do not depend on the previous kernel, so the first ring of
+            // weight blocks is requested before waiting for it; only the token operand waits.
+            int pre = 0;
+            if (pdl) {
+                pre = (p.cluster == 1) ? min(p.stages, nkb) : 0;
+                for (int i = 0; i < pre; ++i) {      // fresh ring: every stage is empty
+                    st.empty_bits ^= (1u << i);
+                    mbar_arrive_expect_tx(&sh.full_bar[i], static_cast<uint32_t>(stage_bytes));
+                    if (p.w_packed)
+                        tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], 0,
+                                         (bx * p.kb_total + kb0 + i) * kBlockM, pol_w);
+                    else
+                        tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], (kb0 + i) * kBlockK, n0, pol_w);
+                }
+                pdl_wait();
+                trace_stamp(p.trace, 1);
+                for (int i = 0; i < pre; ++i)
+                    for (int c = 0; c < p.nt; ++c)
+                        tma_load_2d_hint(smem + i * stage_bytes + kTileABytes + c * p.bn * (kBlockK * 2), tmap_x,
+                                         &sh.full_bar[i], (kb0 + i) * kBlockK, t0 + c * p.bn, pol_x);
+            }
+            for (int i = pre; i < nkb; ++i) {
                 const int s = i % p.stages;
                 if (!mbar_wait(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
                     atomicExch(&g_gemm_timeout_flag, 1);
@@ -163,6 +186,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
         // ---- epilogue phase 1: TMEM -> registers -> smem tile [token][128 n] ----
         const int w4 = warp - 4;               // TMEM lane quarter this warp may access
         const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
+        if (pdl) pdl_wait();                   // the output buffers may still be read by the previous kernel
         const bool acc_ready = mbar_wait(sh.tmem_full_bar, st.tmem_bit);
         st.tmem_bit ^= 1u;
         if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
@@ -207,7 +231,8 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
 template <int EPI>
 __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_x,
                                                 const GemmShared& sh, uint64_t* tmem_empty_bar, const int gx,
-                                                const int gy, const int gz, const int first, const int stride) {
+                                                const int gy, const int gz, const int first, const int stride,
+                                                const bool pdl = false) {
     uint8_t* smem = sh.ring;
     const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -221,11 +246,39 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
             const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
             uint32_t empty_bits = 0;
             int s = 0;
+            int pre = 0;
+            if (pdl) {
+                // weights of the first ring before the PDL wait (see gemm_tile)
+                if (first < n_tiles) {
+                    const int bx = first % gx, by = (first / gx) % gy, bz = first / (gx * gy);
+                    const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
+                    const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                    pre = min(p.stages, kb1 - kb0);
+                    for (int i = 0; i < pre; ++i) {
+                        empty_bits ^= (1u << i);
+                        mbar_arrive_expect_tx(&sh.full_bar[i], static_cast<uint32_t>(stage_bytes));
+                        if (p.w_packed)
+                            tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], 0,
+                                             (bx * p.kb_total + kb0 + i) * kBlockM, pol_w);
+                        else
+                            tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], (kb0 + i) * kBlockK, n0, pol_w);
+                    }
+                    pdl_wait();
+                    trace_stamp(p.trace, 1);
+                    for (int i = 0; i < pre; ++i)
+                        for (int c = 0; c < p.nt; ++c)
+                            tma_load_2d_hint(smem + i * stage_bytes + kTileABytes + c * p.bn * (kBlockK * 2), tmap_x,
+                                             &sh.full_bar[i], (kb0 + i) * kBlockK, t0 + c * p.bn, pol_x);
+                    s = (pre == p.stages) ? 0 : pre;
+                } else {
+                    pdl_wait();
+                }
+            }
             for (int tile = first; tile < n_tiles; tile += stride) {
                 const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
                 const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
                 const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int kb = (tile == first ? kb0 + pre : kb0); kb < kb1; ++kb) {
                     if (!mbar_wait(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) {
                         atomicExch(&g_gemm_timeout_flag, 1);
                         return;
@@ -281,6 +334,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
         const int ntok = p.nt * p.bn;
         uint32_t tmem_bit = 0;
+        if (pdl) pdl_wait();
         for (int tile = first; tile < n_tiles; tile += stride) {
             const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
             const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                const __grid_constant__ CUtensorMap tmap_xs, const GemmDev p) {
     extern __shared__ uint8_t smem_raw[];
+    trace_stamp(p.trace, 0);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
@@ -45,12 +46,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                                       static_cast<uint32_t>(p.tmem_cols), &tmem_base);
     if (p.cluster > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive
     const uint32_t crank = (p.cluster > 1) ? cluster_ctarank() : 0u;
-    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
-    // the previous kernel; its results are needed from here on
-    pdl_wait();
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
+    // previous kernel, and so does the first ring of weight blocks: the producer and the epilogue warps
+    // wait for the previous kernel (griddepcontrol.wait) inside gemm_tile, just before they first touch
+    // the token operand / the output
     pdl_trigger();
     GemmPipe st;
-    gemm_tile<EPI>(p, &tmap_w, &tmap_x, &tmap_xs, sh, st, blockIdx.x, blockIdx.y, blockIdx.z, crank);
+    gemm_tile<EPI>(p, &tmap_w, &tmap_x, &tmap_xs, sh, st, blockIdx.x, blockIdx.y, blockIdx.z, crank, true);
+    trace_stamp(p.trace, 2);
     if (p.cluster > 1) cluster_sync_all();      // no CTA exits while peers may still signal its barriers
     if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                 const GemmDev p, const int gx, const int gy, const int gz) {
     extern __shared__ uint8_t smem_raw[];
+    trace_stamp(p.trace, 0);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
@@ -75,10 +79,10 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         fence_barrier_init();
     }
     __syncthreads();
-    pdl_wait();
     pdl_trigger();
-    gemm_persistent<EPI>(p, &tmap_w, &tmap_x, sh, tmem_empty_bar, gx, gy, gz, blockIdx.x, gridDim.x);
+    gemm_persistent<EPI>(p, &tmap_w, &tmap_x, sh, tmem_empty_bar, gx, gy, gz, blockIdx.x, gridDim.x, true);
     __syncthreads();
+    trace_stamp(p.trace, 2);
     if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
@@ -213,13 +217,15 @@ static constexpr int kRingBytes = 225 * 1024;   // pipeline ring (stand-alone ke
 // each SM still ingests the full tile), so it is off by default; the knob stays for experiments.
 static int g_cluster_max = 1;
 static constexpr int kTargetCtas = 148;   // one CTA per SM of a B200
+static constexpr int kCoResidentSmem = 112 * 1024;   // dynamic smem per CTA that still lets two CTAs share an SM
 void gemm_set_cluster_max(int c) { g_cluster_max = c < 1 ? 1 : (c > 8 ? 8 : c); }
 
 // Measured on B200 (round 1): CTA pairs are correct but not faster at batch 1 (61 vs 59 us on the gate/up
 // shape) — the loss there is per-tile fixed cost, which the persistent kernel removes; pairs help at
-// batch 64 (880 vs 818 TFLOP/s), so the knob stays.
-static int g_use_2cta = 0;
-void gemm_set_use_2cta(int on) { g_use_2cta = on ? 1 : 0; }
+// batch 64 (880 vs 818 TFLOP/s).  -1 = automatic: pairs above 1024 tokens
+// (at 276 tokens they measured 61.8 vs 53.6 us under ncu).
+static int g_use_2cta = -1;
+void gemm_set_use_2cta(int on) { g_use_2cta = on < 0 ? -1 : (on ? 1 : 0); }
 // Persistent kernel: measured on B200 (round 1) it wins only while the epilogue is trivial (T = 16:
 // 33.5 vs 39.9 us on the gate/up shape); from T >= 64 its direct TMEM -> global epilogue (2-byte stores,
 // 4 warps) stalls the next tile's MMAs longer than the bubbles it removes (GeGLU, T = 276: 95 vs 59 us),
@@ -228,13 +234,16 @@ static int g_persistent = 1;
 static constexpr int kPersistentMaxTokens = 32;
 void gemm_set_persistent(int on) { g_persistent = on ? 1 : 0; }
 
+static int g_max_stages = 8;      // tuning knob (tools/time_gemm.py): cap of the TMA ring depth
+void gemm_set_max_stages(int n) { g_max_stages = n < 1 ? 1 : (n > 12 ? 12 : n); }
+
 static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out, int b_div = 1) {
     const int stage_bytes = kTileABytes + nt * (bn / b_div) * kBlockK * 2;
     const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
     const int avail = kRingBytes;
     int stages = avail / stage_bytes;
     if (stages < 1) return false;
-    if (stages > 8) stages = 8;
+    if (stages > g_max_stages) stages = g_max_stages;
     const int want = kb_per_split > 0 ? kb_per_split : 1;
     if (stages > want) stages = want;
     // the epilogue tile aliases the pipeline buffers: keep enough bytes for it
@@ -295,6 +304,19 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
     if (pl.tmem_cols > 512) return pl;
     pl.grid_x = Nw / kBlockM;
     pl.grid_y = gy;
+    // More CTAs than SMs: a ring shallow enough for two CTAs per SM (smem and TMEM halves) lets one
+    // CTA's prologue / epilogue overlap the other's main loop and removes the second wave.  Measured
+    // on the gate/up shape: 16 tokens 28.8 us (4 stages) vs 42.0 (8); 144 tokens 33.5 (3) vs 47.2 (4).
+    if (pl.grid_x * gy * pl.splitk > kTargetCtas && pl.tmem_cols <= 256) {
+        const int stage_bytes = kTileABytes + nt * bn * kBlockK * 2;
+        const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
+        int s2 = (kCoResidentSmem - 1280) / stage_bytes;
+        if (s2 > 4) s2 = 4;
+        if (s2 >= 2 && s2 < pl.stages && s2 * stage_bytes >= tile_bytes) {
+            pl.stages = s2;
+            pl.smem_bytes = s2 * stage_bytes + 1024 + 256;
+        }
+    }
     // activation multicast: the CTAs of a cluster own consecutive weight tiles and share the
     // token tile; each loads 1/C of it (a multiple of 8 rows keeps the 128B swizzle phase)
     pl.cluster = 1;
@@ -306,7 +328,8 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
     pl.slice_rows = nt * bn / pl.cluster;
     // CTA pairs (cta_group::2): consecutive weight tiles share the token operand, each CTA loads half
     pl.two_cta = 0;
-    if (g_use_2cta && pl.cluster == 1 && pl.grid_x % 2 == 0 && nt * bn >= 64 && bn % 16 == 0) {
+    const bool want_pairs = g_use_2cta == 1 || (g_use_2cta < 0 && T > 1024);
+    if (want_pairs && pl.cluster == 1 && pl.grid_x % 2 == 0 && nt * bn >= 64 && bn % 16 == 0) {
         int st2 = 0, sm2 = 0;
         if (plan_fits(bn, nt, pl.kb_per_split, epi, &st2, &sm2, 2)) {
             pl.two_cta = 1;
@@ -384,7 +407,7 @@ int gemm_make_step_op(const GemmCall& c, GemmDev* d, CUtensorMap* tmap_w, CUtens
     d->T = c.T; d->bn = pl.bn; d->nt = pl.nt; d->stages = pl.stages; d->kb_total = pl.kb_total;
     d->kb_per_split = pl.kb_per_split; d->tmem_cols = pl.tmem_cols; d->Nw = c.Nw;
     d->bias = c.bias; d->out = c.out; d->ldo = c.ldo; d->partial = c.partial;
-    d->cluster = 1; d->slice_rows = pl.nt * pl.bn; d->w_packed = c.w_packed;
+    d->cluster = 1; d->slice_rows = pl.nt * pl.bn; d->w_packed = c.w_packed; d->trace = nullptr;
     *grid_x = pl.grid_x; *grid_y = pl.grid_y;
     return pl.splitk;
 }
@@ -413,7 +436,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     d.T = c.T; d.bn = pl.bn; d.nt = pl.nt; d.stages = pl.stages; d.kb_total = pl.kb_total;
     d.kb_per_split = pl.kb_per_split; d.tmem_cols = pl.tmem_cols; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
-    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed;
+    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed; d.trace = c.trace;
     cudaError_t e;
     if (pl.two_cta) {
         CUtensorMap txh;

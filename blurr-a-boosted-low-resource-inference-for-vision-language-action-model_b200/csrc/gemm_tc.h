@@ -32,6 +32,7 @@ struct GemmCall {
     int ldo;
     float* partial;
     int bn_override;          // 0 = automatic token chunking
+    unsigned long long* trace;   // in-graph timeline slot (launch.cuh) or nullptr
 };
 
 // Device-side parameters of one GEMM (filled from a GemmPlan by gemm_launch / gemm_make_step_op).
@@ -51,6 +52,7 @@ struct GemmDev {
     int w_packed;     // weights are tile-packed (see gemm_tc.h)
     int cluster;      // CTAs (consecutive weight tiles) sharing one multicast activation tile
     int slice_rows;   // activation rows each CTA of the cluster loads and multicasts
+    unsigned long long* trace;
 };
 
 struct GemmPlan {
@@ -85,6 +87,7 @@ inline size_t gemm_pack_weight_index(int row, int col, int K) {
 void gemm_set_use_2cta(int on);
 // Persistent one-CTA-per-SM kernel with a direct TMEM -> global epilogue (default) vs one tile per CTA.
 void gemm_set_persistent(int on);
+void gemm_set_max_stages(int n);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
 void gemm_set_cluster_max(int c);

@@ -35,6 +35,7 @@ struct ConsumerArgs {
     float eps;
     bf16* xn_out;           // [T][ldn] normalised output (nullable)
     int ldn;
+    unsigned long long* trace;   // in-graph timeline slot (launch.cuh) or nullptr
 };
 cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a);
 
@@ -57,6 +58,7 @@ struct RopeKvArgs {
     bf16* k_cache;          // layer base: [B][n_slots][256]
     bf16* v_cache;
     int n_slots, slot_base;
+    unsigned long long* trace;
 };
 cudaError_t launch_rope_kv(cudaStream_t stream, const RopeKvArgs& a);
 
@@ -78,11 +80,13 @@ struct AttnMmaArgs {
     // MQA few-query mode (mqa_nq > 0): the tile's rows enumerate (head, query) pairs of one sample,
     // pair p -> head p / mqa_nq, query p % mqa_nq; all pairs share the sample's single K/V head.
     int mqa_nq, mqa_heads;
+    unsigned long long* trace;
 };
 
 // SigLIP MHA (siglip.py:133-152): qkv [T][3*hidden] with head_dim 72, no mask.
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
-                                    int n_heads, int hidden, bf16* out, int ld_out);
+                                    int n_heads, int hidden, bf16* out, int ld_out,
+                                    unsigned long long* trace = nullptr);
 
 // Gemma joint attention, many queries (prefill): soft-clamped, additive mask, MQA.
 struct JointAttnArgs {
@@ -96,6 +100,7 @@ struct JointAttnArgs {
     int64_t mask_bstride, mask_rstride;
     int batch, n_heads;
     bf16* out;              // [B*q_per_sample][n_heads*256]
+    unsigned long long* trace;
 };
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& a);
 // The AttnMmaArgs the two launchers above build (the step kernel runs the same bodies as work items).

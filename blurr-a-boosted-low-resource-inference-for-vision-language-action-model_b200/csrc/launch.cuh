@@ -12,6 +12,21 @@ namespace blurr {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
+// In-graph timeline (option "trace"): a kernel whose argument block carries a non-null trace pointer
+// stamps %globaltimer into 4 u64 words (all reduced with atomicMin over the grid, buffer preset to
+// ~0): [0] first CTA started, [1] first CTA past griddepcontrol.wait, [2] ~(last CTA finished).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_stamp(unsigned long long* p, int word) {
+    if (p != nullptr && threadIdx.x == 0) {
+        const unsigned long long t = globaltimer_ns();
+        atomicMin(p + word, word == 2 ? ~t : t);
+    }
+}
+
 bool pdl_enabled();
 void pdl_set_enabled(bool on);
 

@@ -594,6 +594,27 @@ class _Engine:
         capi.check(self.lib.blurr_pi0_profile_report(self.handle, buf, len(buf)))
         return buf.value.decode()
 
+    def trace(self, fn, warm: int = 3):
+        """Run `fn()` in its normal launch regime (CUDA graph, PDL, streams) with the in-kernel
+        %globaltimer stamps on; returns [(idx, stream, start_us, waited_us, end_us, label)] of the
+        last call."""
+        self.set_option("trace", 1)
+        try:
+            for _ in range(warm + 1):
+                fn()
+            torch.cuda.synchronize(self.device)
+            buf = C.create_string_buffer(1 << 19)
+            capi.check(self.lib.blurr_pi0_trace_report(self.handle, buf, len(buf)))
+        finally:
+            self.set_option("trace", 0)
+        rows = []
+        for line in buf.value.decode().splitlines():
+            if line.startswith("#") or not line.strip():
+                continue
+            idx, stream, s, w, e, label = line.split(" ", 5)
+            rows.append((int(idx), int(stream), float(s), float(w), float(e), label))
+        return rows
+
     def last_op_count(self) -> int:
         return int(self.lib.blurr_pi0_last_op_count(self.handle))
 

@@ -152,13 +152,19 @@ int64_t blurr_pi0_last_launch_count(const blurr_pi0_t* h);
 /* Option "profile" = 1: every kernel is launched eagerly and bracketed by CUDA events; the per-label
  * totals accumulated since "profile" = 2 (reset) are written as text into `buf`. */
 int blurr_pi0_profile_report(blurr_pi0_t* h, char* buf, size_t buf_bytes);
+/* Option "trace" = 1: the GEMM, consumer, RoPE and attention kernels stamp %globaltimer (first CTA
+ * start, first CTA past the programmatic-dependency wait, last CTA end) while the step runs in its
+ * normal regime (CUDA graph, PDL, three streams).  Writes one text line per kernel of the last call:
+ * "idx stream start_us waited_us end_us label". */
+int blurr_pi0_trace_report(blurr_pi0_t* h, char* buf, size_t buf_bytes);
 /* Ops the persistent step kernel executed in the last call (0 when it is off). */
 int64_t blurr_pi0_last_op_count(const blurr_pi0_t* h);
 /* Bytes of repacked weights the step reads (the algorithmic-bytes numerator of the roofline). */
 int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h);
 
 /* Process-wide tuning knobs (no handle): "gemm_cluster_max" (1/2/4/8, activation-multicast cluster
- * size cap of the GEMM kernel), "use_pdl" (0/1). */
+ * size cap of the GEMM kernel), "gemm_use_2cta" (-1 automatic = CTA pairs above 1024 tokens, 0, 1),
+ * "gemm_persistent" (0/1: persistent kernel for GEMMs of <= 32 tokens), "use_pdl" (0/1). */
 int blurr_set_global_option(const char* name, int64_t value);
 
 const char* blurr_last_error(void);

@@ -38,6 +38,29 @@ def test_gemm_store_bias(T, N, K):
     assert bf16_ulp_err(got, ref) <= 1.01
 
 
+@pytest.mark.parametrize("T,N,K,epi", [(552, 2560, 2048, "store"), (1104, 4352, 1152, "gelu"),
+                                         (276, 4096, 2048, "geglu"), (16, 2560, 1024, "store")])
+def test_gemm_variants_agree(T, N, K, epi):
+    """The GEMM variants (one CTA per tile, CTA pairs, persistent) accumulate every output in the same
+    order, so they must agree bit for bit."""
+    lib = capi.load_library()
+    W = _rand((N, K), 1.0 / math.sqrt(K), 21)
+    X = _rand((T, K), 1.0, 22)
+    b = _rand((N,), 0.5, 23) if epi != "geglu" else None
+    code = {"store": capi.EPI_STORE, "gelu": capi.EPI_GELU, "geglu": capi.EPI_GEGLU}[epi]
+    outs = []
+    try:
+        for pairs, persistent in [(0, 0), (1, 0), (0, 1), (-1, 1)]:
+            capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", pairs))
+            capi.check(lib.blurr_set_global_option(b"gemm_persistent", persistent))
+            outs.append(op_gemm(W, X, code, bias=b))
+    finally:
+        capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", -1))
+        capi.check(lib.blurr_set_global_option(b"gemm_persistent", 1))
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 @pytest.mark.parametrize("T,N,K", [(276, 2560, 2048), (17, 256, 192), (4, 1024, 4096)])
 def test_gemm_row_major_weights(T, N, K):
     """Same kernel fed from a plain row-major nn.Linear weight (no packing)."""
@@ -96,7 +119,7 @@ def test_gemm_geglu(T, I, K):
     assert d.max().item() <= 0.05 and (d > 0).float().mean().item() < 0.02
 
 
-@pytest.mark.parametrize("batch", [1, 3])
+@pytest.mark.parametrize("batch", [1, 3, 6])      # 16-, 32- and 64-row tiles
 def test_siglip_attention(batch):
     """siglip.py:133-152: bf16 QK^T * scale, fp32 softmax -> bf16, PV."""
     seq, heads, hidden = 256, 16, 1152
@@ -143,30 +166,31 @@ def _block_mask(B, rows, cols, cnts, row0):
     return m
 
 
-@pytest.mark.parametrize("batch,scale", [(1, 1.0), (2, 6.0)])
+@pytest.mark.parametrize("batch,scale", [(1, 1.0), (2, 6.0), (4, 2.0)])     # batch 4: 32-row tiles
 def test_joint_attention_prefill(batch, scale):
     n_heads, n_keys, slots = 8, 277, 281
     q = _rand((batch * 276, n_heads * 256), scale, 13)
     kc = _rand((batch, slots, 256), scale, 14)
     vc = _rand((batch, slots, 256), 1.0, 15)
-    mask = _block_mask(batch, 277, 277, [268, 261][:batch], 0)
+    mask = _block_mask(batch, 277, 277, [268, 261, 276, 1][:batch], 0)
     got = op_joint_attention(False, q, 276, 0, kc, vc, n_keys, mask, batch, n_heads)
     ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], mask[:, :276], n_heads)
     print(report(f"joint_prefill B={batch} scale={scale}", got, ref))
     assert (got.float() - ref.float()).abs().max().item() <= 0.05
 
 
-@pytest.mark.parametrize("qps,row0,n_keys", [(1, 276, 277), (4, 0, 281)])
-def test_joint_attention_fewq(qps, row0, n_keys):
-    batch, n_heads, slots = 2, 8, 281
+@pytest.mark.parametrize("qps,row0,n_keys,batch", [(1, 276, 277, 2), (4, 0, 281, 2), (4, 0, 281, 160)])
+def test_joint_attention_fewq(qps, row0, n_keys, batch):
+    n_heads, slots = 8, 281
+    cnts = [268, 270] + [200 + (i * 7) % 77 for i in range(batch - 2)]
     q = _rand((batch * qps, n_heads * 256), 4.0, 16)
     kc = _rand((batch, slots, 256), 4.0, 17)
     vc = _rand((batch, slots, 256), 1.0, 18)
     if qps == 1:
-        mask = _block_mask(batch, 277, 277, [268, 270], 0)      # proprio row = row 276 of the prefill mask
+        mask = _block_mask(batch, 277, 277, cnts, 0)      # proprio row = row 276 of the prefill mask
         rows = mask[:, 276:277]
     else:
-        mask = _block_mask(batch, 4, 281, [268, 270], 277)      # action mask rows
+        mask = _block_mask(batch, 4, 281, cnts, 277)      # action mask rows
         rows = mask
     got = op_joint_attention(True, q, qps, row0, kc, vc, n_keys, mask, batch, n_heads)
     ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], rows, n_heads)

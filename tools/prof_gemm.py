@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Run the dominant kernel (Gemma gate/up GEMM + GeGLU, 276 tokens) a few times on rotating
-weight buffers, for `ncu --set full` captures:  ncu ... -k regex:gemm_tc_kernel python tools/prof_gemm.py"""
+weight buffers (tile-packed layout, ldw = 0, as the engine streams them), for `ncu --set full` captures:  ncu ... -k regex:gemm_tc_kernel python tools/prof_gemm.py"""
 import ctypes as C
 import os
 import sys
@@ -24,7 +24,7 @@ out = torch.empty((T, N), device=dev, dtype=torch.bfloat16)
 part = torch.empty((16, T, N), device=dev, dtype=torch.float32) if epi == capi.EPI_PARTIAL else None
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for i in range(8):
-    capi.check(lib.blurr_op_gemm(sp, C.c_void_p(Ws[i % nbuf].data_ptr()), N, K, K, C.c_void_p(X.data_ptr()), T, K, epi,
+    capi.check(lib.blurr_op_gemm(sp, C.c_void_p(Ws[i % nbuf].data_ptr()), N, K, 0, C.c_void_p(X.data_ptr()), T, K, epi,
                                  S, None, C.c_void_p(out.data_ptr()), N // 2 if epi == capi.EPI_GEGLU else N,
                                  C.c_void_p(part.data_ptr()) if part is not None else None))
 torch.cuda.synchronize()
