@@ -715,7 +715,7 @@ struct Run {
         c.epi = epi;
         c.splitk = (epi == EPI_PARTIAL) ? pick_splitk(T, L.Nw, L.K, ws_floats) : 1;
         c.bias = bias ? L.bias : nullptr;
-        c.out = out; c.ldo = ldo; c.partial = ws; c.bn_override = 0;
+        c.out = out; c.ldo = ldo; c.partial = ws; c.bn_override = 0; c.w_static = 1;
         if (epi == EPI_PARTIAL && static_cast<size_t>(c.splitk) * T * L.Nw > ws_floats) {
             rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
             return 1;
@@ -1196,7 +1196,7 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
             cudaStream_t cs;
             int prio_lo = 0, prio_hi = 0;
             cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-            // the captured kernel nodes inherit the capture stream's priority (highest: see s_prop / s_act)
+                // the captured kernel nodes inherit the capture stream's priority (highest: see s_prop / s_act)
             CUDA_TRY(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, prio_hi));
             Run C{h, cs};
             C.s_main = cs;
@@ -1297,6 +1297,7 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_use_2cta") gemm_set_use_2cta(static_cast<int>(value));
     else if (n == "gemm_persistent") gemm_set_persistent(static_cast<int>(value));
     else if (n == "gemm_max_stages") gemm_set_max_stages(static_cast<int>(value));
+    else if (n == "gemm_wide") gemm_set_wide(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
     else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
     return 0;

@@ -33,6 +33,8 @@ struct GemmCall {
     float* partial;
     int bn_override;          // 0 = automatic token chunking
     unsigned long long* trace;   // in-graph timeline slot (launch.cuh) or nullptr
+    int w_static;             // 1: W was written before any kernel still in flight (engine weights), so the
+                              // kernel may fetch it ahead of the programmatic-dependency wait
 };
 
 // Device-side parameters of one GEMM (filled from a GemmPlan by gemm_launch / gemm_make_step_op).
@@ -53,6 +55,7 @@ struct GemmDev {
     int cluster;      // CTAs (consecutive weight tiles) sharing one multicast activation tile
     int slice_rows;   // activation rows each CTA of the cluster loads and multicasts
     unsigned long long* trace;
+    int w_static;     // weights may be fetched before griddepcontrol.wait
 };
 
 struct GemmPlan {
@@ -88,6 +91,7 @@ void gemm_set_use_2cta(int on);
 // Persistent one-CTA-per-SM kernel with a direct TMEM -> global epilogue (default) vs one tile per CTA.
 void gemm_set_persistent(int on);
 void gemm_set_max_stages(int n);
+void gemm_set_wide(int on);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
 void gemm_set_cluster_max(int c);

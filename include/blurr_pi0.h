@@ -164,7 +164,8 @@ int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h);
 
 /* Process-wide tuning knobs (no handle): "gemm_cluster_max" (1/2/4/8, activation-multicast cluster
  * size cap of the GEMM kernel), "gemm_use_2cta" (-1 automatic = CTA pairs above 1024 tokens, 0, 1),
- * "gemm_persistent" (0/1: persistent kernel for GEMMs of <= 32 tokens), "use_pdl" (0/1). */
+ * "gemm_persistent" (0/1: persistent kernel for GEMMs of <= 32 tokens), "gemm_wide" (0/1, default 0:
+ * two weight tiles per CTA for 257..288 tokens), "gemm_max_stages" (TMA ring depth cap), "use_pdl" (0/1). */
 int blurr_set_global_option(const char* name, int64_t value);
 
 const char* blurr_last_error(void);
