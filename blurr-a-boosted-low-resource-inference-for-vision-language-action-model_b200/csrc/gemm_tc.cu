@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_xh,
                 const GemmDev p) {
     extern __shared__ uint8_t smem_raw[];
+    trace_stamp(p.trace, 0);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
@@ -103,12 +104,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                                       &tmem_base, true);
     cluster_sync_all();                         // both CTAs' barriers exist before any remote signal
     const uint32_t crank = cluster_ctarank();
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
+    trace_stamp(p.trace, 1);
     GemmPipe st;
     gemm_tile_2cta<EPI>(p, &tmap_w, &tmap_xh, sh, st, blockIdx.x, blockIdx.y, blockIdx.z, crank);
     tcgen05_fence_before();
     cluster_sync_all();                         // the peer is done with this CTA's smem / TMEM / barriers
+    trace_stamp(p.trace, 2);
     if (warp == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 

@@ -10,7 +10,6 @@ from blurr_b200 import dist as bdist
 from blurr_b200 import synth
 from blurr_b200.config import bridge_config
 from blurr_b200.pizero import PiZeroInference
-from helpers import bf16_ulp_err
 from oracle import pi0_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -41,10 +40,15 @@ def _oracle(sd, cfg, inp, dtype=torch.bfloat16, taps=None):
 
 
 def test_full_model_actions_and_layers(full):
+    """Per-layer parity is judged the way two bf16 runs can be judged: both runs (ours, and the
+    reference's bf16 op sequence on this GPU) are compared with the fp32 run of the same model, and
+    our error must stay within a small factor of the reference's own.  (A direct bf16-vs-bf16 bound in
+    ulps is meaningless on the residual streams: elements near zero are sums of O(10) terms.)"""
     cfg, model, sd = full
     inp = synth.synthetic_inputs(cfg, 1, dtype=torch.bfloat16, device=DEV)
-    taps = {}
+    taps, taps32 = {}, {}
     ref = _oracle(sd, cfg, inp, taps=taps)
+    ref32 = _oracle(sd, cfg, inp, dtype=torch.float32, taps=taps32)
     model.set_engine_options(debug_taps=True)
     with torch.inference_mode():
         got = model(**synth.call_args(inp), noise=inp["noise"])
@@ -53,31 +57,34 @@ def test_full_model_actions_and_layers(full):
     names = ["siglip.embeddings"] + [f"siglip.layer{l}" for l in range(27)] + ["siglip.post_layernorm", "projector",
              "merged_embeds"] + [f"prefill.L{l}.{m}" for l in range(17) for m in ("vlm", "proprio")] + \
             ["flow0.action_embeds"] + [f"flow0.L{l}.action" for l in range(18)] + ["flow0.velocity"]
-    print("\nper-layer activation error, full-size Bridge, ours vs bf16 reference op sequence (same GPU):")
-    worst_mean, worst_ulp = 0.0, 0.0
+    print("\nper-layer activation error, full-size Bridge: ours vs bf16 reference | each vs the fp32 run (same GPU)")
+    worst_ratio = 0.0
     for n in names:
-        r = taps[alias.get(n, n)].float().flatten()
+        key = alias.get(n, n)
+        r = taps[key].float().flatten()
+        hi = taps32[key].float().flatten()
         g = model.debug_tap(n).float().flatten()
         d = (g - r).abs()
-        rms = r.pow(2).mean().sqrt().item()
-        ulp = bf16_ulp_err(g, r)
-        worst_mean = max(worst_mean, d.mean().item() / max(rms, 1e-6))
-        worst_ulp = max(worst_ulp, ulp)
-        print(f"  {n:24s} max_abs={d.max().item():.3e} mean_abs={d.mean().item():.3e} ref_rms={rms:.3e} "
-              f"max_err_in_bf16_ulp={ulp:.1f} mismatch_frac={(d > 0).float().mean().item():.3f}")
+        e_ours, e_ref = (g - hi).abs(), (r - hi).abs()
+        rms = hi.pow(2).mean().sqrt().item()
+        ratio = e_ours.mean().item() / max(e_ref.mean().item(), 1e-4 * rms)
+        worst_ratio = max(worst_ratio, ratio)
+        print(f"  {n:24s} vs bf16-ref max={d.max().item():.3e} mean={d.mean().item():.3e} mismatch={(d > 0).float().mean().item():.3f}"
+              f" | vs fp32: ours max={e_ours.max().item():.3e} mean={e_ours.mean().item():.3e}, bf16-ref max={e_ref.max().item():.3e}"
+              f" mean={e_ref.mean().item():.3e} (rms {rms:.3e})")
+        assert e_ours.mean().item() <= 1.5 * e_ref.mean().item() + 1e-4 * rms, n
+        assert e_ours.max().item() <= 2.0 * e_ref.max().item() + 1e-3 * rms, n
     model.set_engine_options(debug_taps=False)
     err = (got.float() - ref.float()).abs().max().item()
     clamped = (got.float().clamp(-1, 1) - ref.float().clamp(-1, 1)).abs().max().item()
-    ref32 = _oracle(sd, cfg, inp, dtype=torch.float32)
     e_ours, e_ref = (got.float() - ref32).abs().max().item(), (ref.float() - ref32).abs().max().item()
     print(f"actions: ours vs bf16-ref un-clamped {err:.3e}, clamped {clamped:.3e}; vs fp32: ours {e_ours:.3e}, "
-          f"bf16-ref {e_ref:.3e}; range [{ref.min().item():.2f}, {ref.max().item():.2f}]")
+          f"bf16-ref {e_ref:.3e}; range [{ref.min().item():.2f}, {ref.max().item():.2f}]; worst per-layer mean-error ratio "
+          f"ours/bf16-ref {worst_ratio:.2f}")
     assert torch.isfinite(got.float()).all()
     assert clamped <= 1e-2                      # north_star tolerance
+    assert err <= 3.2e-2                        # 2 bf16 ulp at |a| in [2, 4)
     assert e_ours <= e_ref + 1.6e-2             # no worse than the reference's own bf16 error (+1 ulp)
-    # outliers of the residual streams (|x| ~ 16-64) carry 0.125-0.5 per bf16 ulp, so the bound is
-    # in ulps of the element and on the mean error relative to the layer's rms
-    assert worst_ulp <= 16.0 and worst_mean <= 5e-3
 
 
 def test_full_model_sharding_invariance_and_kv_layout(full):

@@ -177,6 +177,22 @@ def test_step_kernel_equals_per_op_kernels(batch, steps):
     assert torch.equal(model.debug_tap("k_cache"), k_ref)
 
 
+def test_in_graph_trace_is_consistent_and_does_not_change_results():
+    """Option "trace": every traced kernel reports start <= wait release <= end inside the step, the
+    three streams appear, and the actions are bit-identical with and without the stamps."""
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    model, sd, inp = _setup(cfg, 2)
+    ref = _run(model, inp)
+    rows = model._engine.trace(lambda: _run(model, inp))
+    assert len(rows) > 50 and {r[1] for r in rows} == {0, 1, 2}
+    span = max(r[4] for r in rows)
+    for idx, stream, start, waited, end, label in rows:
+        assert 0.0 <= start <= end <= span, (idx, label)
+        assert waited < 0 or start - 1e-3 <= waited <= end + 1e-3, (idx, label)
+    assert span < 50_000.0          # microseconds: one reduced-depth step
+    assert torch.equal(_run(model, inp), ref)
+
+
 def test_shrunk_fractal_ten_steps():
     """Config 3: proprio_dim 8, 10 Euler steps with bf16 `t` accumulation, same injected noise."""
     cfg = shrink_config(fractal_config(10), 2, 3)
