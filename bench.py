@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--batched-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-raw-frames", action="store_true", help="skip the e2e leg that starts from raw camera frames")
     ap.add_argument("--flow-steps", type=int, default=1, help="num_inference_steps (1 = --preset blurr)")
     ap.add_argument("--ring", type=int, default=50, help="distinct pre-staged control-step inputs (one episode)")
     return ap.parse_args()
@@ -261,6 +262,42 @@ def run_ours(args):
     e2e_value = world * B * HORIZON * K / e2e_s
     d2h = host_out.numel() * host_out.element_size()
 
+    # ---------------- e2e from RAW observations ----------------
+    # 480x640x3 uint8 camera frames + raw float64 proprio in pinned host memory; per step: H2D of the raw
+    # observation, device-side cv2-equivalent Lanczos resize + normalise + proprio normalise, the model
+    # graph, D2H of the actions.  Beside it: what the reference does on the host CPU for the same step
+    # (cv2 resize + VLAProcessor + mask / position building), timed on this box.
+    raw = None
+    if not args.no_raw_frames:
+        from blurr_b200.episode import Episode
+        stats = {"p01": [0.17, -0.21, -0.04, -3.1, -0.5, -1.2, 0.0], "p99": [0.45, 0.24, 0.28, 3.1, 0.6, 1.3, 1.0]}
+        base = synth.synthetic_inputs(cfg, B, seed=99 + rank, dtype=torch.bfloat16, vary_text=B > 1)
+        ep = Episode(model, base["input_ids"], base["attention_mask"], (480, 640), stats, "bound")
+        g = torch.Generator().manual_seed(5 + rank)
+        frames = [torch.randint(0, 256, (B, 480, 640, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
+        props = [(torch.rand((B, 7), generator=g, dtype=torch.float64) * 0.4).pin_memory() for _ in range(4)]
+        noise = base["noise"].to(dev)
+        with torch.inference_mode():
+            def raw_step(i):
+                a = ep.step(frames[i % 4], props[i % 4], noise=noise)
+                host_out.copy_(a.float(), non_blocking=False)
+            for i in range(W):
+                raw_step(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(K):
+                raw_step(i)
+            torch.cuda.synchronize(dev)
+            raw_s = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+        ep.close()
+        raw = {"value": world * B * HORIZON * K / raw_s, "unit": "actions/s", "ms_per_step": raw_s * 1e3 / K,
+               "h2d_bytes_per_step": B * (480 * 640 * 3 + 7 * 8), "d2h_bytes_per_step": d2h,
+               "observation": "480x640x3 uint8 frame + 7 float64 proprio per episode, pinned host memory",
+               "device_ops": "cv2.INTER_LANCZOS4-equivalent resize + VLAProcessor normalise + bf16 cast + normalize_bound (bit-exact)"}
+        if rank == 0 and world == 1:
+            raw["reference_host_preprocess"] = reference_host_preprocess_ms(cfg, base, B)
+
     line = {
         "metric": "pi0_bridge_actions_per_sec", "value": value, "unit": "actions/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
@@ -275,6 +312,7 @@ def run_ours(args):
                        "note": "per control step at this rank, CUDA events, device-resident inputs"},
         "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3 / K},
+        "e2e_raw_frames": raw,
         "gpu_launches": int(launches_per_step) * K,
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
@@ -340,6 +378,45 @@ def ncu_traffic_bytes():
             return float(json.load(f)["dram_bytes_per_launch"])
     except (OSError, KeyError, ValueError):
         return None
+
+
+def reference_host_preprocess_ms(cfg, base, batch):
+    """The per-step host work of the reference's control loop (env_adapter/simpler.py:52-98 and
+    agent/eval.py:170-183) on this box's CPU: cv2 Lanczos resize (the oracle's restatement when cv2 is
+    missing), VLAProcessor normalisation, normalize_bound, mask / position building, casts to bf16."""
+    import numpy as np
+    import torch
+    from blurr_b200 import masks
+    from oracle import preprocess_oracle as P
+    try:
+        import cv2
+        resize = lambda im: cv2.resize(im, (224, 224), interpolation=cv2.INTER_LANCZOS4)
+        kind = "cv2 " + cv2.__version__
+    except ImportError:
+        resize = lambda im: P.resize_lanczos4_u8(im, 224, 224)
+        kind = "oracle restatement (cv2 not importable)"
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (batch, 480, 640, 3), dtype=np.uint8)
+    stats = {"p01": [0.17, -0.21, -0.04, -3.1, -0.5, -1.2, 0.0], "p99": [0.45, 0.24, 0.28, 3.1, 0.6, 1.3, 1.0]}
+    n_it = cfg["max_image_text_tokens"]
+
+    def one():
+        for b in range(batch):
+            small = resize(frames[b])
+            px = P.process_images(torch.as_tensor(small, dtype=torch.uint8).permute(2, 0, 1)[None]).to(torch.bfloat16)
+            P.preprocess_proprio(rng.normal(0.2, 0.2, 7), stats, "bound")
+        cm, *_ = masks.build_causal_mask_and_position_ids(base["attention_mask"], torch.bfloat16, n_it, cfg["cond_steps"],
+                                                          cfg["horizon_steps"])
+        masks.split_full_mask_into_submasks(cm, n_it, cfg["cond_steps"], cfg["horizon_steps"])
+        return px
+    for _ in range(3):
+        one()
+    t0 = time.perf_counter()
+    n = 20
+    for _ in range(n):
+        one()
+    return {"ms_per_step": (time.perf_counter() - t0) * 1e3 / n, "resize": kind,
+            "note": "host CPU time the reference spends per control step before the model call; not part of its model-only latency"}
 
 
 def dominant_kernel_roofline(dev, peaks):

@@ -84,6 +84,15 @@ _SIGNATURES = [
     ("blurr_pi0_trace_report", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("blurr_pi0_last_op_count", C.c_int64, [C.c_void_p]),
     ("blurr_pi0_weight_bytes", C.c_int64, [C.c_void_p]),
+    ("blurr_preproc_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("blurr_preproc_destroy", None, [C.c_void_p]),
+    ("blurr_preproc_build_tables", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int16)]),
+    ("blurr_preproc_tables", C.c_int,
+     [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int16), C.POINTER(C.c_int32), C.POINTER(C.c_int16)]),
+    ("blurr_preproc_frame", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    ("blurr_op_normalize_proprio", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("blurr_set_global_option", C.c_int, [C.c_char_p, C.c_int64]),
     ("blurr_op_pack_weight", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("blurr_op_gemm", C.c_int,

@@ -28,6 +28,9 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+namespace blurr {
+int record_error(int code, const std::string& msg) { return ::fail(code, msg); }      // for the other translation units
+}
 #define CUDA_TRY(expr)                                                                           \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \

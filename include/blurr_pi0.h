@@ -162,6 +162,33 @@ int64_t blurr_pi0_last_op_count(const blurr_pi0_t* h);
 /* Bytes of repacked weights the step reads (the algorithmic-bytes numerator of the roofline). */
 int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h);
 
+/* ---------------------------------------------------------------------------------------------
+ * Observation preprocessing on the device.  Replaces, bit for bit, the host
+ * work the reference does before every model call:
+ *   cv2.resize(image, image_size, interpolation=cv2.INTER_LANCZOS4)     agent/env_adapter/simpler.py:59-64
+ *   VLAProcessor: uint8 * (1/255.0), (x - 0.5) / 0.5, fp32                model/vla/processing.py:27-58,112-117
+ *   pixel_values.to(bfloat16)                                            agent/eval.py:187
+ *   normalize_bound / normalize_gaussian (float64) -> float32 -> bf16    agent/env_adapter/base.py:8-18,33-40;
+ *                                                                        simpler.py:73-95; eval.py:194
+ * --------------------------------------------------------------------------------------------- */
+typedef struct blurr_preproc blurr_preproc_t;   /* opaque: one per (device, frame geometry) */
+/* Builds OpenCV's 8-tap fixed-point Lanczos tables for src -> dst and uploads them. */
+int blurr_preproc_create(int device, int src_h, int src_w, int dst_h, int dst_w, blurr_preproc_t** out);
+void blurr_preproc_destroy(blurr_preproc_t* p);
+/* Host only (no device needed): the table of one axis, ofs[dst] (first tap = ofs - 3) and alpha[dst*8]. */
+int blurr_preproc_build_tables(int src, int dst, int32_t* ofs, int16_t* alpha);
+/* Host copies of the tables: x_ofs[dst_w], x_alpha[dst_w*8], y_ofs[dst_h], y_alpha[dst_h*8]. */
+int blurr_preproc_tables(const blurr_preproc_t* p, int32_t* x_ofs, int16_t* x_alpha, int32_t* y_ofs, int16_t* y_alpha);
+/* frame_u8: device uint8 [batch][src_h][src_w][3] (HWC; strides in bytes).  pixel_values_bf16: device
+ * bf16 [batch][3][dst_h][dst_w].  resized_u8 (nullable): device uint8 [batch][dst_h][dst_w][3], the
+ * cv2.resize result itself.  Asynchronous on `cuda_stream`. */
+int blurr_preproc_frame(blurr_preproc_t* p, void* cuda_stream, const void* frame_u8, int64_t row_stride_bytes,
+                        int batch, int64_t frame_stride_bytes, void* pixel_values_bf16, void* resized_u8);
+/* raw: device float64 [n][dim]; lo / hi: device float64 [dim] = (p01, p99) for kind 0 "bound", (mean, std)
+ * for kind 1 "gaussian"; out_bf16: device bf16 [n][dim]. */
+int blurr_op_normalize_proprio(void* cuda_stream, const double* raw, const double* lo, const double* hi, int kind,
+                               int n, int dim, void* out_bf16);
+
 /* Process-wide tuning knobs (no handle): "gemm_cluster_max" (1/2/4/8, activation-multicast cluster
  * size cap of the GEMM kernel), "gemm_use_2cta" (-1 automatic = CTA pairs above 1024 tokens, 0, 1),
  * "gemm_persistent" (0/1: persistent kernel for GEMMs of <= 32 tokens), "gemm_wide" (0/1, default 0:
