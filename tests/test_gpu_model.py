@@ -193,6 +193,61 @@ def test_in_graph_trace_is_consistent_and_does_not_change_results():
     assert torch.equal(_run(model, inp), ref)
 
 
+def _inputs_with_text_lengths(cfg, lengths):
+    """synthetic_inputs with an explicit number of instruction tokens per sample (0 .. max)."""
+    from blurr_b200 import masks
+    inp = synth.synthetic_inputs(cfg, len(lengths), dtype=torch.bfloat16, vary_text=False)
+    n_img, n_it = cfg.vision.config.num_image_tokens, cfg.max_image_text_tokens
+    pad = cfg.pad_token_id
+    g = torch.Generator().manual_seed(5)
+    ids = torch.full((len(lengths), n_it), pad, dtype=torch.int64)
+    ids[:, :n_img] = cfg.image_token_index
+    ids[:, n_img] = 2
+    for b, n in enumerate(lengths):
+        ids[b, n_img + 1:n_img + 1 + n] = torch.randint(3, 257000, (n,), generator=g)
+        if n_img + 1 + n < n_it:
+            ids[b, n_img + 1 + n] = 108
+    att = (ids != pad).long()
+    cm, vp, pp, ap = masks.build_causal_mask_and_position_ids(att, torch.bfloat16, n_it, cfg.cond_steps, cfg.horizon_steps)
+    m1, m2 = masks.split_full_mask_into_submasks(cm, n_it, cfg.cond_steps, cfg.horizon_steps)
+    inp.update(input_ids=ids, image_text_proprio_mask=m1, action_mask=m2, vlm_position_ids=vp, proprio_position_ids=pp,
+               action_position_ids=ap, attention_mask=att, causal_mask=cm)
+    return {k: v.to(DEV) for k, v in inp.items()}
+
+
+def test_ragged_and_extreme_instruction_lengths():
+    """Empty instruction (BOS + newline only), a single token, and the longest instruction that fills all
+    20 text slots with no padding, in one batch of 8 with ragged lengths in between: valid-token counts
+    258 .. 276 exercise every mask / position-id / KV-slot edge of the block-attention layout."""
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    max_text = cfg.max_image_text_tokens - cfg.vision.config.num_image_tokens - 1      # no room for the newline
+    lengths = [0, 1, 2, 7, 13, max_text - 1, max_text, 5]
+    sd = synth.synthetic_state_dict(cfg, 0, torch.bfloat16)
+    model = PiZeroInference.from_state_dict(cfg, sd, device=DEV)
+    sd_gpu = {k: v.to(DEV) for k, v in sd.items()}
+    inp = _inputs_with_text_lengths(cfg, lengths)
+    assert inp["attention_mask"].sum(1).tolist() == [257 + n + (1 if n < max_text else 0) for n in lengths]
+    ref, caches = _oracle(sd_gpu, cfg, inp, return_caches=True)
+    got = _run(model, inp)
+    err = (got.float().clamp(-1, 1) - ref.float().clamp(-1, 1)).abs().max().item()
+    print(f"ragged instruction lengths {lengths}: clamped max_abs={err:.3e}")
+    assert torch.isfinite(got.float()).all() and err <= 1e-2
+    # every sample is computed as if it were alone in the batch (same batch size => same split-K plan)
+    solo = _inputs_with_text_lengths(cfg, [lengths[6]] * len(lengths))
+    got_solo = _run(model, solo)
+    inp2 = {k: v.clone() for k, v in solo.items()}
+    for k in ("pixel_values", "proprios", "noise"):
+        inp2[k][0] = inp[k][6]
+        solo[k][0] = inp[k][6]
+    a = _run(model, solo)
+    for k in ("input_ids", "image_text_proprio_mask", "action_mask", "vlm_position_ids", "proprio_position_ids",
+              "action_position_ids"):
+        inp2[k][1:] = inp[k][1:]                       # different companions, same sample 0
+    b = _run(model, inp2)
+    assert torch.equal(a[0], b[0])
+    model.release_engine()
+
+
 def test_shrunk_fractal_ten_steps():
     """Config 3: proprio_dim 8, 10 Euler steps with bf16 `t` accumulation, same injected noise."""
     cfg = shrink_config(fractal_config(10), 2, 3)
