@@ -1301,6 +1301,7 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_persistent") gemm_set_persistent(static_cast<int>(value));
     else if (n == "gemm_max_stages") gemm_set_max_stages(static_cast<int>(value));
     else if (n == "gemm_wide") gemm_set_wide(static_cast<int>(value));
+    else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
     else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
     return 0;

@@ -228,7 +228,9 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
 // with the NEXT tile's operands while the epilogue of the current tile drains TMEM, so HBM stays busy
 // through the prologue / epilogue bubbles that a one-tile-per-CTA launch pays once per wave (measured:
 // 3.4 TB/s instead of ~6 TB/s on the gate/up shape at any token count).  The epilogue goes TMEM ->
-// registers -> global memory directly (no shared-memory tile), so nothing ever aliases the ring.
+// registers -> global memory directly (no shared-memory tile), so nothing ever aliases the ring.  With
+// <= 256 accumulator columns per tile the accumulator is double-buffered in TMEM (p.acc_bufs = 2): the
+// MMAs of tile i+1 run while the epilogue warps drain tile i.
 template <int EPI>
 __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_x,
                                                 const GemmShared& sh, uint64_t* tmem_empty_bar, const int gx,
@@ -301,15 +303,16 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
-            uint32_t full_bits = 0, tmem_empty_bit = 0;
-            int s = 0;
+            uint32_t full_bits = 0, tmem_empty_bits = 0;
+            int s = 0, buf = 0;
             for (int tile = first; tile < n_tiles; tile += stride) {
                 const int bz = tile / (gx * gy);
                 const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                // the epilogue must have drained the previous tile's accumulators
-                if (!mbar_wait(tmem_empty_bar, tmem_empty_bit ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 4); return; }
-                tmem_empty_bit ^= 1u;
+                // the epilogue must have drained the accumulator buffer this tile is going to use
+                if (!mbar_wait(&tmem_empty_bar[buf], ((tmem_empty_bits >> buf) & 1u) ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 4); return; }
+                tmem_empty_bits ^= (1u << buf);
                 tcgen05_fence_after();
+                const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!mbar_wait(&sh.full_bar[s], (full_bits >> s) & 1u)) { atomicExch(&g_gemm_timeout_flag, 2); return; }
                     full_bits ^= (1u << s);
@@ -320,29 +323,31 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                         const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes + c * p.bn * (kBlockK * 2));
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_bf16_ss(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                            umma_bf16_ss(acc + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
                                          (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&sh.empty_bar[s]);
                     s = (s + 1 == p.stages) ? 0 : s + 1;
                 }
-                umma_commit(sh.tmem_full_bar);
+                umma_commit(buf == 0 ? sh.tmem_full_bar : tmem_empty_bar + 2);      // tmem_full[buf]
+                buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
             }
         }
     } else if (warp >= 4) {
         const int w4 = warp - 4;               // TMEM lane quarter this warp may access
         const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
         const int ntok = p.nt * p.bn;
-        uint32_t tmem_bit = 0;
+        uint32_t tmem_bits = 0;
+        int buf = 0;
         if (pdl) pdl_wait();
         for (int tile = first; tile < n_tiles; tile += stride) {
             const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
             const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
-            const bool ready = mbar_wait(sh.tmem_full_bar, tmem_bit);
-            tmem_bit ^= 1u;
+            const bool ready = mbar_wait(buf == 0 ? sh.tmem_full_bar : tmem_empty_bar + 2, (tmem_bits >> buf) & 1u);
+            tmem_bits ^= (1u << buf);
             if (!ready) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 3); return; }
             tcgen05_fence_after();
+            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
             float bias = 0.f;
             if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
             for (int g = 0; g < ntok / 16; ++g) {
@@ -378,7 +383,8 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
             // accumulators are in registers / memory: hand TMEM back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar);
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
         }
     }
 }

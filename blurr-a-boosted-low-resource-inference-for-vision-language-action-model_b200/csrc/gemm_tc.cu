@@ -73,9 +73,11 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
     uint32_t tmem_base;
     GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes, 1, static_cast<uint32_t>(p.tmem_cols), &tmem_base);
-    uint64_t* tmem_empty_bar = sh.tmem_full_bar + 2;      // after tmem_full_bar and the TMEM slot word
+    uint64_t* tmem_empty_bar = sh.tmem_full_bar + 2;      // [0], [1]: after tmem_full_bar and the TMEM slot word
     if (threadIdx.x == 0) {
-        mbar_init(tmem_empty_bar, 4);                      // one arrive per epilogue warp
+        mbar_init(&tmem_empty_bar[0], 4);                  // one arrive per epilogue warp
+        mbar_init(&tmem_empty_bar[1], 4);
+        mbar_init(&tmem_empty_bar[2], 1);                  // tmem_full of the second accumulator buffer
         fence_barrier_init();
     }
     __syncthreads();
@@ -246,8 +248,8 @@ void gemm_set_cluster_max(int c) { g_cluster_max = c < 1 ? 1 : (c > 8 ? 8 : c); 
 
 // Measured on B200 (round 1): CTA pairs are correct but not faster at batch 1 (61 vs 59 us on the gate/up
 // shape) — the loss there is per-tile fixed cost, which the persistent kernel removes; pairs help at
-// batch 64 (880 vs 818 TFLOP/s).  -1 = automatic: pairs above 1024 tokens
-// (at 276 tokens they measured 61.8 vs 53.6 us under ncu).
+// batch 64 (gate/up 1059 vs 952 TFLOP/s with two CTAs per SM).  -1 = automatic: pairs for the GeGLU GEMM above
+// 1024 tokens (at 276 tokens they measured 61.8 vs 53.6 us under ncu).
 static int g_use_2cta = -1;
 void gemm_set_use_2cta(int on) { g_use_2cta = on < 0 ? -1 : (on ? 1 : 0); }
 // Persistent kernel: measured on B200 (round 1) it wins only while the epilogue is trivial (T = 16:
@@ -258,6 +260,17 @@ void gemm_set_use_2cta(int on) { g_use_2cta = on < 0 ? -1 : (on ? 1 : 0); }
 // GEMM of the batch-1 prefill).  Off by default: not faster than one tile per CTA (see gemm_body.cuh).
 static int g_wide = 0;
 void gemm_set_wide(int on) { g_wide = on ? 1 : 0; }
+// Large token counts (batched episodes), measured on B200 at 64 episodes (TFLOP/s; one tile per CTA with two
+// CTAs per SM | CTA pairs, two per SM | persistent 128 x 256 tiles with the accumulator double-buffered in
+// TMEM and a direct TMEM -> global epilogue):
+//   gate/up (GeGLU)   952 | 1059 |  728        down (fp32 partial)  1106 | 1109 | 1211
+//   SigLIP fc1 (GELU) 722 |  718 |  475        VLM qkv (partial)     825 |  725 | 1091
+//   SigLIP qkv (store) 958 | 857 | 1028
+// The double-buffered persistent kernel wins while the epilogue is a plain store (it then hides entirely under
+// the next tile's MMAs) and loses when the epilogue carries the activation math.  -1 = automatic: persistent
+// for store / partial epilogues, pairs for GeGLU, one tile per CTA for GELU; 0 = never persistent; 1 = always.
+static int g_large_t_mode = -1;
+void gemm_set_large_t_mode(int mode) { g_large_t_mode = mode; }
 static int g_persistent = 1;
 static constexpr int kPersistentMaxTokens = 32;
 void gemm_set_persistent(int on) { g_persistent = on ? 1 : 0; }
@@ -356,13 +369,25 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
     pl.slice_rows = nt * bn / pl.cluster;
     // CTA pairs (cta_group::2): consecutive weight tiles share the token operand, each CTA loads half
     pl.two_cta = 0;
-    const bool want_pairs = g_use_2cta == 1 || (g_use_2cta < 0 && T > 1024);
+    const bool want_pairs = g_use_2cta == 1 || (g_use_2cta < 0 && T > 1024 && epi == EPI_GEGLU);
     if (want_pairs && pl.cluster == 1 && pl.grid_x % 2 == 0 && nt * bn >= 64 && bn % 16 == 0) {
         int st2 = 0, sm2 = 0;
         if (plan_fits(bn, nt, pl.kb_per_split, epi, &st2, &sm2, 2)) {
             pl.two_cta = 1;
             pl.stages = st2;
             pl.smem_bytes = sm2;
+            // same co-residency rule as above: two CTAs (of different pairs) per SM overlap one tile's
+            // epilogue with the other's main loop
+            if (pl.grid_x * gy * pl.splitk > kTargetCtas && pl.tmem_cols <= 256) {
+                const int stage_bytes = kTileABytes + nt * (bn / 2) * kBlockK * 2;
+                const int tile_bytes = nt * bn * kBlockM * (epi == EPI_PARTIAL ? 4 : 2);
+                int s2 = (kCoResidentSmem - 1280) / stage_bytes;
+                if (s2 > 4) s2 = 4;
+                if (s2 >= 2 && s2 < pl.stages && s2 * stage_bytes >= tile_bytes) {
+                    pl.stages = s2;
+                    pl.smem_bytes = s2 * stage_bytes + 1024 + 256;
+                }
+            }
         }
     }
     pl.valid = true;
@@ -527,7 +552,19 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         if (e != cudaSuccess) { *err = std::string("gemm (2-CTA) launch failed: ") + cudaGetErrorString(e); return -1; }
         return pl.splitk;
     }
-    if (g_persistent && pl.cluster == 1 && pl.nt * pl.bn <= kPersistentMaxTokens && c.epi != EPI_GEGLU) {
+    d.acc_bufs = 1; d.acc_stride = 0;
+    const bool large_dbuf = (g_large_t_mode == 1 || (g_large_t_mode < 0 && (c.epi == EPI_PARTIAL || c.epi == EPI_STORE))) &&
+                            c.T > 1024 && pl.nt == 1 && pl.tmem_cols <= 256 && pl.cluster == 1 && !pl.two_cta;
+    if (large_dbuf) {
+        d.acc_bufs = 2; d.acc_stride = pl.tmem_cols; d.tmem_cols = 2 * pl.tmem_cols;
+        // the direct epilogue stages nothing in the ring: use all of it
+        const int stage_bytes = kTileABytes + pl.nt * pl.bn * kBlockK * 2;
+        int st = kRingBytes / stage_bytes;
+        if (st > kMaxStages) st = kMaxStages;
+        d.stages = st;
+        pl.smem_bytes = st * stage_bytes + 1024 + 256;
+    }
+    if (large_dbuf || (g_persistent && pl.cluster == 1 && pl.nt * pl.bn <= kPersistentMaxTokens && c.epi != EPI_GEGLU)) {
         switch (c.epi) {
             case EPI_STORE:   e = launch_epip<EPI_STORE>(stream, pl, tw, tx, d); break;
             case EPI_GELU:    e = launch_epip<EPI_GELU>(stream, pl, tw, tx, d); break;

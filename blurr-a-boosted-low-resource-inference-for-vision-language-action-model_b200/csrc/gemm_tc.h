@@ -56,6 +56,8 @@ struct GemmDev {
     int slice_rows;   // activation rows each CTA of the cluster loads and multicasts
     unsigned long long* trace;
     int w_static;     // weights may be fetched before griddepcontrol.wait
+    int acc_bufs;     // persistent kernel: accumulator buffers in TMEM (1 or 2)
+    int acc_stride;   // TMEM columns between them
 };
 
 struct GemmPlan {
@@ -92,6 +94,7 @@ void gemm_set_use_2cta(int on);
 void gemm_set_persistent(int on);
 void gemm_set_max_stages(int n);
 void gemm_set_wide(int on);
+void gemm_set_large_t_mode(int mode);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
 void gemm_set_cluster_max(int c);

@@ -25,6 +25,7 @@ GEMM_SHAPES = [
     (1, 2560, 1024), (4, 1024, 2048), (4, 1024, 4096), (4, 512, 1024),
     (552, 2560, 2048), (1104, 1152, 1152), (16, 128, 64), (17, 256, 192),
     (257, 512, 128), (288, 256, 192),      # edges of the two-tiles-per-CTA variant (256 < T <= 288)
+    (2208, 1152, 1152), (1040, 256, 4352),  # > 1024 tokens: persistent tiles, double-buffered accumulator
 ]
 
 
@@ -40,7 +41,8 @@ def test_gemm_store_bias(T, N, K):
 
 
 @pytest.mark.parametrize("T,N,K,epi", [(552, 2560, 2048, "store"), (1104, 4352, 1152, "gelu"),
-                                         (276, 4096, 2048, "geglu"), (16, 2560, 1024, "store")])
+                                         (276, 4096, 2048, "geglu"), (16, 2560, 1024, "store"),
+                                         (2208, 2560, 2048, "store"), (2100, 4096, 1152, "geglu"), (4416, 1152, 640, "gelu")])
 def test_gemm_variants_agree(T, N, K, epi):
     """The GEMM variants (one CTA per tile, CTA pairs, persistent) accumulate every output in the same
     order, so they must agree bit for bit."""
@@ -51,13 +53,15 @@ def test_gemm_variants_agree(T, N, K, epi):
     code = {"store": capi.EPI_STORE, "gelu": capi.EPI_GELU, "geglu": capi.EPI_GEGLU}[epi]
     outs = []
     try:
-        for pairs, persistent in [(0, 0), (1, 0), (0, 1), (-1, 1)]:
+        for pairs, persistent, large in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (-1, 1, -1), (0, 1, 1)]:
             capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", pairs))
             capi.check(lib.blurr_set_global_option(b"gemm_persistent", persistent))
+            capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", large))
             outs.append(op_gemm(W, X, code, bias=b))
     finally:
         capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", -1))
         capi.check(lib.blurr_set_global_option(b"gemm_persistent", 1))
+        capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", -1))
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
 
@@ -103,7 +107,7 @@ def test_gemm_row_major_weights(T, N, K):
 
 @pytest.mark.parametrize("T,N,K,S", [(276, 2048, 16384, 9), (276, 2560, 2048, 7), (256, 1152, 4352, 16),
                                      (4, 1024, 4096, 16), (1, 2560, 1024, 6), (552, 2048, 2048, 3),
-                                     (276, 2048, 2048, 1)])
+                                     (276, 2048, 2048, 1), (2208, 2048, 2048, 1), (1300, 2560, 640, 1)])
 def test_gemm_partial_splitk(T, N, K, S):
     W = _rand((N, K), 1.0 / math.sqrt(K), 4)
     X = _rand((T, K), 1.0, 5)

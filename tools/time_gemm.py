@@ -12,6 +12,7 @@ from blurr_b200 import capi
 
 lib = capi.load_library()
 dev = torch.device("cuda:0")
+ONLY = os.environ.get("ONLY", "")
 SHAPES = [  # name, N, K, T, epi, splitk
     ("vlm gate/up", 32768, 2048, 276, capi.EPI_GEGLU, 1),
     ("vlm down", 2048, 16384, 276, capi.EPI_PARTIAL, 9),
@@ -25,6 +26,8 @@ SHAPES = [  # name, N, K, T, epi, splitk
     ("vlm gate/up bs64", 32768, 2048, 17664, capi.EPI_GEGLU, 1),
     ("vlm down bs64", 2048, 16384, 17664, capi.EPI_PARTIAL, 1),
     ("siglip fc1 bs64", 4352, 1152, 16384, capi.EPI_GELU, 1),
+    ("siglip qkv bs64", 3456, 1152, 16384, capi.EPI_STORE, 1),
+    ("vlm qkv bs64", 2560, 2048, 17664, capi.EPI_PARTIAL, 1),
 ]
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 # weights: tile-packed (ldw = 0; values are random so no packing pass is needed) vs row-major (ldw = K)
@@ -32,7 +35,10 @@ CASES = [(int(a), "packed") for a in (sys.argv[1:] or ["1", "0"])]
 for use2, LDW_MODE in CASES:
     cmax = use2
     capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", use2))
+    capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", int(os.environ.get("MODE", "0"))))
     for name, N, K, T, epi, S in SHAPES:
+        if ONLY and ONLY not in name:
+            continue
         LDW = 0 if LDW_MODE == "packed" else K
         nbuf = max(2, min(6, int(600e6 // (N * K * 2)) + 1))
         Ws = [torch.empty((N, K), device=dev, dtype=torch.bfloat16).uniform_(-0.02, 0.02) for _ in range(nbuf)]
