@@ -86,14 +86,18 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
         if (v >= nvec) continue;
         const int n = v << 2;
         float4 val;
-        if (a.partial != nullptr) {
-            float4 acc = sum_slices(a.partial + static_cast<size_t>(t) * a.ldp + n,
-                                    static_cast<size_t>(a.T) * a.ldp, a.splitk);
-            if (a.bias != nullptr) {
-                const float4 b = load_bf16x4(a.bias + n);
-                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        if (a.partial != nullptr || a.lin != nullptr) {
+            if (a.lin != nullptr) {
+                val = load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + n);      // already bf16(acc + bias)
+            } else {
+                float4 acc = sum_slices(a.partial + static_cast<size_t>(t) * a.ldp + n,
+                                        static_cast<size_t>(a.T) * a.ldp, a.splitk);
+                if (a.bias != nullptr) {
+                    const float4 b = load_bf16x4(a.bias + n);
+                    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                }
+                val = make_float4(bf16_round(acc.x), bf16_round(acc.y), bf16_round(acc.z), bf16_round(acc.w));
             }
-            val = make_float4(bf16_round(acc.x), bf16_round(acc.y), bf16_round(acc.z), bf16_round(acc.w));
             if (a.out_scale != 1.0f)
                 val = make_float4(bf16_round(val.x * a.out_scale), bf16_round(val.y * a.out_scale),
                                   bf16_round(val.z * a.out_scale), bf16_round(val.w * a.out_scale));
@@ -193,8 +197,14 @@ __device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t) {
         if (it < n_rot) {
             const int h = it >> 5, j = (it & 31) << 2;             // head, first dim of the group
             if (h < a.n_heads && a.q_out == nullptr) continue;
-            float4 x1 = sum_slices(prow + h * 256 + j, sstride, a.splitk);
-            float4 x2 = sum_slices(prow + h * 256 + 128 + j, sstride, a.splitk);
+            float4 x1, x2;
+            if (a.lin != nullptr) {
+                x1 = load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + h * 256 + j);
+                x2 = load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + h * 256 + 128 + j);
+            } else {
+                x1 = sum_slices(prow + h * 256 + j, sstride, a.splitk);
+                x2 = sum_slices(prow + h * 256 + 128 + j, sstride, a.splitk);
+            }
             const float4 cs = *reinterpret_cast<const float4*>(a.cos_table + pos * 128 + j);
             const float4 sn = *reinterpret_cast<const float4*>(a.sin_table + pos * 128 + j);
             float u1[4] = {bf16_round(x1.x), bf16_round(x1.y), bf16_round(x1.z), bf16_round(x1.w)};
@@ -213,7 +223,8 @@ __device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t) {
             store_bf16x4(dst + 128 + j, make_float4(y2[0], y2[1], y2[2], y2[3]));
         } else {
             const int j = (it - n_rot) << 2;
-            const float4 v = sum_slices(prow + (a.n_heads + 1) * 256 + j, sstride, a.splitk);
+            const float4 v = a.lin != nullptr ? load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + (a.n_heads + 1) * 256 + j)
+                                              : sum_slices(prow + (a.n_heads + 1) * 256 + j, sstride, a.splitk);
             store_bf16x4(a.v_cache + cache_row + j,
                          make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w)));
         }

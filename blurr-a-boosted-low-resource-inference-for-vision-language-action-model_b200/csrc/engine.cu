@@ -176,6 +176,7 @@ struct blurr_pi0 {
     bool profile = false;          // eager launches bracketed by CUDA events, per-kernel-label totals
     // in-graph timeline: kernels stamp %globaltimer into trace_buf (launch.cuh); slots are handed out
     // while the step is issued / captured, so every graph replay rewrites the same slots
+    bool lin_mode = true;          // single-slice GEMMs above 1024 tokens hand bf16 (not fp32 partials) to their consumer
     bool trace = false;
     unsigned long long* trace_buf = nullptr;       // [kTraceMax][4]
     std::vector<std::string> trace_labels;
@@ -635,6 +636,7 @@ extern "C" int blurr_pi0_finalize_weights(blurr_pi0_t* h) {
 // the schedule
 // ---------------------------------------------------------------------------
 static constexpr int kTraceMax = 4096;
+static constexpr int kLinModeMinTokens = 1024;   // above this a single-slice GEMM hands bf16 to its consumer
 
 struct Run {
     blurr_pi0* h;
@@ -719,6 +721,16 @@ struct Run {
         c.splitk = (epi == EPI_PARTIAL) ? pick_splitk(T, L.Nw, L.K, ws_floats) : 1;
         c.bias = bias ? L.bias : nullptr;
         c.out = out; c.ldo = ldo; c.partial = ws; c.bn_override = 0; c.w_static = 1;
+        // Batched episodes: a GEMM that needs no K split does not need the fp32 round trip either.  Its store
+        // epilogue writes the Linear output itself, bf16(acc + bias), into the workspace and the consumer reads
+        // that (return value 0 = "bf16 linear output, bias applied"); same bits, half the bytes.
+        bool lin_mode = false;
+        if (h->lin_mode && epi == EPI_PARTIAL && c.splitk == 1 && T > kLinModeMinTokens && !rec) {
+            lin_mode = true;
+            c.epi = EPI_STORE;
+            c.bias = L.bias;            // nullptr where the Linear has none
+            c.out = reinterpret_cast<bf16*>(ws); c.ldo = L.Nw; c.partial = nullptr;
+        }
         if (epi == EPI_PARTIAL && static_cast<size_t>(c.splitk) * T * L.Nw > ws_floats) {
             rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
             return 1;
@@ -734,7 +746,7 @@ struct Run {
             }
         } else {
             char nm[96];
-            snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", epi, T, L.Nw, L.K, c.splitk);
+            snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", c.epi, T, L.Nw, L.K, c.splitk);
             c.trace = trace_slot(nm);
             prof_begin(nm);
             s = gemm_launch(st, c, &err);
@@ -742,7 +754,7 @@ struct Run {
             ++h->launches;
         }
         if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 1; }
-        return s;
+        return lin_mode ? 0 : s;
     }
     void consumer(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
                   float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
@@ -751,6 +763,10 @@ struct Run {
         ConsumerArgs a{};
         a.partial = use_partial ? wsp(alt) : nullptr; a.splitk = splitk; a.T = T; a.N = N; a.ldp = ldp;
         a.bias = bias; a.add_mode = add_mode; a.res = res; a.ldr = ldr;
+        if (use_partial && splitk == 0) {            // the GEMM left bf16(acc + bias) in the workspace (see gemm())
+            a.lin = reinterpret_cast<const bf16*>(wsp(alt)); a.ldl = ldp;
+            a.partial = nullptr; a.bias = nullptr; a.splitk = 1;
+        }
         a.pos = h->pos_emb; a.pos_rows = h->cfg.num_image_tokens; a.out_scale = out_scale;
         a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
         a.xn_out = xn_out; a.ldn = N;
@@ -892,6 +908,7 @@ static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool k
     if (R.rc) return;
     RopeKvArgs a{};
     a.partial = R.wsp(alt); a.splitk = s; a.T = B * sb.tokens_per_sample; a.ldp = qkv.Nw;
+    if (s == 0) { a.lin = reinterpret_cast<const bf16*>(R.wsp(alt)); a.ldl = qkv.Nw; a.splitk = 1; }
     a.n_heads = kv_only ? 0 : c.num_heads;
     a.tokens_per_sample = sb.tokens_per_sample; a.position_ids = sb.pos;
     a.cos_table = M.cos_t; a.sin_table = M.sin_t; a.n_pos = kNumPos;
@@ -1248,6 +1265,14 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
         h->graphs.clear();
     }
     else if (n == "profile") { h->profile = value != 0; if (value == 2) h->prof.clear(); }
+    else if (n == "lin_mode") {
+        h->lin_mode = value != 0;
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
     else if (n == "trace") {                   // in-graph per-kernel timeline (blurr_pi0_trace_report)
         if (value != 0 && h->trace_buf == nullptr &&
             cudaMalloc(&h->trace_buf, static_cast<size_t>(kTraceMax) * 4 * sizeof(unsigned long long)) != cudaSuccess)

@@ -36,6 +36,10 @@ struct ConsumerArgs {
     bf16* xn_out;           // [T][ldn] normalised output (nullable)
     int ldn;
     unsigned long long* trace;   // in-graph timeline slot (launch.cuh) or nullptr
+    // alternative to `partial` (batched episodes, one K slice): the Linear output itself, bf16(acc + bias),
+    // written by the GEMM's store epilogue - half the bytes of the fp32 partial and no bias pass here
+    const bf16* lin;        // [T][ldl] or nullptr
+    int ldl;
 };
 cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a);
 
@@ -59,6 +63,8 @@ struct RopeKvArgs {
     bf16* v_cache;
     int n_slots, slot_base;
     unsigned long long* trace;
+    const bf16* lin;        // alternative to `partial`: the bf16 q|k|v Linear output [T][ldl]
+    int ldl;
 };
 cudaError_t launch_rope_kv(cudaStream_t stream, const RopeKvArgs& a);
 

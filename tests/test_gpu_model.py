@@ -248,6 +248,20 @@ def test_ragged_and_extreme_instruction_lengths():
     model.release_engine()
 
 
+def test_batched_bf16_handoff_equals_fp32_partials():
+    """Above 1024 tokens a GEMM without a K split writes bf16(acc + bias) for its consumer instead of an fp32
+    partial: same accumulator, same rounding point, so the actions and the KV cache are bit-identical."""
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    model, sd, inp = _setup(cfg, 6)
+    model.set_engine_options(reserve_batch=6)
+    a = _run(model, inp)
+    k_a = model.debug_tap("k_cache").clone()
+    model._engine.set_option("lin_mode", 0)
+    b = _run(model, inp)
+    model._engine.set_option("lin_mode", 1)
+    assert torch.equal(a, b) and torch.equal(k_a, model.debug_tap("k_cache"))
+
+
 def test_shrunk_fractal_ten_steps():
     """Config 3: proprio_dim 8, 10 Euler steps with bf16 `t` accumulation, same injected noise."""
     cfg = shrink_config(fractal_config(10), 2, 3)
