@@ -334,9 +334,13 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
             }
         }
     } else if (warp >= 4) {
-        const int w4 = warp - 4;               // TMEM lane quarter this warp may access
+        // 4 epilogue warps (one per TMEM lane quarter) or 8 (two per quarter, each half of the columns)
+        const int w4 = (warp - 4) & 3;         // TMEM lane quarter this warp may access
         const int nl = w4 * 32 + lane;         // local weight row == TMEM lane
         const int ntok = p.nt * p.bn;
+        const int n_groups = ntok / 16;
+        const int g_begin = (blockDim.x > kGemmThreads) ? ((warp - 4) >> 2) * (n_groups / 2) : 0;
+        const int g_end = (blockDim.x > kGemmThreads) ? (((warp - 4) >> 2) == 0 ? n_groups / 2 : n_groups) : n_groups;
         uint32_t tmem_bits = 0;
         int buf = 0;
         if (pdl) pdl_wait();
@@ -350,7 +354,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
             float bias = 0.f;
             if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
-            for (int g = 0; g < ntok / 16; ++g) {
+            for (int g = g_begin; g < g_end; ++g) {
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(lane_addr + g * 16, r);
                 tmem_ld_wait();

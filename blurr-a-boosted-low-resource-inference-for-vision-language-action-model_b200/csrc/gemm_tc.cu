@@ -60,7 +60,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
 // Persistent 1-CTA kernel: at most one CTA per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads + 128, 1)
 gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                 const GemmDev p, const int gx, const int gy, const int gz) {
     extern __shared__ uint8_t smem_raw[];
@@ -75,8 +75,9 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes, 1, static_cast<uint32_t>(p.tmem_cols), &tmem_base);
     uint64_t* tmem_empty_bar = sh.tmem_full_bar + 2;      // [0], [1]: after tmem_full_bar and the TMEM slot word
     if (threadIdx.x == 0) {
-        mbar_init(&tmem_empty_bar[0], 4);                  // one arrive per epilogue warp
-        mbar_init(&tmem_empty_bar[1], 4);
+        const uint32_t epi_warps = blockDim.x / 32 - 4;     // 4, or 8 in the activation-heavy batched launches
+        mbar_init(&tmem_empty_bar[0], epi_warps);           // one arrive per epilogue warp
+        mbar_init(&tmem_empty_bar[1], epi_warps);
         mbar_init(&tmem_empty_bar[2], 1);                  // tmem_full of the second accumulator buffer
         fence_barrier_init();
     }
@@ -267,8 +268,10 @@ void gemm_set_wide(int on) { g_wide = on ? 1 : 0; }
 //   SigLIP fc1 (GELU) 722 |  718 |  475        VLM qkv (partial)     825 |  725 | 1091
 //   SigLIP qkv (store) 958 | 857 | 1028
 // The double-buffered persistent kernel wins while the epilogue is a plain store (it then hides entirely under
-// the next tile's MMAs) and loses when the epilogue carries the activation math.  -1 = automatic: persistent
-// for store / partial epilogues, pairs for GeGLU, one tile per CTA for GELU; 0 = never persistent; 1 = always.
+// the next tile's MMAs) and loses when the epilogue carries the activation math; with two epilogue warps per
+// TMEM lane quarter it reaches 777 (fc1) and 974 (gate/up).  -1 = automatic: pairs for GeGLU, persistent for
+// everything else; 0 = never persistent; 1 = always.  (These kernels run against the 1 kW power cap: numbers
+// taken back to back differ by +-10 % with the order of the launches.)
 static int g_large_t_mode = -1;
 void gemm_set_large_t_mode(int mode) { g_large_t_mode = mode; }
 static int g_persistent = 1;
@@ -406,7 +409,11 @@ static cudaError_t launch_epip(cudaStream_t stream, const GemmPlan& pl, const CU
     }
     const int tiles = pl.grid_x * pl.grid_y * pl.splitk;
     const int ctas = tiles < kTargetCtas ? tiles : kTargetCtas;
-    return launch_kernel(gemm_tcp_kernel<EPI>, dim3(ctas), dim3(kGemmThreads), static_cast<size_t>(pl.smem_bytes), stream,
+    // epilogues with activation math get two warps per TMEM lane quarter so that they stay hidden under the
+    // next tile's MMAs (double-buffered accumulators)
+    const int threads = (d.acc_bufs == 2 && (EPI == EPI_GELU || EPI == EPI_GEGLU) && (pl.nt * pl.bn) % 32 == 0)
+                            ? kGemmThreads + 128 : kGemmThreads;
+    return launch_kernel(gemm_tcp_kernel<EPI>, dim3(ctas), dim3(threads), static_cast<size_t>(pl.smem_bytes), stream,
                          tw, tx, d, pl.grid_x, pl.grid_y, pl.splitk);
 }
 
@@ -553,7 +560,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         return pl.splitk;
     }
     d.acc_bufs = 1; d.acc_stride = 0;
-    const bool large_dbuf = (g_large_t_mode == 1 || (g_large_t_mode < 0 && (c.epi == EPI_PARTIAL || c.epi == EPI_STORE))) &&
+    const bool large_dbuf = (g_large_t_mode == 1 || (g_large_t_mode < 0 && c.epi != EPI_GEGLU)) &&
                             c.T > 1024 && pl.nt == 1 && pl.tmem_cols <= 256 && pl.cluster == 1 && !pl.two_cta;
     if (large_dbuf) {
         d.acc_bufs = 2; d.acc_stride = pl.tmem_cols; d.tmem_cols = 2 * pl.tmem_cols;
