@@ -19,6 +19,8 @@
 #include "bodies.cuh"
 #include "launch.cuh"
 
+#include <string>
+
 namespace blurr {
 
 template <int HD_PAD, int BM, bool GEMMA>
@@ -112,8 +114,14 @@ cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld
     }
 }
 
+cudaError_t launch_joint_attention_prefill_tc(cudaStream_t stream, const JointAttnArgs& j, std::string* err);
+
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& j) {
     if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
+    if (attn_tc_applies(j)) {
+        std::string err;
+        return launch_joint_attention_prefill_tc(stream, j, &err);
+    }
     AttnMmaArgs a = make_prefill_attn_args(j);
     if (attn_tile_rows(j.q_per_sample, j.n_heads, j.batch, 32) == 16)
         return launch_attn<256, 16, true>(stream, a, j.q_per_sample, j.n_heads, j.batch);

@@ -1,0 +1,335 @@
+// Gemma joint-attention prefill on the tcgen05 tensor cores, for batched episodes
+// (joint_model.py:246-288; the mma.sync kernel of attention.cu stays the batch-1 path, where 144 small
+// CTAs beat 18 big ones).  At 64 episodes the mma.sync kernel is HMMA-bound (41 TFLOP/s, 15 % of the step).
+//
+// One CTA = 128 (head, query) pairs of one sample.  All 8 query heads share the sample's single K/V head
+// (MQA), so the 2208 pairs of a sample form 18 row tiles that each read K and V exactly once.
+//   S = Q K^T   : UMMA M=128 x N=288 keys (two N=144 chunks) x K=256, Q and K as K-major SW128 tiles
+//                 (K by TMA straight from the cache, Q copied + swizzled by the CTA because a tile
+//                 straddles two heads), fp32 accumulators in 288 TMEM columns;
+//   softmax     : thread = row (TMEM lane), two warps per lane quarter split the columns; the reference's
+//                 rounding chain per logit (bf16 -> /16 -> *(1/50) -> tanh -> *50 -> +mask, bf16 after every
+//                 op), exact two-pass fp32 softmax over the bf16 logits, probabilities rounded to bf16 and
+//                 written as the K-major SW128 A operand of the second GEMM (over the dead Q / K tiles);
+//   O = P V     : UMMA M=128 x N=256 dims x K=288 keys; V is used where it lies in the cache,
+//                 [key][dim] = MN-major B operand (instruction-descriptor bit 16, canonical SW128 layout
+//                 ((8,n),(8,k)):((1,LBO),(8,SBO)) with LBO = one 64-dim box, SBO = 8 keys x 128 B);
+//                 its TMA loads overlap the softmax.  O reuses the TMEM columns of S.
+#include "bodies.cuh"
+#include "gemm_tc.h"
+#include "launch.cuh"
+
+namespace blurr {
+
+// Set (to the stage number) when a bounded barrier wait expired; read by attn_take_timeout_flag().
+static __device__ int g_attn_timeout_flag = 0;
+
+static constexpr int kTcRows = 128;                  // (head, query) pairs per CTA
+static constexpr int kTcKeys = 288;                  // key columns of S (two UMMA N = 144 chunks)
+static constexpr int kTcKeyBlocks = 5;               // 64-key blocks of P (320 columns, zero past n_keys)
+static constexpr int kTcHd = 256;
+static constexpr int kTcThreads = 256;
+static constexpr int kTcQBytes = kTcRows * kTcHd * 2;                  // 64 KB: 4 k-blocks of [128][64]
+static constexpr int kTcKBytes = kTcKeys * kTcHd * 2;                  // 144 KB: 4 k-blocks of 2 x [144][64]
+static constexpr int kTcPBytes = kTcRows * kTcKeyBlocks * 64 * 2;      // 80 KB: 5 key blocks of [128][64]
+static constexpr int kTcVBytes = kTcKeys * kTcHd * 2;                  // 144 KB: 4.5 key blocks x 4 dim groups
+static constexpr int kTcSmem = kTcPBytes + kTcVBytes + 1024 /*alignment*/ + 1024 /*row stats*/ + 64 /*barriers*/;
+static_assert(kTcQBytes + kTcKBytes <= kTcPBytes + kTcVBytes, "phase 1 operands must fit the phase 2 footprint");
+
+struct AttnTcArgs {
+    const bf16* q;                // [B*q_per_sample][n_heads*256]
+    bf16* out;                    // same shape
+    const bf16* mask; long long mask_bstride, mask_rstride; int q_row_offset;
+    int q_per_sample, n_heads, n_keys, n_slots;
+    unsigned long long* trace;
+};
+
+// tanh through one ex2 and one rcp (relative error ~2^-21): the result is rounded to bf16 right away, so
+// against tanhf it flips about one rounding in 2^12.  |x| <= 50/16/50 * |logit| stays far below the range
+// where exp(2x) overflows; the clamp only guards garbage in padded rows.
+__device__ __forceinline__ float tanh_fast(float x) {
+    x = fminf(fmaxf(x, -15.f), 15.f);
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+// MN-major SW128 operand: 64 elements (128 B) contiguous along N per row, rows = K index
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;      // next 64-element group along N
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                       // next 8 rows along K
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v64,
+               const __grid_constant__ CUtensorMap tmap_v32, const AttnTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    trace_stamp(a.trace, 0);
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* q_s = base;                              // phase 1: Q | K
+    uint8_t* k_s = base + kTcQBytes;
+    uint8_t* p_s = base;                              // phase 2: P | V
+    uint8_t* v_s = base + kTcPBytes;
+    float* stat = reinterpret_cast<float*>(base + kTcPBytes + kTcVBytes);         // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTcPBytes + kTcVBytes + 1024);
+    uint64_t *bar_k = bars, *bar_s = bars + 1, *bar_v = bars + 2, *bar_o = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int n_pairs = a.n_heads * a.q_per_sample;
+    const int ldq = a.n_heads * kTcHd;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v64);
+        tma_prefetch_desc(&tmap_v32);
+        mbar_init(bar_k, 1); mbar_init(bar_s, 1); mbar_init(bar_v, 1); mbar_init(bar_o, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+    trace_stamp(a.trace, 1);
+
+    // ---- K tiles by TMA: k-block kb, chunk c -> [144 keys][64 dims] ----
+    const int key_row0 = b * a.n_slots;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar_k, static_cast<uint32_t>(kTcKBytes));
+        for (int kb = 0; kb < 4; ++kb)
+            for (int c = 0; c < 2; ++c)
+                tma_load_2d(k_s + (kb * 2 + c) * (144 * 128), &tmap_k, bar_k, kb * 64, key_row0 + c * 144);
+    }
+    // ---- Q tile: rows are (head, query) pairs; copy + 128B swizzle, zero rows past the last pair ----
+    for (int idx = threadIdx.x; idx < kTcRows * 32; idx += kTcThreads) {
+        const int r = idx >> 5, ch = idx & 31;               // 32 chunks of 8 dims per row
+        const int p = tile * kTcRows + r;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (p < n_pairs) {
+            const int head = p / a.q_per_sample, qi = p - head * a.q_per_sample;
+            val = __ldcg(reinterpret_cast<const uint4*>(a.q + (static_cast<size_t>(b) * a.q_per_sample + qi) * ldq +
+                                                        head * kTcHd + ch * 8));
+        }
+        const int kb = ch >> 3, c8 = ch & 7;
+        *reinterpret_cast<uint4*>(q_s + kb * (kTcRows * 128) + r * 128 + ((c8 ^ (r & 7)) << 4)) = val;
+    }
+    fence_proxy_async_smem();          // generic-proxy writes of Q before the tensor core reads them
+    __syncthreads();
+
+    // ---- S = Q K^T ----
+    if (warp == 1 && lane == 0) {
+        if (!mbar_wait(bar_k, 0)) atomicExch(&g_attn_timeout_flag, 1);
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_bf16(kTcRows, 144);
+        for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(q_s + kb * (kTcRows * 128)));
+            for (int c = 0; c < 2; ++c) {
+                const uint64_t b_desc = make_smem_desc_sw128(smem_u32(k_s + (kb * 2 + c) * (144 * 128)));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem + c * 144, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+        }
+        umma_commit(bar_s);
+    }
+
+    // ---- softmax: two warps per TMEM lane quarter, each half of the key columns ----
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int pair = tile * kTcRows + row;
+    const bool row_valid = pair < n_pairs;
+    const int head = row_valid ? pair / a.q_per_sample : 0;
+    const int qi = row_valid ? pair - head * a.q_per_sample : 0;
+    const bf16* mrow = a.mask + static_cast<size_t>(b) * a.mask_bstride + static_cast<size_t>(a.q_row_offset + qi) * a.mask_rstride;
+    if (!mbar_wait(bar_s, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 2); }
+    tcgen05_fence_after();
+    __syncthreads();                   // every thread has seen S complete: Q and K tiles are dead
+    if (threadIdx.x == 0) {
+        // V where it lies: key block kb (64 keys; the last one 32), dim group j -> [keys][64 dims]
+        mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(kTcVBytes));
+        for (int kb = 0; kb < 4; ++kb)
+            for (int j = 0; j < 4; ++j)
+                tma_load_2d(v_s + (kb * 4 + j) * 8192, &tmap_v64, bar_v, j * 64, key_row0 + kb * 64);
+        for (int j = 0; j < 4; ++j)
+            tma_load_2d(v_s + 16 * 8192 + j * 4096, &tmap_v32, bar_v, j * 64, key_row0 + 256);
+    }
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * 144;
+    const int col0 = half * 144;
+    float m = -INFINITY;
+    // 16-byte mask loads when the mask rows allow it (the engine stages them with a stride of 280): one thread
+    // owns one mask row, so scalar loads touch 32 sectors per warp request, 16 requests per 16 columns
+    const bool mask_vec = ((a.mask_rstride | a.mask_bstride) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0;
+    // pass 1: rounding chain + mask -> bf16 logits into the P tile, running max
+    for (int g = 0; g < 9; ++g) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+        uint32_t mk[8];
+        if (mask_vec && row_valid && col0 + g * 16 + 16 <= ((a.n_keys + 7) & ~7)) {
+            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow + col0 + g * 16));
+            const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow + col0 + g * 16 + 8));
+            mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w; mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int col = col0 + g * 16 + 2 * i;
+                const float lo = (row_valid && col < a.n_keys) ? bf2f(mrow[col]) : 0.f;
+                const float hi = (row_valid && col + 1 < a.n_keys) ? bf2f(mrow[col + 1]) : 0.f;
+                mk[i] = pack_bf16x2(lo, hi);
+            }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            float s[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = col0 + g * 16 + i + e;
+                float v = bf16_round(__uint_as_float(r[i + e]));
+                v = v * 0.0625f;                                   // / sqrt(256): exact
+                v = bf16_round(v * (1.0f / 50.0f));
+                v = bf16_round(tanh_fast(v));
+                v = bf16_round(v * 50.0f);
+                const float2 mv = unpack_bf16x2(mk[i >> 1]);
+                if (col < a.n_keys && row_valid) v = bf16_round(v + (e == 0 ? mv.x : mv.y));
+                else v = -INFINITY;
+                s[e] = v;
+                m = fmaxf(m, v);
+            }
+            const int col = col0 + g * 16 + i;
+            const int kb = col >> 6, c8 = (col & 63) >> 3;
+            *reinterpret_cast<uint32_t*>(p_s + kb * (kTcRows * 128) + row * 128 + ((c8 ^ (row & 7)) << 4) + (col & 7) * 2) =
+                pack_bf16x2(s[0], s[1]);
+        }
+    }
+    stat[half * 128 + row] = m;
+    __syncthreads();
+    m = fmaxf(stat[row], stat[128 + row]);
+    if (!row_valid) m = 0.f;
+    __syncthreads();
+    // pass 2: sum of exp over this thread's columns
+    float sum = 0.f;
+    for (int c = 0; c < 144; c += 2) {
+        const int col = col0 + c;
+        const int kb = col >> 6, c8 = (col & 63) >> 3;
+        const float2 l = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p_s + kb * (kTcRows * 128) + row * 128 +
+                                                                          ((c8 ^ (row & 7)) << 4) + (col & 7) * 2));
+        sum += __expf(l.x - m) + __expf(l.y - m);
+    }
+    stat[half * 128 + row] = sum;
+    __syncthreads();
+    sum = stat[row] + stat[128 + row];
+    const float inv_sum = row_valid ? 1.f / sum : 0.f;
+    // pass 3: probabilities, bf16, in place
+    for (int c = 0; c < 144; c += 2) {
+        const int col = col0 + c;
+        const int kb = col >> 6, c8 = (col & 63) >> 3;
+        uint32_t* ptr = reinterpret_cast<uint32_t*>(p_s + kb * (kTcRows * 128) + row * 128 + ((c8 ^ (row & 7)) << 4) + (col & 7) * 2);
+        const float2 l = unpack_bf16x2(*ptr);
+        *ptr = row_valid ? pack_bf16x2(__expf(l.x - m) * inv_sum, __expf(l.y - m) * inv_sum) : 0u;
+    }
+    // key columns 288..319 of the last P block are never multiplied (the K loop stops at 288)
+    tcgen05_fence_before();
+    fence_proxy_async_smem();          // P (generic proxy) before the tensor core reads it
+    __syncthreads();
+
+    // ---- O = P V ----
+    if (warp == 1 && lane == 0) {
+        if (!mbar_wait(bar_v, 0)) atomicExch(&g_attn_timeout_flag, 3);
+        tcgen05_fence_after();
+        // M = 128, N = 256, B operand MN-major (bit 16)
+        const uint32_t idesc = make_idesc_bf16(kTcRows, kTcHd) | (1u << 16);
+        for (int kb = 0; kb < kTcKeyBlocks; ++kb) {
+            const int ksteps = (kb < 4) ? 4 : 2;                              // keys 256..287 only
+            const uint32_t vbase = smem_u32(v_s + kb * 4 * 8192);
+            const uint32_t lbo = (kb < 4) ? 8192u : 4096u;                   // one [keys][64 dims] box
+            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(p_s + kb * (kTcRows * 128)));
+            for (int k = 0; k < ksteps; ++k) {
+                const uint64_t b_desc = make_smem_desc_sw128_mn(vbase + k * 2048, lbo);    // 16 keys = 2 x 8 rows
+                umma_bf16_ss(tmem, a_desc + 2 * k, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+        }
+        umma_commit(bar_o);
+    }
+
+    // ---- epilogue: O -> bf16 -> [b*q + query][head*256 + dim] ----
+    if (!mbar_wait(bar_o, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 4); }
+    tcgen05_fence_after();
+    {
+        const uint32_t oaddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
+        bf16* orow = a.out + (static_cast<size_t>(b) * a.q_per_sample + qi) * ldq + head * kTcHd + half * 128;
+        for (int g = 0; g < 8; ++g) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(oaddr + g * 16, r);
+            tmem_ld_wait();
+            if (row_valid) {
+                uint4 lo, hi;
+                lo.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+                lo.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                lo.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+                lo.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                hi.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));
+                hi.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                hi.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
+                hi.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                *reinterpret_cast<uint4*>(orow + g * 16) = lo;
+                *reinterpret_cast<uint4*>(orow + g * 16 + 8) = hi;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    trace_stamp(a.trace, 2);
+    if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+int attn_take_timeout_flag() {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_attn_timeout_flag, sizeof(int)) != cudaSuccess) return -1;
+    if (v != 0) {
+        const int zero = 0;
+        cudaMemcpyToSymbol(g_attn_timeout_flag, &zero, sizeof(int));
+    }
+    return v;
+}
+
+static int g_attn_tc = -1;            // -1 automatic (batched episodes), 0 never, 1 whenever the shape allows
+void attn_set_tc(int mode) { g_attn_tc = mode; }
+
+bool attn_tc_applies(const JointAttnArgs& j) {
+    if (g_attn_tc == 0) return false;
+    const bool shape_ok = j.n_keys <= kTcKeys && j.n_slots >= 1 && j.q_per_sample >= 1 && j.n_heads >= 1;
+    if (!shape_ok) return false;
+    return g_attn_tc == 1 || j.batch >= 8;
+}
+
+cudaError_t launch_joint_attention_prefill_tc(cudaStream_t stream, const JointAttnArgs& j, std::string* err) {
+    CUtensorMap tk, tv64, tv32;
+    const int rows = j.batch * j.n_slots;
+    if (gemm_get_tensor_map(j.k_cache, rows, kTcHd, kTcHd, 144, &tk, err)) return cudaErrorInvalidValue;
+    if (gemm_get_tensor_map(j.v_cache, rows, kTcHd, kTcHd, 64, &tv64, err)) return cudaErrorInvalidValue;
+    if (gemm_get_tensor_map(j.v_cache, rows, kTcHd, kTcHd, 32, &tv32, err)) return cudaErrorInvalidValue;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    AttnTcArgs a{};
+    a.q = j.q; a.out = j.out; a.mask = j.mask; a.mask_bstride = j.mask_bstride; a.mask_rstride = j.mask_rstride;
+    a.q_row_offset = j.q_row_offset; a.q_per_sample = j.q_per_sample; a.n_heads = j.n_heads; a.n_keys = j.n_keys;
+    a.n_slots = j.n_slots; a.trace = j.trace;
+    const int tiles = (j.n_heads * j.q_per_sample + kTcRows - 1) / kTcRows;
+    return launch_kernel(attn_tc_kernel, dim3(tiles, j.batch), dim3(kTcThreads), static_cast<size_t>(kTcSmem), stream, tk, tv64,
+                         tv32, a);
+}
+
+}  // namespace blurr

@@ -65,6 +65,7 @@ struct StageArgs {
     const bf16* mask_act; long long act_bs, act_rs;
     int64_t* d_ids; int64_t* d_vpos; int64_t* d_ppos; int64_t* d_apos;
     bf16* d_proprios; bf16* d_action; bf16* d_mask_itp; bf16* d_mask_act;
+    int itp_ld;      // row stride of the staged image/text/proprio mask (n_itp rounded up to 8)
     int n_ids, n_ppos, n_apos, n_prop, n_noise, itp_dim, act_rows, act_cols, batch;
 };
 // Copies the per-call inputs into the engine's static buffers (the CUDA graph reads those).
@@ -84,7 +85,8 @@ __global__ void stage_inputs_kernel(const StageArgs a) {
     if (i < itp_per * a.batch) {
         const long long b = i / itp_per, rem = i - b * itp_per;
         const long long r = rem / a.itp_dim, c = rem - r * a.itp_dim;
-        a.d_mask_itp[i] = a.mask_itp[b * a.itp_bs + r * a.itp_rs + c];
+        // staged with rows padded to a multiple of 8 elements: 16-byte mask loads in the batched attention
+        a.d_mask_itp[(b * a.itp_dim + r) * a.itp_ld + c] = a.mask_itp[b * a.itp_bs + r * a.itp_rs + c];
         return;
     }
     i -= itp_per * a.batch;
@@ -382,7 +384,7 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
     h->d_proprios = bufb(Tp * c.proprio_dim);
     h->d_action = bufb(Ta * c.action_dim);
     h->d_out = bufb(Ta * c.action_dim);
-    h->d_mask_itp = bufb(B * h->n_itp * h->n_itp);
+    h->d_mask_itp = bufb(static_cast<size_t>(B) * h->n_itp * ((h->n_itp + 7) / 8 * 8));
     h->d_mask_act = bufb(B * c.num_action_tokens * h->n_total);
     h->patches = bufb(Tv * h->patch.K);
     h->xs = bufb(Tv * c.vision_hidden); h->xn = bufb(Tv * c.vision_hidden);
@@ -1027,7 +1029,7 @@ static void run_step(Run& R, int B, int steps) {
     StreamBufs sp{h->Ep, h->Epn, h->Qp, h->AOp, h->Hp, c.num_proprio_tokens, c.max_image_text_tokens,
                   c.max_image_text_tokens, h->d_ppos};
     StreamBufs sa{h->Ea, h->Ean, h->Qa, h->AOa, h->Ha, c.num_action_tokens, h->n_itp, 0, h->d_apos};
-    const long long itp_bs = static_cast<long long>(h->n_itp) * h->n_itp, itp_rs = h->n_itp;
+    const long long itp_rs = (h->n_itp + 7) / 8 * 8, itp_bs = static_cast<long long>(h->n_itp) * itp_rs;
     const long long act_bs = static_cast<long long>(c.num_action_tokens) * h->n_total, act_rs = h->n_total;
 
     // fork: the expert streams start once the inputs are staged
@@ -1155,7 +1157,7 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
     sa.n_ids = batch * c.max_image_text_tokens; sa.n_ppos = batch * c.num_proprio_tokens;
     sa.n_apos = batch * c.num_action_tokens; sa.n_prop = batch * c.num_proprio_tokens * c.proprio_dim;
     sa.n_noise = batch * c.num_action_tokens * c.action_dim;
-    sa.itp_dim = h->n_itp; sa.act_rows = c.num_action_tokens; sa.act_cols = h->n_total; sa.batch = batch;
+    sa.itp_dim = h->n_itp; sa.itp_ld = (h->n_itp + 7) / 8 * 8; sa.act_rows = c.num_action_tokens; sa.act_cols = h->n_total; sa.batch = batch;
     const long long total = static_cast<long long>(sa.n_ids) + sa.n_ppos + sa.n_apos + sa.n_prop + sa.n_noise +
                             static_cast<long long>(batch) * h->n_itp * h->n_itp +
                             static_cast<long long>(batch) * c.num_action_tokens * h->n_total;
@@ -1326,6 +1328,7 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_persistent") gemm_set_persistent(static_cast<int>(value));
     else if (n == "gemm_max_stages") gemm_set_max_stages(static_cast<int>(value));
     else if (n == "gemm_wide") gemm_set_wide(static_cast<int>(value));
+    else if (n == "attn_tc") attn_set_tc(static_cast<int>(value));
     else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
     else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
@@ -1338,6 +1341,8 @@ extern "C" int blurr_pi0_check(blurr_pi0_t* h, void* cuda_stream) {
     CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
     if (int tf = gemm_take_timeout_flag())
         return fail(BLURR_ERR_CUDA, "a GEMM pipeline wait expired (role " + std::to_string(tf) + "): results are invalid");
+    if (int tf = attn_take_timeout_flag())
+        return fail(BLURR_ERR_CUDA, "an attention pipeline wait expired (stage " + std::to_string(tf) + "): results are invalid");
     for (auto& kv : h->programs)
         if (int e = step_program_take_error(kv.second))
             return fail(BLURR_ERR_CUDA, "the persistent step kernel gave up waiting (code " + std::to_string(e) +

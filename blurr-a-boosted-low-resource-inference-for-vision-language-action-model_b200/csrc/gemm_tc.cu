@@ -211,6 +211,10 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
     return 0;
 }
 
+int gemm_get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, std::string* err) {
+    return get_tmap(ptr, rows, cols, ld, box_rows, out, err);
+}
+
 static bool g_pdl_enabled = true;
 bool pdl_enabled() { return g_pdl_enabled; }
 void pdl_set_enabled(bool on) { g_pdl_enabled = on; }

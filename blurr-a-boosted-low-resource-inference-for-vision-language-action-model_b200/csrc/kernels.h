@@ -109,6 +109,10 @@ struct JointAttnArgs {
     unsigned long long* trace;
 };
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& a);
+// attention_tc.cu: the same operator on tcgen05 for batched episodes (one CTA = 128 (head, query) pairs)
+void attn_set_tc(int mode);                      // -1 automatic (batch >= 8), 0 never, 1 whenever the shape allows
+bool attn_tc_applies(const JointAttnArgs& a);
+int attn_take_timeout_flag();
 // The AttnMmaArgs the two launchers above build (the step kernel runs the same bodies as work items).
 AttnMmaArgs make_siglip_attn_args(const bf16* qkv, int ld_qkv, int seq, int n_heads, int hidden, bf16* out,
                                   int ld_out);

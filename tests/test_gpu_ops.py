@@ -214,6 +214,33 @@ def test_joint_attention_prefill(batch, scale):
     assert (got.float() - ref.float()).abs().max().item() <= 0.05
 
 
+@pytest.mark.parametrize("batch,scale", [(1, 1.0), (2, 6.0), (9, 2.0)])
+def test_joint_attention_prefill_tcgen05(batch, scale):
+    """The batched-episode variant (tcgen05 S = QK^T and O = PV, V as an MN-major operand, rows = (head, query)
+    pairs) against the torch restatement and against the mma.sync kernel.  The two kernels round at the same
+    points; only fp32 summation orders differ."""
+    lib = capi.load_library()
+    n_heads, n_keys, slots = 8, 277, 281
+    q = _rand((batch * 276, n_heads * 256), scale, 43)
+    kc = _rand((batch, slots, 256), scale, 44)
+    vc = _rand((batch, slots, 256), 1.0, 45)
+    cnts = ([268, 261, 276, 258] * 3)[:batch]
+    mask = _block_mask(batch, 277, 277, cnts, 0)
+    try:
+        capi.check(lib.blurr_set_global_option(b"attn_tc", 0))
+        base = op_joint_attention(False, q, 276, 0, kc, vc, n_keys, mask, batch, n_heads)
+        capi.check(lib.blurr_set_global_option(b"attn_tc", 1))
+        got = op_joint_attention(False, q, 276, 0, kc, vc, n_keys, mask, batch, n_heads)
+    finally:
+        capi.check(lib.blurr_set_global_option(b"attn_tc", -1))
+    ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], mask[:, :276], n_heads)
+    print(report(f"joint_prefill tcgen05 B={batch} scale={scale}", got, ref))
+    print(report("  vs mma.sync kernel", got, base))
+    assert (got.float() - ref.float()).abs().max().item() <= 0.05
+    assert (got.float() - base.float()).abs().max().item() <= 0.05
+    assert ((got.float() - base.float()).abs() > 0).float().mean().item() < 0.05
+
+
 @pytest.mark.parametrize("qps,row0,n_keys,batch", [(1, 276, 277, 2), (4, 0, 281, 2), (4, 0, 281, 160)])
 def test_joint_attention_fewq(qps, row0, n_keys, batch):
     n_heads, slots = 8, 281
