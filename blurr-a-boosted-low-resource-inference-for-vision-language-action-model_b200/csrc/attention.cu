@@ -101,10 +101,16 @@ int attn_tile_rows(int rows, int heads, int batch, int max_rows) {
     return 64;
 }
 
+bool attn_tc_siglip_applies(int batch, int seq, int n_heads, int hidden);
+cudaError_t launch_siglip_attention_tc(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq, int n_heads,
+                                       int hidden, bf16* out, int ld_out, unsigned long long* trace);
+
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
                                     int n_heads, int hidden, bf16* out, int ld_out, unsigned long long* trace) {
     const int hd = hidden / n_heads;
     if (hd > 80 || seq > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
+    if (attn_tc_siglip_applies(batch, seq, n_heads, hidden))
+        return launch_siglip_attention_tc(stream, qkv, ld_qkv, batch, seq, n_heads, hidden, out, ld_out, trace);
     AttnMmaArgs a = make_siglip_attn_args(qkv, ld_qkv, seq, n_heads, hidden, out, ld_out);
     a.trace = trace;
     switch (attn_tile_rows(seq, n_heads, batch, 64)) {

@@ -44,13 +44,24 @@ struct AttnTcArgs {
     unsigned long long* trace;
 };
 
-// tanh through one ex2 and one rcp (relative error ~2^-21): the result is rounded to bf16 right away, so
-// against tanhf it flips about one rounding in 2^12.  |x| <= 50/16/50 * |logit| stays far below the range
-// where exp(2x) overflows; the clamp only guards garbage in padded rows.
-__device__ __forceinline__ float tanh_fast(float x) {
-    x = fminf(fmaxf(x, -15.f), 15.f);
-    const float e = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, e + 1.f);
+// 16-byte chunk `cidx` (8 consecutive keys) of row `row` in the P operand: 64-key blocks of [128 rows][128 B],
+// 128B-swizzled.  A warp's 32 rows x one chunk is conflict-free (8 rows cover all 32 banks).
+__device__ __forceinline__ uint4* p_chunk(uint8_t* p_s, int row, int cidx) {
+    return reinterpret_cast<uint4*>(p_s + (cidx >> 3) * (kTcRows * 128) + row * 128 + (((cidx & 7) ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ float chunk_exp_sum(const uint4 c, float m) {
+    const float2 a0 = unpack_bf16x2(c.x), a1 = unpack_bf16x2(c.y), a2 = unpack_bf16x2(c.z), a3 = unpack_bf16x2(c.w);
+    return ((__expf(a0.x - m) + __expf(a0.y - m)) + (__expf(a1.x - m) + __expf(a1.y - m))) +
+           ((__expf(a2.x - m) + __expf(a2.y - m)) + (__expf(a3.x - m) + __expf(a3.y - m)));
+}
+__device__ __forceinline__ uint4 chunk_probs(const uint4 c, float m, float inv_sum) {
+    const float2 a0 = unpack_bf16x2(c.x), a1 = unpack_bf16x2(c.y), a2 = unpack_bf16x2(c.z), a3 = unpack_bf16x2(c.w);
+    uint4 o;
+    o.x = pack_bf16x2(__expf(a0.x - m) * inv_sum, __expf(a0.y - m) * inv_sum);
+    o.y = pack_bf16x2(__expf(a1.x - m) * inv_sum, __expf(a1.y - m) * inv_sum);
+    o.z = pack_bf16x2(__expf(a2.x - m) * inv_sum, __expf(a2.y - m) * inv_sum);
+    o.w = pack_bf16x2(__expf(a3.x - m) * inv_sum, __expf(a3.y - m) * inv_sum);
+    return o;
 }
 
 // MN-major SW128 operand: 64 elements (128 B) contiguous along N per row, rows = K index
@@ -187,6 +198,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
             }
         }
         tmem_ld_wait();
+        uint32_t packed[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
             float s[2];
@@ -196,7 +208,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
                 float v = bf16_round(__uint_as_float(r[i + e]));
                 v = v * 0.0625f;                                   // / sqrt(256): exact
                 v = bf16_round(v * (1.0f / 50.0f));
-                v = bf16_round(tanh_fast(v));
+                v = bf16_round(tanh_fast_f32(v));
                 v = bf16_round(v * 50.0f);
                 const float2 mv = unpack_bf16x2(mk[i >> 1]);
                 if (col < a.n_keys && row_valid) v = bf16_round(v + (e == 0 ? mv.x : mv.y));
@@ -204,11 +216,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
                 s[e] = v;
                 m = fmaxf(m, v);
             }
-            const int col = col0 + g * 16 + i;
-            const int kb = col >> 6, c8 = (col & 63) >> 3;
-            *reinterpret_cast<uint32_t*>(p_s + kb * (kTcRows * 128) + row * 128 + ((c8 ^ (row & 7)) << 4) + (col & 7) * 2) =
-                pack_bf16x2(s[0], s[1]);
+            packed[i >> 1] = pack_bf16x2(s[0], s[1]);
         }
+        const int cidx = (col0 + g * 16) >> 3;
+        *p_chunk(p_s, row, cidx) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *p_chunk(p_s, row, cidx + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
     }
     stat[half * 128 + row] = m;
     __syncthreads();
@@ -217,24 +229,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     __syncthreads();
     // pass 2: sum of exp over this thread's columns
     float sum = 0.f;
-    for (int c = 0; c < 144; c += 2) {
-        const int col = col0 + c;
-        const int kb = col >> 6, c8 = (col & 63) >> 3;
-        const float2 l = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p_s + kb * (kTcRows * 128) + row * 128 +
-                                                                          ((c8 ^ (row & 7)) << 4) + (col & 7) * 2));
-        sum += __expf(l.x - m) + __expf(l.y - m);
-    }
+    for (int c = 0; c < 18; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
     stat[half * 128 + row] = sum;
     __syncthreads();
     sum = stat[row] + stat[128 + row];
     const float inv_sum = row_valid ? 1.f / sum : 0.f;
     // pass 3: probabilities, bf16, in place
-    for (int c = 0; c < 144; c += 2) {
-        const int col = col0 + c;
-        const int kb = col >> 6, c8 = (col & 63) >> 3;
-        uint32_t* ptr = reinterpret_cast<uint32_t*>(p_s + kb * (kTcRows * 128) + row * 128 + ((c8 ^ (row & 7)) << 4) + (col & 7) * 2);
-        const float2 l = unpack_bf16x2(*ptr);
-        *ptr = row_valid ? pack_bf16x2(__expf(l.x - m) * inv_sum, __expf(l.y - m) * inv_sum) : 0u;
+    for (int c = 0; c < 18; ++c) {
+        uint4* ptr = p_chunk(p_s, row, (col0 >> 3) + c);
+        *ptr = row_valid ? chunk_probs(*ptr, m, inv_sum) : make_uint4(0u, 0u, 0u, 0u);
     }
     // key columns 288..319 of the last P block are never multiplied (the K loop stops at 288)
     tcgen05_fence_before();
@@ -291,6 +294,189 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SigLIP self-attention (siglip.py:133-152) for batched episodes: one CTA = 128 queries of one head.
+// head_dim 72 is padded to 128 for the tensor cores without touching memory layouts: the Q tile is copied
+// with zeros in dims 72..127 (so whatever the K tile's second 64-dim TMA box drags in from the next head
+// multiplies by zero), V's second 64-dim box only feeds output columns 72..127, which are never stored.
+//   S = Q K^T : M=128 x N=256 keys x K=128 -> TMEM columns 0..255;  O = P V : M=128 x N=128 x K=256 -> 256..383.
+struct AttnTcSiglipArgs {
+    const bf16* qkv; int ld_qkv; int seq, n_heads, hidden; bf16* out; int ld_out; float scale;
+    unsigned long long* trace;
+};
+static constexpr int kSgQBytes = 128 * 128 * 2;           // 32 KB: 2 k-blocks of [128][64]
+static constexpr int kSgKBytes = 256 * 128 * 2;           // 64 KB: 2 k-blocks of [256 keys][64]
+static constexpr int kSgPBytes = 128 * 256 * 2;           // 64 KB: 4 key blocks of [128][64], over Q | K
+static constexpr int kSgVBytes = 256 * 128 * 2;           // 64 KB: 4 key blocks x 2 dim boxes of [64 keys][64]
+static constexpr int kSgSmem = kSgQBytes + kSgKBytes + kSgVBytes + 1024 + 1024 + 64;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                      const AttnTcSiglipArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    trace_stamp(a.trace, 0);
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* q_s = base;
+    uint8_t* k_s = base + kSgQBytes;
+    uint8_t* p_s = base;                                   // P overwrites Q and the first half of K
+    uint8_t* v_s = base + kSgQBytes + kSgKBytes;
+    float* stat = reinterpret_cast<float*>(v_s + kSgVBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + kSgVBytes + 1024);
+    uint64_t *bar_k = bars, *bar_s = bars + 1, *bar_v = bars + 2, *bar_o = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int hd = a.hidden / a.n_heads;                   // 72
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        mbar_init(bar_k, 1); mbar_init(bar_s, 1); mbar_init(bar_v, 1); mbar_init(bar_o, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+    trace_stamp(a.trace, 1);
+
+    const int row0 = b * a.seq;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar_k, static_cast<uint32_t>(kSgKBytes));
+        for (int kb = 0; kb < 2; ++kb)
+            tma_load_2d(k_s + kb * (256 * 128), &tmap_k, bar_k, a.hidden + h * hd + kb * 64, row0);
+        mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(kSgVBytes));
+        for (int kb = 0; kb < 4; ++kb)
+            for (int j = 0; j < 2; ++j)
+                tma_load_2d(v_s + (kb * 2 + j) * 8192, &tmap_v, bar_v, 2 * a.hidden + h * hd + j * 64, row0 + kb * 64);
+    }
+    // Q tile: 128 queries x 128 dims (dims >= 72 zero), swizzled K-major
+    for (int idx = threadIdx.x; idx < kTcRows * 16; idx += kTcThreads) {
+        const int r = idx >> 4, ch = idx & 15;
+        const int qi = tile * kTcRows + r;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (qi < a.seq && ch * 8 < hd)
+            val = __ldcg(reinterpret_cast<const uint4*>(a.qkv + static_cast<size_t>(row0 + qi) * a.ld_qkv + h * hd + ch * 8));
+        const int kb = ch >> 3, c8 = ch & 7;
+        *reinterpret_cast<uint4*>(q_s + kb * (kTcRows * 128) + r * 128 + ((c8 ^ (r & 7)) << 4)) = val;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (warp == 1 && lane == 0) {
+        if (!mbar_wait(bar_k, 0)) atomicExch(&g_attn_timeout_flag, 5);
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_bf16(kTcRows, 256);
+        for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(q_s + kb * (kTcRows * 128)));
+            const uint64_t b_desc = make_smem_desc_sw128(smem_u32(k_s + kb * (256 * 128)));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_s);
+    }
+
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int qi = tile * kTcRows + row;
+    const bool row_valid = qi < a.seq;
+    if (!mbar_wait(bar_s, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 6); }
+    tcgen05_fence_after();
+    __syncthreads();                   // S complete for everyone: Q / K tiles are dead
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
+    const int col0 = half * 128;
+    float m = -INFINITY;
+    for (int g = 0; g < 8; ++g) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+        tmem_ld_wait();
+        uint32_t packed[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            float s[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = col0 + g * 16 + i + e;
+                float v = bf16_round(bf16_round(__uint_as_float(r[i + e])) * a.scale);
+                if (col >= a.seq || !row_valid) v = -INFINITY;
+                s[e] = v;
+                m = fmaxf(m, v);
+            }
+            packed[i >> 1] = pack_bf16x2(s[0], s[1]);
+        }
+        const int cidx = (col0 + g * 16) >> 3;
+        *p_chunk(p_s, row, cidx) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *p_chunk(p_s, row, cidx + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    }
+    stat[half * 128 + row] = m;
+    __syncthreads();
+    m = fmaxf(stat[row], stat[128 + row]);
+    if (!row_valid) m = 0.f;
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = 0; c < 16; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
+    stat[half * 128 + row] = sum;
+    __syncthreads();
+    sum = stat[row] + stat[128 + row];
+    const float inv_sum = row_valid ? 1.f / sum : 0.f;
+    for (int c = 0; c < 16; ++c) {
+        uint4* ptr = p_chunk(p_s, row, (col0 >> 3) + c);
+        *ptr = row_valid ? chunk_probs(*ptr, m, inv_sum) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    tcgen05_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (warp == 1 && lane == 0) {
+        if (!mbar_wait(bar_v, 0)) atomicExch(&g_attn_timeout_flag, 7);
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_bf16(kTcRows, 128) | (1u << 16);          // B (= V) MN-major
+        for (int kb = 0; kb < 4; ++kb) {
+            const uint32_t vbase = smem_u32(v_s + kb * 2 * 8192);
+            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(p_s + kb * (kTcRows * 128)));
+            for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(tmem + 256, a_desc + 2 * k, make_smem_desc_sw128_mn(vbase + k * 2048, 8192u), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_o);
+    }
+
+    if (!mbar_wait(bar_o, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 8); }
+    tcgen05_fence_after();
+    if (half == 0) {
+        // 72 real output dims: four groups of 16 and the first 8 of a fifth
+        const uint32_t oaddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + 256;
+        bf16* orow = a.out + static_cast<size_t>(row0 + qi) * a.ld_out + h * hd;
+        for (int g = 0; g < 5; ++g) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(oaddr + g * 16, r);
+            tmem_ld_wait();
+            if (row_valid) {
+                uint4 lo, hi;
+                lo.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+                lo.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                lo.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+                lo.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                hi.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));
+                hi.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                hi.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
+                hi.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                if (g * 16 < hd) *reinterpret_cast<uint4*>(orow + g * 16) = lo;
+                if (g * 16 + 8 < hd) *reinterpret_cast<uint4*>(orow + g * 16 + 8) = hi;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    trace_stamp(a.trace, 2);
+    if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
 int attn_take_timeout_flag() {
     int v = 0;
     if (cudaMemcpyFromSymbol(&v, g_attn_timeout_flag, sizeof(int)) != cudaSuccess) return -1;
@@ -309,6 +495,33 @@ bool attn_tc_applies(const JointAttnArgs& j) {
     const bool shape_ok = j.n_keys <= kTcKeys && j.n_slots >= 1 && j.q_per_sample >= 1 && j.n_heads >= 1;
     if (!shape_ok) return false;
     return g_attn_tc == 1 || j.batch >= 8;
+}
+
+bool attn_tc_siglip_applies(int batch, int seq, int n_heads, int hidden) {
+    if (g_attn_tc == 0) return false;
+    const int hd = hidden / n_heads;
+    if (seq > 256 || hd > 128 || (hd & 7) != 0) return false;
+    return g_attn_tc == 1 || batch >= 8;
+}
+
+cudaError_t launch_siglip_attention_tc(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq, int n_heads,
+                                       int hidden, bf16* out, int ld_out, unsigned long long* trace) {
+    CUtensorMap tk, tv;
+    std::string err;
+    if (gemm_get_tensor_map(qkv, batch * seq, 3 * hidden, ld_qkv, 256, &tk, &err)) return cudaErrorInvalidValue;
+    if (gemm_get_tensor_map(qkv, batch * seq, 3 * hidden, ld_qkv, 64, &tv, &err)) return cudaErrorInvalidValue;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_siglip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    AttnTcSiglipArgs a{};
+    a.qkv = qkv; a.ld_qkv = ld_qkv; a.seq = seq; a.n_heads = n_heads; a.hidden = hidden; a.out = out; a.ld_out = ld_out;
+    a.scale = static_cast<float>(pow(static_cast<double>(hidden / n_heads), -0.5));
+    a.trace = trace;
+    return launch_kernel(attn_tc_siglip_kernel, dim3((seq + kTcRows - 1) / kTcRows, n_heads, batch), dim3(kTcThreads),
+                         static_cast<size_t>(kSgSmem), stream, tk, tv, a);
 }
 
 cudaError_t launch_joint_attention_prefill_tc(cudaStream_t stream, const JointAttnArgs& j, std::string* err) {

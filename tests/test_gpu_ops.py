@@ -169,6 +169,32 @@ def test_siglip_attention(batch):
     assert (got.float() - ref.float()).abs().max().item() <= 0.03
 
 
+@pytest.mark.parametrize("batch", [1, 3, 9])
+def test_siglip_attention_tcgen05(batch):
+    """Batched-episode SigLIP attention on tcgen05 (head_dim 72 zero-padded to 128 inside the Q tile) against
+    the torch restatement and the mma.sync kernel."""
+    lib = capi.load_library()
+    seq, heads, hidden = 256, 16, 1152
+    hd = hidden // heads
+    qkv = _rand((batch * seq, 3 * hidden), 1.0, 52)
+    try:
+        capi.check(lib.blurr_set_global_option(b"attn_tc", 0))
+        base = op_siglip_attention(qkv, batch, seq, heads, hidden)
+        capi.check(lib.blurr_set_global_option(b"attn_tc", 1))
+        got = op_siglip_attention(qkv, batch, seq, heads, hidden)
+    finally:
+        capi.check(lib.blurr_set_global_option(b"attn_tc", -1))
+    q, k, v = [t.view(batch, seq, heads, hd).transpose(1, 2) for t in qkv.view(batch, seq, 3 * hidden).split(hidden, -1)]
+    w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
+    w = torch.softmax(w, dim=-1, dtype=torch.float32).to(torch.bfloat16)
+    ref = torch.matmul(w, v).transpose(1, 2).contiguous().view(batch * seq, hidden)
+    print(report(f"siglip_attention tcgen05 B={batch}", got, ref))
+    print(report("  vs mma.sync kernel", got, base))
+    assert (got.float() - ref.float()).abs().max().item() <= 0.03
+    assert (got.float() - base.float()).abs().max().item() <= 0.03
+    assert ((got.float() - base.float()).abs() > 0).float().mean().item() < 0.05
+
+
 def _joint_ref(q, kc, vc, mask_rows, n_heads):
     """joint_model.py:273-288 on [B, H, Q, 256] / [B, 1, KV, 256]."""
     B = kc.shape[0]
