@@ -28,12 +28,16 @@ static constexpr int kTcRows = 128;                  // (head, query) pairs per 
 static constexpr int kTcKeys = 288;                  // key columns of S (two UMMA N = 144 chunks)
 static constexpr int kTcKeyBlocks = 5;               // 64-key blocks of P (320 columns, zero past n_keys)
 static constexpr int kTcHd = 256;
-static constexpr int kTcThreads = 256;
+static constexpr int kTcThreads = 384;                // Gemma kernel: 3 softmax warps per TMEM lane quarter (96 key columns each)
+static constexpr int kTcParts = kTcThreads / 128;
+static constexpr int kSgThreads = 512;                // SigLIP kernel: 4 per quarter (64 key columns each)
+static constexpr int kSgParts = kSgThreads / 128;
 static constexpr int kTcQBytes = kTcRows * kTcHd * 2;                  // 64 KB: 4 k-blocks of [128][64]
 static constexpr int kTcKBytes = kTcKeys * kTcHd * 2;                  // 144 KB: 4 k-blocks of 2 x [144][64]
 static constexpr int kTcPBytes = kTcRows * kTcKeyBlocks * 64 * 2;      // 80 KB: 5 key blocks of [128][64]
 static constexpr int kTcVBytes = kTcKeys * kTcHd * 2;                  // 144 KB: 4.5 key blocks x 4 dim groups
-static constexpr int kTcSmem = kTcPBytes + kTcVBytes + 1024 /*alignment*/ + 1024 /*row stats*/ + 64 /*barriers*/;
+static constexpr int kTcSmem = kTcPBytes + kTcVBytes + 1024 /*alignment*/ + kTcParts * 512 /*row stats*/ + 64 /*barriers*/;
+static_assert(kTcSmem <= 227 * 1024, "shared memory budget");
 static_assert(kTcQBytes + kTcKBytes <= kTcPBytes + kTcVBytes, "phase 1 operands must fit the phase 2 footprint");
 
 struct AttnTcArgs {
@@ -85,8 +89,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     uint8_t* k_s = base + kTcQBytes;
     uint8_t* p_s = base;                              // phase 2: P | V
     uint8_t* v_s = base + kTcPBytes;
-    float* stat = reinterpret_cast<float*>(base + kTcPBytes + kTcVBytes);         // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTcPBytes + kTcVBytes + 1024);
+    float* stat = reinterpret_cast<float*>(base + kTcPBytes + kTcVBytes);         // [kTcParts][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTcPBytes + kTcVBytes + kTcParts * 512);
     uint64_t *bar_k = bars, *bar_s = bars + 1, *bar_v = bars + 2, *bar_o = bars + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
@@ -153,8 +157,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
         umma_commit(bar_s);
     }
 
-    // ---- softmax: two warps per TMEM lane quarter, each half of the key columns ----
-    const int quarter = warp & 3, half = warp >> 2;
+    // ---- softmax: kTcParts warps per TMEM lane quarter, each a third of the key columns ----
+    constexpr int kCols = kTcKeys / kTcParts;            // 96
+    const int quarter = warp & 3, half = warp >> 2;      // `half` = column part 0..kTcParts-1
     const int row = quarter * 32 + lane;
     const int pair = tile * kTcRows + row;
     const bool row_valid = pair < n_pairs;
@@ -173,14 +178,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
         for (int j = 0; j < 4; ++j)
             tma_load_2d(v_s + 16 * 8192 + j * 4096, &tmap_v32, bar_v, j * 64, key_row0 + 256);
     }
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * 144;
-    const int col0 = half * 144;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * kCols;
+    const int col0 = half * kCols;
     float m = -INFINITY;
     // 16-byte mask loads when the mask rows allow it (the engine stages them with a stride of 280): one thread
     // owns one mask row, so scalar loads touch 32 sectors per warp request, 16 requests per 16 columns
     const bool mask_vec = ((a.mask_rstride | a.mask_bstride) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0;
     // pass 1: rounding chain + mask -> bf16 logits into the P tile, running max
-    for (int g = 0; g < 9; ++g) {
+    for (int g = 0; g < kCols / 16; ++g) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(lane_addr + g * 16, r);
         uint32_t mk[8];
@@ -224,18 +229,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     }
     stat[half * 128 + row] = m;
     __syncthreads();
-    m = fmaxf(stat[row], stat[128 + row]);
+    m = stat[row];
+#pragma unroll
+    for (int pt = 1; pt < kTcParts; ++pt) m = fmaxf(m, stat[pt * 128 + row]);
     if (!row_valid) m = 0.f;
     __syncthreads();
     // pass 2: sum of exp over this thread's columns
     float sum = 0.f;
-    for (int c = 0; c < 18; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
+    for (int c = 0; c < kCols / 8; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
     stat[half * 128 + row] = sum;
     __syncthreads();
-    sum = stat[row] + stat[128 + row];
+    sum = stat[row];
+#pragma unroll
+    for (int pt = 1; pt < kTcParts; ++pt) sum += stat[pt * 128 + row];
     const float inv_sum = row_valid ? 1.f / sum : 0.f;
     // pass 3: probabilities, bf16, in place
-    for (int c = 0; c < 18; ++c) {
+    for (int c = 0; c < kCols / 8; ++c) {
         uint4* ptr = p_chunk(p_s, row, (col0 >> 3) + c);
         *ptr = row_valid ? chunk_probs(*ptr, m, inv_sum) : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -266,7 +275,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     // ---- epilogue: O -> bf16 -> [b*q + query][head*256 + dim] ----
     if (!mbar_wait(bar_o, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 4); }
     tcgen05_fence_after();
-    {
+    if (half < 2) {
         const uint32_t oaddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
         bf16* orow = a.out + (static_cast<size_t>(b) * a.q_per_sample + qi) * ldq + head * kTcHd + half * 128;
         for (int g = 0; g < 8; ++g) {
@@ -308,9 +317,9 @@ static constexpr int kSgQBytes = 128 * 128 * 2;           // 32 KB: 2 k-blocks o
 static constexpr int kSgKBytes = 256 * 128 * 2;           // 64 KB: 2 k-blocks of [256 keys][64]
 static constexpr int kSgPBytes = 128 * 256 * 2;           // 64 KB: 4 key blocks of [128][64], over Q | K
 static constexpr int kSgVBytes = 256 * 128 * 2;           // 64 KB: 4 key blocks x 2 dim boxes of [64 keys][64]
-static constexpr int kSgSmem = kSgQBytes + kSgKBytes + kSgVBytes + 1024 + 1024 + 64;
+static constexpr int kSgSmem = kSgQBytes + kSgKBytes + kSgVBytes + 1024 + kSgParts * 512 + 64;
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kSgThreads, 1)
 attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                       const AttnTcSiglipArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -321,7 +330,7 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     uint8_t* p_s = base;                                   // P overwrites Q and the first half of K
     uint8_t* v_s = base + kSgQBytes + kSgKBytes;
     float* stat = reinterpret_cast<float*>(v_s + kSgVBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + kSgVBytes + 1024);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + kSgVBytes + kSgParts * 512);
     uint64_t *bar_k = bars, *bar_s = bars + 1, *bar_v = bars + 2, *bar_o = bars + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -355,7 +364,7 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
                 tma_load_2d(v_s + (kb * 2 + j) * 8192, &tmap_v, bar_v, 2 * a.hidden + h * hd + j * 64, row0 + kb * 64);
     }
     // Q tile: 128 queries x 128 dims (dims >= 72 zero), swizzled K-major
-    for (int idx = threadIdx.x; idx < kTcRows * 16; idx += kTcThreads) {
+    for (int idx = threadIdx.x; idx < kTcRows * 16; idx += kSgThreads) {
         const int r = idx >> 4, ch = idx & 15;
         const int qi = tile * kTcRows + r;
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
@@ -388,10 +397,11 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     if (!mbar_wait(bar_s, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 6); }
     tcgen05_fence_after();
     __syncthreads();                   // S complete for everyone: Q / K tiles are dead
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
-    const int col0 = half * 128;
+    constexpr int kCols = 256 / kSgParts;                 // 64
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * kCols;
+    const int col0 = half * kCols;
     float m = -INFINITY;
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < kCols / 16; ++g) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(lane_addr + g * 16, r);
         tmem_ld_wait();
@@ -415,16 +425,20 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     }
     stat[half * 128 + row] = m;
     __syncthreads();
-    m = fmaxf(stat[row], stat[128 + row]);
+    m = stat[row];
+#pragma unroll
+    for (int pt = 1; pt < kSgParts; ++pt) m = fmaxf(m, stat[pt * 128 + row]);
     if (!row_valid) m = 0.f;
     __syncthreads();
     float sum = 0.f;
-    for (int c = 0; c < 16; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
+    for (int c = 0; c < kCols / 8; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
     stat[half * 128 + row] = sum;
     __syncthreads();
-    sum = stat[row] + stat[128 + row];
+    sum = stat[row];
+#pragma unroll
+    for (int pt = 1; pt < kSgParts; ++pt) sum += stat[pt * 128 + row];
     const float inv_sum = row_valid ? 1.f / sum : 0.f;
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < kCols / 8; ++c) {
         uint4* ptr = p_chunk(p_s, row, (col0 >> 3) + c);
         *ptr = row_valid ? chunk_probs(*ptr, m, inv_sum) : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -520,7 +534,7 @@ cudaError_t launch_siglip_attention_tc(cudaStream_t stream, const bf16* qkv, int
     a.qkv = qkv; a.ld_qkv = ld_qkv; a.seq = seq; a.n_heads = n_heads; a.hidden = hidden; a.out = out; a.ld_out = ld_out;
     a.scale = static_cast<float>(pow(static_cast<double>(hidden / n_heads), -0.5));
     a.trace = trace;
-    return launch_kernel(attn_tc_siglip_kernel, dim3((seq + kTcRows - 1) / kTcRows, n_heads, batch), dim3(kTcThreads),
+    return launch_kernel(attn_tc_siglip_kernel, dim3((seq + kTcRows - 1) / kTcRows, n_heads, batch), dim3(kSgThreads),
                          static_cast<size_t>(kSgSmem), stream, tk, tv, a);
 }
 
