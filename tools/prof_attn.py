@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch
 
 from helpers import op_joint_attention, op_siglip_attention
+from blurr_b200 import capi
+if os.environ.get("ATTN_TC"):
+    capi.check(capi.load_library().blurr_set_global_option(b"attn_tc", int(os.environ["ATTN_TC"])))
 
 dev = "cuda"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
@@ -32,5 +35,7 @@ def timeit(fn, n=20):
 
 
 print("prefill  us:", timeit(lambda: op_joint_attention(False, q, 276, 0, kc, vc, 277, mask, B, 8)))
+qp = rnd(B * 1, 2048)
+print("fewq q1  us:", timeit(lambda: op_joint_attention(True, qp, 1, 276, kc, vc, 277, mask, B, 8)))
 print("fewq q4  us:", timeit(lambda: op_joint_attention(True, qa, 4, 0, kc, vc, 281, maska, B, 8)))
 print("siglip   us:", timeit(lambda: op_siglip_attention(qkv, B, 256, 16, 1152)))

@@ -9,6 +9,9 @@ from blurr_b200.config import bridge_config
 from blurr_b200.pizero import PiZeroInference
 
 dev = torch.device("cuda:0")
+if os.environ.get("ATTN_TC"):
+    from blurr_b200 import capi
+    capi.check(capi.load_library().blurr_set_global_option(b"attn_tc", int(os.environ["ATTN_TC"])))
 def timed(model, args, noise, n=30):
     with torch.inference_mode():
         for _ in range(5):
@@ -30,7 +33,7 @@ for steps in (1, 10):
     with torch.inference_mode():
         model(**args, noise=inp["noise"])
     print(f"steps={steps} all (graph, streams): {timed(model, args, inp['noise']):.3f} ms", flush=True)
-    for sk in (0, 1):
+    for sk in (0,):
         model._engine.set_option("use_step_kernel", sk)
         model._engine.set_option("stage_mask", 4)
         print(f"steps={steps} action only, step_kernel={sk}: {timed(model, args, inp['noise']):.3f} ms  ops={model._engine.last_op_count()}", flush=True)
