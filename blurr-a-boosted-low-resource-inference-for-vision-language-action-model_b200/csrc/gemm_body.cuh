@@ -354,6 +354,47 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
             float bias = 0.f;
             if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
+            if (EPI != EPI_PARTIAL && p.staging_bytes > 0) {
+                // Staged epilogue (batched episodes, 8 epilogue warps): the bf16 output tile is assembled in a
+                // shared-memory buffer of its own (it does not alias the ring, the producer keeps loading) and
+                // leaves as 16-byte row stores - the direct path's 2-byte stores (one per lane and token) were
+                // what kept it behind the MMAs.
+                constexpr int OUTW = (EPI == EPI_GEGLU) ? kBlockM / 2 : kBlockM;
+                bf16* stg = reinterpret_cast<bf16*>(smem + p.stages * stage_bytes);
+                for (int g = g_begin; g < g_end; ++g) {
+                    uint32_t r[16];
+                    tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int t = g * 16 + i;
+                        if (EPI == EPI_GEGLU) {
+                            const float v = bf16_round(__uint_as_float(r[i]));
+                            const float up = __shfl_down_sync(0xffffffffu, v, 1);
+                            if ((lane & 1) == 0) stg[t * OUTW + (nl >> 1)] = f2bf(bf16_round(gelu_tanh_f32(v)) * up);
+                        } else {
+                            float v = bf16_round(__uint_as_float(r[i]) + bias);
+                            if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                            stg[t * OUTW + nl] = f2bf(v);
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);          // TMEM drained: the MMAs may reuse it
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");          // the 8 epilogue warps
+                const int et = static_cast<int>(threadIdx.x) - 128;
+                const int col_base = (EPI == EPI_GEGLU) ? bx * (kBlockM / 2) : n0;
+                for (int idx = et; idx < ntok * (OUTW / 8); idx += 256) {
+                    const int t = idx / (OUTW / 8), ch = idx - t * (OUTW / 8);
+                    if (t0 + t < p.T)
+                        *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) =
+                            *reinterpret_cast<const uint4*>(stg + t * OUTW + ch * 8);
+                }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");          // staging free for the next tile
+                buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
+                continue;
+            }
             for (int g = g_begin; g < g_end; ++g) {
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(lane_addr + g * 16, r);

@@ -72,7 +72,8 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
     const int stage_bytes = kTileABytes + p.nt * p.bn * (kBlockK * 2);
     uint32_t tmem_base;
-    GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes, 1, static_cast<uint32_t>(p.tmem_cols), &tmem_base);
+    GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes + p.staging_bytes, 1, static_cast<uint32_t>(p.tmem_cols),
+                                      &tmem_base);
     uint64_t* tmem_empty_bar = sh.tmem_full_bar + 2;      // [0], [1]: after tmem_full_bar and the TMEM slot word
     if (threadIdx.x == 0) {
         const uint32_t epi_warps = blockDim.x / 32 - 4;     // 4, or 8 in the activation-heavy batched launches
@@ -415,8 +416,7 @@ static cudaError_t launch_epip(cudaStream_t stream, const GemmPlan& pl, const CU
     const int ctas = tiles < kTargetCtas ? tiles : kTargetCtas;
     // epilogues with activation math get two warps per TMEM lane quarter so that they stay hidden under the
     // next tile's MMAs (double-buffered accumulators)
-    const int threads = (d.acc_bufs == 2 && (EPI == EPI_GELU || EPI == EPI_GEGLU) && (pl.nt * pl.bn) % 32 == 0)
-                            ? kGemmThreads + 128 : kGemmThreads;
+    const int threads = (d.staging_bytes > 0) ? kGemmThreads + 128 : kGemmThreads;
     return launch_kernel(gemm_tcp_kernel<EPI>, dim3(ctas), dim3(threads), static_cast<size_t>(pl.smem_bytes), stream,
                          tw, tx, d, pl.grid_x, pl.grid_y, pl.splitk);
 }
@@ -563,17 +563,19 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         if (e != cudaSuccess) { *err = std::string("gemm (2-CTA) launch failed: ") + cudaGetErrorString(e); return -1; }
         return pl.splitk;
     }
-    d.acc_bufs = 1; d.acc_stride = 0;
+    d.acc_bufs = 1; d.acc_stride = 0; d.staging_bytes = 0;
     const bool large_dbuf = (g_large_t_mode == 1 || (g_large_t_mode < 0 && c.epi != EPI_GEGLU)) &&
                             c.T > 1024 && pl.nt == 1 && pl.tmem_cols <= 256 && pl.cluster == 1 && !pl.two_cta;
     if (large_dbuf) {
         d.acc_bufs = 2; d.acc_stride = pl.tmem_cols; d.tmem_cols = 2 * pl.tmem_cols;
         // the direct epilogue stages nothing in the ring: use all of it
         const int stage_bytes = kTileABytes + pl.nt * pl.bn * kBlockK * 2;
-        int st = kRingBytes / stage_bytes;
+        if (c.epi != EPI_PARTIAL && (pl.nt * pl.bn) % 32 == 0)       // staged bf16 epilogue (8 epilogue warps)
+            d.staging_bytes = pl.nt * pl.bn * (c.epi == EPI_GEGLU ? kBlockM / 2 : kBlockM) * 2;
+        int st = (kRingBytes - d.staging_bytes) / stage_bytes;
         if (st > kMaxStages) st = kMaxStages;
         d.stages = st;
-        pl.smem_bytes = st * stage_bytes + 1024 + 256;
+        pl.smem_bytes = st * stage_bytes + d.staging_bytes + 1024 + 256;
     }
     if (large_dbuf || (g_persistent && pl.cluster == 1 && pl.nt * pl.bn <= kPersistentMaxTokens && c.epi != EPI_GEGLU)) {
         switch (c.epi) {

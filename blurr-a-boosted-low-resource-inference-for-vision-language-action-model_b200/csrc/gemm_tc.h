@@ -58,6 +58,7 @@ struct GemmDev {
     int w_static;     // weights may be fetched before griddepcontrol.wait
     int acc_bufs;     // persistent kernel: accumulator buffers in TMEM (1 or 2)
     int acc_stride;   // TMEM columns between them
+    int staging_bytes; // persistent kernel: bf16 output staging tile behind the ring (0 = direct epilogue)
 };
 
 struct GemmPlan {
