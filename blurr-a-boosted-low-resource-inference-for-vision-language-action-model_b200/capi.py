@@ -124,7 +124,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
             "g.build()' or python <package>/build.py). The Pi-0 path has no CPU fallback."
         )
     lib = C.CDLL(p)
+    lenient = bool(os.environ.get("BLURR_PI0_LIB_LENIENT"))      # tooling only: A/B against an older build
     for name, restype, argtypes in _SIGNATURES:
+        if lenient and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.restype = restype
         fn.argtypes = argtypes

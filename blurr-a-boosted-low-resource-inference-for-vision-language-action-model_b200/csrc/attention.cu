@@ -27,8 +27,8 @@ template <int HD_PAD, int BM, bool GEMMA>
 __global__ void __launch_bounds__(kAttnThreads) attn_mma_kernel(const AttnMmaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
     trace_stamp(a.trace, 0);
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     trace_stamp(a.trace, 1);
     attn_mma_body<HD_PAD, BM, GEMMA>(a, smem_attn, blockIdx.x, blockIdx.y, blockIdx.z);
     trace_stamp(a.trace, 2);

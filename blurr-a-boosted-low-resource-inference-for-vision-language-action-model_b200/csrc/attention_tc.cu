@@ -112,8 +112,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    pdl_trigger();
     pdl_wait();
+    pdl_trigger();
     trace_stamp(a.trace, 1);
 
     // ---- K tiles by TMA: k-block kb, chunk c -> [144 keys][64 dims] ----
@@ -349,8 +349,8 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    pdl_trigger();
     pdl_wait();
+    pdl_trigger();
     trace_stamp(a.trace, 1);
 
     const int row0 = b * a.seq;

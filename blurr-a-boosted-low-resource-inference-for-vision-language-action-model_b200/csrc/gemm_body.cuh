@@ -120,6 +120,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
                         tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], (kb0 + i) * kBlockK, n0, pol_w);
                 }
                 pdl_wait();
+                pdl_trigger();
                 trace_stamp(p.trace, 1);
                 for (int i = 0; i < pre; ++i)
                     for (int c = 0; c < p.nt; ++c)
@@ -267,6 +268,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                             tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], (kb0 + i) * kBlockK, n0, pol_w);
                     }
                     pdl_wait();
+                    pdl_trigger();
                     trace_stamp(p.trace, 1);
                     for (int i = 0; i < pre; ++i)
                         for (int c = 0; c < p.nt; ++c)
@@ -275,6 +277,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                     s = (pre == p.stages) ? 0 : pre;
                 } else {
                     pdl_wait();
+                    pdl_trigger();
                 }
             }
             for (int tile = first; tile < n_tiles; tile += stride) {
@@ -613,6 +616,7 @@ __device__ __forceinline__ void gemm_wide_tile(const GemmDev& p, const CUtensorM
                                      ((2 * px + t) * p.kb_total + kb0 + i) * kBlockM, pol_w);
             }
             pdl_wait();
+            pdl_trigger();
             trace_stamp(p.trace, 1);
             for (int i = 0; i < pre; ++i) {
                 uint8_t* stg = smem + i * kWideStageBytes + 2 * kTileABytes;

@@ -1,8 +1,9 @@
 // Kernel launch helper: every kernel of the control step is launched with programmatic dependent
 // launch (PDL) so that the launch latency and prologue of kernel N+1 overlap the execution of
 // kernel N, both in eager streams and inside the captured CUDA graph.  Kernels call
-// `pdl_wait()` before touching memory written by their predecessor and `pdl_trigger()` once the
-// successor may start launching.
+// `pdl_wait()` before touching memory written by their predecessor and `pdl_trigger()` right after it:
+// triggering before the wait lets the successor become resident a whole kernel earlier, where it only
+// holds shared memory / TMEM while parked in griddepcontrol.wait (measured: +0.1 ms per bs=1 step).
 #pragma once
 
 #include <cuda_runtime.h>

@@ -8,8 +8,8 @@ namespace blurr {
 
 __global__ void __launch_bounds__(128) im2col_kernel(const bf16* px, long long sb, long long sc, long long sh,
                                                      long long sw, bf16* patches, int ldp) {
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     im2col_body(px, sb, sc, sh, sw, patches, ldp, blockIdx.x, blockIdx.y);
 }
 
@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(256) embed_merge_kernel(const int64_t* ids, in
                                                           long long vocab, const bf16* img, int n_img, int hidden,
                                                           long long image_token, long long pad_token, float inv_div,
                                                           float normalizer, bf16* out, int* err_flag) {
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     embed_merge_body(ids, seq, table, vocab, img, n_img, hidden, image_token, pad_token, inv_div, normalizer, out,
                      err_flag, blockIdx.x, blockIdx.y);
 }
@@ -41,8 +41,8 @@ cudaError_t launch_embed_merge(cudaStream_t stream, const int64_t* input_ids, in
 __global__ void __launch_bounds__(256) small_k_linear_kernel(const bf16* x, int T, int K, const bf16* W,
                                                              const bf16* bias, int N, float scale, bf16* y, int ldy,
                                                              int col_off, const bf16* time_row, int time_cols) {
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     small_k_linear_body(x, T, K, W, bias, N, scale, y, ldy, col_off, time_row, time_cols, blockIdx.x, blockIdx.y);
 }
 
@@ -57,8 +57,8 @@ cudaError_t launch_small_k_linear(cudaStream_t stream, const bf16* x, int T, int
 __global__ void __launch_bounds__(256) action_tail_kernel(const bf16* xn, int T, int hidden, const bf16* W,
                                                           const bf16* bias, int action_dim, float dt, bf16* action,
                                                           bf16* vel_tap) {
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     action_tail_body(xn, T, hidden, W, bias, action_dim, dt, action, vel_tap, blockIdx.x);
 }
 
@@ -70,8 +70,8 @@ cudaError_t launch_action_tail(cudaStream_t stream, const bf16* xn, int T, int h
 }
 
 __global__ void __launch_bounds__(256) clamp_copy_kernel(const bf16* src, bf16* dst, int n, int do_clamp, float clip) {
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     clamp_copy_body(src, dst, n, do_clamp, clip, blockIdx.x);
 }
 

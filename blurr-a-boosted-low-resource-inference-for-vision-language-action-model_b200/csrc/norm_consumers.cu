@@ -16,8 +16,8 @@ namespace blurr {
 template <int VPT>
 __global__ void __launch_bounds__(kRowThreads) consumer_kernel(const ConsumerArgs a) {
     trace_stamp(a.trace, 0);
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     trace_stamp(a.trace, 1);
     consumer_body<VPT>(a, blockIdx.x);
     trace_stamp(a.trace, 2);
@@ -32,8 +32,8 @@ cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a) {
 
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* partial, int splitk, int T, int N, int ldp,
                                                        const bf16* bias, int act, float scale, bf16* out, int ldo) {
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     bias_act_body(partial, splitk, T, N, ldp, bias, act, scale, out, ldo, blockIdx.x);
 }
 
@@ -47,8 +47,8 @@ cudaError_t launch_bias_act(cudaStream_t stream, const float* partial, int split
 
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvArgs a) {
     trace_stamp(a.trace, 0);
-    pdl_trigger();     // the successor may begin its prologue now; it still waits for this grid to finish
     pdl_wait();
+    pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     trace_stamp(a.trace, 1);
     rope_kv_body(a, blockIdx.x);
     trace_stamp(a.trace, 2);
