@@ -687,6 +687,7 @@ struct Run {
         group_items += gx * gy * gz;
         return op;
     }
+    int side_stream_cap = 0;         // > 0 while the experts overlap the prefill (see pick_splitk)
     // split-K so that about one CTA per SM is in flight (each CTA owns ~all of an SM's smem)
     int pick_splitk(int T, int Nw, int K, size_t ws_floats) const {
         GemmPlan p = gemm_make_plan(T, Nw, K, 1, EPI_PARTIAL, 0);
@@ -697,6 +698,10 @@ struct Run {
         const int max_by_k = p.kb_total / 2 > 0 ? p.kb_total / 2 : 1;
         if (s > max_by_k) s = max_by_k;
         if (s > 16) s = 16;
+        // Expert GEMMs that run beside the VLM prefill (proprio expert, action expert of the first flow step):
+        // at most 2 K slices.  With 16 they spread over every SM and keep evicting the main stream's
+        // one-CTA-per-SM GEMMs into second waves; they have slack to spare (same-box A/B: 4.374 -> 4.279 ms).
+        if (side_stream_cap > 0 && T <= 32 && s > side_stream_cap) s = side_stream_cap;
         while (s > 1 && static_cast<size_t>(s) * T * Nw > ws_floats) --s;
         return s;
     }
@@ -1065,6 +1070,7 @@ static void run_step(Run& R, int B, int steps) {
     if (do_prefill)
         R.consumer(1, Tt, c.vlm_hidden, 0, nullptr, ADD_NONE, h->E, c.vlm_hidden, 1.0f, nullptr, NORM_RMS_GEMMA,
                    h->mix[0].layers[0].in_ln, nullptr, c.rms_norm_eps, h->En, false);
+    R.side_stream_cap = do_prefill ? 2 : 0;      // in every launch mode, so that all of them produce the same bits
     for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
         if (do_prefill) {
@@ -1109,6 +1115,7 @@ static void run_step(Run& R, int B, int steps) {
     R.on(2); R.record(h->ev_done_a);
     R.on(0); R.wait(h->ev_done_p); R.wait(h->ev_done_a);
 
+    R.side_stream_cap = 0;
     // ---- remaining Euler steps of the flow (pizero.py:516-538): sequential over the finished cache ----
     R.label = "action";
     for (int s = 1; s < (do_action ? steps : 0); ++s) {

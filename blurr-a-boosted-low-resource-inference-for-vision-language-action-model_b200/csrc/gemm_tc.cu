@@ -282,7 +282,10 @@ static int g_persistent = 1;
 static constexpr int kPersistentMaxTokens = 32;
 void gemm_set_persistent(int on) { g_persistent = on ? 1 : 0; }
 
-static int g_max_stages = 8;      // tuning knob (tools/time_gemm.py): cap of the TMA ring depth
+// Cap of the TMA ring depth.  4 measured best for the whole bs=1 step (4.363 ms vs 4.394 with 8, 4.566 with 3;
+// same-box A/B): deeper rings buy nothing per GEMM (see the planner notes below) and a smaller footprint lets
+// the kernels of the three streams share SMs.
+static int g_max_stages = 4;
 void gemm_set_max_stages(int n) { g_max_stages = n < 1 ? 1 : (n > 12 ? 12 : n); }
 
 static bool plan_fits(int bn, int nt, int kb_per_split, int epi, int* stages_out, int* smem_out, int b_div = 1) {

@@ -7,6 +7,11 @@ from blurr_b200 import synth
 from blurr_b200.config import bridge_config
 from blurr_b200.pizero import PiZeroInference
 dev = torch.device("cuda:0")
+if os.environ.get("OPTS"):          # e.g. OPTS="gemm_persistent=0,gemm_max_stages=4": process-wide tuning knobs
+    from blurr_b200 import capi
+    for kv in os.environ["OPTS"].split(","):
+        k, v = kv.split("=")
+        capi.check(capi.load_library().blurr_set_global_option(k.encode(), int(v)))
 cfg = bridge_config(1)
 model = PiZeroInference.from_state_dict(cfg, synth.random_state_dict_on_device(cfg, dev), device=dev)
 inp = synth.synthetic_inputs(cfg, 1, dtype=torch.bfloat16, device=dev)
