@@ -1104,6 +1104,7 @@ static void run_step(Run& R, int B, int steps) {
             R.on(2); R.label = "action";
             expert_layer_head(R, 2, l, sa, B, false, 2);
             if (do_prefill) { R.wait(h->ev_v[l]); R.wait(h->ev_p[l]); }
+            if (l == L - 1) R.side_stream_cap = 0;       // the VLM is done: the tail of the action expert runs alone
             const bf16* next = (l + 1 < L) ? h->mix[2].layers[l + 1].in_ln : h->mix[2].final_norm;
             expert_layer_tail(R, 2, l, sa, B, h->n_total, h->d_mask_act, act_bs, act_rs, next, 2);
             R.tap("flow0.L" + std::to_string(l) + ".action", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
