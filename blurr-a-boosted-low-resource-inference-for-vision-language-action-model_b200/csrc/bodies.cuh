@@ -39,19 +39,26 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;                      // every thread holds the total
 }
 
-// sum of the split-K slices of 4 consecutive columns, 4 independent 16-byte loads in flight
+// sum of the split-K slices of 4 consecutive columns; up to 8 independent 16-byte loads in flight (the
+// consumers are latency-bound: one round trip to L2 per batch of loads; 8 measured better than 4 and than
+// 16 predicated loads - same-box A/B 4.263 / 4.210 / 4.285 ms per step), accumulated in slice order
 __device__ __forceinline__ float4 sum_slices(const float* __restrict__ base, size_t slice_stride, int splitk) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int z = 0;
-    for (; z + 4 <= splitk; z += 4) {
-        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(base + (z + 0) * slice_stride));
-        const float4 p1 = __ldcg(reinterpret_cast<const float4*>(base + (z + 1) * slice_stride));
-        const float4 p2 = __ldcg(reinterpret_cast<const float4*>(base + (z + 2) * slice_stride));
-        const float4 p3 = __ldcg(reinterpret_cast<const float4*>(base + (z + 3) * slice_stride));
-        acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;     // fixed order z = 0, 1, 2, ...
-        acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
-        acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
-        acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
+    for (; z + 8 <= splitk; z += 8) {
+        float4 p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = __ldcg(reinterpret_cast<const float4*>(base + (z + i) * slice_stride));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc.x += p[i].x; acc.y += p[i].y; acc.z += p[i].z; acc.w += p[i].w; }   // fixed order z = 0, 1, 2, ...
+    }
+    if (z + 4 <= splitk) {
+        float4 p[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = __ldcg(reinterpret_cast<const float4*>(base + (z + i) * slice_stride));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc.x += p[i].x; acc.y += p[i].y; acc.z += p[i].z; acc.w += p[i].w; }
+        z += 4;
     }
     for (; z < splitk; ++z) {
         const float4 p = __ldcg(reinterpret_cast<const float4*>(base + z * slice_stride));
