@@ -248,6 +248,42 @@ def test_ragged_and_extreme_instruction_lengths():
     model.release_engine()
 
 
+@pytest.mark.parametrize("batch", [16, 64])
+def test_batched_episodes_match_oracle(batch):
+    """BASELINE.json configs[3] shapes at reduced depth: 16 / 64 episodes per GPU take the batched variants of
+    every kernel (persistent double-buffered and CTA-pair GEMMs, bf16 hand-off, tcgen05 attention).  Actions and
+    per-layer activations against the oracle's bf16 run, judged like the full-size test (error vs the fp32 run
+    relative to the reference's own)."""
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    cfg.final_action_clip_value = None
+    model, sd, inp = _setup(cfg, batch)
+    model.set_engine_options(reserve_batch=batch, debug_taps=True)
+    taps16, taps32 = {}, {}
+    ref16 = _oracle(sd, cfg, inp, taps16)
+    ref32 = _oracle_fp32(sd, cfg, inp, taps32)
+    got = _run(model, inp)
+    jc, vc = cfg.joint.config, cfg.vision.config
+    names = [f"siglip.layer{l}" for l in range(vc.num_hidden_layers)] + ["projector"]
+    names += [f"prefill.L{l}.{m}" for l in range(jc.num_hidden_layers - 1) for m in ("vlm", "proprio")]
+    names += [f"flow0.L{l}.action" for l in range(jc.num_hidden_layers)] + ["flow0.velocity"]
+    for n in names:
+        hi = taps32[n].float().flatten()
+        e_ours = (model.debug_tap(n).float().flatten()[: hi.numel()] - hi).abs()
+        e_ref = (taps16[n].float().flatten() - hi).abs()
+        rms = hi.pow(2).mean().sqrt().item()
+        assert e_ours.mean().item() <= 1.5 * e_ref.mean().item() + 1e-4 * rms, n
+        assert e_ours.max().item() <= 2.0 * e_ref.max().item() + 1e-3 * rms, n
+    model.set_engine_options(debug_taps=False)
+    fast = _run(model, inp)                       # the production regime: CUDA graph, three streams
+    err = (fast.float().clamp(-1, 1) - ref16.float().clamp(-1, 1)).abs().max().item()
+    e_ours = (fast.float() - ref32).abs().max().item()
+    e_ref = (ref16.float() - ref32).abs().max().item()
+    print(f"batch {batch}: clamped max_abs vs bf16 oracle {err:.3e}; vs fp32: ours {e_ours:.3e}, bf16 oracle {e_ref:.3e}")
+    assert torch.isfinite(fast.float()).all() and err <= 1e-2 and e_ours <= 2.0 * e_ref + 1e-3
+    assert torch.equal(fast, got)                 # taps mode (eager, one stream) and graph mode agree bit for bit
+    model.release_engine()
+
+
 def test_batched_bf16_handoff_equals_fp32_partials():
     """Above 1024 tokens a GEMM without a K split writes bf16(acc + bias) for its consumer instead of an fp32
     partial: same accumulator, same rounding point, so the actions and the KV cache are bit-identical."""
