@@ -28,13 +28,14 @@ __device__ __forceinline__ bf16x8 ldcg_bf16x8(const bf16* p) {
 // ===========================================================================
 static constexpr int kRowThreads = 256;
 
+template <int THREADS = kRowThreads>
 __device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     __syncthreads();               // protect `red` from the previous use
     if (l == 0) red[w] = v;
     __syncthreads();
-    float t = (l < (kRowThreads / 32)) ? red[l] : 0.f;
+    float t = (l < (THREADS / 32)) ? red[l] : 0.f;
     t = warp_sum(t);
     return t;                      // every thread holds the total
 }
@@ -80,15 +81,17 @@ __device__ __forceinline__ void store_bf16x4(bf16* p, float4 v) {
 }
 
 // One CTA per token row; each thread owns VPT groups of 4 consecutive columns in registers.
-template <int VPT>
+// THREADS x VPT >= N / 4; the stand-alone kernel picks an exact fit (SigLIP's 1152 columns: 288 threads x 1),
+// the persistent step kernel always runs 256 threads.
+template <int VPT, int THREADS = kRowThreads>
 __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t) {
-    __shared__ float red[kRowThreads / 32];
+    __shared__ float red[(THREADS + 31) / 32];
     const int nvec = a.N >> 2;
     float4 x[VPT];
     float lsum = 0.f, lsq = 0.f;
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
-        const int v = threadIdx.x + i * kRowThreads;
+        const int v = threadIdx.x + i * THREADS;
         x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (v >= nvec) continue;
         const int n = v << 2;
@@ -128,11 +131,11 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
     if (a.norm_mode == NORM_NONE || a.xn_out == nullptr) return;
 
     if (a.norm_mode == NORM_RMS_GEMMA) {
-        const float ms = block_sum(lsq, red) / static_cast<float>(a.N);
+        const float ms = block_sum<THREADS>(lsq, red) / static_cast<float>(a.N);
         const float r = rsqrtf(ms + a.eps);
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
-            const int v = threadIdx.x + i * kRowThreads;
+            const int v = threadIdx.x + i * THREADS;
             if (v >= nvec) continue;
             const int n = v << 2;
             const float4 w = load_bf16x4(a.norm_w + n);
@@ -141,20 +144,20 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
             store_bf16x4(a.xn_out + static_cast<size_t>(t) * a.ldn + n, y);
         }
     } else {
-        const float mean = block_sum(lsum, red) / static_cast<float>(a.N);
+        const float mean = block_sum<THREADS>(lsum, red) / static_cast<float>(a.N);
         float lvar = 0.f;
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
-            const int v = threadIdx.x + i * kRowThreads;
+            const int v = threadIdx.x + i * THREADS;
             if (v >= nvec) continue;
             const float dx = x[i].x - mean, dy = x[i].y - mean, dz = x[i].z - mean, dw = x[i].w - mean;
             lvar += (dx * dx + dy * dy) + (dz * dz + dw * dw);
         }
-        const float var = block_sum(lvar, red) / static_cast<float>(a.N);
+        const float var = block_sum<THREADS>(lvar, red) / static_cast<float>(a.N);
         const float rstd = rsqrtf(var + a.eps);
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
-            const int v = threadIdx.x + i * kRowThreads;
+            const int v = threadIdx.x + i * THREADS;
             if (v >= nvec) continue;
             const int n = v << 2;
             const float4 w = load_bf16x4(a.norm_w + n), b = load_bf16x4(a.norm_b + n);

@@ -13,21 +13,24 @@
 
 namespace blurr {
 
-template <int VPT>
-__global__ void __launch_bounds__(kRowThreads) consumer_kernel(const ConsumerArgs a) {
+template <int VPT, int THREADS>
+__global__ void __launch_bounds__(THREADS) consumer_kernel(const ConsumerArgs a) {
     trace_stamp(a.trace, 0);
     pdl_wait();
     pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     trace_stamp(a.trace, 1);
-    consumer_body<VPT>(a, blockIdx.x);
+    consumer_body<VPT, THREADS>(a, blockIdx.x);
     trace_stamp(a.trace, 2);
 }
 
 cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a) {
     if ((a.N & 3) || a.N > 2 * 4 * kRowThreads || (a.ldp & 3)) return cudaErrorInvalidValue;
+    // exact fits: every thread owns the same number of 4-column groups (1152 columns on 256 threads left 7/8 of
+    // the CTA idle in the second pass and cost an occupancy-limiting 46 registers)
+    if (a.N == 4 * 288) return launch_kernel(consumer_kernel<1, 288>, dim3(a.T), dim3(288), 0, stream, a);
     if (a.N <= 4 * kRowThreads)
-        return launch_kernel(consumer_kernel<1>, dim3(a.T), dim3(kRowThreads), 0, stream, a);
-    return launch_kernel(consumer_kernel<2>, dim3(a.T), dim3(kRowThreads), 0, stream, a);
+        return launch_kernel(consumer_kernel<1, kRowThreads>, dim3(a.T), dim3(kRowThreads), 0, stream, a);
+    return launch_kernel(consumer_kernel<2, kRowThreads>, dim3(a.T), dim3(kRowThreads), 0, stream, a);
 }
 
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* partial, int splitk, int T, int N, int ldp,
