@@ -203,7 +203,7 @@ __device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t) {
     const size_t sstride = static_cast<size_t>(a.T) * a.ldp;
     const int n_rot = (a.n_heads + 1) * 32;
     const int n_items = n_rot + 64;
-    for (int it = threadIdx.x; it < n_items; it += 256) {
+    for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
         if (it < n_rot) {
             const int h = it >> 5, j = (it & 31) << 2;             // head, first dim of the group
             if (h < a.n_heads && a.q_out == nullptr) continue;

@@ -48,7 +48,7 @@ cudaError_t launch_bias_act(cudaStream_t stream, const float* partial, int split
                          ldp, bias, act, scale, out, ldo);
 }
 
-__global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvArgs a) {
+__global__ void __launch_bounds__(384) rope_kv_kernel(const RopeKvArgs a) {
     trace_stamp(a.trace, 0);
     pdl_wait();
     pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvArgs a) {
 
 cudaError_t launch_rope_kv(cudaStream_t stream, const RopeKvArgs& a) {
     if (a.ldp & 3) return cudaErrorInvalidValue;
-    return launch_kernel(rope_kv_kernel, dim3(a.T), dim3(256), 0, stream, a);
+    // one work item (4 rotated pairs or 4 value columns) per thread: (n_heads + 1) * 32 + 64 items per token
+    const int items = (a.n_heads + 1) * 32 + 64;
+    const int threads = items <= 384 ? (items + 31) / 32 * 32 : 256;
+    return launch_kernel(rope_kv_kernel, dim3(a.T), dim3(threads), 0, stream, a);
 }
 
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, int n_pos, float* __restrict__ cos_t,
