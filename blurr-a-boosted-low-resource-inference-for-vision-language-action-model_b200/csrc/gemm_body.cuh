@@ -555,6 +555,149 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
 // Ring + barrier carve-up of a dynamic shared-memory block and one-time initialisation.
 // Returns the shared view; `smem_raw` needs ring_bytes + 1024 (alignment) + 256 (barriers).
 // ---------------------------------------------------------------------------------------------
+// Persistent CTA pairs (batched episodes, bf16 epilogues): the pair walks 256-weight-row x 256-token tiles;
+// each CTA loads its 128 weight rows and 128 of the tokens (tcgen05 cta_group::2 reads the other half from the
+// peer), the accumulator is double-buffered in TMEM (2 x 256 columns per CTA) and the epilogue - 8 warps,
+// staged in a buffer of its own, 16-byte row stores - runs under the MMAs of the next tile.
+//   leader (rank 0): full[s] collects the bytes of both CTAs, issues the MMAs, its commits arrive on empty[s]
+//   and tmem_full[buf] of both CTAs; tmem_empty[buf] lives in the leader and counts the 16 epilogue warps of
+//   the pair (the peer's arrive remotely).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+
+template <int EPI>
+__device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_xh,
+                                                     const GemmShared& sh, uint64_t* xbar, const int gxp, const int gy,
+                                                     const uint32_t crank, const int first, const int stride) {
+    static_assert(EPI != EPI_PARTIAL, "bf16 epilogues only");
+    uint8_t* smem = sh.ring;
+    const int half = p.bn / 2;
+    const int stage_bytes = kTileABytes + half * (kBlockK * 2);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tmem_base = sh.tmem_base;
+    const bool leader = (crank == 0);
+    const int n_tiles = gxp * gy;
+    uint64_t* tmem_empty = xbar;                     // [2], used in the leader
+    uint64_t* tmem_full1 = xbar + 2;                 // tmem_full of buffer 1 (buffer 0: sh.tmem_full_bar)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol_w = make_policy_evict_first();
+            const uint64_t pol_x = make_policy_evict_last();
+            uint32_t empty_bits = 0;
+            int s = 0;
+            pdl_wait();
+            pdl_trigger();
+            trace_stamp(p.trace, 1);
+            for (int tile = first; tile < n_tiles; tile += stride) {
+                const int bx = 2 * (tile % gxp) + static_cast<int>(crank), t0 = (tile / gxp) * p.bn;
+                for (int kb = 0; kb < p.kb_total; ++kb) {
+                    if (!mbar_wait(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 1); return; }
+                    empty_bits ^= (1u << s);
+                    uint8_t* stg = smem + s * stage_bytes;
+                    if (leader) mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+                    const uint32_t bar = map_to_cta(&sh.full_bar[s], 0u);
+                    tma_load_2d_2sm_hint(stg, tmap_w, bar, 0, (bx * p.kb_total + kb) * kBlockM, pol_w);
+                    tma_load_2d_2sm_hint(stg + kTileABytes, tmap_xh, bar, kb * kBlockK, t0 + static_cast<int>(crank) * half, pol_x);
+                    s = (s + 1 == p.stages) ? 0 : s + 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, static_cast<uint32_t>(p.bn));
+            uint32_t full_bits = 0, tmem_empty_bits = 0;
+            int s = 0, buf = 0;
+            for (int tile = first; tile < n_tiles; tile += stride) {
+                if (!mbar_wait(&tmem_empty[buf], ((tmem_empty_bits >> buf) & 1u) ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 4); return; }
+                tmem_empty_bits ^= (1u << buf);
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
+                for (int kb = 0; kb < p.kb_total; ++kb) {
+                    if (!mbar_wait(&sh.full_bar[s], (full_bits >> s) & 1u)) { atomicExch(&g_gemm_timeout_flag, 2); return; }
+                    full_bits ^= (1u << s);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                    const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                    const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16_ss_2sm(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2sm(&sh.empty_bar[s]);
+                    s = (s + 1 == p.stages) ? 0 : s + 1;
+                }
+                umma_commit_2sm(buf == 0 ? sh.tmem_full_bar : tmem_full1);
+                buf ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int w4 = (warp - 4) & 3, hf = (warp - 4) >> 2;
+        const int nl = w4 * 32 + lane;
+        const int n_groups = p.bn / 16;
+        const int g_begin = hf * (n_groups / 2), g_end = hf == 0 ? n_groups / 2 : n_groups;
+        constexpr int OUTW = (EPI == EPI_GEGLU) ? kBlockM / 2 : kBlockM;
+        bf16* stg = reinterpret_cast<bf16*>(smem + p.stages * stage_bytes);
+        const uint32_t empty_remote0 = map_to_cta(&tmem_empty[0], 0u), empty_remote1 = map_to_cta(&tmem_empty[1], 0u);
+        uint32_t tmem_bits = 0;
+        int buf = 0;
+        pdl_wait();
+        for (int tile = first; tile < n_tiles; tile += stride) {
+            const int bx = 2 * (tile % gxp) + static_cast<int>(crank), t0 = (tile / gxp) * p.bn;
+            const int n0 = bx * kBlockM;
+            const bool ready = mbar_wait(buf == 0 ? sh.tmem_full_bar : tmem_full1, (tmem_bits >> buf) & 1u);
+            tmem_bits ^= (1u << buf);
+            if (!ready) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 3); return; }
+            tcgen05_fence_after();
+            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
+            float bias = 0.f;
+            if (p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
+            for (int g = g_begin; g < g_end; ++g) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(lane_addr + g * 16, r);
+                tmem_ld_wait();
+                if (EPI == EPI_GEGLU) {
+                    // lanes 2j / 2j+1 hold gate_j / up_j.  Two tokens per step so that both lanes of a pair do a
+                    // GELU: the even lane finishes token i, the odd lane token i + 1, after one exchange.
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float v0 = bf16_round(__uint_as_float(r[i])), v1 = bf16_round(__uint_as_float(r[i + 1]));
+                        const float recv = __shfl_xor_sync(0xffffffffu, (lane & 1) ? v0 : v1, 1);
+                        const float gate = (lane & 1) ? recv : v0, up = (lane & 1) ? v1 : recv;
+                        stg[(g * 16 + i + (lane & 1)) * OUTW + (nl >> 1)] = f2bf(bf16_round(gelu_tanh_f32(gate)) * up);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = bf16_round(__uint_as_float(r[i]) + bias);
+                        if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                        stg[(g * 16 + i) * OUTW + nl] = f2bf(v);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&tmem_empty[buf]);
+                else mbar_arrive_cluster(buf == 0 ? empty_remote0 : empty_remote1);
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            const int et = static_cast<int>(threadIdx.x) - 128;
+            const int col_base = (EPI == EPI_GEGLU) ? bx * (kBlockM / 2) : n0;
+            for (int idx = et; idx < p.bn * (OUTW / 8); idx += 256) {
+                const int t = idx / (OUTW / 8), ch = idx - t * (OUTW / 8);
+                if (t0 + t < p.T)
+                    *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) =
+                        *reinterpret_cast<const uint4*>(stg + t * OUTW + ch * 8);
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            buf ^= 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // "Wide" variant for 256 < T <= 288 tokens (the batch-1 Gemma prefill, T = 276): one CTA owns TWO
 // consecutive 128-row weight tiles and streams the token operand once for both, which cuts the bytes
 // every SM has to ingest per weight tile from 16 + 36 KB to 16 + 18 KB per k-block (the measured

@@ -119,6 +119,40 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     if (warp == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
+// Persistent CTA pairs with double-buffered accumulators (gemm_pair_persistent in gemm_body.cuh).
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads + 128, 1)
+gemm_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_xh, const GemmDev p,
+                 const int gxp, const int gy) {
+    extern __shared__ uint8_t smem_raw[];
+    trace_stamp(p.trace, 0);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp == 0 && elect_one_sync()) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_xh);
+    }
+    const int stage_bytes = kTileABytes + (p.bn / 2) * (kBlockK * 2);
+    uint32_t tmem_base;
+    GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes + p.staging_bytes, 1, static_cast<uint32_t>(p.tmem_cols),
+                                      &tmem_base, true);
+    uint64_t* xbar = sh.tmem_full_bar + 2;
+    if (threadIdx.x == 0) {
+        mbar_init(&xbar[0], 16);                            // tmem_empty[buf]: 8 epilogue warps of each CTA of the pair
+        mbar_init(&xbar[1], 16);
+        mbar_init(&xbar[2], 1);                             // tmem_full of the second accumulator buffer
+        fence_barrier_init();
+    }
+    __syncthreads();
+    cluster_sync_all();                                     // both CTAs' barriers exist before any remote signal
+    const uint32_t crank = cluster_ctarank();
+    gemm_pair_persistent<EPI>(p, &tmap_w, &tmap_xh, sh, xbar, gxp, gy, crank, static_cast<int>(blockIdx.x >> 1),
+                              static_cast<int>(gridDim.x >> 1));
+    tcgen05_fence_before();
+    cluster_sync_all();                                     // the peer is done with this CTA's smem / TMEM / barriers
+    trace_stamp(p.trace, 2);
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
 // Two weight tiles per CTA for 256 < T <= 288 tokens (gemm_wide_tile in gemm_body.cuh).
 template <int EPI>
 __global__ void __launch_bounds__(kWideThreads, 1)
@@ -273,8 +307,9 @@ void gemm_set_wide(int on) { g_wide = on ? 1 : 0; }
 //   SigLIP qkv (store) 958 | 857 | 1028
 // The double-buffered persistent kernel wins while the epilogue is a plain store (it then hides entirely under
 // the next tile's MMAs) and loses when the epilogue carries the activation math; with two epilogue warps per
-// TMEM lane quarter it reaches 777 (fc1) and 974 (gate/up).  -1 = automatic: pairs for GeGLU, persistent for
-// everything else; 0 = never persistent; 1 = always.  (These kernels run against the 1 kW power cap: numbers
+// TMEM lane quarter it reaches 777 (fc1) and 974 (gate/up).  -1 = automatic: persistent CTA pairs for GeGLU
+// (gemm_launch_pairp), persistent single CTAs for everything else; 0 = never persistent; 1 = single-CTA
+// persistent for every epilogue; 2 = same as automatic.  (These kernels run against the 1 kW power cap: numbers
 // taken back to back differ by +-10 % with the order of the launches.)
 static int g_large_t_mode = -1;
 void gemm_set_large_t_mode(int mode) { g_large_t_mode = mode; }
@@ -492,6 +527,50 @@ static cudaError_t launch_wide(cudaStream_t stream, int grid_x, int smem, const 
                          tw, tx256, tx32, d);
 }
 
+template <int EPI>
+static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, const CUtensorMap& tw, const CUtensorMap& txh,
+                                const GemmDev& d, int gxp, int gy) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcp2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    return launch_kernel_cluster(gemm_tcp2_kernel<EPI>, dim3(2 * n_pairs), dim3(kGemmThreads + 128), static_cast<size_t>(smem),
+                                 stream, 2, tw, txh, d, gxp, gy);
+}
+
+// Batched GeGLU GEMM (automatic, or mode 2 of "gemm_large_t_mode"): persistent CTA pairs, 1142 TFLOP/s on the gate/up
+// shape at 64 episodes against 1050 for one tile per CTA pair (two pairs' CTAs per SM).
+static bool gemm_pairp_applies(const GemmCall& c) {
+    return (g_large_t_mode == 2 || g_large_t_mode < 0) && c.w_packed && c.epi == EPI_GEGLU && c.splitk <= 1 && c.bn_override == 0 && c.T > 1024 &&
+           c.Nw % (2 * kBlockM) == 0 && c.K % kBlockK == 0;
+}
+
+static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string* err) {
+    const int kb_total = c.K / kBlockK;
+    const int bn = 256, half = bn / 2;
+    CUtensorMap tw, txh;
+    if (get_tmap(c.W, c.Nw * kb_total, kBlockK, kBlockK, kBlockM, &tw, err)) return -1;
+    if (get_tmap(c.X, c.T, c.K, c.ldx, half, &txh, err)) return -1;
+    GemmDev d{};
+    d.T = c.T; d.bn = bn; d.nt = 1; d.kb_total = kb_total; d.kb_per_split = kb_total;
+    d.tmem_cols = 512; d.acc_bufs = 2; d.acc_stride = 256; d.Nw = c.Nw;
+    d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = nullptr;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static;
+    d.staging_bytes = bn * (kBlockM / 2) * 2;
+    const int stage_bytes = kTileABytes + half * kBlockK * 2;
+    d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
+    if (d.stages > kMaxStages) d.stages = kMaxStages;
+    const int smem = d.stages * stage_bytes + d.staging_bytes + 1024 + 256;
+    const int gxp = c.Nw / (2 * kBlockM), gy = (c.T + bn - 1) / bn;
+    const int tiles = gxp * gy;
+    const int n_pairs = tiles < kTargetCtas / 2 ? tiles : kTargetCtas / 2;
+    const cudaError_t e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, gy);
+    if (e != cudaSuccess) { *err = std::string("gemm (persistent pairs) launch failed: ") + cudaGetErrorString(e); return -1; }
+    return 1;
+}
+
 static bool gemm_wide_applies(const GemmCall& c) {
     return g_wide && c.w_packed && c.epi != EPI_PARTIAL && c.splitk <= 1 && c.bn_override == 0 &&
            c.T > kWideMain && c.T <= kWideMain + kWideTail && c.Nw % (2 * kBlockM) == 0 && c.K % kBlockK == 0;
@@ -527,6 +606,7 @@ static int gemm_launch_wide(cudaStream_t stream, const GemmCall& c, std::string*
 
 int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     if (gemm_wide_applies(c)) return gemm_launch_wide(stream, c, err);
+    if (gemm_pairp_applies(c)) return gemm_launch_pairp(stream, c, err);
     GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
     if (!pl.valid) {
         *err = "gemm_launch: unsupported shape T=" + std::to_string(c.T) + " Nw=" + std::to_string(c.Nw) +
@@ -566,7 +646,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         return pl.splitk;
     }
     d.acc_bufs = 1; d.acc_stride = 0; d.staging_bytes = 0;
-    const bool large_dbuf = (g_large_t_mode == 1 || (g_large_t_mode < 0 && c.epi != EPI_GEGLU)) &&
+    const bool large_dbuf = (g_large_t_mode == 1 || ((g_large_t_mode < 0 || g_large_t_mode == 2) && c.epi != EPI_GEGLU)) &&
                             c.T > 1024 && pl.nt == 1 && pl.tmem_cols <= 256 && pl.cluster == 1 && !pl.two_cta;
     if (large_dbuf) {
         d.acc_bufs = 2; d.acc_stride = pl.tmem_cols; d.tmem_cols = 2 * pl.tmem_cols;
