@@ -540,10 +540,12 @@ static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, cons
                                  stream, 2, tw, txh, d, gxp, gy);
 }
 
-// Batched GeGLU GEMM (automatic, or mode 2 of "gemm_large_t_mode"): persistent CTA pairs, 1142 TFLOP/s on the gate/up
+// Batched GeGLU / GELU GEMMs (automatic, or mode 2 of "gemm_large_t_mode"; mode 3 also plain stores): persistent CTA pairs, 1142 TFLOP/s on the gate/up
 // shape at 64 episodes against 1050 for one tile per CTA pair (two pairs' CTAs per SM).
 static bool gemm_pairp_applies(const GemmCall& c) {
-    return (g_large_t_mode == 2 || g_large_t_mode < 0) && c.w_packed && c.epi == EPI_GEGLU && c.splitk <= 1 && c.bn_override == 0 && c.T > 1024 &&
+    // GeGLU and GELU (SigLIP fc1: 1041 vs 910 TFLOP/s); plain stores gain nothing over the single-CTA persistent kernel
+    const bool epi_ok = c.epi == EPI_GEGLU || c.epi == EPI_GELU || (g_large_t_mode == 3 && c.epi == EPI_STORE);
+    return (g_large_t_mode >= 2 || g_large_t_mode < 0) && c.w_packed && epi_ok && c.splitk <= 1 && c.bn_override == 0 && c.T > 1024 &&
            c.Nw % (2 * kBlockM) == 0 && c.K % kBlockK == 0;
 }
 
@@ -558,7 +560,7 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     d.tmem_cols = 512; d.acc_bufs = 2; d.acc_stride = 256; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = nullptr;
     d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static;
-    d.staging_bytes = bn * (kBlockM / 2) * 2;
+    d.staging_bytes = bn * (c.epi == EPI_GEGLU ? kBlockM / 2 : kBlockM) * 2;
     const int stage_bytes = kTileABytes + half * kBlockK * 2;
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
     if (d.stages > kMaxStages) d.stages = kMaxStages;
@@ -566,7 +568,12 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     const int gxp = c.Nw / (2 * kBlockM), gy = (c.T + bn - 1) / bn;
     const int tiles = gxp * gy;
     const int n_pairs = tiles < kTargetCtas / 2 ? tiles : kTargetCtas / 2;
-    const cudaError_t e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, gy);
+    cudaError_t e;
+    switch (c.epi) {
+        case EPI_GEGLU: e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
+        case EPI_GELU:  e = launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
+        default:        e = launch_pairp<EPI_STORE>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
+    }
     if (e != cudaSuccess) { *err = std::string("gemm (persistent pairs) launch failed: ") + cudaGetErrorString(e); return -1; }
     return 1;
 }
@@ -646,7 +653,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         return pl.splitk;
     }
     d.acc_bufs = 1; d.acc_stride = 0; d.staging_bytes = 0;
-    const bool large_dbuf = (g_large_t_mode == 1 || ((g_large_t_mode < 0 || g_large_t_mode == 2) && c.epi != EPI_GEGLU)) &&
+    const bool large_dbuf = (g_large_t_mode == 1 || ((g_large_t_mode < 0 || g_large_t_mode >= 2) && c.epi != EPI_GEGLU && c.epi != EPI_GELU)) &&
                             c.T > 1024 && pl.nt == 1 && pl.tmem_cols <= 256 && pl.cluster == 1 && !pl.two_cta;
     if (large_dbuf) {
         d.acc_bufs = 2; d.acc_stride = pl.tmem_cols; d.tmem_cols = 2 * pl.tmem_cols;

@@ -53,7 +53,7 @@ def test_gemm_variants_agree(T, N, K, epi):
     code = {"store": capi.EPI_STORE, "gelu": capi.EPI_GELU, "geglu": capi.EPI_GEGLU}[epi]
     outs = []
     try:
-        for pairs, persistent, large in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (-1, 1, -1), (0, 1, 1), (-1, 1, 2)]:
+        for pairs, persistent, large in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (-1, 1, -1), (0, 1, 1), (-1, 1, 2), (-1, 1, 3)]:
             capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", pairs))
             capi.check(lib.blurr_set_global_option(b"gemm_persistent", persistent))
             capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", large))
