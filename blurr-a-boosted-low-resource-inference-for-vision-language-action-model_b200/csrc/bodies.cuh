@@ -83,8 +83,30 @@ __device__ __forceinline__ void store_bf16x4(bf16* p, float4 v) {
 // One CTA per token row; each thread owns VPT groups of 4 consecutive columns in registers.
 // THREADS x VPT >= N / 4; the stand-alone kernel picks an exact fit (SigLIP's 1152 columns: 288 threads x 1),
 // the persistent step kernel always runs 256 threads.
-template <int VPT, int THREADS = kRowThreads>
-__device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t) {
+// Inputs of one row that a streaming launch fetched ahead of time (bf16 hand-off mode only).
+template <int VPT>
+struct ConsumerRowIn { uint2 lin[VPT], add[VPT]; };
+__device__ __forceinline__ float4 unpack_bf16x4(uint2 u) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <int VPT, int THREADS>
+__device__ __forceinline__ void consumer_prefetch(const ConsumerArgs& a, const int t, ConsumerRowIn<VPT>& in) {
+    const int nvec = a.N >> 2;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int v = threadIdx.x + i * THREADS;
+        in.lin[i] = make_uint2(0u, 0u); in.add[i] = make_uint2(0u, 0u);
+        if (v >= nvec) continue;
+        const int n = v << 2;
+        in.lin[i] = __ldcg(reinterpret_cast<const uint2*>(a.lin + static_cast<size_t>(t) * a.ldl + n));
+        if (a.add_mode == ADD_RESIDUAL) in.add[i] = __ldcg(reinterpret_cast<const uint2*>(a.res + static_cast<size_t>(t) * a.ldr + n));
+        else if (a.add_mode == ADD_POSEMB) in.add[i] = __ldcg(reinterpret_cast<const uint2*>(a.pos + static_cast<size_t>(t % a.pos_rows) * a.N + n));
+    }
+}
+
+template <int VPT, int THREADS = kRowThreads, bool PRELOADED = false>
+__device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t, const ConsumerRowIn<VPT>* pre = nullptr) {
     __shared__ float red[(THREADS + 31) / 32];
     const int nvec = a.N >> 2;
     float4 x[VPT];
@@ -97,7 +119,9 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
         const int n = v << 2;
         float4 val;
         if (a.partial != nullptr || a.lin != nullptr) {
-            if (a.lin != nullptr) {
+            if (PRELOADED) {
+                val = unpack_bf16x4(pre->lin[i]);
+            } else if (a.lin != nullptr) {
                 val = load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + n);      // already bf16(acc + bias)
             } else {
                 float4 acc = sum_slices(a.partial + static_cast<size_t>(t) * a.ldp + n,
@@ -112,11 +136,12 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
                 val = make_float4(bf16_round(val.x * a.out_scale), bf16_round(val.y * a.out_scale),
                                   bf16_round(val.z * a.out_scale), bf16_round(val.w * a.out_scale));
             if (a.add_mode == ADD_RESIDUAL) {
-                const float4 r = load_bf16x4(a.res + static_cast<size_t>(t) * a.ldr + n);
+                const float4 r = PRELOADED ? unpack_bf16x4(pre->add[i]) : load_bf16x4(a.res + static_cast<size_t>(t) * a.ldr + n);
                 val = make_float4(bf16_round(r.x + val.x), bf16_round(r.y + val.y), bf16_round(r.z + val.z),
                                   bf16_round(r.w + val.w));
             } else if (a.add_mode == ADD_POSEMB) {
-                const float4 r = load_bf16x4(a.pos + static_cast<size_t>(t % a.pos_rows) * a.N + n);
+                const float4 r = PRELOADED ? unpack_bf16x4(pre->add[i])
+                                           : load_bf16x4(a.pos + static_cast<size_t>(t % a.pos_rows) * a.N + n);
                 val = make_float4(bf16_round(val.x + r.x), bf16_round(val.y + r.y), bf16_round(val.z + r.z),
                                   bf16_round(val.w + r.w));
             }

@@ -23,7 +23,35 @@ __global__ void __launch_bounds__(THREADS) consumer_kernel(const ConsumerArgs a)
     trace_stamp(a.trace, 2);
 }
 
+// Batched episodes, bf16 hand-off mode: a fixed grid streams the rows, every CTA fetching the inputs of its next
+// row before it reduces the current one (the one-row-per-CTA launch is latency-bound: 1.7-2.4 TB/s at 64 episodes).
+template <int VPT, int THREADS>
+__global__ void __launch_bounds__(THREADS) consumer_stream_kernel(const ConsumerArgs a) {
+    trace_stamp(a.trace, 0);
+    pdl_wait();
+    pdl_trigger();
+    trace_stamp(a.trace, 1);
+    int t = blockIdx.x;
+    ConsumerRowIn<VPT> cur, nxt;
+    if (t < a.T) consumer_prefetch<VPT, THREADS>(a, t, cur);
+    for (; t < a.T; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        if (tn < a.T) consumer_prefetch<VPT, THREADS>(a, tn, nxt);
+        consumer_body<VPT, THREADS, true>(a, t, &cur);
+        cur = nxt;
+    }
+    trace_stamp(a.trace, 2);
+}
+
+static constexpr int kStreamMinRows = 2048;
+
 cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a) {
+    if (a.lin != nullptr && a.T >= kStreamMinRows && !(a.N & 3) && a.partial == nullptr) {
+        const int grid = 148 * 6;
+        if (a.N == 4 * 288) return launch_kernel(consumer_stream_kernel<1, 288>, dim3(grid), dim3(288), 0, stream, a);
+        if (a.N == 4 * 512) return launch_kernel(consumer_stream_kernel<2, kRowThreads>, dim3(grid), dim3(kRowThreads), 0, stream, a);
+        if (a.N == 4 * 256) return launch_kernel(consumer_stream_kernel<1, kRowThreads>, dim3(grid), dim3(kRowThreads), 0, stream, a);
+    }
     if ((a.N & 3) || a.N > 2 * 4 * kRowThreads || (a.ldp & 3)) return cudaErrorInvalidValue;
     // exact fits: every thread owns the same number of 4-column groups (1152 columns on 256 threads left 7/8 of
     // the CTA idle in the second pass and cost an occupancy-limiting 46 registers)
