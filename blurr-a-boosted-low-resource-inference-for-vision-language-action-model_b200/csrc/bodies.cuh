@@ -217,9 +217,29 @@ __device__ __forceinline__ void bias_act_body(const float* partial, int splitk, 
 // One CTA per token.  Work items: for every rotated head (queries + the key head) 32 pairs of
 // float4 column groups (dims [4j,4j+4) and [128+4j,128+4j+4): the rotate_half partners), plus 64
 // plain float4 groups of the value head.
-__device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t) {
+// The bf16 inputs and the position of one work item of one row, fetched ahead of time by the streaming launch.
+struct RopeItemIn { uint2 x1, x2; long long pos; };
+__device__ __forceinline__ void rope_prefetch(const RopeKvArgs& a, const int t, RopeItemIn& in) {
     const int b = t / a.tokens_per_sample, i = t - b * a.tokens_per_sample;
-    long long pos = __ldcg(a.position_ids + static_cast<size_t>(b) * a.tokens_per_sample + i);
+    in.pos = __ldcg(a.position_ids + static_cast<size_t>(b) * a.tokens_per_sample + i);
+    const int n_rot = (a.n_heads + 1) * 32;
+    const int it = threadIdx.x;
+    in.x1 = make_uint2(0u, 0u); in.x2 = make_uint2(0u, 0u);
+    if (it < n_rot) {
+        const int h = it >> 5, j = (it & 31) << 2;
+        if (h < a.n_heads && a.q_out == nullptr) return;
+        in.x1 = __ldcg(reinterpret_cast<const uint2*>(a.lin + static_cast<size_t>(t) * a.ldl + h * 256 + j));
+        in.x2 = __ldcg(reinterpret_cast<const uint2*>(a.lin + static_cast<size_t>(t) * a.ldl + h * 256 + 128 + j));
+    } else if (it < n_rot + 64) {
+        const int j = (it - n_rot) << 2;
+        in.x1 = __ldcg(reinterpret_cast<const uint2*>(a.lin + static_cast<size_t>(t) * a.ldl + (a.n_heads + 1) * 256 + j));
+    }
+}
+
+template <bool PRELOADED = false>
+__device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t, const RopeItemIn* pre = nullptr) {
+    const int b = t / a.tokens_per_sample, i = t - b * a.tokens_per_sample;
+    long long pos = PRELOADED ? pre->pos : __ldcg(a.position_ids + static_cast<size_t>(b) * a.tokens_per_sample + i);
     if (pos < 0) pos = 0;
     if (pos >= a.n_pos) pos = a.n_pos - 1;   // host validates the range; never read out of bounds
     const int slot = a.slot_base + i;
@@ -233,7 +253,10 @@ __device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t) {
             const int h = it >> 5, j = (it & 31) << 2;             // head, first dim of the group
             if (h < a.n_heads && a.q_out == nullptr) continue;
             float4 x1, x2;
-            if (a.lin != nullptr) {
+            if (PRELOADED) {
+                x1 = unpack_bf16x4(pre->x1);
+                x2 = unpack_bf16x4(pre->x2);
+            } else if (a.lin != nullptr) {
                 x1 = load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + h * 256 + j);
                 x2 = load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + h * 256 + 128 + j);
             } else {
@@ -258,8 +281,9 @@ __device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t) {
             store_bf16x4(dst + 128 + j, make_float4(y2[0], y2[1], y2[2], y2[3]));
         } else {
             const int j = (it - n_rot) << 2;
-            const float4 v = a.lin != nullptr ? load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + (a.n_heads + 1) * 256 + j)
-                                              : sum_slices(prow + (a.n_heads + 1) * 256 + j, sstride, a.splitk);
+            const float4 v = PRELOADED ? unpack_bf16x4(pre->x1)
+                             : a.lin != nullptr ? load_bf16x4(a.lin + static_cast<size_t>(t) * a.ldl + (a.n_heads + 1) * 256 + j)
+                                                : sum_slices(prow + (a.n_heads + 1) * 256 + j, sstride, a.splitk);
             store_bf16x4(a.v_cache + cache_row + j,
                          make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w)));
         }

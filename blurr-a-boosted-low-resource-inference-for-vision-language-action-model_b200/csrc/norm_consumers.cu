@@ -81,12 +81,35 @@ __global__ void __launch_bounds__(384) rope_kv_kernel(const RopeKvArgs a) {
     pdl_wait();
     pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
     trace_stamp(a.trace, 1);
-    rope_kv_body(a, blockIdx.x);
+    rope_kv_body<false>(a, blockIdx.x);
+    trace_stamp(a.trace, 2);
+}
+
+// Batched episodes, bf16 hand-off mode: fixed grid, one work item per thread, next row's inputs fetched early.
+__global__ void __launch_bounds__(384) rope_kv_stream_kernel(const RopeKvArgs a) {
+    trace_stamp(a.trace, 0);
+    pdl_wait();
+    pdl_trigger();
+    trace_stamp(a.trace, 1);
+    int t = blockIdx.x;
+    RopeItemIn cur, nxt;
+    if (t < a.T) rope_prefetch(a, t, cur);
+    for (; t < a.T; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        if (tn < a.T) rope_prefetch(a, tn, nxt);
+        rope_kv_body<true>(a, t, &cur);
+        cur = nxt;
+    }
     trace_stamp(a.trace, 2);
 }
 
 cudaError_t launch_rope_kv(cudaStream_t stream, const RopeKvArgs& a) {
     if (a.ldp & 3) return cudaErrorInvalidValue;
+    if (a.lin != nullptr && a.T >= kStreamMinRows) {
+        const int items = (a.n_heads + 1) * 32 + 64;
+        if (items <= 384)
+            return launch_kernel(rope_kv_stream_kernel, dim3(148 * 5), dim3((items + 31) / 32 * 32), 0, stream, a);
+    }
     // one work item (4 rotated pairs or 4 value columns) per thread: (n_heads + 1) * 32 + 64 items per token
     const int items = (a.n_heads + 1) * 32 + 64;
     const int threads = items <= 384 ? (items + 31) / 32 * 32 : 256;

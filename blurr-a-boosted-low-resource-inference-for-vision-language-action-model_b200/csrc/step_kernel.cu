@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepOp* __r
                     bias_act_body(a.partial, a.splitk, a.T, a.N, a.ldp, a.bias, a.act, a.scale, a.out, a.ldo, bx);
                     break;
                 }
-                case OP_ROPE_KV: rope_kv_body(hot.u.rope, bx); break;
+                case OP_ROPE_KV: rope_kv_body<false>(hot.u.rope, bx); break;
                 case OP_ATTN_SIGLIP: attn_step_tile<80, false>(hot.u.attn, sh.ring, bx, by, bz); break;
                 case OP_ATTN_PREFILL: attn_step_tile<256, true>(hot.u.attn, sh.ring, bx, by, bz); break;
                 case OP_ATTN_FEWQ: attn_step_tile<256, true>(hot.u.attn, sh.ring, bx, by, bz); break;
