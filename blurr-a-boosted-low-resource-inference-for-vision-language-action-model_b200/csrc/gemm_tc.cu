@@ -543,8 +543,9 @@ static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, cons
 // Batched GeGLU / GELU GEMMs (automatic, or mode 2 of "gemm_large_t_mode"; mode 3 also plain stores): persistent CTA pairs, 1142 TFLOP/s on the gate/up
 // shape at 64 episodes against 1050 for one tile per CTA pair (two pairs' CTAs per SM).
 static bool gemm_pairp_applies(const GemmCall& c) {
-    // GeGLU and GELU (SigLIP fc1: 1041 vs 910 TFLOP/s); plain stores gain nothing over the single-CTA persistent kernel
-    const bool epi_ok = c.epi == EPI_GEGLU || c.epi == EPI_GELU || (g_large_t_mode == 3 && c.epi == EPI_STORE);
+    // every bf16 epilogue with an even number of weight tiles: GeGLU 1142 vs 1050, GELU (SigLIP fc1) 1041 vs 910, plain
+    // stores (the bf16 hand-off of down / qkv / o) 1403 vs 1115 and 1295 vs 1072 TFLOP/s against the single-CTA kernels
+    const bool epi_ok = c.epi == EPI_GEGLU || c.epi == EPI_GELU || c.epi == EPI_STORE;
     return (g_large_t_mode >= 2 || g_large_t_mode < 0) && c.w_packed && epi_ok && c.splitk <= 1 && c.bn_override == 0 && c.T > 1024 &&
            c.Nw % (2 * kBlockM) == 0 && c.K % kBlockK == 0;
 }

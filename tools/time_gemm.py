@@ -28,6 +28,9 @@ SHAPES = [  # name, N, K, T, epi, splitk
     ("siglip fc1 bs64", 4352, 1152, 16384, capi.EPI_GELU, 1),
     ("siglip qkv bs64", 3456, 1152, 16384, capi.EPI_STORE, 1),
     ("vlm qkv bs64", 2560, 2048, 17664, capi.EPI_PARTIAL, 1),
+    ("vlm down bs64 store", 2048, 16384, 17664, capi.EPI_STORE, 1),
+    ("vlm qkv bs64 store", 2560, 2048, 17664, capi.EPI_STORE, 1),
+    ("siglip fc2 bs64 store", 1152, 4352, 16384, capi.EPI_STORE, 1),
 ]
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 # weights: tile-packed (ldw = 0; values are random so no packing pass is needed) vs row-major (ldw = K)
