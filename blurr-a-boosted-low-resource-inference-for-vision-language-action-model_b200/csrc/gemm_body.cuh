@@ -651,8 +651,9 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
             if (!ready) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 3); return; }
             tcgen05_fence_after();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
+            const bool real_tile = n0 < p.Nw;               // false: the padding CTA of an odd tile count
             float bias = 0.f;
-            if (p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
+            if (p.bias != nullptr && real_tile) bias = bf2f(p.bias[n0 + nl]);
             for (int g = g_begin; g < g_end; ++g) {
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(lane_addr + g * 16, r);
@@ -685,7 +686,7 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
             asm volatile("bar.sync 1, 256;\n" ::: "memory");
             const int et = static_cast<int>(threadIdx.x) - 128;
             const int col_base = (EPI == EPI_GEGLU) ? bx * (kBlockM / 2) : n0;
-            for (int idx = et; idx < p.bn * (OUTW / 8); idx += 256) {
+            for (int idx = et; real_tile && idx < p.bn * (OUTW / 8); idx += 256) {
                 const int t = idx / (OUTW / 8), ch = idx - t * (OUTW / 8);
                 if (t0 + t < p.T)
                     *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) =

@@ -547,7 +547,7 @@ static bool gemm_pairp_applies(const GemmCall& c) {
     // stores (the bf16 hand-off of down / qkv / o) 1403 vs 1115 and 1295 vs 1072 TFLOP/s against the single-CTA kernels
     const bool epi_ok = c.epi == EPI_GEGLU || c.epi == EPI_GELU || c.epi == EPI_STORE;
     return (g_large_t_mode >= 2 || g_large_t_mode < 0) && c.w_packed && epi_ok && c.splitk <= 1 && c.bn_override == 0 && c.T > 1024 &&
-           c.Nw % (2 * kBlockM) == 0 && c.K % kBlockK == 0;
+           c.Nw % kBlockM == 0 && c.K % kBlockK == 0 && (c.epi != EPI_GEGLU || c.Nw % (2 * kBlockM) == 0);
 }
 
 static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string* err) {
@@ -566,7 +566,8 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
     if (d.stages > kMaxStages) d.stages = kMaxStages;
     const int smem = d.stages * stage_bytes + d.staging_bytes + 1024 + 256;
-    const int gxp = c.Nw / (2 * kBlockM), gy = (c.T + bn - 1) / bn;
+    // an odd number of weight tiles: the last pair's second CTA multiplies TMA's out-of-bounds zeros and stores nothing
+    const int gxp = (c.Nw / kBlockM + 1) / 2, gy = (c.T + bn - 1) / bn;
     const int tiles = gxp * gy;
     const int n_pairs = tiles < kTargetCtas / 2 ? tiles : kTargetCtas / 2;
     cudaError_t e;

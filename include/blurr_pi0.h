@@ -191,9 +191,9 @@ int blurr_op_normalize_proprio(void* cuda_stream, const double* raw, const doubl
 
 /* Process-wide tuning knobs (no handle): "gemm_cluster_max" (1/2/4/8, activation-multicast cluster
  * size cap of the GEMM kernel), "gemm_use_2cta" (-1 automatic = CTA pairs for the GeGLU GEMM above 1024 tokens, 0, 1),
- * "gemm_large_t_mode" (above 1024 tokens: -1 automatic = persistent CTA pairs for GeGLU / GELU, persistent single
- * CTAs otherwise; 0 never persistent; 1 single-CTA persistent for every epilogue; 2 = automatic; 3 = pairs also for
- * plain stores), "attn_tc" (-1 automatic = tcgen05 attention from 8 episodes per GPU, 0 never, 1 always),
+ * "gemm_large_t_mode" (above 1024 tokens: -1 automatic = persistent CTA pairs for every bf16 epilogue (GeGLU, GELU,
+ * plain store), persistent single CTAs for fp32 partial / residual epilogues; 0 never persistent; 1 single-CTA
+ * persistent for every epilogue; 2 and 3 = same as automatic), "attn_tc" (-1 automatic = tcgen05 attention from 8 episodes per GPU, 0 never, 1 always),
  * "gemm_persistent" (0/1: persistent kernel for GEMMs of <= 32 tokens), "gemm_wide" (0/1, default 0:
  * two weight tiles per CTA for 257..288 tokens), "gemm_max_stages" (TMA ring depth cap), "use_pdl" (0/1). */
 int blurr_set_global_option(const char* name, int64_t value);

@@ -42,7 +42,8 @@ def test_gemm_store_bias(T, N, K):
 
 @pytest.mark.parametrize("T,N,K,epi", [(552, 2560, 2048, "store"), (1104, 4352, 1152, "gelu"),
                                          (276, 4096, 2048, "geglu"), (16, 2560, 1024, "store"),
-                                         (2208, 2560, 2048, "store"), (2100, 4096, 1152, "geglu"), (4416, 1152, 640, "gelu")])
+                                         (2208, 2560, 2048, "store"), (2100, 4096, 1152, "geglu"), (4416, 1152, 640, "gelu"),
+                                         (2304, 3456, 1152, "store")])      # odd tile counts: 9 and 27
 def test_gemm_variants_agree(T, N, K, epi):
     """The GEMM variants (one CTA per tile, CTA pairs, persistent) accumulate every output in the same
     order, so they must agree bit for bit."""
