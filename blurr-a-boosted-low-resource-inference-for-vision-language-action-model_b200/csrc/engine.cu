@@ -1338,6 +1338,8 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_wide") gemm_set_wide(static_cast<int>(value));
     else if (n == "attn_tc") attn_set_tc(static_cast<int>(value));
     else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
+    else if (n == "gemm_pair_band") gemm_set_pair_band(static_cast<int>(value));
+    else if (n == "gemm_pair_policy") gemm_set_pair_policy(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
     else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
     return 0;

@@ -313,6 +313,10 @@ void gemm_set_wide(int on) { g_wide = on ? 1 : 0; }
 // taken back to back differ by +-10 % with the order of the launches.)
 static int g_large_t_mode = -1;
 void gemm_set_large_t_mode(int mode) { g_large_t_mode = mode; }
+static int g_pair_band = 0;
+static int g_pair_policy = -1;
+void gemm_set_pair_policy(int policy) { g_pair_policy = policy; }
+void gemm_set_pair_band(int band) { g_pair_band = band; }
 static int g_persistent = 1;
 static constexpr int kPersistentMaxTokens = 32;
 void gemm_set_persistent(int on) { g_persistent = on ? 1 : 0; }
@@ -570,6 +574,17 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     const int gxp = (c.Nw / kBlockM + 1) / 2, gy = (c.T + bn - 1) / bn;
     const int tiles = gxp * gy;
     const int n_pairs = tiles < kTargetCtas / 2 ? tiles : kTargetCtas / 2;
+    // Raster bands (pair_tile_coords).  When one wave of pairs cannot hold every weight tile pair, weight-fastest
+    // order streams the whole weight matrix from DRAM once per token tile; bands of ~32 MB of weights keep a band
+    // L2-resident while the tokens stream past it once per band.
+    d.l2_policy = g_pair_policy >= 0 ? g_pair_policy : 1;       // both operands are re-read by later tiles: plain LRU (measured best)
+    d.band = gxp;
+    if (g_pair_band > 0) d.band = g_pair_band < gxp ? g_pair_band : gxp;
+    else if (gxp > n_pairs) {
+        const long long pair_bytes = 2LL * kBlockM * c.K * 2;
+        long long band = (32LL << 20) / pair_bytes;
+        d.band = static_cast<int>(band < 4 ? 4 : (band > gxp ? gxp : band));
+    }
     cudaError_t e;
     switch (c.epi) {
         case EPI_GEGLU: e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
@@ -659,6 +674,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
                             c.T > 1024 && pl.nt == 1 && pl.tmem_cols <= 256 && pl.cluster == 1 && !pl.two_cta;
     if (large_dbuf) {
         d.acc_bufs = 2; d.acc_stride = pl.tmem_cols; d.tmem_cols = 2 * pl.tmem_cols;
+        d.l2_policy = g_pair_policy >= 0 ? (g_pair_policy == 1 ? 1 : 0) : 1;
         // the direct epilogue stages nothing in the ring: use all of it
         const int stage_bytes = kTileABytes + pl.nt * pl.bn * kBlockK * 2;
         if (c.epi != EPI_PARTIAL && (pl.nt * pl.bn) % 32 == 0)       // staged bf16 epilogue (8 epilogue warps)

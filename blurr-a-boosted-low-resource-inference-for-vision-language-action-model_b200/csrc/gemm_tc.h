@@ -59,6 +59,8 @@ struct GemmDev {
     int acc_bufs;     // persistent kernel: accumulator buffers in TMEM (1 or 2)
     int acc_stride;   // TMEM columns between them
     int staging_bytes; // persistent kernel: bf16 output staging tile behind the ring (0 = direct epilogue)
+    int l2_policy;    // persistent pairs: 0 = weights evict_first / tokens evict_last, 1 = both evict_normal, 2 = weights evict_last / tokens evict_first
+    int band;         // persistent pairs: weight tile pairs per raster band (the band sweeps every token tile before the next one starts)
 };
 
 struct GemmPlan {
@@ -99,6 +101,8 @@ void gemm_set_wide(int on);
 // box_rows x 64 columns; returns nonzero and sets *err on failure.
 int gemm_get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, std::string* err);
 void gemm_set_large_t_mode(int mode);
+void gemm_set_pair_band(int band);          // 0 = automatic
+void gemm_set_pair_policy(int policy);      // -1 = automatic
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
 void gemm_set_cluster_max(int c);

@@ -67,6 +67,32 @@ def test_gemm_variants_agree(T, N, K, epi):
         assert torch.equal(o, outs[0])
 
 
+@pytest.mark.parametrize("T,N,K,epi,band", [(2100, 4096, 1152, "geglu", 3), (2304, 3456, 1152, "store", 4),
+                                              (5000, 4352, 640, "gelu", 5), (1500, 40960, 128, "geglu", 0)])
+@pytest.mark.parametrize("policy", [0, 1, 2])
+def test_gemm_pair_raster_bands(T, N, K, epi, band, policy):
+    """Persistent CTA pairs visit the tiles in bands of weight tile pairs (last band narrower; band 0 = the
+    automatic choice, which only bands when there are more weight tile pairs than CTA pairs: N = 40960).
+    The raster order and the L2 eviction hints must not change a single bit."""
+    lib = capi.load_library()
+    W = _rand((N, K), 1.0 / math.sqrt(K), 41)
+    X = _rand((T, K), 1.0, 42)
+    b = _rand((N,), 0.5, 43) if epi != "geglu" else None
+    code = {"store": capi.EPI_STORE, "gelu": capi.EPI_GELU, "geglu": capi.EPI_GEGLU}[epi]
+    try:
+        capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", 0))
+        ref = op_gemm(W, X, code, bias=b)
+        capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", -1))
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_band", band))
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_policy", policy))
+        got = op_gemm(W, X, code, bias=b)
+    finally:
+        capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", -1))
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_band", 0))
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_policy", -1))
+    assert torch.equal(got, ref)
+
+
 @pytest.mark.parametrize("T,N,K,epi", [(276, 4096, 2048, "geglu"), (276, 2560, 2048, "store"), (270, 512, 4352, "gelu")])
 def test_gemm_wide_variant(T, N, K, epi):
     """Two weight tiles per CTA (256 < T <= 288): tokens 0..255 accumulate on tcgen05 exactly as in the

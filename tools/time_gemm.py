@@ -39,6 +39,9 @@ for use2, LDW_MODE in CASES:
     cmax = use2
     capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", use2))
     capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", int(os.environ.get("MODE", "0"))))
+    for kv in filter(None, os.environ.get("OPTS", "").split(",")):      # e.g. OPTS="gemm_pair_band=16,gemm_pair_policy=1"
+        k, v = kv.split("=")
+        capi.check(lib.blurr_set_global_option(k.encode(), int(v)))
     for name, N, K, T, epi, S in SHAPES:
         if ONLY and ONLY not in name:
             continue
