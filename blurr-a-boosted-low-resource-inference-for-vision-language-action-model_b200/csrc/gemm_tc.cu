@@ -544,11 +544,11 @@ static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, cons
                                  stream, 2, tw, txh, d, gxp, gy);
 }
 
-// Batched GeGLU / GELU GEMMs (automatic, or mode 2 of "gemm_large_t_mode"; mode 3 also plain stores): persistent CTA pairs, 1142 TFLOP/s on the gate/up
-// shape at 64 episodes against 1050 for one tile per CTA pair (two pairs' CTAs per SM).
+// Batched GEMMs with a bf16 epilogue (above 1024 tokens; automatic, or modes 2 / 3 of "gemm_large_t_mode"):
+// persistent CTA pairs, tiles visited in raster bands.  At 64 episodes: gate/up 1429 TFLOP/s (1050 for one tile
+// per CTA pair, 1086 for persistent pairs before the bands), SigLIP fc1 1112 vs 910, the plain stores (bf16
+// hand-off of down / qkv / o) 1450 and 1335 against 1115 and 1072 for the single-CTA persistent kernel.
 static bool gemm_pairp_applies(const GemmCall& c) {
-    // every bf16 epilogue with an even number of weight tiles: GeGLU 1142 vs 1050, GELU (SigLIP fc1) 1041 vs 910, plain
-    // stores (the bf16 hand-off of down / qkv / o) 1403 vs 1115 and 1295 vs 1072 TFLOP/s against the single-CTA kernels
     const bool epi_ok = c.epi == EPI_GEGLU || c.epi == EPI_GELU || c.epi == EPI_STORE;
     return (g_large_t_mode >= 2 || g_large_t_mode < 0) && c.w_packed && epi_ok && c.splitk <= 1 && c.bn_override == 0 && c.T > 1024 &&
            c.Nw % kBlockM == 0 && c.K % kBlockK == 0 && (c.epi != EPI_GEGLU || c.Nw % (2 * kBlockM) == 0);
