@@ -101,6 +101,8 @@ _SIGNATURES = [
     ("blurr_op_gemm_async", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("blurr_op_pair_raster", C.c_int,
+     [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int32), C.c_int]),
     ("blurr_op_siglip_attention", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     ("blurr_op_joint_attention", C.c_int,

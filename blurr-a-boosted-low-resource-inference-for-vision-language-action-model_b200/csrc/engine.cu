@@ -1449,6 +1449,12 @@ extern "C" int blurr_op_pack_weight(void* cuda_stream, const void* W, int N, int
     return 0;
 }
 
+extern "C" int blurr_op_pair_raster(int N, int K, int T, int* band, int* n_pairs, int32_t* order, int capacity) {
+    const int tiles = gemm_pair_raster(N, K, T, band, n_pairs, order, capacity);
+    if (tiles < 0) return fail(BLURR_ERR_INVALID, "blurr_op_pair_raster: N must be a positive multiple of 128, K and T positive");
+    return tiles;
+}
+
 extern "C" int blurr_op_gemm_async(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T,
                                    int ldx, int epi, int splitk, const void* bias, void* out, int ldo,
                                    float* partial) {

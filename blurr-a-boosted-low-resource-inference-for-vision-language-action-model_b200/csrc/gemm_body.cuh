@@ -573,10 +573,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // weights stay in L2 while every token tile streams past them once.  Weight-fastest over all of gxp (the
 // old order) cycles the whole weight matrix through L2 once per token tile: for gate/up at 64 episodes ncu
 // counted 8.8 GB of DRAM reads against 0.2 GB of operands.
-__device__ __forceinline__ void pair_tile_coords(const int tile, const int gxp, const int gy, const int band, int& xp, int& ty) {
+__host__ __device__ __forceinline__ void pair_tile_coords(const int tile, const int gxp, const int gy, const int band, int& xp, int& ty) {
     const int per_band = band * gy;
     const int b = tile / per_band, r = tile - b * per_band;
-    const int w = min(band, gxp - b * band);
+    const int w = (gxp - b * band < band) ? gxp - b * band : band;      // the last band may be narrower
     ty = r / w;
     xp = b * band + (r - ty * w);
 }

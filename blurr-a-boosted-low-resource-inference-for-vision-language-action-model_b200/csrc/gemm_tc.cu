@@ -554,6 +554,33 @@ static bool gemm_pairp_applies(const GemmCall& c) {
            c.Nw % kBlockM == 0 && c.K % kBlockK == 0 && (c.epi != EPI_GEGLU || c.Nw % (2 * kBlockM) == 0);
 }
 
+static int pair_band_for(int gxp, int n_pairs, int K) {
+    if (g_pair_band > 0) return g_pair_band < gxp ? g_pair_band : gxp;
+    if (gxp <= n_pairs) return gxp;                 // one wave of pairs already holds every weight tile pair
+    const long long pair_bytes = 2LL * kBlockM * K * 2;
+    const long long band = (32LL << 20) / pair_bytes;
+    return static_cast<int>(band < 4 ? 4 : (band > gxp ? gxp : band));
+}
+
+// Host-side view of the raster (C ABI `blurr_op_pair_raster`): the order in which the persistent pairs visit the
+// tiles of a [T][N] output, from the same pair_tile_coords() the kernel runs.
+int gemm_pair_raster(int N, int K, int T, int* band_out, int* n_pairs_out, int32_t* order, int capacity) {
+    if (N <= 0 || K <= 0 || T <= 0 || N % kBlockM != 0) return -1;
+    const int bn = 256;
+    const int gxp = (N / kBlockM + 1) / 2, gy = (T + bn - 1) / bn;
+    const int tiles = gxp * gy;
+    const int n_pairs = tiles < kTargetCtas / 2 ? tiles : kTargetCtas / 2;
+    const int band = pair_band_for(gxp, n_pairs, K);
+    if (band_out) *band_out = band;
+    if (n_pairs_out) *n_pairs_out = n_pairs;
+    for (int t = 0; order != nullptr && t < tiles && t < capacity; ++t) {
+        int xp, ty;
+        pair_tile_coords(t, gxp, gy, band, xp, ty);
+        order[2 * t] = xp; order[2 * t + 1] = ty;
+    }
+    return tiles;
+}
+
 static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string* err) {
     const int kb_total = c.K / kBlockK;
     const int bn = 256, half = bn / 2;
@@ -578,13 +605,7 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     // order streams the whole weight matrix from DRAM once per token tile; bands of ~32 MB of weights keep a band
     // L2-resident while the tokens stream past it once per band.
     d.l2_policy = g_pair_policy >= 0 ? g_pair_policy : 1;       // both operands are re-read by later tiles: plain LRU (measured best)
-    d.band = gxp;
-    if (g_pair_band > 0) d.band = g_pair_band < gxp ? g_pair_band : gxp;
-    else if (gxp > n_pairs) {
-        const long long pair_bytes = 2LL * kBlockM * c.K * 2;
-        long long band = (32LL << 20) / pair_bytes;
-        d.band = static_cast<int>(band < 4 ? 4 : (band > gxp ? gxp : band));
-    }
+    d.band = pair_band_for(gxp, n_pairs, c.K);
     cudaError_t e;
     switch (c.epi) {
         case EPI_GEGLU: e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;

@@ -103,6 +103,7 @@ int gemm_get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_row
 void gemm_set_large_t_mode(int mode);
 void gemm_set_pair_band(int band);          // 0 = automatic
 void gemm_set_pair_policy(int policy);      // -1 = automatic
+int gemm_pair_raster(int N, int K, int T, int* band_out, int* n_pairs_out, int32_t* order, int capacity);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
 void gemm_set_cluster_max(int c);

@@ -214,6 +214,11 @@ int blurr_op_pack_weight(void* cuda_stream, const void* W, int N, int K, int ldw
  * [splitk_used][T][N]); returns the number of split-K slices used (>=1) or a negative status. */
 int blurr_op_gemm(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,
                   int epi, int splitk, const void* bias, void* out, int ldo, float* partial);
+/* Host-only (no GPU needed): the order in which the persistent CTA pairs of the batched GEMM (> 1024 tokens, bf16
+ * epilogue) visit the tiles of a [T][N] output under the current global options.  Writes the band width (weight
+ * tile pairs per raster band), the number of CTA pairs, and up to `capacity` (weight_tile_pair, token_tile)
+ * int32 pairs in visiting order; returns the number of tiles or a negative status. */
+int blurr_op_pair_raster(int N, int K, int T, int* band, int* n_pairs, int32_t* order, int capacity);
 /* Same launch without the trailing stream synchronisation / pipeline-timeout check (for timing
  * loops); returns the split-K slice count or a negative status. */
 int blurr_op_gemm_async(void* cuda_stream, const void* W, int N, int K, int ldw, const void* X, int T, int ldx,

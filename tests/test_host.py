@@ -150,3 +150,47 @@ def test_synthetic_inputs_layout():
     assert base["attention_mask"].sum().item() == 268
     assert base["input_ids"][0, 257:267].tolist() == [179378, 5125, 195997, 211369, 93264, 178254, 3810, 17301,
                                                       14683, 160681]
+
+
+@pytest.mark.parametrize("N,K,T,band", [(32768, 2048, 17664, 0), (32768, 2048, 4416, 0), (2048, 16384, 17664, 0),
+                                        (3456, 1152, 16384, 0), (4352, 1152, 16384, 5), (4096, 1152, 2100, 3),
+                                        (1152, 4352, 16384, 2), (40960, 128, 1500, 7), (256, 64, 1025, 1)])
+def test_pair_raster_visits_every_tile_once_in_bands(N, K, T, band):
+    """The raster order of the batched GEMM's persistent CTA pairs (csrc/gemm_body.cuh pair_tile_coords, the
+    function the kernel runs, exposed host-side through blurr_op_pair_raster): every (weight tile pair, token
+    tile) exactly once; a band's weight tile pairs sweep all token tiles before the next band starts; inside a
+    band the weight index runs fastest.  Automatic banding only when one wave of pairs cannot hold every weight
+    tile pair (gate/up: 128 pairs of tiles, 74 CTA pairs -> bands of 32 MB of weights)."""
+    import ctypes as C
+    import numpy as np
+    lib = capi.load_library()
+    gxp, gy = (N // 128 + 1) // 2, (T + 255) // 256
+    order = np.full((gxp * gy, 2), -1, np.int32)
+    b, p = C.c_int(), C.c_int()
+    try:
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_band", band))
+        tiles = lib.blurr_op_pair_raster(N, K, T, C.byref(b), C.byref(p), order.ctypes.data_as(C.POINTER(C.c_int32)), len(order))
+    finally:
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_band", 0))
+    assert tiles == gxp * gy and p.value == min(tiles, 74)
+    if band:
+        assert b.value == min(band, gxp)
+    elif gxp <= p.value:
+        assert b.value == gxp
+    else:
+        assert b.value == max(4, min(gxp, (32 << 20) // (2 * 128 * K * 2)))
+    assert sorted(map(tuple, order.tolist())) == [(x, y) for x in range(gxp) for y in range(gy)]
+    bands = order[:, 0] // b.value
+    assert (np.diff(bands) >= 0).all()                                   # bands in order, never revisited
+    for bi in np.unique(bands):
+        sub = order[bands == bi]
+        w = min(b.value, gxp - bi * b.value)
+        assert len(sub) == w * gy
+        assert (sub[:, 0] == bi * b.value + np.arange(len(sub)) % w).all()   # weight index fastest
+        assert (sub[:, 1] == np.arange(len(sub)) // w).all()                 # token tiles ascending
+
+
+def test_pair_raster_rejects_bad_shapes():
+    lib = capi.load_library()
+    assert lib.blurr_op_pair_raster(100, 64, 2048, None, None, None, 0) < 0
+    assert lib.blurr_op_pair_raster(128, 64, 0, None, None, None, 0) < 0
