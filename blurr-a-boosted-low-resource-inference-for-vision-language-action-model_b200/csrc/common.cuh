@@ -121,6 +121,13 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     return true;
 }
 
+// Same wait executed by a whole converged warp; the verdict is agreed across the lanes so that the code
+// after it stays warp-uniform (the issue loops keep all 32 lanes converged, see gemm_body.cuh).
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    const bool ok = mbar_wait(bar, parity);
+    return __all_sync(0xffffffffu, ok);
+}
+
 // ---------------------------------------------------------------------------
 // TMA: 2D tiled load global -> shared (SWIZZLE_128B tensor maps), completes on an mbarrier
 // ---------------------------------------------------------------------------

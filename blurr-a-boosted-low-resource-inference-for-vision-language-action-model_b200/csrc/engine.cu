@@ -1335,7 +1335,6 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_use_2cta") gemm_set_use_2cta(static_cast<int>(value));
     else if (n == "gemm_persistent") gemm_set_persistent(static_cast<int>(value));
     else if (n == "gemm_max_stages") gemm_set_max_stages(static_cast<int>(value));
-    else if (n == "gemm_wide") gemm_set_wide(static_cast<int>(value));
     else if (n == "attn_tc") attn_set_tc(static_cast<int>(value));
     else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
     else if (n == "gemm_pair_band") gemm_set_pair_band(static_cast<int>(value));

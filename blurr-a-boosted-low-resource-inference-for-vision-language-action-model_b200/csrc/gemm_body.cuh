@@ -101,17 +101,21 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
     const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
     const int nkb = kb1 - kb0;
 
+    // Issue discipline (measured with tools/mma_probe.cu, round 2): the producer and the MMA warp run with all 32
+    // lanes converged and warp-uniform operands; only the TMA / tcgen05 instructions sit under elect.sync.  Issued
+    // from an `if (lane == 0)` region ptxas wraps EVERY UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST + BRA.U.ANY
+    // loop (~110-160 cycles per instruction): 908 instead of 724 cycles per k-block at 2 x 144 tokens, 632
+    // instead of 448 below 128 tokens, and the TMA side could not issue a k-block in less than ~0.22 us.
     if (warp == 0) {
-        if (lane == 0) {
-            const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
-            const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
-            // Launched with PDL: the weights do not depend on the previous kernel, so the first ring of
-            // weight blocks is requested before waiting for it; only the token operand waits.
-            int pre = 0;
-            if (pdl) {
-                pre = (p.cluster == 1 && p.w_static) ? min(p.stages, nkb) : 0;
+        const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
+        const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
+        // Launched with PDL: the weights do not depend on the previous kernel, so the first ring of
+        // weight blocks is requested before waiting for it; only the token operand waits.
+        int pre = 0;
+        if (pdl) {
+            pre = (p.cluster == 1 && p.w_static) ? min(p.stages, nkb) : 0;
+            if (elect_one_sync()) {
                 for (int i = 0; i < pre; ++i) {      // fresh ring: every stage is empty
-                    st.empty_bits ^= (1u << i);
                     mbar_arrive_expect_tx(&sh.full_bar[i], static_cast<uint32_t>(stage_bytes));
                     if (p.w_packed)
                         tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], 0,
@@ -119,21 +123,28 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
                     else
                         tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], (kb0 + i) * kBlockK, n0, pol_w);
                 }
-                pdl_wait();
-                pdl_trigger();
-                trace_stamp(p.trace, 1);
+            }
+            __syncwarp();
+            for (int i = 0; i < pre; ++i) st.empty_bits ^= (1u << i);
+            pdl_wait();
+            pdl_trigger();
+            trace_stamp(p.trace, 1);
+            if (elect_one_sync()) {
                 for (int i = 0; i < pre; ++i)
                     for (int c = 0; c < p.nt; ++c)
                         tma_load_2d_hint(smem + i * stage_bytes + kTileABytes + c * p.bn * (kBlockK * 2), tmap_x,
                                          &sh.full_bar[i], (kb0 + i) * kBlockK, t0 + c * p.bn, pol_x);
             }
-            for (int i = pre; i < nkb; ++i) {
-                const int s = i % p.stages;
-                if (!mbar_wait(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
-                    atomicExch(&g_gemm_timeout_flag, 1);
-                    break;
-                }
-                st.empty_bits ^= (1u << s);
+            __syncwarp();
+        }
+        int s = pre % p.stages;
+        for (int i = pre; i < nkb; ++i) {
+            if (!mbar_wait_warp(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
+                if (lane == 0) atomicExch(&g_gemm_timeout_flag, 1);
+                break;
+            }
+            st.empty_bits ^= (1u << s);
+            if (elect_one_sync()) {
                 uint8_t* stg = smem + s * stage_bytes;
                 mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(stage_bytes));
                 const int kcoord = (kb0 + i) * kBlockK;
@@ -152,20 +163,22 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
                                          kcoord, t0 + c * p.bn, pol_x);
                 }
             }
+            __syncwarp();
+            s = (s + 1 == p.stages) ? 0 : s + 1;
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
-            bool ok = true;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                if (!mbar_wait(&sh.full_bar[s], (st.full_bits >> s) & 1u)) {
-                    atomicExch(&g_gemm_timeout_flag, 2);
-                    ok = false;
-                    break;
-                }
-                st.full_bits ^= (1u << s);
-                tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
+        bool ok = true;
+        int s = 0;
+        for (int i = 0; i < nkb; ++i) {
+            if (!mbar_wait_warp(&sh.full_bar[s], (st.full_bits >> s) & 1u)) {
+                if (lane == 0) atomicExch(&g_gemm_timeout_flag, 2);
+                ok = false;
+                break;
+            }
+            st.full_bits ^= (1u << s);
+            tcgen05_fence_after();
+            if (elect_one_sync()) {
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                 const uint64_t a_desc = make_smem_desc_sw128(a_addr);
                 for (int c = 0; c < p.nt; ++c) {
@@ -182,8 +195,11 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
                 if (p.cluster > 1) umma_commit_multicast(&sh.empty_bar[s], cmask);
                 else umma_commit(&sh.empty_bar[s]);
             }
-            if (ok) umma_commit(sh.tmem_full_bar);   // accumulators complete
+            __syncwarp();
+            s = (s + 1 == p.stages) ? 0 : s + 1;
         }
+        if (ok && elect_one_sync()) umma_commit(sh.tmem_full_bar);   // accumulators complete
+        __syncwarp();
     } else if (warp >= 4) {
         // ---- epilogue phase 1: TMEM -> registers -> smem tile [token][128 n] ----
         const int w4 = warp - 4;               // TMEM lane quarter this warp may access
@@ -245,23 +261,23 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
     const int n_tiles = gx * gy * gz;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // few tokens: weights are streamed once, activations re-read by every CTA.  Above 1024 tokens
-            // (l2_policy 1) both operands are re-read by later tiles and plain LRU does better.
-            const uint64_t pol_w = p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
-            const uint64_t pol_x = p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_last();
-            uint32_t empty_bits = 0;
-            int s = 0;
-            int pre = 0;
-            if (pdl) {
-                // weights of the first ring before the PDL wait (see gemm_tile)
-                if (first < n_tiles) {
-                    const int bx = first % gx, by = (first / gx) % gy, bz = first / (gx * gy);
-                    const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
-                    const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                    pre = p.w_static ? min(p.stages, kb1 - kb0) : 0;
+        // all 32 lanes converged, operands warp-uniform, issue under elect.sync (see gemm_tile)
+        // few tokens: weights are streamed once, activations re-read by every CTA.  Above 1024 tokens
+        // (l2_policy 1) both operands are re-read by later tiles and plain LRU does better.
+        const uint64_t pol_w = p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
+        const uint64_t pol_x = p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_last();
+        uint32_t empty_bits = 0;
+        int s = 0;
+        int pre = 0;
+        if (pdl) {
+            // weights of the first ring before the PDL wait (see gemm_tile)
+            if (first < n_tiles) {
+                const int bx = first % gx, by = (first / gx) % gy, bz = first / (gx * gy);
+                const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
+                const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                pre = p.w_static ? min(p.stages, kb1 - kb0) : 0;
+                if (elect_one_sync()) {
                     for (int i = 0; i < pre; ++i) {
-                        empty_bits ^= (1u << i);
                         mbar_arrive_expect_tx(&sh.full_bar[i], static_cast<uint32_t>(stage_bytes));
                         if (p.w_packed)
                             tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], 0,
@@ -269,29 +285,36 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                         else
                             tma_load_2d_hint(smem + i * stage_bytes, tmap_w, &sh.full_bar[i], (kb0 + i) * kBlockK, n0, pol_w);
                     }
-                    pdl_wait();
-                    pdl_trigger();
-                    trace_stamp(p.trace, 1);
+                }
+                __syncwarp();
+                for (int i = 0; i < pre; ++i) empty_bits ^= (1u << i);
+                pdl_wait();
+                pdl_trigger();
+                trace_stamp(p.trace, 1);
+                if (elect_one_sync()) {
                     for (int i = 0; i < pre; ++i)
                         for (int c = 0; c < p.nt; ++c)
                             tma_load_2d_hint(smem + i * stage_bytes + kTileABytes + c * p.bn * (kBlockK * 2), tmap_x,
                                              &sh.full_bar[i], (kb0 + i) * kBlockK, t0 + c * p.bn, pol_x);
-                    s = (pre == p.stages) ? 0 : pre;
-                } else {
-                    pdl_wait();
-                    pdl_trigger();
                 }
+                __syncwarp();
+                s = (pre == p.stages) ? 0 : pre;
+            } else {
+                pdl_wait();
+                pdl_trigger();
             }
-            for (int tile = first; tile < n_tiles; tile += stride) {
-                const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
-                const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
-                const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                for (int kb = (tile == first ? kb0 + pre : kb0); kb < kb1; ++kb) {
-                    if (!mbar_wait(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) {
-                        atomicExch(&g_gemm_timeout_flag, 1);
-                        return;
-                    }
-                    empty_bits ^= (1u << s);
+        }
+        for (int tile = first; tile < n_tiles; tile += stride) {
+            const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
+            const int n0 = bx * kBlockM, t0 = by * p.nt * p.bn;
+            const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            for (int kb = (tile == first ? kb0 + pre : kb0); kb < kb1; ++kb) {
+                if (!mbar_wait_warp(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) {
+                    if (lane == 0) atomicExch(&g_gemm_timeout_flag, 1);
+                    return;
+                }
+                empty_bits ^= (1u << s);
+                if (elect_one_sync()) {
                     uint8_t* stg = smem + s * stage_bytes;
                     mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(stage_bytes));
                     if (p.w_packed)
@@ -301,27 +324,28 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                     for (int c = 0; c < p.nt; ++c)
                         tma_load_2d_hint(stg + kTileABytes + c * p.bn * (kBlockK * 2), tmap_x, &sh.full_bar[s],
                                          kb * kBlockK, t0 + c * p.bn, pol_x);
-                    s = (s + 1 == p.stages) ? 0 : s + 1;
                 }
+                __syncwarp();
+                s = (s + 1 == p.stages) ? 0 : s + 1;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
-            uint32_t full_bits = 0, tmem_empty_bits = 0;
-            int s = 0, buf = 0;
-            for (int tile = first; tile < n_tiles; tile += stride) {
-                const int bz = tile / (gx * gy);
-                const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                // the epilogue must have drained the accumulator buffer this tile is going to use
-                if (!mbar_wait(&tmem_empty_bar[buf], ((tmem_empty_bits >> buf) & 1u) ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 4); return; }
-                tmem_empty_bits ^= (1u << buf);
+        const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<uint32_t>(p.bn));
+        uint32_t full_bits = 0, tmem_empty_bits = 0;
+        int s = 0, buf = 0;
+        for (int tile = first; tile < n_tiles; tile += stride) {
+            const int bz = tile / (gx * gy);
+            const int kb0 = bz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            // the epilogue must have drained the accumulator buffer this tile is going to use
+            if (!mbar_wait_warp(&tmem_empty_bar[buf], ((tmem_empty_bits >> buf) & 1u) ^ 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 4); return; }
+            tmem_empty_bits ^= (1u << buf);
+            tcgen05_fence_after();
+            const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (!mbar_wait_warp(&sh.full_bar[s], (full_bits >> s) & 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 2); return; }
+                full_bits ^= (1u << s);
                 tcgen05_fence_after();
-                const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    if (!mbar_wait(&sh.full_bar[s], (full_bits >> s) & 1u)) { atomicExch(&g_gemm_timeout_flag, 2); return; }
-                    full_bits ^= (1u << s);
-                    tcgen05_fence_after();
+                if (elect_one_sync()) {
                     const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                     const uint64_t a_desc = make_smem_desc_sw128(a_addr);
                     for (int c = 0; c < p.nt; ++c) {
@@ -332,11 +356,12 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                                          (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&sh.empty_bar[s]);
-                    s = (s + 1 == p.stages) ? 0 : s + 1;
+                    if (kb + 1 == kb1) umma_commit(buf == 0 ? sh.tmem_full_bar : tmem_empty_bar + 2);      // tmem_full[buf]
                 }
-                umma_commit(buf == 0 ? sh.tmem_full_bar : tmem_empty_bar + 2);      // tmem_full[buf]
-                buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
+                __syncwarp();
+                s = (s + 1 == p.stages) ? 0 : s + 1;
             }
+            buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
         }
     } else if (warp >= 4) {
         // 4 epilogue warps (one per TMEM lane quarter) or 8 (two per quarter, each half of the columns)
@@ -466,16 +491,17 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
     const int nkb = kb1 - kb0;
 
     if (warp == 0) {
-        if (lane == 0) {
-            const uint64_t pol_w = make_policy_evict_first();
-            const uint64_t pol_x = make_policy_evict_last();
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                if (!mbar_wait(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
-                    atomicExch(&g_gemm_timeout_flag, 1);
-                    break;
-                }
-                st.empty_bits ^= (1u << s);
+        // all 32 lanes converged, operands warp-uniform, issue under elect.sync (see gemm_tile)
+        const uint64_t pol_w = make_policy_evict_first();
+        const uint64_t pol_x = make_policy_evict_last();
+        int s = 0;
+        for (int i = 0; i < nkb; ++i) {
+            if (!mbar_wait_warp(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
+                if (lane == 0) atomicExch(&g_gemm_timeout_flag, 1);
+                break;
+            }
+            st.empty_bits ^= (1u << s);
+            if (elect_one_sync()) {
                 uint8_t* stg = smem + s * stage_bytes;
                 if (leader) mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
                 const uint32_t bar = map_to_cta(&sh.full_bar[s], 0u);       // the leader's barrier
@@ -488,32 +514,39 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
                     tma_load_2d_2sm_hint(stg + kTileABytes + c * half * (kBlockK * 2), tmap_xh, bar, kcoord,
                                          t0 + c * p.bn + static_cast<int>(crank) * half, pol_x);
             }
+            __syncwarp();
+            s = (s + 1 == p.stages) ? 0 : s + 1;
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
             const uint32_t idesc = make_idesc_bf16(2 * kBlockM, static_cast<uint32_t>(p.bn));
             bool ok = true;
+            int s = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                if (!mbar_wait(&sh.full_bar[s], (st.full_bits >> s) & 1u)) {
-                    atomicExch(&g_gemm_timeout_flag, 2);
+                if (!mbar_wait_warp(&sh.full_bar[s], (st.full_bits >> s) & 1u)) {
+                    if (lane == 0) atomicExch(&g_gemm_timeout_flag, 2);
                     ok = false;
                     break;
                 }
                 st.full_bits ^= (1u << s);
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-                for (int c = 0; c < p.nt; ++c) {
-                    const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes + c * half * (kBlockK * 2));
+                if (elect_one_sync()) {
+                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                    const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                    for (int c = 0; c < p.nt; ++c) {
+                        const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes + c * half * (kBlockK * 2));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16_ss_2sm(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                         (i > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_ss_2sm(tmem_base + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                             (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&sh.empty_bar[s]);      // frees stage s in both CTAs
                 }
-                umma_commit_2sm(&sh.empty_bar[s]);      // frees stage s in both CTAs
+                __syncwarp();
+                s = (s + 1 == p.stages) ? 0 : s + 1;
             }
-            if (ok) umma_commit_2sm(sh.tmem_full_bar);  // both epilogues may start
+            if (ok && elect_one_sync()) umma_commit_2sm(sh.tmem_full_bar);  // both epilogues may start
+            __syncwarp();
         }
     } else if (warp >= 4) {
         const int w4 = warp - 4;
@@ -598,54 +631,60 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
     uint64_t* tmem_full1 = xbar + 2;                 // tmem_full of buffer 1 (buffer 0: sh.tmem_full_bar)
 
     if (warp == 0) {
-        if (lane == 0) {
-            const uint64_t pol_w = p.l2_policy == 0 ? make_policy_evict_first() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_last();
-            const uint64_t pol_x = p.l2_policy == 0 ? make_policy_evict_last() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
-            uint32_t empty_bits = 0;
-            int s = 0;
-            pdl_wait();
-            pdl_trigger();
-            trace_stamp(p.trace, 1);
-            for (int tile = first; tile < n_tiles; tile += stride) {
-                int xp, ty;
-                pair_tile_coords(tile, gxp, gy, p.band, xp, ty);
-                const int bx = 2 * xp + static_cast<int>(crank), t0 = ty * p.bn;
-                for (int kb = 0; kb < p.kb_total; ++kb) {
-                    if (!mbar_wait(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 1); return; }
-                    empty_bits ^= (1u << s);
+        // all 32 lanes converged, operands warp-uniform, issue under elect.sync (see gemm_tile)
+        const uint64_t pol_w = p.l2_policy == 0 ? make_policy_evict_first() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_last();
+        const uint64_t pol_x = p.l2_policy == 0 ? make_policy_evict_last() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
+        uint32_t empty_bits = 0;
+        int s = 0;
+        pdl_wait();
+        pdl_trigger();
+        trace_stamp(p.trace, 1);
+        const uint32_t bar0 = map_to_cta(&sh.full_bar[0], 0u);      // the leader's full[0]; full[s] is 8 bytes further per stage
+        for (int tile = first; tile < n_tiles; tile += stride) {
+            int xp, ty;
+            pair_tile_coords(tile, gxp, gy, p.band, xp, ty);
+            const int bx = 2 * xp + static_cast<int>(crank), t0 = ty * p.bn;
+            for (int kb = 0; kb < p.kb_total; ++kb) {
+                if (!mbar_wait_warp(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 1); return; }
+                empty_bits ^= (1u << s);
+                if (elect_one_sync()) {
                     uint8_t* stg = smem + s * stage_bytes;
                     if (leader) mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
-                    const uint32_t bar = map_to_cta(&sh.full_bar[s], 0u);
+                    const uint32_t bar = bar0 + static_cast<uint32_t>(s) * 8u;
                     tma_load_2d_2sm_hint(stg, tmap_w, bar, 0, (bx * p.kb_total + kb) * kBlockM, pol_w);
                     tma_load_2d_2sm_hint(stg + kTileABytes, tmap_xh, bar, kb * kBlockK, t0 + static_cast<int>(crank) * half, pol_x);
-                    s = (s + 1 == p.stages) ? 0 : s + 1;
                 }
+                __syncwarp();
+                s = (s + 1 == p.stages) ? 0 : s + 1;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
             const uint32_t idesc = make_idesc_bf16(2 * kBlockM, static_cast<uint32_t>(p.bn));
             uint32_t full_bits = 0, tmem_empty_bits = 0;
             int s = 0, buf = 0;
             for (int tile = first; tile < n_tiles; tile += stride) {
-                if (!mbar_wait(&tmem_empty[buf], ((tmem_empty_bits >> buf) & 1u) ^ 1u)) { atomicExch(&g_gemm_timeout_flag, 4); return; }
+                if (!mbar_wait_warp(&tmem_empty[buf], ((tmem_empty_bits >> buf) & 1u) ^ 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 4); return; }
                 tmem_empty_bits ^= (1u << buf);
                 tcgen05_fence_after();
                 const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
                 for (int kb = 0; kb < p.kb_total; ++kb) {
-                    if (!mbar_wait(&sh.full_bar[s], (full_bits >> s) & 1u)) { atomicExch(&g_gemm_timeout_flag, 2); return; }
+                    if (!mbar_wait_warp(&sh.full_bar[s], (full_bits >> s) & 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 2); return; }
                     full_bits ^= (1u << s);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                    const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-                    const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes);
+                    if (elect_one_sync()) {
+                        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                        const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16_ss_2sm(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_commit_2sm(&sh.empty_bar[s]);
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_ss_2sm(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_2sm(&sh.empty_bar[s]);
+                        if (kb + 1 == p.kb_total) umma_commit_2sm(buf == 0 ? sh.tmem_full_bar : tmem_full1);
+                    }
+                    __syncwarp();
                     s = (s + 1 == p.stages) ? 0 : s + 1;
                 }
-                umma_commit_2sm(buf == 0 ? sh.tmem_full_bar : tmem_full1);
                 buf ^= 1;
             }
         }
@@ -714,227 +753,6 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
             asm volatile("bar.sync 1, 256;\n" ::: "memory");
             buf ^= 1;
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// "Wide" variant for 256 < T <= 288 tokens (the batch-1 Gemma prefill, T = 276): one CTA owns TWO
-// consecutive 128-row weight tiles and streams the token operand once for both, which cuts the bytes
-// every SM has to ingest per weight tile from 16 + 36 KB to 16 + 18 KB per k-block (the measured
-// bound of these GEMMs is operand ingest, not HBM).  EXPERIMENT, off by default ("gemm_wide"): on the
-// gate/up shape it measures 60.6 us against 62.1 us for one tile per CTA.  With the math removed the
-// operand stream alone takes 39 us, with only the tcgen05 part 44-49 us, with only the mma.sync part
-// 42 us: the legacy HMMA path shares the tensor pipe with tcgen05 and runs at roughly 1/20 of its rate
-// on B200, so the 256 HMMAs per k-block of the tail cost more than the ingest they save.
-// Two 128 x 288 fp32 accumulators do not fit the 512 TMEM columns, so the tile is split by tokens:
-//   * tokens 0..255   -> tcgen05.mma, two 128 x 256 accumulators = all 512 TMEM columns;
-//   * tokens 256..287 -> warp-level mma.sync (m16n8k16, fp32 accumulators in registers) by eight
-//     otherwise idle warps, reading the SAME swizzled shared-memory stages with ldmatrix.
-// 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM owner, warps 4..11 tail MMA
-// (warp w: weight rows (w-4)*32.. of the 256), warps 4..7 also drain TMEM in the epilogue.
-static constexpr int kWideThreads = 384;
-static constexpr int kWideMain = 256;
-static constexpr int kWideTail = 32;
-static constexpr int kWideStageBytes = 2 * kTileABytes + (kWideMain + kWideTail) * kBlockK * 2;   // 68 KB
-static constexpr int kWideTailWarps = 8;
-
-// byte offset of (row, 16-byte chunk) inside a 128B-swizzled K-major tile (rows of 128 bytes)
-__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
-    return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
-}
-
-template <int EPI>
-__device__ __forceinline__ void gemm_wide_tile(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_x256,
-                                               const CUtensorMap* tmap_x32, const GemmShared& sh, const int px,
-                                               const int bz) {
-    static_assert(EPI != EPI_PARTIAL, "the wide variant stages bf16 tiles only");
-    uint8_t* smem = sh.ring;
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-    const int lane = threadIdx.x & 31;
-    const uint32_t tmem_base = sh.tmem_base;
-    const int kb0 = bz * p.kb_per_split;
-    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-    const int nkb = kb1 - kb0;
-    float acc[2][4][4];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            const uint64_t pol_w = make_policy_evict_first();
-            const uint64_t pol_x = make_policy_evict_last();
-            uint32_t empty_bits = 0;
-            // weights of the first ring before the PDL wait (they do not depend on the previous kernel)
-            const int pre = p.w_static ? min(p.stages, nkb) : 0;
-            for (int i = 0; i < pre; ++i) {
-                empty_bits ^= (1u << i);
-                uint8_t* stg = smem + i * kWideStageBytes;
-                mbar_arrive_expect_tx(&sh.full_bar[i], static_cast<uint32_t>(kWideStageBytes));
-                for (int t = 0; t < 2; ++t)
-                    tma_load_2d_hint(stg + t * kTileABytes, tmap_w, &sh.full_bar[i], 0,
-                                     ((2 * px + t) * p.kb_total + kb0 + i) * kBlockM, pol_w);
-            }
-            pdl_wait();
-            pdl_trigger();
-            trace_stamp(p.trace, 1);
-            for (int i = 0; i < pre; ++i) {
-                uint8_t* stg = smem + i * kWideStageBytes + 2 * kTileABytes;
-                tma_load_2d_hint(stg, tmap_x256, &sh.full_bar[i], (kb0 + i) * kBlockK, 0, pol_x);
-                tma_load_2d_hint(stg + kWideMain * (kBlockK * 2), tmap_x32, &sh.full_bar[i], (kb0 + i) * kBlockK,
-                                 kWideMain, pol_x);
-            }
-            for (int i = pre; i < nkb; ++i) {
-                const int s = i % p.stages;
-                if (!mbar_wait(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) {
-                    atomicExch(&g_gemm_timeout_flag, 1);
-                    break;
-                }
-                empty_bits ^= (1u << s);
-                uint8_t* stg = smem + s * kWideStageBytes;
-                mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(kWideStageBytes));
-                for (int t = 0; t < 2; ++t)
-                    tma_load_2d_hint(stg + t * kTileABytes, tmap_w, &sh.full_bar[s], 0,
-                                     ((2 * px + t) * p.kb_total + kb0 + i) * kBlockM, pol_w);
-                tma_load_2d_hint(stg + 2 * kTileABytes, tmap_x256, &sh.full_bar[s], (kb0 + i) * kBlockK, 0, pol_x);
-                tma_load_2d_hint(stg + 2 * kTileABytes + kWideMain * (kBlockK * 2), tmap_x32, &sh.full_bar[s],
-                                 (kb0 + i) * kBlockK, kWideMain, pol_x);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(kBlockM, kWideMain);
-            uint32_t full_bits = 0;
-            bool ok = true;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                if (!mbar_wait(&sh.full_bar[s], (full_bits >> s) & 1u)) {
-                    atomicExch(&g_gemm_timeout_flag, 2);
-                    ok = false;
-                    break;
-                }
-                full_bits ^= (1u << s);
-                tcgen05_fence_after();
-                const uint32_t stg = smem_u32(smem + s * kWideStageBytes);
-                const uint64_t b_desc = make_smem_desc_sw128(stg + 2 * kTileABytes);
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const uint64_t a_desc = make_smem_desc_sw128(stg + t * kTileABytes);
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16_ss(tmem_base + t * kWideMain, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                     (i > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&sh.empty_bar[s]);     // one of the 1 + kWideTailWarps arrivals that free the stage
-            }
-            if (ok) umma_commit(sh.tmem_full_bar);
-        }
-    } else if (warp >= 4) {
-        // ---- tail tokens on mma.sync: D[token][weight row] += X_tail[token][k] * W[row][k] ----
-        const int tw = warp - 4;
-        const int wt = tw >> 2;                      // weight tile of the pair
-        const int wr0 = (tw & 3) * 32;               // first local weight row of this warp
-        pdl_wait();
-        uint32_t full_bits = 0;
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % p.stages;
-            if (!mbar_wait(&sh.full_bar[s], (full_bits >> s) & 1u)) {
-                if (lane == 0) atomicExch(&g_gemm_timeout_flag, 5);
-                break;
-            }
-            full_bits ^= (1u << s);
-            __syncwarp();       // lanes leave the polling loop at different times; ldmatrix / mma.sync need the warp converged
-            const uint32_t stg = smem_u32(smem + s * kWideStageBytes);
-            const uint32_t wbase = stg + wt * kTileABytes;
-            const uint32_t xbase = stg + 2 * kTileABytes + kWideMain * (kBlockK * 2);
-            // all fragments of the k-block into registers first, so that the stage is released after the
-            // shared-memory reads (not after the 32 HMMAs): with a 3-deep ring the stage hold time matters
-            uint32_t af[kBlockK / 16][2][4], bfr[kBlockK / 16][2][4];
-#pragma unroll
-            for (int ks = 0; ks < kBlockK / 16; ++ks) {
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-                    ldmatrix_x4(af[ks][mt], xbase + sw128_off(mt * 16 + (lane & 15), 2 * ks + (lane >> 4)));
-#pragma unroll
-                for (int np = 0; np < 2; ++np) {
-                    const int row = wr0 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-                    ldmatrix_x4(bfr[ks][np], wbase + sw128_off(row, 2 * ks + ((lane >> 3) & 1)));
-                }
-            }
-            // The stage may be refilled by TMA (async proxy) as soon as the arrive lands, and ptxas is free
-            // to schedule the arrive right behind the ISSUE of the last LDSM, whose read of the stage may
-            // then still be in flight (observed without the fence: ~20 % of launches wrong).  The
-            // cross-proxy fence drains this warp's outstanding shared-memory reads first.
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
-#pragma unroll
-            for (int ks = 0; ks < kBlockK / 16; ++ks)
-#pragma unroll
-                for (int np = 0; np < 2; ++np)
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        mma_bf16_16816(acc[mt][np * 2 + 0], af[ks][mt], bfr[ks][np][0], bfr[ks][np][1]);
-                        mma_bf16_16816(acc[mt][np * 2 + 1], af[ks][mt], bfr[ks][np][2], bfr[ks][np][3]);
-                    }
-        }
-    }
-
-    // ---- epilogue: accumulators complete, every warp is done with the ring ----
-    bool acc_ready = true;
-    if (warp >= 4 && warp < 8) {
-        acc_ready = mbar_wait(sh.tmem_full_bar, 0u);
-        if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
-        tcgen05_fence_after();
-    }
-    __syncthreads();
-    bf16* tile = reinterpret_cast<bf16*>(smem);      // [288 tokens][128 weight rows], aliases the ring
-    for (int t = 0; t < 2; ++t) {
-        const int n0 = (2 * px + t) * kBlockM;
-        if (warp >= 4 && warp < 8) {
-            const int w4 = warp - 4;
-            const int nl = w4 * 32 + lane;
-            float bias = 0.f;
-            if (p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
-            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16) + t * kWideMain;
-            for (int g = 0; acc_ready && g < kWideMain / 16; ++g) {
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(lane_addr + g * 16, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float v = bf16_round(__uint_as_float(r[i]) + bias);
-                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
-                    tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
-                }
-            }
-            tcgen05_fence_before();
-        }
-        if (warp >= 4 && ((warp - 4) >> 2) == t) {
-            const int wr0 = ((warp - 4) & 3) * 32;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int col = wr0 + nt * 8 + (lane & 3) * 2;
-                    float b0 = 0.f, b1 = 0.f;
-                    if (p.bias != nullptr) { b0 = bf2f(p.bias[n0 + col]); b1 = bf2f(p.bias[n0 + col + 1]); }
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int row = kWideMain + mt * 16 + (lane >> 2) + half * 8;
-                        float v0 = bf16_round(acc[mt][nt][half * 2 + 0] + b0);
-                        float v1 = bf16_round(acc[mt][nt][half * 2 + 1] + b1);
-                        if (EPI == EPI_GELU) { v0 = gelu_tanh_f32(v0); v1 = gelu_tanh_f32(v1); }
-                        *reinterpret_cast<uint32_t*>(tile + row * kBlockM + col) = pack_bf16x2(v0, v1);
-                    }
-                }
-        }
-        __syncthreads();
-        gemm_epilogue_store<EPI>(p, smem, 2 * px + t, bz, n0, 0, kWideMain + kWideTail, kWideThreads);
-        __syncthreads();
     }
 }
 

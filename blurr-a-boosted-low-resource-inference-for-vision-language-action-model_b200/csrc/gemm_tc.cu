@@ -153,26 +153,6 @@ gemm_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (warp == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
-// Two weight tiles per CTA for 256 < T <= 288 tokens (gemm_wide_tile in gemm_body.cuh).
-template <int EPI>
-__global__ void __launch_bounds__(kWideThreads, 1)
-gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x256,
-                 const __grid_constant__ CUtensorMap tmap_x32, const GemmDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    trace_stamp(p.trace, 0);
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-    if (warp == 0 && elect_one_sync()) {
-        tma_prefetch_desc(&tmap_w);
-        tma_prefetch_desc(&tmap_x256);
-        tma_prefetch_desc(&tmap_x32);
-    }
-    uint32_t tmem_base;
-    GemmShared sh = gemm_setup_shared(smem_raw, p.stages * kWideStageBytes, 1 + kWideTailWarps, 512u, &tmem_base);
-    gemm_wide_tile<EPI>(p, &tmap_w, &tmap_x256, &tmap_x32, sh, blockIdx.x, blockIdx.z);
-    trace_stamp(p.trace, 2);
-    if (warp == 2) tmem_dealloc(tmem_base, 512u);
-}
-
 // ---------------------------------------------------------------------------
 // host side: tensor-map cache + launcher
 // ---------------------------------------------------------------------------
@@ -295,10 +275,6 @@ void gemm_set_use_2cta(int on) { g_use_2cta = on < 0 ? -1 : (on ? 1 : 0); }
 // 33.5 vs 39.9 us on the gate/up shape); from T >= 64 its direct TMEM -> global epilogue (2-byte stores,
 // 4 warps) stalls the next tile's MMAs longer than the bubbles it removes (GeGLU, T = 276: 95 vs 59 us),
 // so it is used for few-token GEMMs only.
-// Wide (two weight tiles per CTA) variant for 256 < T <= 288 tokens with a bf16 epilogue (the Gemma gate/up
-// GEMM of the batch-1 prefill).  Off by default: not faster than one tile per CTA (see gemm_body.cuh).
-static int g_wide = 0;
-void gemm_set_wide(int on) { g_wide = on ? 1 : 0; }
 // Large token counts (batched episodes), measured on B200 at 64 episodes (TFLOP/s; one tile per CTA with two
 // CTAs per SM | CTA pairs, two per SM | persistent 128 x 256 tiles with the accumulator double-buffered in
 // TMEM and a direct TMEM -> global epilogue):
@@ -518,20 +494,6 @@ int gemm_make_step_op(const GemmCall& c, GemmDev* d, CUtensorMap* tmap_w, CUtens
 }
 
 template <int EPI>
-static cudaError_t launch_wide(cudaStream_t stream, int grid_x, int smem, const CUtensorMap& tw, const CUtensorMap& tx256,
-                               const CUtensorMap& tx32, const GemmDev& d) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_wide_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kSmemBudget);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    return launch_kernel(gemm_wide_kernel<EPI>, dim3(grid_x, 1, 1), dim3(kWideThreads), static_cast<size_t>(smem), stream,
-                         tw, tx256, tx32, d);
-}
-
-template <int EPI>
 static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, const CUtensorMap& tw, const CUtensorMap& txh,
                                 const GemmDev& d, int gxp, int gy) {
     static bool attr_set = false;
@@ -616,41 +578,7 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     return 1;
 }
 
-static bool gemm_wide_applies(const GemmCall& c) {
-    return g_wide && c.w_packed && c.epi != EPI_PARTIAL && c.splitk <= 1 && c.bn_override == 0 &&
-           c.T > kWideMain && c.T <= kWideMain + kWideTail && c.Nw % (2 * kBlockM) == 0 && c.K % kBlockK == 0;
-}
-
-static int gemm_launch_wide(cudaStream_t stream, const GemmCall& c, std::string* err) {
-    const int kb_total = c.K / kBlockK;
-    CUtensorMap tw, tx256, tx32;
-    if (get_tmap(c.W, c.Nw * kb_total, kBlockK, kBlockK, kBlockM, &tw, err)) return -1;
-    if (get_tmap(c.X, c.T, c.K, c.ldx, kWideMain, &tx256, err)) return -1;
-    if (get_tmap(c.X, c.T, c.K, c.ldx, kWideTail, &tx32, err)) return -1;
-    GemmDev d{};
-    d.T = c.T; d.bn = kWideMain; d.nt = 1; d.kb_total = kb_total; d.kb_per_split = kb_total;
-    d.stages = kRingBytes / kWideStageBytes;
-    if (d.stages > kb_total) d.stages = kb_total;
-    // the bf16 epilogue tile [288][128] aliases the ring
-    while (d.stages * kWideStageBytes < (kWideMain + kWideTail) * kBlockM * 2) ++d.stages;
-    d.tmem_cols = 512; d.Nw = c.Nw;
-    d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = nullptr;
-    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static;
-    const int smem = d.stages * kWideStageBytes + 1024 + 256;
-    const int grid_x = c.Nw / (2 * kBlockM);
-    cudaError_t e;
-    switch (c.epi) {
-        case EPI_STORE: e = launch_wide<EPI_STORE>(stream, grid_x, smem, tw, tx256, tx32, d); break;
-        case EPI_GELU:  e = launch_wide<EPI_GELU>(stream, grid_x, smem, tw, tx256, tx32, d); break;
-        case EPI_GEGLU: e = launch_wide<EPI_GEGLU>(stream, grid_x, smem, tw, tx256, tx32, d); break;
-        default: *err = "gemm_launch: bad epilogue"; return -1;
-    }
-    if (e != cudaSuccess) { *err = std::string("gemm (wide) launch failed: ") + cudaGetErrorString(e); return -1; }
-    return 1;
-}
-
 int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
-    if (gemm_wide_applies(c)) return gemm_launch_wide(stream, c, err);
     if (gemm_pairp_applies(c)) return gemm_launch_pairp(stream, c, err);
     GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
     if (!pl.valid) {

@@ -96,7 +96,6 @@ void gemm_set_use_2cta(int on);
 // Persistent one-CTA-per-SM kernel with a direct TMEM -> global epilogue (default) vs one tile per CTA.
 void gemm_set_persistent(int on);
 void gemm_set_max_stages(int n);
-void gemm_set_wide(int on);
 // Cached SWIZZLE_128B tensor map over a row-major bf16 matrix [rows][cols] (row stride ld elements) with boxes of
 // box_rows x 64 columns; returns nonzero and sets *err on failure.
 int gemm_get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, std::string* err);

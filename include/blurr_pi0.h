@@ -197,8 +197,8 @@ int blurr_op_normalize_proprio(void* cuda_stream, const double* raw, const doubl
  * "gemm_pair_band" (persistent pairs: weight tile pairs per raster band, 0 = automatic), "gemm_pair_policy" (L2
  * hints above 1024 tokens: -1 automatic = 1; 0 weights evict_first / tokens evict_last; 1 both evict_normal; 2 weights
  * evict_last / tokens evict_first),
- * "gemm_persistent" (0/1: persistent kernel for GEMMs of <= 32 tokens), "gemm_wide" (0/1, default 0:
- * two weight tiles per CTA for 257..288 tokens), "gemm_max_stages" (TMA ring depth cap), "use_pdl" (0/1). */
+ * "gemm_persistent" (0/1: persistent kernel for GEMMs of <= 32 tokens), "gemm_max_stages" (TMA ring depth cap),
+ * "use_pdl" (0/1). */
 int blurr_set_global_option(const char* name, int64_t value);
 
 const char* blurr_last_error(void);

@@ -32,7 +32,6 @@ for name, N, K, epi, S in SHAPES:
         for use2 in PAIRS:
             for stages, persist in [(a, b) for a in STAGES for b in PERSIST]:
                 capi.check(lib.blurr_set_global_option(b"gemm_persistent", persist))
-                capi.check(lib.blurr_set_global_option(b"gemm_wide", int(os.environ.get("WIDE", "0"))))
                 capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", use2))
                 capi.check(lib.blurr_set_global_option(b"gemm_max_stages", stages))
 
