@@ -20,7 +20,7 @@ BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(LIB_DIR, "libblurr_pi0.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 
-SOURCES = ["gemm_tc.cu", "norm_consumers.cu", "attention.cu", "attention_tc.cu", "misc_kernels.cu", "step_kernel.cu", "engine.cu",
+SOURCES = ["gemm_tc.cu", "norm_consumers.cu", "attention.cu", "attention_tc.cu", "misc_kernels.cu", "engine.cu",
            "preprocess.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

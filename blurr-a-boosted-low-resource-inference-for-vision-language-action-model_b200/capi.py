@@ -82,7 +82,6 @@ _SIGNATURES = [
     ("blurr_pi0_last_launch_count", C.c_int64, [C.c_void_p]),
     ("blurr_pi0_profile_report", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("blurr_pi0_trace_report", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
-    ("blurr_pi0_last_op_count", C.c_int64, [C.c_void_p]),
     ("blurr_pi0_weight_bytes", C.c_int64, [C.c_void_p]),
     ("blurr_preproc_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ("blurr_preproc_destroy", None, [C.c_void_p]),

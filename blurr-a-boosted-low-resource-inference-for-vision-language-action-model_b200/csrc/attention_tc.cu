@@ -118,7 +118,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
 
     // ---- K tiles by TMA: k-block kb, chunk c -> [144 keys][64 dims] ----
     const int key_row0 = b * a.n_slots;
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one_sync()) {       // issue from a converged warp under elect.sync (see gemm_body.cuh)
         mbar_arrive_expect_tx(bar_k, static_cast<uint32_t>(kTcKBytes));
         for (int kb = 0; kb < 4; ++kb)
             for (int c = 0; c < 2; ++c)
@@ -141,20 +141,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     __syncthreads();
 
     // ---- S = Q K^T ----
-    if (warp == 1 && lane == 0) {
-        if (!mbar_wait(bar_k, 0)) atomicExch(&g_attn_timeout_flag, 1);
+    if (warp == 1) {
+        if (!mbar_wait_warp(bar_k, 0) && lane == 0) atomicExch(&g_attn_timeout_flag, 1);
         tcgen05_fence_after();
-        const uint32_t idesc = make_idesc_bf16(kTcRows, 144);
-        for (int kb = 0; kb < 4; ++kb) {
-            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(q_s + kb * (kTcRows * 128)));
-            for (int c = 0; c < 2; ++c) {
-                const uint64_t b_desc = make_smem_desc_sw128(smem_u32(k_s + (kb * 2 + c) * (144 * 128)));
+        if (elect_one_sync()) {
+            const uint32_t idesc = make_idesc_bf16(kTcRows, 144);
+            for (int kb = 0; kb < 4; ++kb) {
+                const uint64_t a_desc = make_smem_desc_sw128(smem_u32(q_s + kb * (kTcRows * 128)));
+                for (int c = 0; c < 2; ++c) {
+                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(k_s + (kb * 2 + c) * (144 * 128)));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(tmem + c * 144, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tmem + c * 144, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
             }
+            umma_commit(bar_s);
         }
-        umma_commit(bar_s);
+        __syncwarp();
     }
 
     // ---- softmax: kTcParts warps per TMEM lane quarter, each a third of the key columns ----
@@ -169,7 +172,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     if (!mbar_wait(bar_s, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 2); }
     tcgen05_fence_after();
     __syncthreads();                   // every thread has seen S complete: Q and K tiles are dead
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one_sync()) {
         // V where it lies: key block kb (64 keys; the last one 32), dim group j -> [keys][64 dims]
         mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(kTcVBytes));
         for (int kb = 0; kb < 4; ++kb)
@@ -254,22 +257,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     __syncthreads();
 
     // ---- O = P V ----
-    if (warp == 1 && lane == 0) {
-        if (!mbar_wait(bar_v, 0)) atomicExch(&g_attn_timeout_flag, 3);
+    if (warp == 1) {
+        if (!mbar_wait_warp(bar_v, 0) && lane == 0) atomicExch(&g_attn_timeout_flag, 3);
         tcgen05_fence_after();
-        // M = 128, N = 256, B operand MN-major (bit 16)
-        const uint32_t idesc = make_idesc_bf16(kTcRows, kTcHd) | (1u << 16);
-        for (int kb = 0; kb < kTcKeyBlocks; ++kb) {
-            const int ksteps = (kb < 4) ? 4 : 2;                              // keys 256..287 only
-            const uint32_t vbase = smem_u32(v_s + kb * 4 * 8192);
-            const uint32_t lbo = (kb < 4) ? 8192u : 4096u;                   // one [keys][64 dims] box
-            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(p_s + kb * (kTcRows * 128)));
-            for (int k = 0; k < ksteps; ++k) {
-                const uint64_t b_desc = make_smem_desc_sw128_mn(vbase + k * 2048, lbo);    // 16 keys = 2 x 8 rows
-                umma_bf16_ss(tmem, a_desc + 2 * k, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        if (elect_one_sync()) {
+            // M = 128, N = 256, B operand MN-major (bit 16)
+            const uint32_t idesc = make_idesc_bf16(kTcRows, kTcHd) | (1u << 16);
+            for (int kb = 0; kb < kTcKeyBlocks; ++kb) {
+                const int ksteps = (kb < 4) ? 4 : 2;                              // keys 256..287 only
+                const uint32_t vbase = smem_u32(v_s + kb * 4 * 8192);
+                const uint32_t lbo = (kb < 4) ? 8192u : 4096u;                   // one [keys][64 dims] box
+                const uint64_t a_desc = make_smem_desc_sw128(smem_u32(p_s + kb * (kTcRows * 128)));
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t b_desc = make_smem_desc_sw128_mn(vbase + k * 2048, lbo);    // 16 keys = 2 x 8 rows
+                    umma_bf16_ss(tmem, a_desc + 2 * k, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
             }
+            umma_commit(bar_o);
         }
-        umma_commit(bar_o);
+        __syncwarp();
     }
 
     // ---- epilogue: O -> bf16 -> [b*q + query][head*256 + dim] ----
@@ -354,7 +360,7 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     trace_stamp(a.trace, 1);
 
     const int row0 = b * a.seq;
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one_sync()) {
         mbar_arrive_expect_tx(bar_k, static_cast<uint32_t>(kSgKBytes));
         for (int kb = 0; kb < 2; ++kb)
             tma_load_2d(k_s + kb * (256 * 128), &tmap_k, bar_k, a.hidden + h * hd + kb * 64, row0);
@@ -376,18 +382,21 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     fence_proxy_async_smem();
     __syncthreads();
 
-    if (warp == 1 && lane == 0) {
-        if (!mbar_wait(bar_k, 0)) atomicExch(&g_attn_timeout_flag, 5);
+    if (warp == 1) {
+        if (!mbar_wait_warp(bar_k, 0) && lane == 0) atomicExch(&g_attn_timeout_flag, 5);
         tcgen05_fence_after();
-        const uint32_t idesc = make_idesc_bf16(kTcRows, 256);
-        for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(q_s + kb * (kTcRows * 128)));
-            const uint64_t b_desc = make_smem_desc_sw128(smem_u32(k_s + kb * (256 * 128)));
+        if (elect_one_sync()) {
+            const uint32_t idesc = make_idesc_bf16(kTcRows, 256);
+            for (int kb = 0; kb < 2; ++kb) {
+                const uint64_t a_desc = make_smem_desc_sw128(smem_u32(q_s + kb * (kTcRows * 128)));
+                const uint64_t b_desc = make_smem_desc_sw128(smem_u32(k_s + kb * (256 * 128)));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma_bf16_ss(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_s);
         }
-        umma_commit(bar_s);
+        __syncwarp();
     }
 
     const int quarter = warp & 3, half = warp >> 2;
@@ -446,18 +455,21 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     fence_proxy_async_smem();
     __syncthreads();
 
-    if (warp == 1 && lane == 0) {
-        if (!mbar_wait(bar_v, 0)) atomicExch(&g_attn_timeout_flag, 7);
+    if (warp == 1) {
+        if (!mbar_wait_warp(bar_v, 0) && lane == 0) atomicExch(&g_attn_timeout_flag, 7);
         tcgen05_fence_after();
-        const uint32_t idesc = make_idesc_bf16(kTcRows, 128) | (1u << 16);          // B (= V) MN-major
-        for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t vbase = smem_u32(v_s + kb * 2 * 8192);
-            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(p_s + kb * (kTcRows * 128)));
-            for (int k = 0; k < 4; ++k)
-                umma_bf16_ss(tmem + 256, a_desc + 2 * k, make_smem_desc_sw128_mn(vbase + k * 2048, 8192u), idesc,
-                             (kb > 0 || k > 0) ? 1u : 0u);
+        if (elect_one_sync()) {
+            const uint32_t idesc = make_idesc_bf16(kTcRows, 128) | (1u << 16);          // B (= V) MN-major
+            for (int kb = 0; kb < 4; ++kb) {
+                const uint32_t vbase = smem_u32(v_s + kb * 2 * 8192);
+                const uint64_t a_desc = make_smem_desc_sw128(smem_u32(p_s + kb * (kTcRows * 128)));
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem + 256, a_desc + 2 * k, make_smem_desc_sw128_mn(vbase + k * 2048, 8192u), idesc,
+                                 (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_o);
         }
-        umma_commit(bar_o);
+        __syncwarp();
     }
 
     if (!mbar_wait(bar_o, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 8); }

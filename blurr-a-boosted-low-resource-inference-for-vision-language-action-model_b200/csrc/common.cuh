@@ -302,6 +302,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+// Same wait, tied to the 16 destination registers of an earlier tcgen05.ld so that no use of them can be scheduled
+// above it (software-pipelined drains keep a second load in flight while the first one's values are consumed).
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
 
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as [rows][64] (128 B per
 // row) with the 128-byte swizzle TMA writes (CU_TENSOR_MAP_SWIZZLE_128B): 8-row groups are

@@ -7,7 +7,6 @@
 #include "gemm_tc.h"
 #include "kernels.h"
 #include "launch.cuh"
-#include "step_kernel.h"
 
 #include <cmath>
 #include <cstdio>
@@ -170,11 +169,6 @@ struct blurr_pi0 {
     // options / bookkeeping
     bool use_graph = true, debug = false;
     int stage_mask = 7;            // bit 0 vision, bit 1 prefill, bit 2 action flow (timing experiments)
-    // One persistent cooperative kernel per step instead of a kernel graph.  Measured slower on B200
-    // (round 1: 7.8 ms vs 6.7 ms at bs=1): the step is bound by per-SM operand ingest and per-op
-    // parallelism, not by launch latency, and resident CTAs cannot oversubscribe an SM the way many
-    // small kernels do.  Kept as an option; results are bit-identical.
-    bool use_step_kernel = false;
     bool profile = false;          // eager launches bracketed by CUDA events, per-kernel-label totals
     // in-graph timeline: kernels stamp %globaltimer into trace_buf (launch.cuh); slots are handed out
     // while the step is issued / captured, so every graph replay rewrites the same slots
@@ -186,8 +180,6 @@ struct blurr_pi0 {
     struct ProfEntry { int count = 0; double ms = 0.0; };
     std::map<std::string, ProfEntry> prof;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending;
-    std::map<long long, StepProgram> programs;
-    int64_t step_ops = 0;
     int64_t launches = 0;
     std::map<std::string, TapBuf> taps;
     struct GraphEntry { cudaGraph_t graph; cudaGraphExec_t exec; int64_t launches; };
@@ -293,7 +285,6 @@ extern "C" void blurr_pi0_destroy(blurr_pi0_t* h) {
         cudaGraphExecDestroy(kv.second.exec);
         cudaGraphDestroy(kv.second.graph);
     }
-    for (auto& kv : h->programs) step_program_free(kv.second);
     for (cudaEvent_t e : h->ev_v) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_p) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {h->ev_fork, h->ev_done_p, h->ev_done_a}) if (e) cudaEventDestroy(e);
@@ -606,8 +597,6 @@ extern "C" int blurr_pi0_set_time_table(blurr_pi0_t* h, const void* dev_table, i
     CUDA_TRY(cudaMemcpy(h->time_table, dev_table, static_cast<size_t>(num_steps) * h->cfg.expert_hidden * 2,
                         cudaMemcpyDeviceToDevice));
     // a different step count changes the captured schedule
-    for (auto& kv : h->programs) step_program_free(kv.second);
-    h->programs.clear();
     for (auto& kv : h->graphs) {
         cudaGraphExecDestroy(kv.second.exec);
         cudaGraphDestroy(kv.second.graph);
@@ -645,47 +634,28 @@ struct Run {
     cudaStream_t st;
     int rc = 0;
     unsigned long long* trace_slot(const char* what) {
-        if (!h->trace || rec || h->trace_buf == nullptr) return nullptr;
+        if (!h->trace || h->trace_buf == nullptr) return nullptr;
         const size_t idx = h->trace_labels.size();
         if (idx >= static_cast<size_t>(kTraceMax)) return nullptr;
         h->trace_labels.push_back(label.empty() ? std::string(what) : label + ":" + what);
         h->trace_streams.push_back(st == s_main ? 0 : (st == h->s_prop ? 1 : 2));
         return h->trace_buf + idx * 4;
     }
-    StepProgram* rec = nullptr;      // non-null: record step-kernel ops instead of launching kernels
-    int group = 0, group_items = 0;
-
     std::string label;               // profile mode: current phase label
     void prof_begin(const char* what) {
-        if (!h->profile || rec) return;
+        if (!h->profile) return;
         cudaEvent_t a, b;
         cudaEventCreate(&a); cudaEventCreate(&b);
         cudaEventRecord(a, st);
         h->prof_pending.push_back({label.empty() ? std::string(what) : label + ":" + what, {a, b}});
     }
     void prof_end() {
-        if (!h->profile || rec || h->prof_pending.empty()) return;
+        if (!h->profile || h->prof_pending.empty()) return;
         cudaEventRecord(h->prof_pending.back().second.second, st);
     }
     void launched(cudaError_t e, const char* what) {
         ++h->launches;
         if (e != cudaSuccess && rc == 0) rc = fail(BLURR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-    }
-    // ops recorded between group_begin/group_end are independent: one grid barrier after the last
-    void group_begin() { ++group; group_items = 0; }
-    void group_end() {
-        --group;
-        if (rec && !rec->ops.empty()) rec->ops.back().hot.barrier_after = 1;
-    }
-    StepOp& push(int type, int gx, int gy, int gz) {
-        rec->ops.emplace_back();
-        StepOp& op = rec->ops.back();
-        memset(&op, 0, sizeof(StepOp));
-        op.hot.type = type; op.hot.gx = gx; op.hot.gy = gy; op.hot.gz = gz;
-        op.hot.barrier_after = group > 0 ? 0 : 1;
-        op.hot.pad0 = group > 0 ? group_items % kNumSMs : 0;      // first CTA of this op inside a group
-        group_items += gx * gy * gz;
-        return op;
     }
     int side_stream_cap = 0;         // > 0 while the experts overlap the prefill (see pick_splitk)
     // split-K so that about one CTA per SM is in flight (each CTA owns ~all of an SM's smem)
@@ -712,10 +682,10 @@ struct Run {
     bool multi = false;
     void on(int which) { st = !multi ? s_main : (which == 0 ? s_main : (which == 1 ? h->s_prop : h->s_act)); }
     void record(cudaEvent_t ev) {
-        if (multi && !rec && rc == 0 && cudaEventRecord(ev, st) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaEventRecord failed");
+        if (multi && rc == 0 && cudaEventRecord(ev, st) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaEventRecord failed");
     }
     void wait(cudaEvent_t ev) {
-        if (multi && !rec && rc == 0 && cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaStreamWaitEvent failed");
+        if (multi && rc == 0 && cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaStreamWaitEvent failed");
     }
     int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, int alt = 0) {
         if (rc) return 1;
@@ -732,7 +702,7 @@ struct Run {
         // epilogue writes the Linear output itself, bf16(acc + bias), into the workspace and the consumer reads
         // that (return value 0 = "bf16 linear output, bias applied"); same bits, half the bytes.
         bool lin_mode = false;
-        if (h->lin_mode && epi == EPI_PARTIAL && c.splitk == 1 && T > kLinModeMinTokens && !rec) {
+        if (h->lin_mode && epi == EPI_PARTIAL && c.splitk == 1 && T > kLinModeMinTokens) {
             lin_mode = true;
             c.epi = EPI_STORE;
             c.bias = L.bias;            // nullptr where the Linear has none
@@ -743,23 +713,13 @@ struct Run {
             return 1;
         }
         std::string err;
-        int s;
-        if (rec) {
-            GemmDev d; CUtensorMap tw, tx; int gx = 0, gy = 0;
-            s = gemm_make_step_op(c, &d, &tw, &tx, &gx, &gy, &err);
-            if (s >= 0) {
-                StepOp& op = push(OP_GEMM, gx, gy, s);
-                op.tmap_w = tw; op.tmap_x = tx; op.hot.epi = epi; op.hot.u.gemm = d;
-            }
-        } else {
-            char nm[96];
-            snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", c.epi, T, L.Nw, L.K, c.splitk);
-            c.trace = trace_slot(nm);
-            prof_begin(nm);
-            s = gemm_launch(st, c, &err);
-            prof_end();
-            ++h->launches;
-        }
+        char nm[96];
+        snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", c.epi, T, L.Nw, L.K, c.splitk);
+        c.trace = trace_slot(nm);
+        prof_begin(nm);
+        const int s = gemm_launch(st, c, &err);
+        prof_end();
+        ++h->launches;
         if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 1; }
         return lin_mode ? 0 : s;
     }
@@ -777,64 +737,47 @@ struct Run {
         a.pos = h->pos_emb; a.pos_rows = h->cfg.num_image_tokens; a.out_scale = out_scale;
         a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
         a.xn_out = xn_out; a.ldn = N;
-        if (rec) push(OP_CONSUMER, T, 1, 1).hot.u.consumer = a;
-        else { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
+        { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
     }
     void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo, int alt) {
         if (rc) return;
-        if (rec) {
-            BiasActArgs a{wsp(alt), splitk, T, N, ldp, bias, act, scale, out, ldo};
-            push(OP_BIAS_ACT, (T * (N >> 2) + 255) / 256, 1, 1).hot.u.bias_act = a;
-        } else { prof_begin("bias_act"); launched(launch_bias_act(st, wsp(alt), splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act"); prof_end(); }
+        { prof_begin("bias_act"); launched(launch_bias_act(st, wsp(alt), splitk, T, N, ldp, bias, act, scale, out, ldo), "bias_act"); prof_end(); }
     }
     void rope(RopeKvArgs a) {
         if (rc) return;
-        if (rec) push(OP_ROPE_KV, a.T, 1, 1).hot.u.rope = a;
-        else { char nm[64]; snprintf(nm, sizeof nm, "rope_kv[T%d]", a.T); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_rope_kv(st, a), "rope_kv"); prof_end(); }
+        { char nm[64]; snprintf(nm, sizeof nm, "rope_kv[T%d]", a.T); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_rope_kv(st, a), "rope_kv"); prof_end(); }
     }
     void attn_siglip(const bf16* qkv, int ld_qkv, int B, int seq, int heads, int hidden, bf16* out, int ld_out) {
         if (rc) return;
-        if (rec) push(OP_ATTN_SIGLIP, (seq + kAttnTileRows - 1) / kAttnTileRows, heads, B).hot.u.attn =
-                     make_siglip_attn_args(qkv, ld_qkv, seq, heads, hidden, out, ld_out);
-        else { prof_begin("siglip_attention"); launched(launch_siglip_attention(st, qkv, ld_qkv, B, seq, heads, hidden, out, ld_out, trace_slot("siglip_attention")), "siglip_attention"); prof_end(); }
+        { prof_begin("siglip_attention"); launched(launch_siglip_attention(st, qkv, ld_qkv, B, seq, heads, hidden, out, ld_out, trace_slot("siglip_attention")), "siglip_attention"); prof_end(); }
     }
     void attn_joint(JointAttnArgs a, bool fewq) {
         if (rc) return;
         a.trace = nullptr;
-        if (rec) {
-            if (fewq) push(OP_ATTN_FEWQ, (a.n_heads * a.q_per_sample + kAttnTileRows - 1) / kAttnTileRows, 1, a.batch).hot.u.attn =
-                          make_fewq_attn_args(a);
-            else push(OP_ATTN_PREFILL, (a.q_per_sample + kAttnTileRows - 1) / kAttnTileRows, a.n_heads, a.batch).hot.u.attn =
-                     make_prefill_attn_args(a);
-        } else if (fewq) { char nm[64]; snprintf(nm, sizeof nm, "attention_fewq[q%d]", a.q_per_sample); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_joint_attention_fewq(st, a), "attention_fewq"); prof_end(); }
+        if (fewq) { char nm[64]; snprintf(nm, sizeof nm, "attention_fewq[q%d]", a.q_per_sample); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_joint_attention_fewq(st, a), "attention_fewq"); prof_end(); }
         else { a.trace = trace_slot("attention_prefill"); prof_begin("attention_prefill"); launched(launch_joint_attention_prefill(st, a), "attention_prefill"); prof_end(); }
     }
     void embed_merge(const EmbedMergeArgs& a, int B) {
         if (rc) return;
-        if (rec) push(OP_EMBED_MERGE, a.seq, B, 1).hot.u.embed = a;
-        else { prof_begin("embed_merge"); launched(launch_embed_merge(st, a.ids, B, a.seq, a.table, a.vocab, a.img, a.n_img, a.hidden, a.image_token,
+        { prof_begin("embed_merge"); launched(launch_embed_merge(st, a.ids, B, a.seq, a.table, a.vocab, a.img, a.n_img, a.hidden, a.image_token,
                                          a.pad_token, a.inv_div, a.normalizer, a.out, a.err_flag), "embed_merge"); prof_end(); }
     }
     void small_k(const SmallKArgs& a) {
         if (rc) return;
-        const int cols = a.N > a.time_cols ? a.N : a.time_cols;
-        if (rec) push(OP_SMALL_K, (cols + 255) / 256, a.T, 1).hot.u.small_k = a;
-        else { prof_begin("small_k_linear"); launched(launch_small_k_linear(st, a.x, a.T, a.K, a.W, a.bias, a.N, a.scale, a.y, a.ldy, a.col_off, a.time_row,
+        { prof_begin("small_k_linear"); launched(launch_small_k_linear(st, a.x, a.T, a.K, a.W, a.bias, a.N, a.scale, a.y, a.ldy, a.col_off, a.time_row,
                                             a.time_cols), "small_k_linear"); prof_end(); }
     }
     void action_tail(const ActionTailArgs& a) {
         if (rc) return;
-        if (rec) push(OP_ACTION_TAIL, (a.T * a.action_dim * 32 + 255) / 256, 1, 1).hot.u.tail = a;
-        else { prof_begin("action_tail"); launched(launch_action_tail(st, a.xn, a.T, a.hidden, a.W, a.bias, a.action_dim, a.dt, a.action, a.vel_tap),
+        { prof_begin("action_tail"); launched(launch_action_tail(st, a.xn, a.T, a.hidden, a.W, a.bias, a.action_dim, a.dt, a.action, a.vel_tap),
                       "action_tail"); prof_end(); }
     }
     void clamp(const ClampArgs& a) {
         if (rc) return;
-        if (rec) push(OP_CLAMP, (a.n + 255) / 256, 1, 1).hot.u.clamp = a;
-        else { prof_begin("clamp"); launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip), "clamp"); prof_end(); }
+        { prof_begin("clamp"); launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip), "clamp"); prof_end(); }
     }
     void tap(const std::string& name, const void* src, size_t bytes) {
-        if (!h->debug || rc || rec) return;
+        if (!h->debug || rc) return;
         auto it = h->taps.find(name);
         if (it == h->taps.end() || it->second.bytes != bytes) {
             if (it != h->taps.end()) cudaFree(it->second.ptr);
@@ -1005,7 +948,7 @@ static void action_decode(Run& R, int B, int s, float dt) {
     const auto& c = h->cfg;
     const int Ta = B * c.num_action_tokens;
     bf16* vel_tap = nullptr;
-    if (h->debug && !R.rec) {
+    if (h->debug) {
         const std::string nm = "flow" + std::to_string(s) + ".velocity";
         R.tap(nm, h->d_action, static_cast<size_t>(Ta) * c.action_dim * 2);   // allocates the slot
         if (!R.rc) vel_tap = static_cast<bf16*>(h->taps[nm].ptr);
@@ -1017,7 +960,7 @@ static void action_decode(Run& R, int B, int s, float dt) {
 static void run_step(Run& R, int B, int steps) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
-    if (h->trace && !R.rec && h->trace_buf != nullptr) {
+    if (h->trace && h->trace_buf != nullptr) {
         // every issue / capture of the step hands out the same slot sequence; each replay re-arms it
         h->trace_labels.clear();
         h->trace_streams.clear();
@@ -1178,28 +1121,8 @@ extern "C" int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int bat
     Run R{h, st};
     R.s_main = st;
     R.multi = h->use_streams && !h->debug && !h->profile;
-    const bool stepk = h->use_step_kernel && !h->debug && !h->profile;
     const bool graph = h->use_graph && !h->debug && !h->profile;
-    if (stepk) {
-        // one persistent cooperative kernel walks the whole schedule (step_kernel.h)
-        const long long key = static_cast<long long>(batch) * 4096 + steps;
-        auto it = h->programs.find(key);
-        if (it == h->programs.end()) {
-            StepProgram prog;
-            Run C{h, st};
-            C.s_main = st;
-            C.rec = &prog;
-            run_step(C, batch, steps);
-            if (C.rc) return C.rc;
-            std::string err;
-            if (step_program_upload(prog, &err)) return fail(BLURR_ERR_CUDA, err);
-            it = h->programs.emplace(key, std::move(prog)).first;
-        }
-        std::string err;
-        if (step_program_launch(it->second, st, &err)) return fail(BLURR_ERR_CUDA, err);
-        h->step_ops = static_cast<int64_t>(it->second.ops.size());
-        h->launches = pre_launches + 1;
-    } else if (!graph) {
+    if (!graph) {
         run_step(R, batch, steps);
         if (R.rc) return R.rc;
         h->launches += pre_launches;
@@ -1265,7 +1188,6 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     if (!h || !name) return fail(BLURR_ERR_INVALID, "set_option: null argument");
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
-    else if (n == "use_step_kernel") h->use_step_kernel = value != 0;
     else if (n == "use_streams") {
         h->use_streams = value != 0;
         for (auto& kv : h->graphs) {
@@ -1297,8 +1219,6 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     else if (n == "debug_taps") h->debug = value != 0;
     else if (n == "stage_mask") {              // timing experiments only: run a subset of the stages
         h->stage_mask = static_cast<int>(value) & 7;
-        for (auto& kv : h->programs) step_program_free(kv.second);
-        h->programs.clear();
         for (auto& kv : h->graphs) {
             cudaGraphExecDestroy(kv.second.exec);
             cudaGraphDestroy(kv.second.graph);
@@ -1338,8 +1258,10 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "attn_tc") attn_set_tc(static_cast<int>(value));
     else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
     else if (n == "gemm_pair_band") gemm_set_pair_band(static_cast<int>(value));
+    else if (n == "gemm_pair_small") gemm_set_pair_small(static_cast<int>(value));
     else if (n == "gemm_pair_policy") gemm_set_pair_policy(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
+    else if (n == "gemm_cta_trace") { if (gemm_set_cta_trace(reinterpret_cast<void*>(static_cast<intptr_t>(value)))) return fail(BLURR_ERR_CUDA, "gemm_cta_trace: cudaMemcpyToSymbol failed"); }
     else return fail(BLURR_ERR_INVALID, "unknown global option " + n);
     return 0;
 }
@@ -1352,10 +1274,6 @@ extern "C" int blurr_pi0_check(blurr_pi0_t* h, void* cuda_stream) {
         return fail(BLURR_ERR_CUDA, "a GEMM pipeline wait expired (role " + std::to_string(tf) + "): results are invalid");
     if (int tf = attn_take_timeout_flag())
         return fail(BLURR_ERR_CUDA, "an attention pipeline wait expired (stage " + std::to_string(tf) + "): results are invalid");
-    for (auto& kv : h->programs)
-        if (int e = step_program_take_error(kv.second))
-            return fail(BLURR_ERR_CUDA, "the persistent step kernel gave up waiting (code " + std::to_string(e) +
-                                            "): results are invalid");
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag != 0) {
@@ -1433,7 +1351,6 @@ extern "C" int blurr_pi0_trace_report(blurr_pi0_t* h, char* buf, size_t buf_byte
     return 0;
 }
 
-extern "C" int64_t blurr_pi0_last_op_count(const blurr_pi0_t* h) { return h ? h->step_ops : 0; }
 extern "C" int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h) { return h ? static_cast<int64_t>(h->weight_bytes) : 0; }
 
 // ---------------------------------------------------------------------------

@@ -34,6 +34,18 @@ struct GemmPipe {
 // Set (to 1 + role) when a pipeline wait expired; read by gemm_take_timeout_flag().
 static __device__ int g_gemm_timeout_flag = 0;
 
+// Per-CTA timeline for kernel tuning (global option "gemm_cta_trace" = device pointer to [n_cta][8] u64, 0 = off):
+// %globaltimer at 0 kernel entry, 1 setup done, 2 producer past the dependency wait, 3 first stage landed,
+// 4 last MMA issued, 5 accumulators complete (epilogue warps), 6 TMEM drained, 7 tile stored.
+static __device__ unsigned long long* g_cta_trace = nullptr;
+__device__ __forceinline__ void cta_stamp(int slot) {
+    unsigned long long* t = g_cta_trace;
+    if (t != nullptr && (threadIdx.x & 31) == 0) {
+        const size_t cta = blockIdx.x + static_cast<size_t>(gridDim.x) * (blockIdx.y + static_cast<size_t>(gridDim.y) * blockIdx.z);
+        t[cta * 8 + slot] = globaltimer_ns();
+    }
+}
+
 // Epilogue phase 2: the [token][128] tile staged in shared memory -> global memory with 16-byte
 // row-wise stores (all 256 threads).
 template <int EPI>
@@ -129,6 +141,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
             pdl_wait();
             pdl_trigger();
             trace_stamp(p.trace, 1);
+            cta_stamp(2);
             if (elect_one_sync()) {
                 for (int i = 0; i < pre; ++i)
                     for (int c = 0; c < p.nt; ++c)
@@ -178,6 +191,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
             }
             st.full_bits ^= (1u << s);
             tcgen05_fence_after();
+            if (i == 0) cta_stamp(3);
             if (elect_one_sync()) {
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                 const uint64_t a_desc = make_smem_desc_sw128(a_addr);
@@ -200,6 +214,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
         }
         if (ok && elect_one_sync()) umma_commit(sh.tmem_full_bar);   // accumulators complete
         __syncwarp();
+        cta_stamp(4);
     } else if (warp >= 4) {
         // ---- epilogue phase 1: TMEM -> registers -> smem tile [token][128 n] ----
         const int w4 = warp - 4;               // TMEM lane quarter this warp may access
@@ -209,6 +224,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
         st.tmem_bit ^= 1u;
         if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
         tcgen05_fence_after();
+        if (warp == 4) cta_stamp(5);
         float bias = 0.f;
         if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
@@ -234,9 +250,11 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
         tcgen05_fence_before();
     }
     __syncthreads();
+    if (warp == 0) cta_stamp(6);
 
     gemm_epilogue_store<EPI>(p, smem, bx, bz, n0, t0);
     __syncthreads();     // the tile aliases the ring: it must be drained before the next tile's TMA writes
+    if (warp == 0) cta_stamp(7);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -530,6 +548,7 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
                 }
                 st.full_bits ^= (1u << s);
                 tcgen05_fence_after();
+                if (i == 0) cta_stamp(3);
                 if (elect_one_sync()) {
                     const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                     const uint64_t a_desc = make_smem_desc_sw128(a_addr);
@@ -547,6 +566,7 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
             }
             if (ok && elect_one_sync()) umma_commit_2sm(sh.tmem_full_bar);  // both epilogues may start
             __syncwarp();
+            cta_stamp(4);
         }
     } else if (warp >= 4) {
         const int w4 = warp - 4;
@@ -555,6 +575,7 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
         st.tmem_bit ^= 1u;
         if (!acc_ready && lane == 0) atomicExch(&g_gemm_timeout_flag, 3);
         tcgen05_fence_after();
+        if (warp == 4) cta_stamp(5);
         float bias = 0.f;
         if (EPI != EPI_PARTIAL && p.bias != nullptr) bias = bf2f(p.bias[n0 + nl]);
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
@@ -583,8 +604,10 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
     // half until the pair's accumulators are complete.  Warps 4..7 only write after tmem_full, which
     // the leader commits after every MMA of the tile — so the ring is free by then in both CTAs.
     __syncthreads();
+    if (warp == 0) cta_stamp(6);
     gemm_epilogue_store<EPI>(p, smem, bx, bz, n0, t0);
     __syncthreads();
+    if (warp == 0) cta_stamp(7);
 }
 
 // Ring + barrier carve-up of a dynamic shared-memory block and one-time initialisation.
@@ -614,19 +637,24 @@ __host__ __device__ __forceinline__ void pair_tile_coords(const int tile, const 
     xp = b * band + (r - ty * w);
 }
 
+// Generalised in round 2 for the batch-1 Gemma prefill (T = 276 = two UMMA-N chunks of 144 tokens, one 288-column
+// accumulator, split-K slices as a third tile dimension, fp32-partial epilogue straight from TMEM): what bounds the
+// one-CTA kernel there is shared-memory bandwidth (per k-block 69 KB of operand reads by the tensor core + 52 KB of
+// TMA writes = 945 clk at 128 B/clk, measured 945); a pair halves the token bytes each SM stages and reads.
 template <int EPI>
 __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUtensorMap* tmap_w, const CUtensorMap* tmap_xh,
                                                      const GemmShared& sh, uint64_t* xbar, const int gxp, const int gy,
-                                                     const uint32_t crank, const int first, const int stride) {
-    static_assert(EPI != EPI_PARTIAL, "bf16 epilogues only");
+                                                     const int gz, const uint32_t crank, const int first, const int stride) {
     uint8_t* smem = sh.ring;
-    const int half = p.bn / 2;
-    const int stage_bytes = kTileABytes + half * (kBlockK * 2);
+    const int half = p.bn / 2;                                            // token rows of a chunk staged by one CTA
+    const int stage_bytes = kTileABytes + p.nt * half * (kBlockK * 2);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const uint32_t tmem_base = sh.tmem_base;
     const bool leader = (crank == 0);
-    const int n_tiles = gxp * gy;
+    const int tiles_xy = gxp * gy;
+    const int n_tiles = tiles_xy * gz;
+    const int ntok = p.nt * p.bn;                    // tokens (TMEM columns) of one tile
     uint64_t* tmem_empty = xbar;                     // [2], used in the leader
     uint64_t* tmem_full1 = xbar + 2;                 // tmem_full of buffer 1 (buffer 0: sh.tmem_full_bar)
 
@@ -636,23 +664,52 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
         const uint64_t pol_x = p.l2_policy == 0 ? make_policy_evict_last() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
         uint32_t empty_bits = 0;
         int s = 0;
+        const uint32_t bar0 = map_to_cta(&sh.full_bar[0], 0u);      // the leader's full[0]; full[s] is 8 bytes further per stage
+        // Engine weights do not depend on the previous kernel: the weight blocks of the first ring are requested before
+        // the programmatic-dependency wait, only the token operand waits.
+        int pre = 0;
+        if (p.w_static && first < n_tiles) {
+            const int tz = first / tiles_xy;
+            int xp, ty;
+            pair_tile_coords(first - tz * tiles_xy, gxp, gy, p.band, xp, ty);
+            const int bx = 2 * xp + static_cast<int>(crank);
+            const int kb0 = tz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            pre = min(p.stages, kb1 - kb0);
+            if (elect_one_sync()) {
+                for (int i = 0; i < pre; ++i) {
+                    if (leader) mbar_arrive_expect_tx(&sh.full_bar[i], static_cast<uint32_t>(2 * stage_bytes));
+                    tma_load_2d_2sm_hint(smem + i * stage_bytes, tmap_w, bar0 + static_cast<uint32_t>(i) * 8u, 0,
+                                         (bx * p.kb_total + kb0 + i) * kBlockM, pol_w);
+                }
+            }
+            __syncwarp();
+        }
         pdl_wait();
         pdl_trigger();
         trace_stamp(p.trace, 1);
-        const uint32_t bar0 = map_to_cta(&sh.full_bar[0], 0u);      // the leader's full[0]; full[s] is 8 bytes further per stage
+        cta_stamp(2);
         for (int tile = first; tile < n_tiles; tile += stride) {
+            const int tz = tile / tiles_xy;
             int xp, ty;
-            pair_tile_coords(tile, gxp, gy, p.band, xp, ty);
-            const int bx = 2 * xp + static_cast<int>(crank), t0 = ty * p.bn;
-            for (int kb = 0; kb < p.kb_total; ++kb) {
-                if (!mbar_wait_warp(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 1); return; }
+            pair_tile_coords(tile - tz * tiles_xy, gxp, gy, p.band, xp, ty);
+            const int bx = 2 * xp + static_cast<int>(crank), t0 = ty * ntok;
+            const int kb0 = tz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const bool w_requested = (tile == first && kb - kb0 < pre);     // its weight block is already in flight
+                if (!w_requested) {
+                    if (!mbar_wait_warp(&sh.empty_bar[s], ((empty_bits >> s) & 1u) ^ 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 1); return; }
+                }
                 empty_bits ^= (1u << s);
                 if (elect_one_sync()) {
                     uint8_t* stg = smem + s * stage_bytes;
-                    if (leader) mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
                     const uint32_t bar = bar0 + static_cast<uint32_t>(s) * 8u;
-                    tma_load_2d_2sm_hint(stg, tmap_w, bar, 0, (bx * p.kb_total + kb) * kBlockM, pol_w);
-                    tma_load_2d_2sm_hint(stg + kTileABytes, tmap_xh, bar, kb * kBlockK, t0 + static_cast<int>(crank) * half, pol_x);
+                    if (!w_requested) {
+                        if (leader) mbar_arrive_expect_tx(&sh.full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+                        tma_load_2d_2sm_hint(stg, tmap_w, bar, 0, (bx * p.kb_total + kb) * kBlockM, pol_w);
+                    }
+                    for (int c = 0; c < p.nt; ++c)
+                        tma_load_2d_2sm_hint(stg + kTileABytes + c * half * (kBlockK * 2), tmap_xh, bar, kb * kBlockK,
+                                             t0 + c * p.bn + static_cast<int>(crank) * half, pol_x);
                 }
                 __syncwarp();
                 s = (s + 1 == p.stages) ? 0 : s + 1;
@@ -664,34 +721,40 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
             uint32_t full_bits = 0, tmem_empty_bits = 0;
             int s = 0, buf = 0;
             for (int tile = first; tile < n_tiles; tile += stride) {
+                const int tz = tile / tiles_xy;
+                const int kb0 = tz * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
                 if (!mbar_wait_warp(&tmem_empty[buf], ((tmem_empty_bits >> buf) & 1u) ^ 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 4); return; }
                 tmem_empty_bits ^= (1u << buf);
                 tcgen05_fence_after();
                 const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * p.acc_stride);
-                for (int kb = 0; kb < p.kb_total; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     if (!mbar_wait_warp(&sh.full_bar[s], (full_bits >> s) & 1u)) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 2); return; }
                     full_bits ^= (1u << s);
                     tcgen05_fence_after();
+                    if (tile == first && kb == kb0) cta_stamp(3);
                     if (elect_one_sync()) {
                         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                         const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-                        const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes);
+                        for (int c = 0; c < p.nt; ++c) {
+                            const uint64_t b_desc = make_smem_desc_sw128(a_addr + kTileABytes + c * half * (kBlockK * 2));
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_bf16_ss_2sm(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_bf16_ss_2sm(acc + c * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
                         umma_commit_2sm(&sh.empty_bar[s]);
-                        if (kb + 1 == p.kb_total) umma_commit_2sm(buf == 0 ? sh.tmem_full_bar : tmem_full1);
+                        if (kb + 1 == kb1) umma_commit_2sm(buf == 0 ? sh.tmem_full_bar : tmem_full1);
                     }
                     __syncwarp();
                     s = (s + 1 == p.stages) ? 0 : s + 1;
                 }
-                buf ^= 1;
+                buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
             }
+            cta_stamp(4);
         }
     } else if (warp >= 4) {
         const int w4 = (warp - 4) & 3, hf = (warp - 4) >> 2;
         const int nl = w4 * 32 + lane;
-        const int n_groups = p.bn / 16;
+        const int n_groups = ntok / 16;
         const int g_begin = hf * (n_groups / 2), g_end = hf == 0 ? n_groups / 2 : n_groups;
         constexpr int OUTW = (EPI == EPI_GEGLU) ? kBlockM / 2 : kBlockM;
         bf16* stg = reinterpret_cast<bf16*>(smem + p.stages * stage_bytes);
@@ -700,23 +763,62 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
         int buf = 0;
         pdl_wait();
         for (int tile = first; tile < n_tiles; tile += stride) {
+            const int tz = tile / tiles_xy;
             int xp, ty;
-            pair_tile_coords(tile, gxp, gy, p.band, xp, ty);
-            const int bx = 2 * xp + static_cast<int>(crank), t0 = ty * p.bn;
+            pair_tile_coords(tile - tz * tiles_xy, gxp, gy, p.band, xp, ty);
+            const int bx = 2 * xp + static_cast<int>(crank), t0 = ty * ntok;
             const int n0 = bx * kBlockM;
             const bool ready = mbar_wait(buf == 0 ? sh.tmem_full_bar : tmem_full1, (tmem_bits >> buf) & 1u);
             tmem_bits ^= (1u << buf);
             if (!ready) { if (lane == 0) atomicExch(&g_gemm_timeout_flag, 3); return; }
             tcgen05_fence_after();
+            if (warp == 4 && tile == first) cta_stamp(5);
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16) + static_cast<uint32_t>(buf * p.acc_stride);
             const bool real_tile = n0 < p.Nw;               // false: the padding CTA of an odd tile count
+            // The drains below keep one tcgen05.ld in flight while the previous 16 columns are consumed.
+            if (EPI == EPI_PARTIAL) {
+                // fp32 partial sums of split-K slice tz, straight from TMEM: a warp's 32 lanes are 32 consecutive
+                // features, so every store instruction writes one full 128-byte line of a token row
+                float* dst = p.partial + static_cast<size_t>(tz) * p.T * p.Nw + n0 + nl;
+                uint32_t ra[16], rb[16];
+                tmem_ld_32x32b_x16(lane_addr + g_begin * 16, ra);
+                for (int g = g_begin; g < g_end; g += 2) {
+                    tmem_ld_wait_regs(ra);
+                    if (g + 1 < g_end) tmem_ld_32x32b_x16(lane_addr + (g + 1) * 16, rb);
+                    {
+                        const int tb = t0 + g * 16;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (real_tile && tb + i < p.T) dst[static_cast<size_t>(tb + i) * p.Nw] = __uint_as_float(ra[i]);
+                    }
+                    if (g + 1 < g_end) {
+                        tmem_ld_wait_regs(rb);
+                        if (g + 2 < g_end) tmem_ld_32x32b_x16(lane_addr + (g + 2) * 16, ra);
+                        const int tb = t0 + (g + 1) * 16;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (real_tile && tb + i < p.T) dst[static_cast<size_t>(tb + i) * p.Nw] = __uint_as_float(rb[i]);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) mbar_arrive(&tmem_empty[buf]);
+                    else mbar_arrive_cluster(buf == 0 ? empty_remote0 : empty_remote1);
+                }
+                if (warp == 4 && tile == first) { cta_stamp(6); cta_stamp(7); }
+                buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
+                continue;
+            }
             float bias = 0.f;
             if (p.bias != nullptr && real_tile) bias = bf2f(p.bias[n0 + nl]);
-            for (int g = g_begin; g < g_end; ++g) {
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(lane_addr + g * 16, r);
-                tmem_ld_wait();
-                if (EPI == EPI_GEGLU) {
+            // One accumulator buffer (batch 1): the next tile's MMAs wait for this drain, so GeGLU leaves TMEM as raw
+            // bf16 gate / up values ([token][128]) and the activation math runs from the staging tile, under the next
+            // tile's main loop.  Two buffers (batched): the drain is off the critical path, GeGLU is applied in
+            // registers and the staging tile is half as large.
+            const bool raw_geglu = (EPI == EPI_GEGLU) && p.acc_bufs == 1;
+            auto consume = [&](const uint32_t (&r)[16], const int g) {
+                if (EPI == EPI_GEGLU && !raw_geglu) {
                     // lanes 2j / 2j+1 hold gate_j / up_j.  Two tokens per step so that both lanes of a pair do a
                     // GELU: the even lane finishes token i, the odd lane token i + 1, after one exchange.
 #pragma unroll
@@ -726,12 +828,34 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                         const float gate = (lane & 1) ? recv : v0, up = (lane & 1) ? v1 : recv;
                         stg[(g * 16 + i + (lane & 1)) * OUTW + (nl >> 1)] = f2bf(bf16_round(gelu_tanh_f32(gate)) * up);
                     }
-                } else {
+                } else if (EPI == EPI_GELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float v = bf16_round(__uint_as_float(r[i]) + bias);
-                        if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
-                        stg[(g * 16 + i) * OUTW + nl] = f2bf(v);
+                        const float v = gelu_tanh_f32(bf16_round(__uint_as_float(r[i]) + bias));
+                        stg[(g * 16 + i) * kBlockM + nl] = f2bf(v);
+                    }
+                } else {
+                    // one packed conversion per two tokens (cvt throughput bounds this drain: 16 per clock per SM)
+                    unsigned short* stg16 = reinterpret_cast<unsigned short*>(stg);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const uint32_t pk = pack_bf16x2(__uint_as_float(r[i]) + bias, __uint_as_float(r[i + 1]) + bias);
+                        stg16[(g * 16 + i) * kBlockM + nl] = static_cast<unsigned short>(pk & 0xffffu);
+                        stg16[(g * 16 + i + 1) * kBlockM + nl] = static_cast<unsigned short>(pk >> 16);
+                    }
+                }
+            };
+            {
+                uint32_t ra[16], rb[16];
+                tmem_ld_32x32b_x16(lane_addr + g_begin * 16, ra);
+                for (int g = g_begin; g < g_end; g += 2) {
+                    tmem_ld_wait_regs(ra);
+                    if (g + 1 < g_end) tmem_ld_32x32b_x16(lane_addr + (g + 1) * 16, rb);
+                    consume(ra, g);
+                    if (g + 1 < g_end) {
+                        tmem_ld_wait_regs(rb);
+                        if (g + 2 < g_end) tmem_ld_32x32b_x16(lane_addr + (g + 2) * 16, ra);
+                        consume(rb, g + 1);
                     }
                 }
             }
@@ -742,16 +866,38 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                 else mbar_arrive_cluster(buf == 0 ? empty_remote0 : empty_remote1);
             }
             asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            if (warp == 4 && tile == first) cta_stamp(6);
             const int et = static_cast<int>(threadIdx.x) - 128;
             const int col_base = (EPI == EPI_GEGLU) ? bx * (kBlockM / 2) : n0;
-            for (int idx = et; real_tile && idx < p.bn * (OUTW / 8); idx += 256) {
-                const int t = idx / (OUTW / 8), ch = idx - t * (OUTW / 8);
-                if (t0 + t < p.T)
-                    *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) =
-                        *reinterpret_cast<const uint4*>(stg + t * OUTW + ch * 8);
+            if (raw_geglu) {
+                // weight rows alternate gate_j, up_j: 16 consecutive staged columns give 8 outputs
+                const bf16x8* tile_s = reinterpret_cast<const bf16x8*>(stg);
+                for (int idx = et; real_tile && idx < ntok * 8; idx += 256) {
+                    const int t = idx >> 3, ch = idx & 7;
+                    if (t0 + t >= p.T) continue;
+                    const bf16x8 lo = tile_s[t * 16 + 2 * ch];
+                    const bf16x8 hi = tile_s[t * 16 + 2 * ch + 1];
+                    bf16x8 o;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float2 a0 = unpack_bf16x2(lo.u[2 * j]), a1 = unpack_bf16x2(lo.u[2 * j + 1]);
+                        const float2 b0 = unpack_bf16x2(hi.u[2 * j]), b1 = unpack_bf16x2(hi.u[2 * j + 1]);
+                        o.u[j] = pack_bf16x2(bf16_round(gelu_tanh_f32(a0.x)) * a0.y, bf16_round(gelu_tanh_f32(a1.x)) * a1.y);
+                        o.u[2 + j] = pack_bf16x2(bf16_round(gelu_tanh_f32(b0.x)) * b0.y, bf16_round(gelu_tanh_f32(b1.x)) * b1.y);
+                    }
+                    *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) = o;
+                }
+            } else {
+                for (int idx = et; real_tile && idx < ntok * (OUTW / 8); idx += 256) {
+                    const int t = idx / (OUTW / 8), ch = idx - t * (OUTW / 8);
+                    if (t0 + t < p.T)
+                        *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) =
+                            *reinterpret_cast<const uint4*>(stg + t * OUTW + ch * 8);
+                }
             }
             asm volatile("bar.sync 1, 256;\n" ::: "memory");
-            buf ^= 1;
+            if (warp == 4 && tile == first) cta_stamp(7);
+            buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
         }
     }
 }

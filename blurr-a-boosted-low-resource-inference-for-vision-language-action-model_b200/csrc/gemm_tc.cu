@@ -36,6 +36,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     trace_stamp(p.trace, 0);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp == 0) cta_stamp(0);
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(p.cluster > 1 ? &tmap_xs : &tmap_x);
@@ -46,6 +47,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                                       static_cast<uint32_t>(p.tmem_cols), &tmem_base);
     if (p.cluster > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive
     const uint32_t crank = (p.cluster > 1) ? cluster_ctarank() : 0u;
+    if (warp == 0) cta_stamp(1);
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
     // previous kernel, and so does the first ring of weight blocks: the producer and the epilogue warps
     // wait for the previous kernel (griddepcontrol.wait) inside gemm_tile, just before they first touch
@@ -98,6 +100,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     trace_stamp(p.trace, 0);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp == 0) cta_stamp(0);
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_xh);
@@ -108,9 +111,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                                       &tmem_base, true);
     cluster_sync_all();                         // both CTAs' barriers exist before any remote signal
     const uint32_t crank = cluster_ctarank();
+    if (warp == 0) cta_stamp(1);
     pdl_wait();
     pdl_trigger();
     trace_stamp(p.trace, 1);
+    if (warp == 0) cta_stamp(2);
     GemmPipe st;
     gemm_tile_2cta<EPI>(p, &tmap_w, &tmap_xh, sh, st, blockIdx.x, blockIdx.y, blockIdx.z, crank);
     tcgen05_fence_before();
@@ -119,19 +124,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     if (warp == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
-// Persistent CTA pairs with double-buffered accumulators (gemm_pair_persistent in gemm_body.cuh).
+// Persistent CTA pairs (gemm_pair_persistent in gemm_body.cuh): batched episodes with double-buffered accumulators,
+// and the batch-1 Gemma prefill GEMMs (two 144-token chunks, split-K slices as tiles).
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads + 128, 1)
 gemm_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_xh, const GemmDev p,
-                 const int gxp, const int gy) {
+                 const int gxp, const int gy, const int gz) {
     extern __shared__ uint8_t smem_raw[];
     trace_stamp(p.trace, 0);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (warp == 0) cta_stamp(0);
     if (warp == 0 && elect_one_sync()) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_xh);
     }
-    const int stage_bytes = kTileABytes + (p.bn / 2) * (kBlockK * 2);
+    const int stage_bytes = kTileABytes + p.nt * (p.bn / 2) * (kBlockK * 2);
     uint32_t tmem_base;
     GemmShared sh = gemm_setup_shared(smem_raw, p.stages * stage_bytes + p.staging_bytes, 1, static_cast<uint32_t>(p.tmem_cols),
                                       &tmem_base, true);
@@ -145,7 +152,8 @@ gemm_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     __syncthreads();
     cluster_sync_all();                                     // both CTAs' barriers exist before any remote signal
     const uint32_t crank = cluster_ctarank();
-    gemm_pair_persistent<EPI>(p, &tmap_w, &tmap_xh, sh, xbar, gxp, gy, crank, static_cast<int>(blockIdx.x >> 1),
+    if (warp == 0) cta_stamp(1);
+    gemm_pair_persistent<EPI>(p, &tmap_w, &tmap_xh, sh, xbar, gxp, gy, gz, crank, static_cast<int>(blockIdx.x >> 1),
                               static_cast<int>(gridDim.x >> 1));
     tcgen05_fence_before();
     cluster_sync_all();                                     // the peer is done with this CTA's smem / TMEM / barriers
@@ -241,6 +249,11 @@ int gemm_take_timeout_flag() {
         cudaMemcpyToSymbol(g_gemm_timeout_flag, &zero, sizeof(int));
     }
     return v;
+}
+
+int gemm_set_cta_trace(void* dev_ptr) {
+    unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+    return cudaMemcpyToSymbol(g_cta_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
 }
 
 void gemm_forget_tensor_maps() {
@@ -468,34 +481,9 @@ static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUt
                                  stream, pl.cluster, tw, tx, txs, d);
 }
 
-int gemm_make_step_op(const GemmCall& c, GemmDev* d, CUtensorMap* tmap_w, CUtensorMap* tmap_x, int* grid_x,
-                      int* grid_y, std::string* err) {
-    const int saved = g_cluster_max, saved2 = g_use_2cta;
-    g_cluster_max = 1;
-    g_use_2cta = 0;
-    GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
-    g_cluster_max = saved;
-    g_use_2cta = saved2;
-    if (!pl.valid) { *err = "gemm_make_step_op: unsupported shape"; return -1; }
-    if (c.epi != EPI_PARTIAL && pl.splitk != 1) { *err = "gemm_make_step_op: split-K needs EPI_PARTIAL"; return -1; }
-    if (c.w_packed) {
-        if (get_tmap(c.W, c.Nw * pl.kb_total, kBlockK, kBlockK, kBlockM, tmap_w, err)) return -1;
-    } else {
-        if (get_tmap(c.W, c.Nw, c.K, c.ldw, kBlockM, tmap_w, err)) return -1;
-    }
-    if (get_tmap(c.X, c.T, c.K, c.ldx, pl.bn, tmap_x, err)) return -1;
-    *d = GemmDev{};
-    d->T = c.T; d->bn = pl.bn; d->nt = pl.nt; d->stages = pl.stages; d->kb_total = pl.kb_total;
-    d->kb_per_split = pl.kb_per_split; d->tmem_cols = pl.tmem_cols; d->Nw = c.Nw;
-    d->bias = c.bias; d->out = c.out; d->ldo = c.ldo; d->partial = c.partial;
-    d->cluster = 1; d->slice_rows = pl.nt * pl.bn; d->w_packed = c.w_packed; d->trace = nullptr; d->w_static = 0;
-    *grid_x = pl.grid_x; *grid_y = pl.grid_y;
-    return pl.splitk;
-}
-
 template <int EPI>
 static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, const CUtensorMap& tw, const CUtensorMap& txh,
-                                const GemmDev& d, int gxp, int gy) {
+                                const GemmDev& d, int gxp, int gy, int gz = 1) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcp2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -503,7 +491,7 @@ static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, cons
         attr_set = true;
     }
     return launch_kernel_cluster(gemm_tcp2_kernel<EPI>, dim3(2 * n_pairs), dim3(kGemmThreads + 128), static_cast<size_t>(smem),
-                                 stream, 2, tw, txh, d, gxp, gy);
+                                 stream, 2, tw, txh, d, gxp, gy, gz);
 }
 
 // Batched GEMMs with a bf16 epilogue (above 1024 tokens; automatic, or modes 2 / 3 of "gemm_large_t_mode"):
@@ -578,7 +566,59 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     return 1;
 }
 
+// Batch-1 Gemma prefill (256 < T <= 288 tokens: the accumulator of a 128-row weight tile is 288 TMEM columns, so one
+// tile per SM at a time): persistent CTA pairs, two chunks of T/2 tokens, split-K slices as extra tiles.  Measured on
+// B200 on the gate/up shape (tools/cta_timeline.py): main loop per tile 11.5 us against 15.4 us for one CTA per tile.
+// In the step (in-graph trace, same box): gate/up 46.3 -> 38.6 us, down 19.8 -> 19.6, o 11.3 -> 14.6, qkv 8.3 -> 8.9 —
+// the split-K GEMMs run one short tile per CTA, where the pair's longer set-up (cluster barrier, 2-SM TMEM
+// allocation) costs more than its main loop saves.  1 (default) = GeGLU only, 2 = every epilogue, 0 = never.
+static int g_pair_small = 1;
+void gemm_set_pair_small(int mode) { g_pair_small = mode < 0 ? 0 : mode; }
+static bool gemm_pair_small_applies(const GemmCall& c) {
+    if (g_pair_small == 0 || (g_pair_small == 1 && c.epi != EPI_GEGLU)) return false;
+    return c.w_packed && c.bn_override == 0 && c.T > 256 && c.T <= 288 && c.Nw % kBlockM == 0 &&
+           c.K % kBlockK == 0 && (c.epi != EPI_GEGLU || c.Nw % (2 * kBlockM) == 0) && (c.epi == EPI_PARTIAL || c.splitk <= 1);
+}
+
+static int gemm_launch_pair_small(cudaStream_t stream, const GemmCall& c, std::string* err) {
+    const int kb_total = c.K / kBlockK;
+    int splitk = c.splitk < 1 ? 1 : c.splitk;
+    if (splitk > kb_total) splitk = kb_total;
+    const int kb_per_split = (kb_total + splitk - 1) / splitk;
+    splitk = (kb_total + kb_per_split - 1) / kb_per_split;            // no empty slices
+    const int bn = ((c.T + 1) / 2 + 15) / 16 * 16, half = bn / 2, ntok = 2 * bn;
+    CUtensorMap tw, txh;
+    if (get_tmap(c.W, c.Nw * kb_total, kBlockK, kBlockK, kBlockM, &tw, err)) return -1;
+    if (get_tmap(c.X, c.T, c.K, c.ldx, half, &txh, err)) return -1;
+    GemmDev d{};
+    d.T = c.T; d.bn = bn; d.nt = 2; d.kb_total = kb_total; d.kb_per_split = kb_per_split;
+    d.tmem_cols = 512; d.acc_bufs = 1; d.acc_stride = 0; d.Nw = c.Nw;
+    d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static;
+    d.staging_bytes = c.epi == EPI_PARTIAL ? 0 : ntok * kBlockM * 2;      // GeGLU is staged as raw gate / up values (one accumulator buffer)
+    const int stage_bytes = kTileABytes + 2 * half * kBlockK * 2;
+    d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
+    if (d.stages > kMaxStages) d.stages = kMaxStages;
+    if (d.stages > kb_per_split) d.stages = kb_per_split < 2 ? 2 : kb_per_split;
+    const int smem = d.stages * stage_bytes + d.staging_bytes + 1024 + 256;
+    const int gxp = (c.Nw / kBlockM + 1) / 2;
+    const int tiles = gxp * splitk;
+    const int n_pairs = tiles < kTargetCtas / 2 ? tiles : kTargetCtas / 2;
+    d.l2_policy = 0;                 // weights are streamed once, the token tile is re-read by every pair
+    d.band = gxp;
+    cudaError_t e;
+    switch (c.epi) {
+        case EPI_GEGLU:   e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
+        case EPI_GELU:    e = launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
+        case EPI_PARTIAL: e = launch_pairp<EPI_PARTIAL>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
+        default:          e = launch_pairp<EPI_STORE>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
+    }
+    if (e != cudaSuccess) { *err = std::string("gemm (persistent pairs, batch 1) launch failed: ") + cudaGetErrorString(e); return -1; }
+    return splitk;
+}
+
 int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
+    if (gemm_pair_small_applies(c)) return gemm_launch_pair_small(stream, c, err);
     if (gemm_pairp_applies(c)) return gemm_launch_pairp(stream, c, err);
     GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
     if (!pl.valid) {

@@ -72,12 +72,6 @@ struct GemmPlan {
 
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override);
 
-// Fill the device parameters and the two TMA tensor maps of a GEMM without launching it (used by the
-// persistent step kernel, which runs GEMM tiles as work items).  Cluster multicast is not used there.
-// Returns the split-K slice count or -1.
-int gemm_make_step_op(const GemmCall& call, GemmDev* dev, CUtensorMap* tmap_w, CUtensorMap* tmap_x,
-                      int* grid_x, int* grid_y, std::string* err);
-
 // Returns the number of split-K slices actually used (>= 1), or -1 with *err set.
 int gemm_launch(cudaStream_t stream, const GemmCall& call, std::string* err);
 
@@ -101,11 +95,13 @@ void gemm_set_max_stages(int n);
 int gemm_get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, std::string* err);
 void gemm_set_large_t_mode(int mode);
 void gemm_set_pair_band(int band);          // 0 = automatic
+void gemm_set_pair_small(int mode);         // persistent CTA pairs for 257..288 tokens: 0 never, 1 GeGLU only (default), 2 every epilogue
 void gemm_set_pair_policy(int policy);      // -1 = automatic
 int gemm_pair_raster(int N, int K, int T, int* band_out, int* n_pairs_out, int32_t* order, int capacity);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
 void gemm_set_cluster_max(int c);
+int gemm_set_cta_trace(void* dev_ptr);      // per-CTA timeline buffer [n_cta][8] u64 (0 = off); see gemm_body.cuh
 
 // Tensor maps are cached by (pointer, shape); call when buffers are freed.
 void gemm_forget_tensor_maps();

@@ -154,4 +154,16 @@ cudaError_t launch_clamp_copy(cudaStream_t stream, const bf16* src, bf16* dst, i
 cudaError_t launch_rope_table(cudaStream_t stream, const float* inv_freq, int n_pos, float* cos_t,
                               float* sin_t);
 
+// argument bundles of the small single-purpose kernels (engine.cu builds them once per op)
+struct EmbedMergeArgs {
+    const int64_t* ids; int seq; const bf16* table; long long vocab; const bf16* img; int n_img, hidden;
+    long long image_token, pad_token; float inv_div, normalizer; bf16* out; int* err_flag;
+};
+struct SmallKArgs {
+    const bf16* x; int T, K; const bf16* W; const bf16* bias; int N; float scale; bf16* y; int ldy, col_off;
+    const bf16* time_row; int time_cols;
+};
+struct ActionTailArgs { const bf16* xn; int T, hidden; const bf16* W; const bf16* bias; int action_dim; float dt; bf16* action; bf16* vel_tap; };
+struct ClampArgs { const bf16* src; bf16* dst; int n, do_clamp; float clip; };
+
 }  // namespace blurr

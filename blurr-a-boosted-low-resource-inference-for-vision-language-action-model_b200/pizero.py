@@ -263,7 +263,6 @@ class PiZero(nn.Module):
         object.__setattr__(self, "_debug_taps", False)
         object.__setattr__(self, "_use_cuda_graph", True)
         object.__setattr__(self, "_reserve_batch", 1)
-        object.__setattr__(self, "_use_step_kernel", False)
 
     @classmethod
     def from_state_dict(cls, cfg, state_dict: Dict[str, torch.Tensor], device=None, dtype=None):
@@ -337,13 +336,11 @@ class PiZero(nn.Module):
         return out
 
     def set_engine_options(self, *, debug_taps: Optional[bool] = None, use_cuda_graph: Optional[bool] = None,
-                           reserve_batch: Optional[int] = None, use_step_kernel: Optional[bool] = None):
+                           reserve_batch: Optional[int] = None):
         """`reserve_batch`: size the engine's workspace for at least this many episodes up front (a
         larger batch later re-creates the engine and re-uploads the weights)."""
         if reserve_batch is not None:
             object.__setattr__(self, "_reserve_batch", int(reserve_batch))
-        if use_step_kernel is not None:
-            object.__setattr__(self, "_use_step_kernel", bool(use_step_kernel))
         if debug_taps is not None:
             object.__setattr__(self, "_debug_taps", bool(debug_taps))
         if use_cuda_graph is not None:
@@ -352,7 +349,6 @@ class PiZero(nn.Module):
         if eng is not None:
             eng.set_option("debug_taps", int(self._debug_taps))
             eng.set_option("use_cuda_graph", int(self._use_cuda_graph))
-            eng.set_option("use_step_kernel", int(self._use_step_kernel))
 
     def release_engine(self):
         eng = self._engine
@@ -487,7 +483,6 @@ class _Engine:
             raise
         self.set_option("debug_taps", int(model._debug_taps))
         self.set_option("use_cuda_graph", int(model._use_cuda_graph))
-        self.set_option("use_step_kernel", int(model._use_step_kernel))
 
     def _upload(self, model: PiZero):
         sd = model.state_dict()
@@ -614,9 +609,6 @@ class _Engine:
             idx, stream, s, w, e, label = line.split(" ", 5)
             rows.append((int(idx), int(stream), float(s), float(w), float(e), label))
         return rows
-
-    def last_op_count(self) -> int:
-        return int(self.lib.blurr_pi0_last_op_count(self.handle))
 
     def weight_bytes(self) -> int:
         return int(self.lib.blurr_pi0_weight_bytes(self.handle))

@@ -131,9 +131,7 @@ typedef struct blurr_pi0_inputs {
 int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const blurr_pi0_inputs* in,
                            void* actions_out);
 
-/* Options: "use_step_kernel" (default 0; 1: the whole step runs as ONE persistent cooperative kernel
- * that walks a device-resident op list with grid barriers — bit-identical, measured slower),
- * "use_cuda_graph" (default 1; replay of the per-op kernels as a CUDA graph when the step kernel is off), "debug_taps" (default 0; implies eager launches),
+/* Options: "use_cuda_graph" (default 1; replay of the step's kernels as a CUDA graph), "debug_taps" (default 0; implies eager launches),
  * "use_pdl" (default 1: programmatic dependent launch between the step's kernels; process-wide),
  * "num_inference_steps". */
 int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t value);
@@ -157,8 +155,6 @@ int blurr_pi0_profile_report(blurr_pi0_t* h, char* buf, size_t buf_bytes);
  * normal regime (CUDA graph, PDL, three streams).  Writes one text line per kernel of the last call:
  * "idx stream start_us waited_us end_us label". */
 int blurr_pi0_trace_report(blurr_pi0_t* h, char* buf, size_t buf_bytes);
-/* Ops the persistent step kernel executed in the last call (0 when it is off). */
-int64_t blurr_pi0_last_op_count(const blurr_pi0_t* h);
 /* Bytes of repacked weights the step reads (the algorithmic-bytes numerator of the roofline). */
 int64_t blurr_pi0_weight_bytes(const blurr_pi0_t* h);
 

@@ -41,7 +41,8 @@ def test_gemm_store_bias(T, N, K):
 
 
 @pytest.mark.parametrize("T,N,K,epi", [(552, 2560, 2048, "store"), (1104, 4352, 1152, "gelu"),
-                                         (276, 4096, 2048, "geglu"), (16, 2560, 1024, "store"),
+                                         (276, 4096, 2048, "geglu"), (16, 2560, 1024, "store"), (276, 2560, 2048, "store"),
+                                         (270, 1152, 640, "gelu"), (288, 65536, 128, "geglu"),
                                          (2208, 2560, 2048, "store"), (2100, 4096, 1152, "geglu"), (4416, 1152, 640, "gelu"),
                                          (2304, 3456, 1152, "store")])      # odd tile counts: 9 and 27
 def test_gemm_variants_agree(T, N, K, epi):
@@ -54,15 +55,18 @@ def test_gemm_variants_agree(T, N, K, epi):
     code = {"store": capi.EPI_STORE, "gelu": capi.EPI_GELU, "geglu": capi.EPI_GEGLU}[epi]
     outs = []
     try:
-        for pairs, persistent, large in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (-1, 1, -1), (0, 1, 1), (-1, 1, 2), (-1, 1, 3)]:
+        for pairs, persistent, large, small in [(0, 0, 0, 0), (1, 0, 0, 0), (0, 1, 0, 0), (-1, 1, -1, 0), (0, 1, 1, 0), (-1, 1, 2, 0),
+                                                (-1, 1, 3, 0), (-1, 1, -1, 2)]:
             capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", pairs))
             capi.check(lib.blurr_set_global_option(b"gemm_persistent", persistent))
             capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", large))
+            capi.check(lib.blurr_set_global_option(b"gemm_pair_small", small))      # persistent pairs for 257..288 tokens
             outs.append(op_gemm(W, X, code, bias=b))
     finally:
         capi.check(lib.blurr_set_global_option(b"gemm_use_2cta", -1))
         capi.check(lib.blurr_set_global_option(b"gemm_persistent", 1))
         capi.check(lib.blurr_set_global_option(b"gemm_large_t_mode", -1))
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_small", 1))
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
 
@@ -115,6 +119,23 @@ def test_gemm_partial_splitk(T, N, K, S):
     err = (got - ref).abs().max().item()
     print(f"gemm_partial T={T} N={N} K={K} S={part.shape[0]}: max_abs={err:.3e}")
     assert err <= 2e-3
+
+
+@pytest.mark.parametrize("T,N,K,S", [(276, 2048, 16384, 9), (276, 2560, 2048, 7), (260, 1152, 640, 3)])
+def test_gemm_partial_splitk_pairs(T, N, K, S):
+    """The persistent CTA-pair kernel with split-K slices as tiles (option gemm_pair_small=2) writes the same fp32
+    partial sums as one CTA per (tile, slice): every output accumulates its k-blocks in the same order."""
+    lib = capi.load_library()
+    W = _rand((N, K), 1.0 / math.sqrt(K), 4)
+    X = _rand((T, K), 1.0, 5)
+    try:
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_small", 0))
+        ref = op_gemm(W, X, capi.EPI_PARTIAL, splitk=S)
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_small", 2))
+        got = op_gemm(W, X, capi.EPI_PARTIAL, splitk=S)
+    finally:
+        capi.check(lib.blurr_set_global_option(b"gemm_pair_small", 1))
+    assert got.shape == ref.shape and torch.equal(got, ref)
 
 
 @pytest.mark.parametrize("T,N,K", [(256, 4352, 1152), (17, 256, 192)])

@@ -33,11 +33,8 @@ for steps in (1, 10):
     with torch.inference_mode():
         model(**args, noise=inp["noise"])
     print(f"steps={steps} all (graph, streams): {timed(model, args, inp['noise']):.3f} ms", flush=True)
-    for sk in (0,):
-        model._engine.set_option("use_step_kernel", sk)
-        model._engine.set_option("stage_mask", 4)
-        print(f"steps={steps} action only, step_kernel={sk}: {timed(model, args, inp['noise']):.3f} ms  ops={model._engine.last_op_count()}", flush=True)
-        model._engine.set_option("stage_mask", 7)
-    model._engine.set_option("use_step_kernel", 0)
+    model._engine.set_option("stage_mask", 4)
+    print(f"steps={steps} action only: {timed(model, args, inp['noise']):.3f} ms", flush=True)
+    model._engine.set_option("stage_mask", 7)
     model.release_engine()
     del model

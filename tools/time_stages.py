@@ -12,8 +12,13 @@ from blurr_b200 import synth
 from blurr_b200.config import bridge_config
 from blurr_b200.pizero import PiZeroInference
 
+from blurr_b200 import capi
+
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+for kv in filter(None, os.environ.get("OPTS", "").split(",")):      # e.g. OPTS="attn_tc=1,gemm_pair_small=2"
+    k, v = kv.split("=")
+    capi.check(capi.load_library().blurr_set_global_option(k.encode(), int(v)))
 cfg = bridge_config(1)
 model = PiZeroInference.from_state_dict(cfg, synth.random_state_dict_on_device(cfg, dev), device=dev)
 inp = synth.synthetic_inputs(cfg, B, dtype=torch.bfloat16, device=dev, vary_text=B > 1)
@@ -39,18 +44,5 @@ with torch.inference_mode():
 for name, mask in [("all", 7), ("vision only", 1), ("prefill only", 2), ("action only", 4), ("staging only", 0)]:
     model._engine.set_option("stage_mask", mask)
     ms, launches = timed(30 if B == 1 else 5)
-    ops = model._engine.last_op_count()
-    print(f"B={B} {name:14s}: {ms:8.3f} ms  launches={launches} ops={ops} ({1e3 * ms / max(ops, 1):.2f} us/op)", flush=True)
-model._engine.set_option("stage_mask", 7)
-print("--- per-op kernels (CUDA graph + PDL) instead of the persistent step kernel")
-model._engine.set_option("use_step_kernel", 0)
-for name, mask in [("all", 7), ("vision only", 1), ("prefill only", 2), ("action only", 4)]:
-    model._engine.set_option("stage_mask", mask)
-    ms, launches = timed(30 if B == 1 else 5)
     print(f"B={B} {name:14s}: {ms:8.3f} ms  launches={launches}", flush=True)
 model._engine.set_option("stage_mask", 7)
-for opt, val in [("use_pdl", 0), ("use_cuda_graph", 0)]:
-    model._engine.set_option(opt, val)
-    ms, launches = timed(30 if B == 1 else 5)
-    print(f"B={B} all, {opt}=0: {ms:8.3f} ms", flush=True)
-    model._engine.set_option(opt, 1)
