@@ -162,6 +162,7 @@ struct blurr_pi0 {
     // concurrently with the VLM prefill: layer l of either only needs layer l's K/V of the streams
     // before it, so they pipeline one layer behind instead of adding ~290 kernels to the critical path.
     bool use_streams = true;
+    bool chunked_splitk = true;    // split-K GEMMs of 128..288 tokens may also split the tokens across CTAs (Run::plan_partial)
     cudaStream_t s_prop = nullptr, s_act = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_done_p = nullptr, ev_done_a = nullptr;
     std::vector<cudaEvent_t> ev_v, ev_p;
@@ -675,7 +676,48 @@ struct Run {
         while (s > 1 && static_cast<size_t>(s) * T * Nw > ws_floats) --s;
         return s;
     }
-    // returns split-K slices used; `alt` selects the second workspace
+    // Split-K GEMMs of the batch-1 main stream (128..288 tokens): how many token chunks (CTAs along the tokens) and K
+    // slices?  One chunk with many slices keeps the main loop shortest but every CTA then writes a 128 x T fp32 tile
+    // (a CTA stores at ~55 GB/s: 2.4-2.8 us) and the consumer re-reads slices x T x N x 4 bytes; more chunks with fewer
+    // slices shrink both at the price of a longer k-loop (>= 448 clk per k-block whatever the chunk width).  Cost model
+    // from the per-CTA timelines (tools/cta_timeline.py); returns the slices, *bn_override = tokens per chunk (0 = one CTA
+    // holds all tokens).
+    int plan_partial(int T, int Nw, int K, size_t ws_floats, int* bn_override) const {
+        *bn_override = 0;
+        int best_s = pick_splitk(T, Nw, K, ws_floats);
+        if (!h->chunked_splitk || side_stream_cap > 0 && T <= 32) return best_s;
+        if (T < 128 || T > 288 || Nw % 128 != 0) return best_s;
+        const int tiles = Nw / 128, kb = (K + 63) / 64;
+        // CTA budget: while the expert streams run beside the prefill a GEMM that needs every SM gets split into two
+        // waves by whatever expert kernel holds a few of them (in-graph trace: o-proj with 144 CTAs 13.7 us, with 128
+        // CTAs 11.3 us), so leave them some room
+        const int budget = side_stream_cap > 0 ? kNumSMs - 16 : kNumSMs;
+        double best_cost = 1e30;
+        int best_bn = 0;
+        for (int chunks = 1; chunks <= 4; ++chunks) {
+            const int bn = ((T + chunks - 1) / chunks + 15) / 16 * 16;
+            if (chunks > 1 && bn < 64) break;
+            int sl = budget / (tiles * chunks);
+            if (sl < 1) break;
+            if (sl > kb / 2) sl = kb / 2 > 0 ? kb / 2 : 1;
+            if (sl > 16) sl = 16;
+            while (sl > 1 && static_cast<size_t>(sl) * T * Nw > ws_floats) --sl;
+            const int kb_per = (kb + sl - 1) / sl;
+            sl = (kb + kb_per - 1) / kb_per;
+            // time per k-block (tools/sweep_splitk.py, B200): two 144-token chunks in one CTA (T > 256, one CTA holds all
+            // tokens) 0.40 us (shared-memory bound); one chunk per CTA 0.25 us whatever its width (>= 112 clk per MMA)
+            const double us_kb = (chunks == 1 && T > 256) ? 0.40 : 0.25;
+            const double main_us = kb_per * us_kb;
+            const double tile_tokens = chunks == 1 ? (T > 256 ? 288 : (T + 15) / 16 * 16) : bn;
+            const double store_us = 128.0 * tile_tokens * 4.0 / 55e3;                  // one CTA's fp32 tile at ~55 GB/s
+            const double read_us = static_cast<double>(sl) * T * Nw * 4.0 / 6e6;       // the consumer's slices at ~6 TB/s
+            const double cost = main_us + store_us + read_us;
+            if (cost < best_cost) { best_cost = cost; best_s = sl; best_bn = chunks == 1 ? 0 : bn; }
+        }
+        *bn_override = best_bn;
+        return best_s;
+    }
+    // `alt` selects the split-K workspace
     float* wsp(int alt) const { return alt == 0 ? h->ws : (alt == 1 ? h->ws2 : h->ws3); }
     // streams: 0 = caller's stream (SigLIP, VLM), 1 = proprio expert, 2 = action expert
     cudaStream_t s_main = nullptr;
@@ -695,9 +737,10 @@ struct Run {
         c.W = L.w; c.Nw = L.Nw; c.K = L.K; c.ldw = L.ld; c.w_packed = 1;
         c.X = X; c.T = T; c.ldx = L.K;
         c.epi = epi;
-        c.splitk = (epi == EPI_PARTIAL) ? pick_splitk(T, L.Nw, L.K, ws_floats) : 1;
+        c.bn_override = 0;
+        c.splitk = (epi == EPI_PARTIAL) ? plan_partial(T, L.Nw, L.K, ws_floats, &c.bn_override) : 1;
         c.bias = bias ? L.bias : nullptr;
-        c.out = out; c.ldo = ldo; c.partial = ws; c.bn_override = 0; c.w_static = 1;
+        c.out = out; c.ldo = ldo; c.partial = ws; c.w_static = 1;
         // Batched episodes: a GEMM that needs no K split does not need the fp32 round trip either.  Its store
         // epilogue writes the Linear output itself, bf16(acc + bias), into the workspace and the consumer reads
         // that (return value 0 = "bf16 linear output, bias applied"); same bits, half the bytes.
@@ -1197,6 +1240,14 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
         h->graphs.clear();
     }
     else if (n == "profile") { h->profile = value != 0; if (value == 2) h->prof.clear(); }
+    else if (n == "chunked_splitk") {
+        h->chunked_splitk = value != 0;
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
     else if (n == "lin_mode") {
         h->lin_mode = value != 0;
         for (auto& kv : h->graphs) {
@@ -1248,6 +1299,8 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     return 0;
 }
 
+static int g_op_bn_override = 0;      // tuning: token chunk width used by the stand-alone GEMM operator entry points
+
 extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     if (!name) return fail(BLURR_ERR_INVALID, "set_global_option: null name");
     const std::string n(name);
@@ -1259,6 +1312,7 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
     else if (n == "gemm_pair_band") gemm_set_pair_band(static_cast<int>(value));
     else if (n == "gemm_pair_small") gemm_set_pair_small(static_cast<int>(value));
+    else if (n == "op_gemm_bn") g_op_bn_override = static_cast<int>(value);
     else if (n == "gemm_pair_policy") gemm_set_pair_policy(static_cast<int>(value));
     else if (n == "use_pdl") pdl_set_enabled(value != 0);
     else if (n == "gemm_cta_trace") { if (gemm_set_cta_trace(reinterpret_cast<void*>(static_cast<intptr_t>(value)))) return fail(BLURR_ERR_CUDA, "gemm_cta_trace: cudaMemcpyToSymbol failed"); }
@@ -1378,7 +1432,7 @@ extern "C" int blurr_op_gemm_async(void* cuda_stream, const void* W, int N, int 
     c.W = static_cast<const bf16*>(W); c.Nw = N; c.K = K; c.ldw = ldw > 0 ? ldw : K; c.w_packed = ldw <= 0;
     c.X = static_cast<const bf16*>(X); c.T = T; c.ldx = ldx; c.epi = epi; c.splitk = splitk;
     c.bias = static_cast<const bf16*>(bias); c.out = static_cast<bf16*>(out); c.ldo = ldo; c.partial = partial;
-    c.bn_override = 0;
+    c.bn_override = g_op_bn_override;
     std::string err;
     const int s = gemm_launch(static_cast<cudaStream_t>(cuda_stream), c, &err);
     if (s < 0) return fail(BLURR_ERR_INVALID, err);

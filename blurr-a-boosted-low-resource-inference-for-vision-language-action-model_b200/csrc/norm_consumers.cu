@@ -58,6 +58,9 @@ cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a) {
     if (a.N == 4 * 288) return launch_kernel(consumer_kernel<1, 288>, dim3(a.T), dim3(288), 0, stream, a);
     if (a.N <= 4 * kRowThreads)
         return launch_kernel(consumer_kernel<1, kRowThreads>, dim3(a.T), dim3(kRowThreads), 0, stream, a);
+    // Gemma's 2048 columns: one 4-column group per thread on 512 threads, so that all of a row's split-K loads go out
+    // in two round trips to L2 instead of four (the kernel is latency-bound)
+    if (a.N == 4 * 512) return launch_kernel(consumer_kernel<1, 512>, dim3(a.T), dim3(512), 0, stream, a);
     return launch_kernel(consumer_kernel<2, kRowThreads>, dim3(a.T), dim3(kRowThreads), 0, stream, a);
 }
 

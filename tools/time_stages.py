@@ -41,6 +41,9 @@ def timed(n=30):
 
 with torch.inference_mode():
     model(**args, noise=inp["noise"])
+for kv in filter(None, os.environ.get("ENGINE_OPTS", "").split(",")):      # e.g. ENGINE_OPTS="chunked_splitk=0"
+    k, v = kv.split("=")
+    model._engine.set_option(k, int(v))
 for name, mask in [("all", 7), ("vision only", 1), ("prefill only", 2), ("action only", 4), ("staging only", 0)]:
     model._engine.set_option("stage_mask", mask)
     ms, launches = timed(30 if B == 1 else 5)
