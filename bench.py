@@ -2,20 +2,29 @@
 """Benchmark of the Pi-0 Bridge control step (BASELINE.json metric), one JSON line on stdout.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
 
 A *step* is one control step: one `PiZeroInference.forward` (= `infer_action`, reference
 `src/model/vla/pizero.py:473-547`) per episode, producing a chunk of `horizon_steps` = 4 actions.
 
-Workload at every N: BASELINE.json configs[1] — Bridge config, bf16, batch 1 per GPU, 1 flow step
-(`--preset blurr`), random-init weights, synthetic inputs, a fresh image + proprio every control
-step of a 50-step episode; for N > 1 every rank runs its own independent episode (weights
-replicated, no data-path collective; one NCCL all_gather of the final actions), `"scaling":
-"weak"`.  `value` = actions/s over all ranks with inputs resident in HBM; `e2e` = the same through
-the public call with all 8 input tensors copied from pinned host memory and the actions read back
-every step (what `src/agent/eval.py:207-218,239` does).  The same line carries the bs=1 latency
-percentiles, the secondary batched-episode measurement (configs[3], 64 episodes per GPU), the
-roofline of the dominant kernel and the CPU baseline (the oracle on the box's host cores).
+BASELINE.json's metric has two halves, and every line carries both measurements:
+  * `latency`  — configs[1]: Bridge, bf16, ONE episode per GPU, 1 flow step (`--preset blurr`), a fresh image + proprio
+                 every control step of a 50-step episode; p50 latency per control step.
+  * `batched`  — configs[3]: 64 episodes per GPU, episode-sharded (weights replicated, no data-path collective, one NCCL
+                 all_gather of the final actions); actions/s over all GPUs.
+Which one is the line's headline (`value`, `ms_per_step`, `config.workload`, `e2e`, `clocks`) is `--workload`:
+  auto (default) = `latency` for a single-GPU run on a single-GPU box (the driver's BENCH run), `batched` whenever the run
+  is a point of the 1/2/4/8-GPU scaling curve: N > 1, or N = 1 on a box that shows more than one GPU (so that every point
+  of the curve, N = 1 included, is the bs=64/GPU workload the metric names and v_N / (N v_1) compares like with like).
+The other measurement is still taken and reported under its own key (`latency_bs1` / `batched`).
+
+For N > 1 the batched leg also deals the ranks contiguous 64-episode blocks of ONE seeded global batch
+(`blurr_b200.dist.infer_sharded`), gathers the actions over NCCL, and rank 0 recomputes every block locally:
+`actions_equal_across_gpus` = `torch.equal` of the two.
+
+`e2e` = the headline workload through the public call with all input tensors copied from pinned host memory and the
+actions read back every step (what `src/agent/eval.py:207-218,239` does).  The line also carries the roofline of the
+dominant kernel, the whole-step roofline and the CPU baseline (`cpu_baseline`; N = 1 only).
 """
 
 from __future__ import annotations
@@ -44,9 +53,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=1, help="episodes per GPU in the primary measurement")
-    ap.add_argument("--batched", type=int, default=64, help="episodes per GPU of the secondary measurement (0 = skip)")
-    ap.add_argument("--batched-steps", type=int, default=10)
+    ap.add_argument("--workload", choices=["auto", "latency", "batched"], default="auto",
+                    help="headline measurement (see the module docstring)")
+    ap.add_argument("--batch", type=int, default=1, help="episodes per GPU of the latency measurement")
+    ap.add_argument("--batched", type=int, default=64, help="episodes per GPU of the batched measurement (0 = skip)")
+    ap.add_argument("--batched-steps", type=int, default=0, help="timed steps of the batched leg when it is not the headline (0 = 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-raw-frames", action="store_true", help="skip the e2e leg that starts from raw camera frames")
@@ -166,201 +177,299 @@ def make_ring(cfg, batch, n, device, seed, pinned=False):
     return ring
 
 
-def run_ours(args):
-    import torch
-    from blurr_b200 import capi, synth
-    from blurr_b200.config import bridge_config
-    from blurr_b200.pizero import PiZeroInference
+class Ctx:
+    """What every leg needs: the model, the process group, timing helpers."""
 
-    world, rank, local = dist_setup(args)
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    peaks = measured_peaks()
-    cfg = bridge_config(args.flow_steps)
-    sd = synth.random_state_dict_on_device(cfg, dev, seed=0)
-    model = PiZeroInference.from_state_dict(cfg, sd, device=dev)
-    del sd
-    model.set_engine_options(reserve_batch=max(args.batch, args.batched))
-    K, W, B = args.steps, max(args.warmup, 3), args.batch
+    def __init__(self, args):
+        import torch
+        from blurr_b200 import synth
+        from blurr_b200.config import bridge_config
+        from blurr_b200.pizero import PiZeroInference
+        self.args = args
+        self.world, self.rank, self.local = dist_setup(args)
+        self.dev = torch.device("cuda", self.local)
+        torch.cuda.set_device(self.dev)
+        self.peaks = measured_peaks()
+        self.cfg = bridge_config(args.flow_steps)
+        sd = synth.random_state_dict_on_device(self.cfg, self.dev, seed=0)     # identical replicas on every rank
+        self.model = PiZeroInference.from_state_dict(self.cfg, sd, device=self.dev)
+        del sd
+        self.model.set_engine_options(reserve_batch=max(args.batch, args.batched))
 
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        import torch
+        if self.world > 1:
             import torch.distributed as dist
             dist.barrier()
-        torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(self.dev)
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
+    def max_over_ranks(self, x: float) -> float:
+        import torch
+        if self.world == 1:
             return x
         import torch.distributed as dist
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- primary: device-resident inputs ----------------
-    ring = make_ring(cfg, B, min(args.ring, max(K, 1)), dev, seed=1234 + rank)
+    def step(self, r):
+        from blurr_b200 import synth
+        return self.model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+
+
+def timed_device_loop(ctx, ring, K, W, sample_clocks):
+    """W warm-up + K timed steps on device-resident inputs: CUDA events on the launching stream, barrier +
+    synchronize on both sides, max over ranks.  Returns (total_ms, per-step latencies, launches per step, clocks)."""
+    import torch
+    model, dev = ctx.model, ctx.dev
+    clocks = None
     with torch.inference_mode():
-        sampler = ClockSampler(local)
-        sampler.start()                     # nvidia-smi needs a few 100 ms to come up: start before warm-up
+        sampler = ClockSampler(ctx.local) if sample_clocks else None
+        if sampler:
+            sampler.start()                 # nvidia-smi needs a few 100 ms to come up: start before warm-up
         for i in range(W):
-            r = ring[i % len(ring)]
-            out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+            ctx.step(ring[i % len(ring)])
         model._engine.check()
-        launches_per_step = model.last_launch_count
-        barrier()
-        sampler.mark()
+        launches = model.last_launch_count
+        ctx.barrier()
+        if sampler:
+            sampler.mark()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         evs[0].record()
         for i in range(K):
-            r = ring[i % len(ring)]
-            out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
+            ctx.step(ring[i % len(ring)])
             evs[i + 1].record()
-        if world > 1:       # the one collective of the path: gather the final actions of every episode
-            import torch.distributed as dist
-            gathered = [torch.empty_like(out) for _ in range(world)]
-            dist.all_gather(gathered, out)
-        end = torch.cuda.Event(enable_timing=True)
-        end.record()
-        barrier()
-        # a short timed region ends before nvidia-smi has sampled it a few times: keep the same load
-        # running (untimed) until there are enough samples of the clocks under this workload
-        tail_steps, t_tail = 0, time.perf_counter()
-        while sampler.proc is not None and sampler.count() < 6 and time.perf_counter() - t_tail < 3.0:
-            r = ring[tail_steps % len(ring)]
-            model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
-            tail_steps += 1
-            if tail_steps % 8 == 0:
-                torch.cuda.synchronize(dev)
-        torch.cuda.synchronize(dev)
-        clocks = sampler.stop()
-        clocks["untimed_tail_steps"] = tail_steps
-        model._engine.check()
-    total_ms = max_over_ranks(evs[0].elapsed_time(end))
+        ctx.barrier()
+        if sampler:
+            # a short timed region ends before nvidia-smi has sampled it a few times: keep the same load
+            # running (untimed) until there are enough samples of the clocks under this workload
+            tail_steps, t_tail = 0, time.perf_counter()
+            while sampler.proc is not None and sampler.count() < 6 and time.perf_counter() - t_tail < 3.0:
+                ctx.step(ring[tail_steps % len(ring)])
+                tail_steps += 1
+                if tail_steps % 8 == 0:
+                    torch.cuda.synchronize(dev)
+            torch.cuda.synchronize(dev)
+            clocks = sampler.stop()
+            clocks["untimed_tail_steps"] = tail_steps
+        model._engine.check()       # device-side flags (pipeline time-outs, bad token ids): results are invalid if set
+    total_ms = ctx.max_over_ranks(evs[0].elapsed_time(evs[K]))
     lat = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
-    ms_per_step = total_ms / K
-    value = world * B * HORIZON * K / (total_ms / 1e3)
+    return total_ms, lat, int(launches), clocks
 
-    # ---------------- e2e: pinned host inputs, H2D + D2H inside the timed region ----------------
-    hring = make_ring(cfg, B, min(8, len(ring)), dev, seed=4321 + rank, pinned=True)
+
+def timed_e2e_loop(ctx, hring, K, W, B):
+    """The same steps through the public call from pinned host memory: H2D of all inputs and D2H of the actions
+    inside the timed region (wall clock between synchronised points, max over ranks)."""
+    import torch
+    from blurr_b200 import synth
+    dev = ctx.dev
     h2d = sum(t.numel() * t.element_size() for t in hring[0].values())
-    host_out = torch.empty((B, HORIZON, cfg.action_dim), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((B, HORIZON, ctx.cfg.action_dim), dtype=torch.float32).pin_memory()
     with torch.inference_mode():
         def e2e_step(r):
             d = {k: v.to(dev, non_blocking=True) for k, v in r.items()}
-            a = model(**{k: d[k] for k in synth.CALL_KEYS}, noise=d["noise"])
+            a = ctx.model(**{k: d[k] for k in synth.CALL_KEYS}, noise=d["noise"])
             host_out.copy_(a.float(), non_blocking=False)        # `actions.float().cpu()` (eval.py:239)
             return a
         for i in range(W):
             e2e_step(hring[i % len(hring)])
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for i in range(K):
             e2e_step(hring[i % len(hring)])
         torch.cuda.synchronize(dev)
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-    e2e_value = world * B * HORIZON * K / e2e_s
+        e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+        ctx.barrier()
+        ctx.model._engine.check()
     d2h = host_out.numel() * host_out.element_size()
+    return {"value": ctx.world * B * HORIZON * K / e2e_s, "unit": "actions/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3 / K}, host_out
 
-    # ---------------- e2e from RAW observations ----------------
-    # 480x640x3 uint8 camera frames + raw float64 proprio in pinned host memory; per step: H2D of the raw
-    # observation, device-side cv2-equivalent Lanczos resize + normalise + proprio normalise, the model
-    # graph, D2H of the actions.  Beside it: what the reference does on the host CPU for the same step
-    # (cv2 resize + VLAProcessor + mask / position building), timed on this box.
-    raw = None
-    if not args.no_raw_frames:
-        from blurr_b200.episode import Episode
-        stats = {"p01": [0.17, -0.21, -0.04, -3.1, -0.5, -1.2, 0.0], "p99": [0.45, 0.24, 0.28, 3.1, 0.6, 1.3, 1.0]}
-        base = synth.synthetic_inputs(cfg, B, seed=99 + rank, dtype=torch.bfloat16, vary_text=B > 1)
-        ep = Episode(model, base["input_ids"], base["attention_mask"], (480, 640), stats, "bound")
-        g = torch.Generator().manual_seed(5 + rank)
-        frames = [torch.randint(0, 256, (B, 480, 640, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
-        props = [(torch.rand((B, 7), generator=g, dtype=torch.float64) * 0.4).pin_memory() for _ in range(4)]
-        noise = base["noise"].to(dev)
+
+def leg_latency(ctx, K, W, headline):
+    """configs[1]: one episode per GPU, p50 latency per control step."""
+    args, cfg, world, rank = ctx.args, ctx.cfg, ctx.world, ctx.rank
+    B = args.batch
+    ring = make_ring(cfg, B, min(args.ring, max(K, 1)), ctx.dev, seed=1234 + rank)
+    total_ms, lat, launches, clocks = timed_device_loop(ctx, ring, K, W, sample_clocks=headline)
+    res = {"workload": "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[1])", "episodes_per_gpu": B,
+           "steps": K, "warmup": W, "value": world * B * HORIZON * K / (total_ms / 1e3), "unit": "actions/s",
+           "ms_per_step": total_ms / K, "gpu_launches_per_step": launches,
+           "latency_ms": {"p50": pct(lat, 0.5), "p90": pct(lat, 0.9), "mean": statistics.fmean(lat), "min": min(lat),
+                          "note": "per control step at this rank, CUDA events, device-resident inputs"},
+           "clocks": clocks}
+    if B == 1 and args.flow_steps == 1:
+        t_hbm = ALG_WEIGHT_BYTES_STEP / (ctx.peaks["hbm_gbs"] * 1e9) * 1e3
+        res["step_roofline"] = {
+            "hbm_time_ms": t_hbm, "tensor_time_ms": ALG_FLOPS_STEP / (ctx.peaks["bf16_tflops"] * 1e12) * 1e3,
+            "frac_of_hbm_roofline": t_hbm / pct(lat, 0.5), "target_frac": 1 / 1.5, "target_p50_ms": 1.5 * t_hbm,
+            "alg_bytes_per_step": ALG_WEIGHT_BYTES_STEP, "peaks": ctx.peaks["source"]}
+    if headline or world == 1:
+        hring = make_ring(cfg, B, min(8, len(ring)), ctx.dev, seed=4321 + rank, pinned=True)
+        res["e2e"], host_out = timed_e2e_loop(ctx, hring, K, W, B)
+        if not args.no_raw_frames:
+            res["e2e_raw_frames"] = leg_raw_frames(ctx, K, W, B, host_out)
+    return res
+
+
+def leg_raw_frames(ctx, K, W, B, host_out):
+    """e2e from RAW observations: 480x640x3 uint8 camera frames + raw float64 proprio in pinned
+    host memory; per step: H2D of the raw observation, device-side cv2-equivalent Lanczos resize + normalise + proprio
+    normalise, the model graph, D2H of the actions.  Beside it: what the reference does on the host CPU for the same
+    step (cv2 resize + VLAProcessor + mask / position building), timed on this box."""
+    import torch
+    from blurr_b200 import synth
+    from blurr_b200.episode import Episode
+    cfg, dev, rank, world = ctx.cfg, ctx.dev, ctx.rank, ctx.world
+    stats = {"p01": [0.17, -0.21, -0.04, -3.1, -0.5, -1.2, 0.0], "p99": [0.45, 0.24, 0.28, 3.1, 0.6, 1.3, 1.0]}
+    base = synth.synthetic_inputs(cfg, B, seed=99 + rank, dtype=torch.bfloat16, vary_text=B > 1)
+    ep = Episode(ctx.model, base["input_ids"], base["attention_mask"], (480, 640), stats, "bound")
+    g = torch.Generator().manual_seed(5 + rank)
+    frames = [torch.randint(0, 256, (B, 480, 640, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
+    props = [(torch.rand((B, 7), generator=g, dtype=torch.float64) * 0.4).pin_memory() for _ in range(4)]
+    noise = base["noise"].to(dev)
+    with torch.inference_mode():
+        def raw_step(i):
+            a = ep.step(frames[i % 4], props[i % 4], noise=noise)
+            host_out.copy_(a.float(), non_blocking=False)
+        for i in range(W):
+            raw_step(i)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            raw_step(i)
+        torch.cuda.synchronize(dev)
+        raw_s = ctx.max_over_ranks(time.perf_counter() - t0)
+        ctx.barrier()
+    ep.close()
+    raw = {"value": world * B * HORIZON * K / raw_s, "unit": "actions/s", "ms_per_step": raw_s * 1e3 / K,
+           "h2d_bytes_per_step": B * (480 * 640 * 3 + 7 * 8), "d2h_bytes_per_step": host_out.numel() * host_out.element_size(),
+           "observation": "480x640x3 uint8 frame + 7 float64 proprio per episode, pinned host memory",
+           "device_ops": "cv2.INTER_LANCZOS4-equivalent resize + VLAProcessor normalise + bf16 cast + normalize_bound (bit-exact)"}
+    if rank == 0 and world == 1:
+        raw["reference_host_preprocess"] = reference_host_preprocess_ms(cfg, base, B)
+    return raw
+
+
+def global_batch(cfg, episodes_per_gpu, world, seed):
+    """ONE seeded batch of `episodes_per_gpu * world` episodes (distinct images, per-episode instruction lengths),
+    identical on every rank; rank r owns the contiguous block r (blurr_b200.dist.shard_inputs)."""
+    import torch
+    from blurr_b200 import synth
+    return synth.synthetic_inputs(cfg, episodes_per_gpu * world, seed=seed, dtype=torch.bfloat16, vary_text=True)
+
+
+def leg_batched(ctx, K, W, headline):
+    """configs[3]: 64 episodes per GPU, episode-sharded; actions/s over all GPUs, fraction of the bf16 tensor roofline,
+    and for N > 1 the cross-GPU equality check of SURVEY.md 8(d) config 4."""
+    import torch
+    from blurr_b200 import dist as bdist
+    from blurr_b200 import synth
+    args, cfg, world, rank, dev = ctx.args, ctx.cfg, ctx.world, ctx.rank, ctx.dev
+    Bb = args.batched
+    keys = list(synth.CALL_KEYS) + ["noise"]
+    # two input sets per rank (2 x 30 MB on the device): this rank's blocks of two seeded global batches
+    ring = []
+    for s in range(2):
+        glob = global_batch(cfg, Bb, world, seed=7000 + s)
+        local = bdist.shard_inputs({k: glob[k] for k in keys}, world, rank)
+        ring.append({k: v.to(dev) for k, v in local.items()})
+        if s == 0:
+            check_inputs = glob
+    total_ms, lat, launches, clocks = timed_device_loop(ctx, ring, K, W, sample_clocks=headline)
+    value = world * Bb * HORIZON * K / (total_ms / 1e3)
+    flops = ALG_FLOPS_STEP * Bb * K / (total_ms / 1e3) / 1e12          # per GPU
+    res = {"workload": "bridge_bs64_per_gpu_episode_sharded (BASELINE.json configs[3])", "episodes_per_gpu": Bb,
+           "steps": K, "warmup": W, "value": value, "actions_per_sec": value, "unit": "actions/s",
+           "ms_per_step": total_ms / K, "gpu_launches_per_step": launches, "clocks": clocks,
+           "latency_ms": {"p50": pct(lat, 0.5), "p90": pct(lat, 0.9), "mean": statistics.fmean(lat), "min": min(lat),
+                          "note": "per 64-episode control step at this rank"},
+           "tensor_roofline": {"bound": "tensor", "achieved": flops, "peak": ctx.peaks["bf16_tflops_sustained"],
+                               "unit": "TFLOP/s", "frac": flops / ctx.peaks["bf16_tflops_sustained"],
+                               "note": "algorithmic FLOPs per GPU / step time, of " + ctx.peaks["source"] + " sustained cuBLAS bf16"}}
+    if headline:
+        hring = []
+        for r in ring:
+            hring.append({k: v.cpu().contiguous().pin_memory() for k, v in r.items()})
+        res["e2e"], _ = timed_e2e_loop(ctx, hring, K, W, Bb)
+    # ---- cross-GPU equality: the gathered actions of the sharded run == the same blocks computed on ONE GPU ----
+    if world > 1:
         with torch.inference_mode():
-            def raw_step(i):
-                a = ep.step(frames[i % 4], props[i % 4], noise=noise)
-                host_out.copy_(a.float(), non_blocking=False)
-            for i in range(W):
-                raw_step(i)
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(K):
-                raw_step(i)
-            torch.cuda.synchronize(dev)
-            raw_s = max_over_ranks(time.perf_counter() - t0)
-            barrier()
-        ep.close()
-        raw = {"value": world * B * HORIZON * K / raw_s, "unit": "actions/s", "ms_per_step": raw_s * 1e3 / K,
-               "h2d_bytes_per_step": B * (480 * 640 * 3 + 7 * 8), "d2h_bytes_per_step": d2h,
-               "observation": "480x640x3 uint8 frame + 7 float64 proprio per episode, pinned host memory",
-               "device_ops": "cv2.INTER_LANCZOS4-equivalent resize + VLAProcessor normalise + bf16 cast + normalize_bound (bit-exact)"}
-        if rank == 0 and world == 1:
-            raw["reference_host_preprocess"] = reference_host_preprocess_ms(cfg, base, B)
+            dev_inputs = {k: check_inputs[k].to(dev) for k in keys}
+            step_fn = lambda **kw: ctx.model(**{k: kw[k] for k in synth.CALL_KEYS}, noise=kw["noise"])
+            gathered = bdist.infer_sharded(step_fn, dev_inputs)                 # NCCL all_gather, every rank gets all blocks
+            ctx.model._engine.check()
+            equal = None
+            if rank == 0:
+                blocks = []
+                for r in range(world):                                          # one 64-episode block at a time, on this GPU
+                    blk = bdist.shard_inputs(dev_inputs, world, r)
+                    blocks.append(step_fn(**blk).clone())
+                ctx.model._engine.check()
+                equal = bool(torch.equal(torch.cat(blocks, 0), gathered))
+            ctx.barrier()
+        res["actions_equal_across_gpus"] = equal
+        res["equality_check"] = (f"{world} x {Bb} episodes of one seeded global batch: NCCL-gathered actions of the sharded run vs "
+                                 "the same blocks run one at a time on rank 0 (equal per-GPU batch size), torch.equal")
+    return res
+
+
+def run_ours(args):
+    import torch
+    ctx = Ctx(args)
+    world, rank = ctx.world, ctx.rank
+    visible = torch.cuda.device_count()
+    workload = args.workload
+    if workload == "auto":
+        workload = "latency" if (world == 1 and visible == 1) or args.batched <= 0 else "batched"
+    K, W = args.steps, max(args.warmup, 3)
+
+    legs = {}
+    if workload == "latency":
+        legs["latency"] = leg_latency(ctx, K, W, headline=True)
+        if args.batched > 0:
+            legs["batched"] = leg_batched(ctx, args.batched_steps or 10, 3, headline=False)
+        head = legs["latency"]
+    else:
+        # the batched step is ~80 ms: cap the timed steps so that the run stays within minutes at any --steps
+        Kb = min(K, 50)
+        legs["batched"] = leg_batched(ctx, Kb, W, headline=True)
+        legs["latency"] = leg_latency(ctx, min(K, 100), W, headline=False)
+        head = legs["batched"]
 
     line = {
-        "metric": "pi0_bridge_actions_per_sec", "value": value, "unit": "actions/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "metric": "pi0_bridge_actions_per_sec", "value": head["value"], "unit": "actions/s",
+        "n_gpus": world, "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (random-init weights, random uint8 images, random proprio, injected flow noise)",
-        "config": {"workload": "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[1])",
-                   "episodes_per_gpu": B, "flow_steps": args.flow_steps, "actions_per_step": HORIZON,
+        "config": {"workload": head["workload"], "episodes_per_gpu": head["episodes_per_gpu"],
+                   "flow_steps": args.flow_steps, "actions_per_step": HORIZON,
                    "parallelism": f"episode-sharded x{world}, weights replicated",
+                   "workload_rule": f"--workload {args.workload}: visible GPUs {visible}, N {world} -> {workload}",
                    "l2": "inputs larger than L2: each step streams 5.79 GB of weights (L2 is 126 MB)",
                    "cuda_graph": True},
-        "latency_ms": {"p50": pct(lat, 0.5), "p90": pct(lat, 0.9), "mean": statistics.fmean(lat), "min": min(lat),
-                       "note": "per control step at this rank, CUDA events, device-resident inputs"},
-        "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3 / K},
-        "e2e_raw_frames": raw,
-        "gpu_launches": int(launches_per_step) * K,
-        "gpu_launches_per_step": int(launches_per_step),
-        "clocks": clocks,
-        "step_roofline": {
-            "hbm_time_ms": ALG_WEIGHT_BYTES_STEP / (peaks["hbm_gbs"] * 1e9) * 1e3,
-            "tensor_time_ms": ALG_FLOPS_STEP / (peaks["bf16_tflops"] * 1e12) * 1e3,
-            "frac_of_hbm_roofline": (ALG_WEIGHT_BYTES_STEP / (peaks["hbm_gbs"] * 1e9) * 1e3) / pct(lat, 0.5)
-            if B == 1 and args.flow_steps == 1 else None,
-            "peaks": peaks["source"]},
+        "latency_ms": legs["latency"]["latency_ms"],
+        "e2e": head.get("e2e"),
+        "gpu_launches": head["gpu_launches_per_step"] * head["steps"],
+        "gpu_launches_per_step": head["gpu_launches_per_step"],
+        "clocks": head["clocks"],
+        "latency_bs1": {k: v for k, v in legs["latency"].items() if k != "clocks" or workload != "latency"},
     }
-
+    if "step_roofline" in legs["latency"]:
+        line["step_roofline"] = legs["latency"]["step_roofline"]
+    if "e2e_raw_frames" in legs["latency"]:
+        line["e2e_raw_frames"] = legs["latency"]["e2e_raw_frames"]
+    if "batched" in legs:
+        line["batched"] = {k: v for k, v in legs["batched"].items() if k != "clocks" or workload != "batched"}
+        if "actions_equal_across_gpus" in legs["batched"]:
+            line["actions_equal_across_gpus"] = legs["batched"]["actions_equal_across_gpus"]
     # ---------------- roofline of the dominant kernel (rank 0) ----------------
     if rank == 0 and not args.no_roofline:
-        line["roofline"] = dominant_kernel_roofline(dev, peaks)
-    # ---------------- secondary: batched episodes (BASELINE.json configs[3]) ----------------
-    if args.batched > 0:
-        Bb, Kb = args.batched, args.batched_steps
-        bring = make_ring(cfg, Bb, 2, dev, seed=99 + rank)
-        with torch.inference_mode():
-            for i in range(3):
-                r = bring[i % 2]
-                out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
-            model._engine.check()
-            bl = model.last_launch_count
-            barrier()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for i in range(Kb):
-                r = bring[i % 2]
-                out = model(**{k: r[k] for k in synth.CALL_KEYS}, noise=r["noise"])
-            if world > 1:
-                import torch.distributed as dist
-                gathered = [torch.empty_like(out) for _ in range(world)]
-                dist.all_gather(gathered, out)
-            e.record()
-            barrier()
-        bms = max_over_ranks(s.elapsed_time(e))
-        b_value = world * Bb * HORIZON * Kb / (bms / 1e3)
-        flops = ALG_FLOPS_STEP * Bb * Kb / (bms / 1e3) / 1e12
-        line["batched"] = {"workload": "bridge_bs64_per_gpu_episode_sharded (BASELINE.json configs[3])",
-                           "episodes_per_gpu": Bb, "steps": Kb, "actions_per_sec": b_value,
-                           "ms_per_step": bms / Kb, "gpu_launches_per_step": int(bl),
-                           "tensor_roofline": {"bound": "tensor", "achieved": flops, "peak": peaks["bf16_tflops_sustained"],
-                                               "unit": "TFLOP/s", "frac": flops / peaks["bf16_tflops_sustained"],
-                                               "note": "algorithmic FLOPs per GPU / step time, of " + peaks["source"] + " sustained cuBLAS bf16"}}
+        line["roofline"] = dominant_kernel_roofline(ctx.dev, ctx.peaks)
     # ---------------- CPU baseline (rank 0, N = 1) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg, model, warm=1, timed=2)
+        line["cpu_baseline"] = cpu_baseline(ctx.cfg, ctx.model, warm=1, timed=2)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -442,55 +551,78 @@ def dominant_kernel_roofline(dev, peaks):
     for i in range(nbuf):
         capi.check(launch(i))
     torch.cuda.synchronize(dev)
-    times = []
-    pairs = []
+    # (a) back to back, one event pair around `iters` launches on the launching stream: the average launch duration in
+    #     the regime the step runs in (successive kernels overlap their set-up through programmatic dependent launch)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(stream)
     for i in range(iters):
+        capi.check(launch(i))
+    e.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = s.elapsed_time(e) / iters
+    # (b) isolated launches (synchronise in between): includes the full launch latency of a cluster kernel
+    times = []
+    for i in range(10):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(stream)
         capi.check(launch(i))
         e.record(stream)
-        pairs.append((s, e))
-    torch.cuda.synchronize(dev)
-    times = [s.elapsed_time(e) for s, e in pairs]
-    ms = statistics.fmean(times)
+        torch.cuda.synchronize(dev)
+        times.append(s.elapsed_time(e))
     alg_bytes = N * Kd * 2
     achieved = alg_bytes / (ms / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": "gemm_tc_kernel<EPI_GEGLU> (Gemma gate/up, 276 tokens)",
+    return {"bound": "hbm", "kernel": "gemm_tcp2_kernel<EPI_GEGLU> (Gemma gate/up, 276 tokens, persistent CTA pairs)",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": ncu_traffic_bytes(), "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "ms_min": min(times),
+            "traffic": ncu_traffic_bytes(), "alg_bytes_per_launch": alg_bytes, "ms_per_launch": ms,
+            "ms_isolated_launch_median": statistics.median(times), "launches_timed": iters,
             "note": "algorithmic bytes = the 32768x2048 bf16 weight tile stream; peak = " + peaks["source"] + " copy bandwidth"}
 
 
 def cpu_baseline(cfg, model, warm=1, timed=2, state_dict=None):
-    """The oracle (a port of the reference's op sequence, `oracle/pi0_oracle.py`) on the box's host
-    cores: fp32, bs=1, full-size model (BASELINE.json configs[0])."""
+    """The reference's CPU path on the box's host cores: fp32, bs=1, full-size model (BASELINE.json configs[0]) —
+    the unmodified reference when reachable (`kind: "reference"`, see run_reference), else the oracle port."""
     import torch
     from blurr_b200 import synth
     from oracle import pi0_oracle as O
+    from oracle import ref_harness
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     if state_dict is None:
         state_dict = {k: v.detach().to("cpu", torch.float32) for k, v in model.state_dict().items()}
     inp = synth.synthetic_inputs(cfg, 1, dtype=torch.float32)
+    kind = "port"
+    call = lambda: O.infer_action(state_dict, cfg, **synth.call_args(inp), noise=inp["noise"])
+    if ref_harness.reference_available():
+        try:
+            ref = ref_harness.load_reference_model(cfg, state_dict, torch.float32)
+            def call():
+                with ref_harness.patched_randn(inp["noise"]):
+                    return ref(**{k: (v.clone() if k == "pixel_values" else v) for k, v in synth.call_args(inp).items()})
+            kind = "reference"
+        except Exception as exc:
+            print(f"reference import failed ({type(exc).__name__}: {exc}); timing the port", file=sys.stderr)
     ts = []
     with torch.inference_mode():
         for i in range(warm + timed):
             t0 = time.perf_counter()
-            O.infer_action(state_dict, cfg, **synth.call_args(inp), noise=inp["noise"])
+            call()
             dt = time.perf_counter() - t0
             if i >= warm:
                 ts.append(dt)
     sec = statistics.median(ts)
-    return {"value": HORIZON / sec, "unit": "actions/s", "cores": cores, "kind": "port",
+    return {"value": HORIZON / sec, "unit": "actions/s", "cores": cores, "kind": kind,
             "ms_per_step": sec * 1e3,
             "sample": f"{timed} full-size Bridge control steps (bs=1, fp32, 1 flow step) after {warm} warm-up; "
                       f"torch {torch.__version__} with {torch.get_num_threads()} threads"}
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
-    pure Python/PyTorch and cannot travel to the GPU box, so its pinned restatement (the oracle)
-    is timed on the host cores, rank 0 only."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, rank 0 only.
+    When the unmodified reference is reachable (`/root/reference` in the build container, the copy that
+    `__graft_entry__.build()` ships in the git-ignored `baseline/_ref/` on the GPU box) it is the thing timed
+    (`kind: "reference"`): `PiZeroInference` imported through `oracle/ref_harness.py`, called exactly like
+    `scripts/benchmark_pi0.py:238-242`.  Otherwise its pinned restatement, the oracle (`kind: "port"`).
+    fp32 on all host cores, bs=1, the same synthetic inputs every step, mean over the timed steps (bounded to 150 s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -498,36 +630,52 @@ def run_reference(args):
     from blurr_b200 import synth
     from blurr_b200.config import bridge_config
     from oracle import pi0_oracle as O
+    from oracle import ref_harness
     cfg = bridge_config(args.flow_steps)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synth.synthetic_state_dict(cfg, 0, torch.float32)
     inp = synth.synthetic_inputs(cfg, 1, dtype=torch.float32)
+    kind = "port"
+    call = lambda: O.infer_action(sd, cfg, **synth.call_args(inp), noise=inp["noise"])
+    if ref_harness.reference_available():
+        try:
+            model = ref_harness.load_reference_model(cfg, sd, torch.float32)
+            def call():
+                with ref_harness.patched_randn(inp["noise"]):
+                    return model(**{k: (v.clone() if k == "pixel_values" else v) for k, v in synth.call_args(inp).items()})
+            kind = "reference"
+        except Exception as exc:       # a broken shipped copy must not take the arm down: fall back to the port
+            print(f"reference import failed ({type(exc).__name__}: {exc}); timing the port", file=sys.stderr)
     W = max(1, min(args.warmup, 2))
     budget_s = 150.0
     ts = []
     with torch.inference_mode():
         for _ in range(W):
-            O.infer_action(sd, cfg, **synth.call_args(inp), noise=inp["noise"])
+            call()
         t_begin = time.perf_counter()
         for _ in range(args.steps):
             t0 = time.perf_counter()
-            O.infer_action(sd, cfg, **synth.call_args(inp), noise=inp["noise"])
+            call()
             ts.append(time.perf_counter() - t0)
             if time.perf_counter() - t_begin > budget_s:
                 break
     sec = statistics.fmean(ts)
     value = HORIZON / sec
-    sample = (f"{len(ts)} of {args.steps} requested full-size Bridge control steps (bs=1, fp32, {args.flow_steps} flow "
-              f"step) after {W} warm-up, bounded to {budget_s:.0f} s; torch {torch.__version__}, {cores} threads")
+    what = ("the unmodified reference PiZeroInference (" + ref_harness.REF_ROOT + ")") if kind == "reference" else \
+        "the oracle port of the reference's op sequence (reference tree not reachable)"
+    sample = (f"{what}: {len(ts)} of {args.steps} requested full-size Bridge control steps (bs=1, fp32, {args.flow_steps} flow "
+              f"step, identical inputs every step, mean) after {W} warm-up, bounded to {budget_s:.0f} s; torch {torch.__version__}, "
+              f"{cores} threads")
     line = {
         "impl": "reference", "metric": "pi0_bridge_actions_per_sec", "value": value, "unit": "actions/s",
         "n_gpus": args.gpus, "steps": len(ts), "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[1])",
+        "config": {"workload": "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[0]: the reference's CPU-runnable case)",
                    "episodes_per_gpu": 1, "flow_steps": args.flow_steps, "actions_per_step": HORIZON,
-                   "parallelism": "host CPU, rank 0 only"},
-        "cpu_baseline": {"value": value, "unit": "actions/s", "cores": cores, "kind": "port", "sample": sample},
+                   "parallelism": "host CPU, rank 0 only",
+                   "differs_from_gpu_arm": "fp32 instead of bf16, at most 2 warm-up steps, one episode whatever the GPU arm's batch"},
+        "cpu_baseline": {"value": value, "unit": "actions/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -6,8 +6,10 @@ generated (`tests/golden/make_golden.py`).  The reference imports `hydra` and `o
 (`src/model/vla/pizero.py:13`, `src/model/vla/joint_model.py:18`), which are not installed
 here; the two call sites (`hydra.utils.instantiate(cfg.x)`, `OmegaConf.merge(a, b)`) are
 served by the small stubs below.  Nothing from the reference is copied: it is imported from
-where it lies.  `/root/reference` exists only in the build container, never on the GPU box,
-so everything here is used by `-m "not gpu"` tests and by the golden generator only.
+where it lies.  `/root/reference` exists only in the build container; for the GPU box
+`__graft_entry__.build()` places an unmodified copy of the reference's `open_pi_zero/src` tree in the
+git-ignored `baseline/_ref/` (it travels with the snapshot like the built `.so`), which only
+`bench.py --impl reference` uses there: the reference itself timed on the box's host cores.
 """
 
 from __future__ import annotations
@@ -20,7 +22,20 @@ from typing import Optional
 
 import torch
 
-REF_ROOT = os.environ.get("BLURR_REF_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SHIPPED = os.path.join(_REPO_ROOT, "baseline", "_ref")      # git-ignored copy made by __graft_entry__.build(); travels to the GPU box
+
+
+def _pick_ref_root() -> str:
+    env = os.environ.get("BLURR_REF_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference"):
+        return "/root/reference"
+    return _SHIPPED
+
+
+REF_ROOT = _pick_ref_root()
 OPZ_ROOT = os.path.join(REF_ROOT, "third_party", "open_pi_zero")
 
 
@@ -75,6 +90,25 @@ def build_reference_model(cfg, seed: Optional[int] = 0, dtype: torch.dtype = tor
     if seed is not None:
         torch.manual_seed(seed)
     model = pz.PiZeroInference(cfg, use_ddp=False)
+    model.freeze_all_weights()
+    model.to(dtype)
+    model.eval()
+    return model
+
+
+def load_reference_model(cfg, state_dict, dtype: torch.dtype = torch.float32):
+    """The reference `PiZeroInference` carrying the given weights: built on the meta device (skips ~45 s of default
+    initialisation), weights adopted with `load_state_dict(assign=True)`, the two non-persistent buffers rebuilt the way
+    the reference's constructors compute them, then frozen / cast / eval like `scripts/benchmark_pi0.py:140-146`."""
+    pz = import_reference()
+    with torch.device("meta"):
+        model = pz.PiZeroInference(cfg, use_ddp=False)
+    model.load_state_dict(state_dict, strict=True, assign=True)
+    for m in model.modules():   # non-persistent buffers are not in the state_dict
+        if type(m).__name__ == "GemmaRotaryEmbedding":
+            m.inv_freq = 1.0 / (m.base ** (torch.arange(0, m.dim, 2, dtype=torch.int64).float() / m.dim))
+        if type(m).__name__ == "SiglipVisionEmbeddings":
+            m.position_ids = torch.arange(m.num_positions).expand((1, -1))
     model.freeze_all_weights()
     model.to(dtype)
     model.eval()

@@ -15,19 +15,7 @@ pytestmark = pytest.mark.skipif(not ref_harness.reference_available(),
 
 
 def _ref_model(cfg, sd, dtype):
-    pz = ref_harness.import_reference()
-    with torch.device("meta"):
-        model = pz.PiZeroInference(cfg, use_ddp=False)
-    model.load_state_dict(sd, strict=True, assign=True)
-    for m in model.modules():   # non-persistent buffers are not in the state_dict
-        if type(m).__name__ == "GemmaRotaryEmbedding":
-            m.inv_freq = 1.0 / (m.base ** (torch.arange(0, m.dim, 2, dtype=torch.int64).float() / m.dim))
-        if type(m).__name__ == "SiglipVisionEmbeddings":
-            m.position_ids = torch.arange(m.num_positions).expand((1, -1))
-    model.freeze_all_weights()
-    model.to(dtype)
-    model.eval()
-    return model
+    return ref_harness.load_reference_model(cfg, sd, dtype)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
