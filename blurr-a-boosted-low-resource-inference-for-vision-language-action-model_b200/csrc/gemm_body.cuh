@@ -752,10 +752,13 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
             cta_stamp(4);
         }
     } else if (warp >= 4) {
+        // 8 epilogue warps (batched episodes) or 12 (batch 1, where the drain and the last tile's activation math are
+        // on the critical path): `parts` warps per TMEM lane quarter, each a share of the columns
         const int w4 = (warp - 4) & 3, hf = (warp - 4) >> 2;
         const int nl = w4 * 32 + lane;
         const int n_groups = ntok / 16;
-        const int g_begin = hf * (n_groups / 2), g_end = hf == 0 ? n_groups / 2 : n_groups;
+        const int epi_threads = static_cast<int>(blockDim.x) - 128, parts = epi_threads >> 7;
+        const int g_begin = hf * n_groups / parts, g_end = (hf + 1) * n_groups / parts;
         constexpr int OUTW = (EPI == EPI_GEGLU) ? kBlockM / 2 : kBlockM;
         bf16* stg = reinterpret_cast<bf16*>(smem + p.stages * stage_bytes);
         const uint32_t empty_remote0 = map_to_cta(&tmem_empty[0], 0u), empty_remote1 = map_to_cta(&tmem_empty[1], 0u);
@@ -865,14 +868,14 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                 if (leader) mbar_arrive(&tmem_empty[buf]);
                 else mbar_arrive_cluster(buf == 0 ? empty_remote0 : empty_remote1);
             }
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            asm volatile("bar.sync 1, %0;\n" ::"r"(epi_threads) : "memory");
             if (warp == 4 && tile == first) cta_stamp(6);
             const int et = static_cast<int>(threadIdx.x) - 128;
             const int col_base = (EPI == EPI_GEGLU) ? bx * (kBlockM / 2) : n0;
             if (raw_geglu) {
                 // weight rows alternate gate_j, up_j: 16 consecutive staged columns give 8 outputs
                 const bf16x8* tile_s = reinterpret_cast<const bf16x8*>(stg);
-                for (int idx = et; real_tile && idx < ntok * 8; idx += 256) {
+                for (int idx = et; real_tile && idx < ntok * 8; idx += epi_threads) {
                     const int t = idx >> 3, ch = idx & 7;
                     if (t0 + t >= p.T) continue;
                     const bf16x8 lo = tile_s[t * 16 + 2 * ch];
@@ -888,14 +891,14 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                     *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) = o;
                 }
             } else {
-                for (int idx = et; real_tile && idx < ntok * (OUTW / 8); idx += 256) {
+                for (int idx = et; real_tile && idx < ntok * (OUTW / 8); idx += epi_threads) {
                     const int t = idx / (OUTW / 8), ch = idx - t * (OUTW / 8);
                     if (t0 + t < p.T)
                         *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) =
                             *reinterpret_cast<const uint4*>(stg + t * OUTW + ch * 8);
                 }
             }
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            asm volatile("bar.sync 1, %0;\n" ::"r"(epi_threads) : "memory");
             if (warp == 4 && tile == first) cta_stamp(7);
             buf = (buf + 1 == p.acc_bufs) ? 0 : buf + 1;
         }

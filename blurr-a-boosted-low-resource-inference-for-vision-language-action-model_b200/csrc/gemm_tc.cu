@@ -127,7 +127,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 // Persistent CTA pairs (gemm_pair_persistent in gemm_body.cuh): batched episodes with double-buffered accumulators,
 // and the batch-1 Gemma prefill GEMMs (two 144-token chunks, split-K slices as tiles).
 template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads + 128, 1)
+__global__ void __launch_bounds__(kGemmThreads + 256, 1)
 gemm_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_xh, const GemmDev p,
                  const int gxp, const int gy, const int gz) {
     extern __shared__ uint8_t smem_raw[];
@@ -144,8 +144,9 @@ gemm_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                                       &tmem_base, true);
     uint64_t* xbar = sh.tmem_full_bar + 2;
     if (threadIdx.x == 0) {
-        mbar_init(&xbar[0], 16);                            // tmem_empty[buf]: 8 epilogue warps of each CTA of the pair
-        mbar_init(&xbar[1], 16);
+        const uint32_t epi_warps = blockDim.x / 32 - 4;     // 8, or 12 in the batch-1 launches
+        mbar_init(&xbar[0], 2 * epi_warps);                 // tmem_empty[buf]: the epilogue warps of both CTAs of the pair
+        mbar_init(&xbar[1], 2 * epi_warps);
         mbar_init(&xbar[2], 1);                             // tmem_full of the second accumulator buffer
         fence_barrier_init();
     }
@@ -483,14 +484,14 @@ static cudaError_t launch_epi(cudaStream_t stream, const GemmPlan& pl, const CUt
 
 template <int EPI>
 static cudaError_t launch_pairp(cudaStream_t stream, int n_pairs, int smem, const CUtensorMap& tw, const CUtensorMap& txh,
-                                const GemmDev& d, int gxp, int gy, int gz = 1) {
+                                const GemmDev& d, int gxp, int gy, int gz = 1, int threads = kGemmThreads + 128) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcp2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    return launch_kernel_cluster(gemm_tcp2_kernel<EPI>, dim3(2 * n_pairs), dim3(kGemmThreads + 128), static_cast<size_t>(smem),
+    return launch_kernel_cluster(gemm_tcp2_kernel<EPI>, dim3(2 * n_pairs), dim3(threads), static_cast<size_t>(smem),
                                  stream, 2, tw, txh, d, gxp, gy, gz);
 }
 
@@ -608,10 +609,10 @@ static int gemm_launch_pair_small(cudaStream_t stream, const GemmCall& c, std::s
     d.band = gxp;
     cudaError_t e;
     switch (c.epi) {
-        case EPI_GEGLU:   e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
-        case EPI_GELU:    e = launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
-        case EPI_PARTIAL: e = launch_pairp<EPI_PARTIAL>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
-        default:          e = launch_pairp<EPI_STORE>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk); break;
+        case EPI_GEGLU:   e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
+        case EPI_GELU:    e = launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
+        case EPI_PARTIAL: e = launch_pairp<EPI_PARTIAL>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
+        default:          e = launch_pairp<EPI_STORE>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
     }
     if (e != cudaSuccess) { *err = std::string("gemm (persistent pairs, batch 1) launch failed: ") + cudaGetErrorString(e); return -1; }
     return splitk;

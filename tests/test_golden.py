@@ -80,5 +80,5 @@ def test_cuda_path_vs_reference_cpu_golden(name):
     # the fp32 reference is the tie-breaker: our bf16 error must not exceed the reference's own
     # bf16 error by more than ~one bf16 ulp of the un-clamped range (|a| < 4 -> 1.6e-2)
     assert e_ours <= e_ref + 1.6e-2
-    assert clamped <= 2e-2
+    assert clamped <= 1e-2          # north_star tolerance (clamped actions), here against the reference's CPU bf16 run
     model.release_engine()

