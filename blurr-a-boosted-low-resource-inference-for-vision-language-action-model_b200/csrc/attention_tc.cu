@@ -503,6 +503,11 @@ attn_tc_siglip_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_c
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+const int* attn_timeout_flag_ptr() {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_attn_timeout_flag) == cudaSuccess ? static_cast<const int*>(p) : nullptr;
+}
+
 int attn_take_timeout_flag() {
     int v = 0;
     if (cudaMemcpyFromSymbol(&v, g_attn_timeout_flag, sizeof(int)) != cudaSuccess) return -1;

@@ -145,7 +145,7 @@ struct blurr_pi0 {
     std::set<std::string> expected, seen;
     bool finalized = false;
     // time table
-    bf16* time_table = nullptr; int time_steps = 0;
+    bf16* time_table = nullptr; int time_steps = 0, time_capacity = 0;
     // static inputs
     int64_t *d_ids, *d_vpos, *d_ppos, *d_apos;
     bf16 *d_proprios, *d_action, *d_mask_itp, *d_mask_act, *d_out;
@@ -167,6 +167,7 @@ struct blurr_pi0 {
     cudaEvent_t ev_fork = nullptr, ev_done_p = nullptr, ev_done_a = nullptr;
     std::vector<cudaEvent_t> ev_v, ev_p;
     int* d_err = nullptr;
+    const int *flag_gemm = nullptr, *flag_attn = nullptr;    // sticky pipeline time-out words of the kernels (NaN-poison the actions)
     // options / bookkeeping
     bool use_graph = true, debug = false;
     int stage_mask = 7;            // bit 0 vision, bit 1 prefill, bit 2 action flow (timing experiments)
@@ -424,6 +425,8 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
         ok &= ev_ok;
     }
     h->d_err = static_cast<int*>(dalloc(h, 16));
+    h->flag_gemm = gemm_timeout_flag_ptr();
+    h->flag_attn = attn_timeout_flag_ptr();
     ok &= h->ws && h->ws2 && h->ws3 && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
     if (!ok) {
         blurr_pi0_destroy(h);
@@ -590,9 +593,10 @@ extern "C" int blurr_pi0_set_rope_inv_freq(blurr_pi0_t* h, const char* mixture, 
 extern "C" int blurr_pi0_set_time_table(blurr_pi0_t* h, const void* dev_table, int num_steps) {
     if (!h || !dev_table || num_steps < 1) return fail(BLURR_ERR_INVALID, "set_time_table: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (num_steps > h->time_steps) {
+    if (num_steps > h->time_capacity) {      // capacity is tracked apart from the step count: 1 -> 10 -> 1 -> 10 allocates once
         h->time_table = static_cast<bf16*>(dalloc(h, static_cast<size_t>(num_steps) * h->cfg.expert_hidden * 2));
         if (!h->time_table) return fail(BLURR_ERR_CUDA, "set_time_table: allocation failed");
+        h->time_capacity = num_steps;
     }
     h->time_steps = num_steps;
     CUDA_TRY(cudaMemcpy(h->time_table, dev_table, static_cast<size_t>(num_steps) * h->cfg.expert_hidden * 2,
@@ -817,7 +821,7 @@ struct Run {
     }
     void clamp(const ClampArgs& a) {
         if (rc) return;
-        { prof_begin("clamp"); launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip), "clamp"); prof_end(); }
+        { prof_begin("clamp"); launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip, h->d_err, h->flag_gemm, h->flag_attn), "clamp"); prof_end(); }
     }
     void tap(const std::string& name, const void* src, size_t bytes) {
         if (!h->debug || rc) return;

@@ -252,6 +252,11 @@ int gemm_take_timeout_flag() {
     return v;
 }
 
+const int* gemm_timeout_flag_ptr() {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_gemm_timeout_flag) == cudaSuccess ? static_cast<const int*>(p) : nullptr;
+}
+
 int gemm_set_cta_trace(void* dev_ptr) {
     unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
     return cudaMemcpyToSymbol(g_cta_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1;

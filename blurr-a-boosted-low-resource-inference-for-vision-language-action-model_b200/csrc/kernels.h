@@ -148,8 +148,11 @@ cudaError_t launch_small_k_linear(cudaStream_t stream, const bf16* x, int T, int
 cudaError_t launch_action_tail(cudaStream_t stream, const bf16* xn, int T, int hidden, const bf16* W,
                                const bf16* b, int action_dim, float dt, bf16* action, bf16* velocity_tap);
 
-cudaError_t launch_clamp_copy(cudaStream_t stream, const bf16* src, bf16* dst, int n, int do_clamp,
-                              float clip);
+cudaError_t launch_clamp_copy(cudaStream_t stream, const bf16* src, bf16* dst, int n, int do_clamp, float clip,
+                              const int* flag0 = nullptr, const int* flag1 = nullptr, const int* flag2 = nullptr);
+// device addresses of the sticky pipeline time-out words (gemm_tc.cu / attention_tc.cu), or nullptr
+const int* gemm_timeout_flag_ptr();
+const int* attn_timeout_flag_ptr();
 
 cudaError_t launch_rope_table(cudaStream_t stream, const float* inv_freq, int n_pos, float* cos_t,
                               float* sin_t);

@@ -69,15 +69,26 @@ cudaError_t launch_action_tail(cudaStream_t stream, const bf16* xn, int T, int h
                          b, action_dim, dt, action, velocity_tap);
 }
 
-__global__ void __launch_bounds__(256) clamp_copy_kernel(const bf16* src, bf16* dst, int n, int do_clamp, float clip) {
+// Last kernel of a control step.  `flags` are the device-side sticky error words of the step (GEMM / attention pipeline
+// time-outs, input validation): if any is set the step's results are not trustworthy, so the actions leave as NaN —
+// a robot loop that never calls blurr_pi0_check() still cannot act on garbage (the reference would have raised).
+__global__ void __launch_bounds__(256) clamp_copy_kernel(const bf16* src, bf16* dst, int n, int do_clamp, float clip,
+                                                         const int* flag0, const int* flag1, const int* flag2) {
     pdl_wait();
     pdl_trigger();     // only now: a successor that is resident earlier just holds SM resources while it waits (measured)
+    const bool bad = (flag0 != nullptr && *flag0 != 0) || (flag1 != nullptr && *flag1 != 0) || (flag2 != nullptr && *flag2 != 0);
+    if (bad) {
+        const int i = blockIdx.x * 256 + threadIdx.x;
+        if (i < n) dst[i] = __float2bfloat16(__int_as_float(0x7fc00000));
+        return;
+    }
     clamp_copy_body(src, dst, n, do_clamp, clip, blockIdx.x);
 }
 
 cudaError_t launch_clamp_copy(cudaStream_t stream, const bf16* src, bf16* dst, int n, int do_clamp,
-                              float clip) {
-    return launch_kernel(clamp_copy_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, src, dst, n, do_clamp, clip);
+                              float clip, const int* flag0, const int* flag1, const int* flag2) {
+    return launch_kernel(clamp_copy_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, src, dst, n, do_clamp, clip, flag0,
+                         flag1, flag2);
 }
 
 }  // namespace blurr

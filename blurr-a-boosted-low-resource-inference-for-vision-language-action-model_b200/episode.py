@@ -39,7 +39,7 @@ class FramePreprocessor:
         self.dst_w, self.dst_h = int(size[0]), int(size[1])          # cv2 convention: (width, height)
         self.lib = capi.load_library()
         handle = C.c_void_p()
-        capi.check(self.lib.blurr_preproc_create(self.device.index or 0, self.src_h, self.src_w, self.dst_h, self.dst_w,
+        capi.check(self.lib.blurr_preproc_create(self.device.index if self.device.index is not None else torch.cuda.current_device(), self.src_h, self.src_w, self.dst_h, self.dst_w,
                                                  C.byref(handle)))
         self.handle = handle
 
@@ -146,9 +146,16 @@ class Episode:
         self._prop_dev = torch.empty_like(self._prop_host, device=dev)
         self.pixel_values = torch.empty((self.batch, 3, self.pre.dst_h, self.pre.dst_w), device=dev, dtype=dtype)
         self.proprios = torch.empty((self.batch, 1, dim), device=dev, dtype=dtype)
+        # the pinned staging buffers are rewritten by the host every step: an event recorded after each step's H2D copies
+        # is waited for before the next rewrite, so steps issued without a synchronise cannot corrupt a copy in flight
+        self._staged = torch.cuda.Event()
+        self._staged_pending = False
 
     def preprocess(self, frame_u8, raw_proprio):
         """Raw observation -> the model's `pixel_values` / `proprios` on the device (asynchronous)."""
+        if self._staged_pending:
+            self._staged.synchronize()
+            self._staged_pending = False
         f = torch.as_tensor(frame_u8)
         if f.dim() == 3:
             f = f[None]
@@ -171,17 +178,25 @@ class Episode:
                 p = self._prop_host
             self._prop_dev.copy_(p, non_blocking=True)
             prop = self._prop_dev
+        if frames is self._frame_dev or prop is self._prop_dev:
+            self._staged.record(torch.cuda.current_stream(self.device))
+            self._staged_pending = True
         self.pre(frames, out=self.pixel_values)
         normalize_proprio(prop, self.lo, self.hi, self.kind, out=self.proprios.view(self.batch, -1))
         return self.pixel_values, self.proprios
 
-    def step(self, frame_u8, raw_proprio, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def step(self, frame_u8, raw_proprio, noise: Optional[torch.Tensor] = None, check: bool = False) -> torch.Tensor:
+        """One control step from a raw observation.  `check=True` synchronises and raises on a device-side error
+        (`PiZero.check`); without it a failed step is still visible: its actions are NaN."""
         pixel_values, proprios = self.preprocess(frame_u8, raw_proprio)
         kwargs = {} if noise is None else {"noise": noise}
         with torch.inference_mode():
-            return self.model(self.input_ids, pixel_values, self.image_text_proprio_mask, self.action_mask,
-                              self.vlm_position_ids, self.proprio_position_ids, self.action_position_ids, proprios,
-                              **kwargs)
+            out = self.model(self.input_ids, pixel_values, self.image_text_proprio_mask, self.action_mask,
+                             self.vlm_position_ids, self.proprio_position_ids, self.action_position_ids, proprios,
+                             **kwargs)
+        if check:
+            self.model.check()
+        return out
 
     def close(self):
         self.pre.close()

@@ -421,6 +421,17 @@ class PiZero(nn.Module):
         return eng.infer_action(input_ids, pixel_values, image_text_proprio_mask, action_mask,
                                 vlm_position_ids, proprio_position_ids, action_position_ids, proprios, noise)
 
+    def check(self) -> None:
+        """Synchronise the current stream and raise `BlurrError` if a control step since the last check tripped a
+        device-side error (a bounded pipeline wait that expired inside a kernel, a token id outside the embedding
+        table, more image tokens than the config allows).  Such a step already returned NaN actions — the last kernel
+        of the step poisons them when any of the sticky flags is set — so a caller that never checks still cannot act
+        on garbage; `check()` says why and clears the flags.  (The reference would have raised inside the call; this
+        path is asynchronous, so the report comes with the first synchronising read or with this call.)"""
+        eng = self._engine
+        if eng is not None:
+            eng.check()
+
     @torch.compiler.disable
     def infer_action_naive(self, input_ids, pixel_values, causal_mask, vlm_position_ids,
                            proprio_position_ids, action_position_ids, proprios,
@@ -486,6 +497,12 @@ class _Engine:
 
     def _upload(self, model: PiZero):
         sd = model.state_dict()
+        # The repack kernels and the table copies of the C side run on the legacy default stream; the tensors they read
+        # were produced on torch's CURRENT stream (`.to()`, `.contiguous()`, the time table).  Drain it first so that an
+        # engine built under `torch.cuda.stream(side)` (a non-blocking stream) cannot read weights that are still being
+        # written, and keep every temporary alive until the C calls have synchronised (finalize does).
+        torch.cuda.current_stream(self.device).synchronize()
+        keep = []
         with torch.cuda.device(self.device):
             for key, tensor in sd.items():
                 if tensor.device != self.device and tensor.device.type != "cuda":
@@ -494,6 +511,9 @@ class _Engine:
                     raise NotImplementedError(
                         f"parameter {key} is {tensor.dtype}; the B200 path needs model.to(torch.bfloat16)")
                 t = tensor.detach().contiguous()
+                keep.append(t)
+                if t.data_ptr() != tensor.data_ptr():       # .contiguous() made a copy on torch's current stream
+                    torch.cuda.current_stream(self.device).synchronize()
                 shape = (C.c_int64 * t.dim())(*t.shape)
                 capi.check(self.lib.blurr_pi0_set_weight(self.handle, key.encode(), C.c_void_p(t.data_ptr()),
                                                          shape, t.dim(), capi.BLURR_BF16))
@@ -504,9 +524,11 @@ class _Engine:
                 capi.check(self.lib.blurr_pi0_set_rope_inv_freq(self.handle, name.encode(), arr, inv.numel()))
             table = sinusoidal_time_table(model.num_inference_steps, model.action_hidden_size,
                                           model.time_max_period, self.device, torch.bfloat16)
+            torch.cuda.current_stream(self.device).synchronize()
             capi.check(self.lib.blurr_pi0_set_time_table(self.handle, C.c_void_p(table.data_ptr()),
                                                          model.num_inference_steps))
-            capi.check(self.lib.blurr_pi0_finalize_weights(self.handle))
+            capi.check(self.lib.blurr_pi0_finalize_weights(self.handle))      # cudaDeviceSynchronize inside
+        del keep
 
     def set_steps(self, model: "PiZero", steps: int):
         """Change `num_inference_steps` without re-uploading weights."""
@@ -514,6 +536,7 @@ class _Engine:
         with torch.cuda.device(self.device):
             table = sinusoidal_time_table(steps, model.action_hidden_size, model.time_max_period, self.device,
                                           torch.bfloat16)
+            torch.cuda.current_stream(self.device).synchronize()      # the C side copies on the legacy stream (blocking copy)
             capi.check(self.lib.blurr_pi0_set_time_table(self.handle, C.c_void_p(table.data_ptr()), steps))
         self.num_steps = steps
 

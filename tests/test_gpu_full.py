@@ -161,7 +161,8 @@ def test_full_model_ten_step_vs_single_step(full):
         floor = (ref_b8.clamp(-1, 1) - ref.clamp(-1, 1)).abs().max().item()
         print(f"steps={steps}: ours vs bf16-ref max_abs {((got - ref).abs().max().item()):.3e}, clamped {clamped:.3e}; "
               f"bf16-ref vs itself inside a batch of 8: clamped {floor:.3e}")
-        assert clamped <= max(1e-2, floor)
+        # bf16 actions in [0.5, 1) are 2^-8 = 3.9e-3 apart: allow the reference's own floor plus one such step
+        assert clamped <= max(1e-2, floor + 2 ** -8)
     d_ours = (out[10][0] - out[1][0]).abs().max().item()
     d_ref = (out[10][1] - out[1][1]).abs().max().item()
     print(f"10-step vs 1-step action difference: ours {d_ours:.3e}, reference {d_ref:.3e}")

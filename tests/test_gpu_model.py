@@ -362,3 +362,24 @@ def test_channels_last_pixels_and_default_noise():
     inp3["noise"] = nz
     d = _run(model, inp3)
     assert torch.equal(c, d)
+
+
+def test_device_error_poisons_actions_and_check_raises():
+    """A step that trips a device-side error flag (here: a token id outside the embedding table) must not hand the
+    robot loop plausible numbers: the last kernel of the step writes NaN actions, the public `model.check()` raises and
+    names the cause, and the next clean step is unaffected."""
+    from blurr_b200.capi import BlurrError
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    model, sd, inp = _setup(cfg, 2)
+    good = _run(model, inp).clone()
+    bad = dict(inp)
+    bad["input_ids"] = inp["input_ids"].clone()
+    bad["input_ids"][1, 260] = cfg.vocab_size + 5
+    with torch.inference_mode():
+        out = model(**synth.call_args(bad), noise=bad["noise"]).float()
+    torch.cuda.synchronize()
+    assert torch.isnan(out).all()
+    with pytest.raises(BlurrError):
+        model.check()
+    again = _run(model, inp)            # flags cleared by check(): clean inputs give the clean result again
+    assert torch.equal(again, good)
