@@ -136,6 +136,10 @@ cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnA
 
 cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& j) {
     if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
+    if (attn_tc_fewq_applies(j)) {
+        std::string err;
+        return launch_joint_attention_prefill_tc(stream, j, &err);
+    }
     AttnMmaArgs a = make_fewq_attn_args(j);
     const int pairs = j.n_heads * j.q_per_sample;
     if (attn_tile_rows(pairs, 1, j.batch, 32) == 16) return launch_attn<256, 16, true>(stream, a, pairs, 1, j.batch);

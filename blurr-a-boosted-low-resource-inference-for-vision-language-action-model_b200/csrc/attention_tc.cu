@@ -24,6 +24,21 @@ namespace blurr {
 // Set (to the stage number) when a bounded barrier wait expired; read by attn_take_timeout_flag().
 static __device__ int g_attn_timeout_flag = 0;
 
+// Per-CTA timeline for tuning (global option "attn_cta_trace" = device pointer to [n_cta][8] u64, 0 = off): %globaltimer at
+// 0 entry, 1 past the dependency wait, 2 Q staged, 3 S complete, 4 probabilities written, 5 V landed, 6 O complete, 7 stored.
+static __device__ unsigned long long* g_attn_cta_trace = nullptr;
+__device__ __forceinline__ void attn_stamp(int slot) {
+    unsigned long long* t = g_attn_cta_trace;
+    if (t != nullptr && threadIdx.x == 0) {
+        const size_t cta = blockIdx.x + static_cast<size_t>(gridDim.x) * (blockIdx.y + static_cast<size_t>(gridDim.y) * blockIdx.z);
+        t[cta * 8 + slot] = globaltimer_ns();
+    }
+}
+int attn_set_cta_trace(void* dev_ptr) {
+    unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+    return cudaMemcpyToSymbol(g_attn_cta_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
+}
+
 static constexpr int kTcRows = 128;                  // (head, query) pairs per CTA
 static constexpr int kTcKeys = 288;                  // key columns of S (two UMMA N = 144 chunks)
 static constexpr int kTcKeyBlocks = 5;               // 64-key blocks of P (320 columns, zero past n_keys)
@@ -84,6 +99,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_v32, const AttnTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     trace_stamp(a.trace, 0);
+    attn_stamp(0);
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* q_s = base;                              // phase 1: Q | K
     uint8_t* k_s = base + kTcQBytes;
@@ -115,6 +131,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     pdl_wait();
     pdl_trigger();
     trace_stamp(a.trace, 1);
+    attn_stamp(1);
 
     // ---- K tiles by TMA: k-block kb, chunk c -> [144 keys][64 dims] ----
     const int key_row0 = b * a.n_slots;
@@ -139,6 +156,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     }
     fence_proxy_async_smem();          // generic-proxy writes of Q before the tensor core reads them
     __syncthreads();
+    attn_stamp(2);
 
     // ---- S = Q K^T ----
     if (warp == 1) {
@@ -172,6 +190,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     if (!mbar_wait(bar_s, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 2); }
     tcgen05_fence_after();
     __syncthreads();                   // every thread has seen S complete: Q and K tiles are dead
+    attn_stamp(3);
     if (warp == 0 && elect_one_sync()) {
         // V where it lies: key block kb (64 keys; the last one 32), dim group j -> [keys][64 dims]
         mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(kTcVBytes));
@@ -184,11 +203,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * kCols;
     const int col0 = half * kCols;
     float m = -INFINITY;
+    // few-query tiles (1 or 4 queries per sample: 8 or 32 valid rows of 128): warps whose 32 rows are all padding skip
+    // the softmax arithmetic (their P rows stay whatever the dead Q / K tiles left there; the O rows they feed are never stored)
+    const bool warp_live = tile * kTcRows + quarter * 32 < n_pairs;
     // 16-byte mask loads when the mask rows allow it (the engine stages them with a stride of 280): one thread
     // owns one mask row, so scalar loads touch 32 sectors per warp request, 16 requests per 16 columns
     const bool mask_vec = ((a.mask_rstride | a.mask_bstride) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0;
     // pass 1: rounding chain + mask -> bf16 logits into the P tile, running max
-    for (int g = 0; g < kCols / 16; ++g) {
+    for (int g = 0; warp_live && g < kCols / 16; ++g) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(lane_addr + g * 16, r);
         uint32_t mk[8];
@@ -239,7 +261,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     __syncthreads();
     // pass 2: sum of exp over this thread's columns
     float sum = 0.f;
-    for (int c = 0; c < kCols / 8; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
+    for (int c = 0; warp_live && c < kCols / 8; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
     stat[half * 128 + row] = sum;
     __syncthreads();
     sum = stat[row];
@@ -247,7 +269,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     for (int pt = 1; pt < kTcParts; ++pt) sum += stat[pt * 128 + row];
     const float inv_sum = row_valid ? 1.f / sum : 0.f;
     // pass 3: probabilities, bf16, in place
-    for (int c = 0; c < kCols / 8; ++c) {
+    for (int c = 0; warp_live && c < kCols / 8; ++c) {
         uint4* ptr = p_chunk(p_s, row, (col0 >> 3) + c);
         *ptr = row_valid ? chunk_probs(*ptr, m, inv_sum) : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -255,6 +277,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     tcgen05_fence_before();
     fence_proxy_async_smem();          // P (generic proxy) before the tensor core reads it
     __syncthreads();
+    attn_stamp(4);
 
     // ---- O = P V ----
     if (warp == 1) {
@@ -281,6 +304,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     // ---- epilogue: O -> bf16 -> [b*q + query][head*256 + dim] ----
     if (!mbar_wait(bar_o, 0)) { if (lane == 0) atomicExch(&g_attn_timeout_flag, 4); }
     tcgen05_fence_after();
+    attn_stamp(6);
     if (half < 2) {
         const uint32_t oaddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
         bf16* orow = a.out + (static_cast<size_t>(b) * a.q_per_sample + qi) * ldq + head * kTcHd + half * 128;
@@ -306,6 +330,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     trace_stamp(a.trace, 2);
+    attn_stamp(7);
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
@@ -520,6 +545,16 @@ int attn_take_timeout_flag() {
 
 static int g_attn_tc = -1;            // -1 automatic (batched episodes), 0 never, 1 whenever the shape allows
 void attn_set_tc(int mode) { g_attn_tc = mode; }
+// Few-query attention (proprio: 1 query per sample, action: 4) on the tcgen05 kernel: the (head, query) pairs of a sample
+// are one 128-row tile.  Measured slower than the mma.sync tile kernel at batch 1 (per-CTA timeline, tools/attn_timeline.py:
+// 21 us against 18 us): with 8 or 32 live rows the softmax runs on three warps (a warp can only read its own TMEM lane
+// quarter), one row per thread, 96 serial columns each - 15 us of dependent ALU / MUFU latency.  Option only: 1 = on.
+static int g_attn_tc_fewq = 0;
+void attn_set_tc_fewq(int mode) { g_attn_tc_fewq = mode; }
+bool attn_tc_fewq_applies(const JointAttnArgs& j) {
+    if (g_attn_tc_fewq <= 0) return false;
+    return j.n_keys <= kTcKeys && j.n_slots >= 1 && j.q_per_sample >= 1 && j.n_heads * j.q_per_sample <= kTcRows;
+}
 
 bool attn_tc_applies(const JointAttnArgs& j) {
     if (g_attn_tc == 0) return false;

@@ -112,7 +112,10 @@ cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnA
 // attention_tc.cu: the same operator on tcgen05 for batched episodes (one CTA = 128 (head, query) pairs)
 void attn_set_tc(int mode);                      // -1 automatic (batch >= 8), 0 never, 1 whenever the shape allows
 bool attn_tc_applies(const JointAttnArgs& a);
+void attn_set_tc_fewq(int mode);                 // few-query attention on the tcgen05 kernel: 1 on, 0 / -1 off (default: measured slower at batch 1)
+bool attn_tc_fewq_applies(const JointAttnArgs& a);
 int attn_take_timeout_flag();
+int attn_set_cta_trace(void* dev_ptr);          // per-CTA timeline of the tcgen05 attention kernel (attention_tc.cu)
 // The AttnMmaArgs the two launchers above build (the step kernel runs the same bodies as work items).
 AttnMmaArgs make_siglip_attn_args(const bf16* qkv, int ld_qkv, int seq, int n_heads, int hidden, bf16* out,
                                   int ld_out);

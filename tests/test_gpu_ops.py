@@ -298,7 +298,16 @@ def test_joint_attention_fewq(qps, row0, n_keys, batch):
     else:
         mask = _block_mask(batch, 4, 281, cnts, 277)      # action mask rows
         rows = mask
-    got = op_joint_attention(True, q, qps, row0, kc, vc, n_keys, mask, batch, n_heads)
+    lib = capi.load_library()
     ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], rows, n_heads)
-    print(report(f"joint_fewq qps={qps}", got, ref))
-    assert (got.float() - ref.float()).abs().max().item() <= 0.05
+    outs = {}
+    try:
+        for mode in (0, 1):        # 0: mma.sync tile kernel, 1: the tcgen05 kernel (one 128-row tile of (head, query) pairs per sample)
+            capi.check(lib.blurr_set_global_option(b"attn_tc_fewq", mode))
+            outs[mode] = op_joint_attention(True, q, qps, row0, kc, vc, n_keys, mask, batch, n_heads)
+            print(report(f"joint_fewq qps={qps} tcgen05={mode}", outs[mode], ref))
+            assert (outs[mode].float() - ref.float()).abs().max().item() <= 0.05
+    finally:
+        capi.check(lib.blurr_set_global_option(b"attn_tc_fewq", -1))
+    d = (outs[0].float() - outs[1].float()).abs()
+    assert d.max().item() <= 0.05 and (d > 0).float().mean().item() < 0.05
