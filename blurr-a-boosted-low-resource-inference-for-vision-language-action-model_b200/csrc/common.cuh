@@ -21,8 +21,20 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------------------
 // bf16 rounding helpers
 // ---------------------------------------------------------------------------
+// Round to bf16 and back.  Through the PACKED converter (cvt.rn.bf16x2.f32 = F2FP.BF16.F32.PACK_AB, FMA pipe, full
+// rate) and a shift: the scalar cvt.rn.bf16.f32 is an F2F on the XU / MIO path (16 per clock per SM), and the rounding
+// chains of the attention softmax and the GEMM epilogues execute several per element (ncu, round 2: F2F.BF16.F32 with
+// `mio` stalls all over the tcgen05 attention kernel).  Same result bit for bit (round to nearest even, NaN / Inf kept).
 __device__ __forceinline__ float bf16_round(float x) {
-    return __bfloat162float(__float2bfloat16_rn(x));
+    __nv_bfloat162 v = __floats2bfloat162_rn(x, 0.0f);
+    return __uint_as_float(*reinterpret_cast<uint32_t*>(&v) << 16);
+}
+// two at once: one conversion instruction for both
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    const uint32_t u = *reinterpret_cast<uint32_t*>(&v);
+    a = __uint_as_float(u << 16);
+    b = __uint_as_float(u & 0xffff0000u);
 }
 __device__ __forceinline__ float bf2f(bf16 x) { return __bfloat162float(x); }
 __device__ __forceinline__ bf16 f2bf(float x) { return __float2bfloat16_rn(x); }
@@ -74,6 +86,14 @@ __device__ __forceinline__ bool elect_one_sync() {
         "}\n"
         : "=r"(pred));
     return pred != 0;
+}
+
+// First 1024-byte aligned byte of a dynamic shared-memory array, as pointer arithmetic ON the array: the compiler keeps
+// the shared address space (STS / LDS).  Rounding the address through uintptr_t loses it and every access to the carved
+// buffers becomes a generic ST.E / LD.E (found in the SASS of the GEMM staging stores and the attention softmax, round 2).
+__device__ __forceinline__ uint8_t* smem_align_1024(uint8_t* smem_raw) {
+    const uint32_t a = smem_u32(smem_raw);
+    return smem_raw + ((1024u - (a & 1023u)) & 1023u);
 }
 
 // ---------------------------------------------------------------------------

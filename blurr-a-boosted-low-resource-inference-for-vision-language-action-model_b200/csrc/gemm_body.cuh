@@ -909,7 +909,7 @@ __device__ __forceinline__ GemmShared gemm_setup_shared(uint8_t* smem_raw, int r
                                                         uint32_t tmem_cols, uint32_t* tmem_slot_out,
                                                         bool two_sm = false) {
     GemmShared sh;
-    sh.ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    sh.ring = smem_align_1024(smem_raw);
     sh.full_bar = reinterpret_cast<uint64_t*>(sh.ring + ring_bytes);
     sh.empty_bar = sh.full_bar + kMaxStages;
     sh.tmem_full_bar = sh.empty_bar + kMaxStages;
