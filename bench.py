@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-raw-frames", action="store_true", help="skip the e2e leg that starts from raw camera frames")
     ap.add_argument("--flow-steps", type=int, default=1, help="num_inference_steps (1 = --preset blurr)")
+    ap.add_argument("--robot", choices=["bridge", "fractal"], default="bridge", help="config family (BASELINE.json configs[2]: fractal)")
     ap.add_argument("--ring", type=int, default=50, help="distinct pre-staged control-step inputs (one episode)")
     return ap.parse_args()
 
@@ -183,14 +184,14 @@ class Ctx:
     def __init__(self, args):
         import torch
         from blurr_b200 import synth
-        from blurr_b200.config import bridge_config
+        from blurr_b200.config import bridge_config, fractal_config
         from blurr_b200.pizero import PiZeroInference
         self.args = args
         self.world, self.rank, self.local = dist_setup(args)
         self.dev = torch.device("cuda", self.local)
         torch.cuda.set_device(self.dev)
         self.peaks = measured_peaks()
-        self.cfg = bridge_config(args.flow_steps)
+        self.cfg = fractal_config(args.flow_steps) if args.robot == "fractal" else bridge_config(args.flow_steps)
         sd = synth.random_state_dict_on_device(self.cfg, self.dev, seed=0)     # identical replicas on every rank
         self.model = PiZeroInference.from_state_dict(self.cfg, sd, device=self.dev)
         del sd
@@ -293,7 +294,10 @@ def leg_latency(ctx, K, W, headline):
     B = args.batch
     ring = make_ring(cfg, B, min(args.ring, max(K, 1)), ctx.dev, seed=1234 + rank)
     total_ms, lat, launches, clocks = timed_device_loop(ctx, ring, K, W, sample_clocks=headline)
-    res = {"workload": "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[1])", "episodes_per_gpu": B,
+    wl = "bridge_bs1_blurr_preset_50step_episode (BASELINE.json configs[1])"
+    if args.robot == "fractal" or args.flow_steps != 1:
+        wl = f"{args.robot}_bs1_{args.flow_steps}_flow_steps (BASELINE.json configs[2])"
+    res = {"workload": wl, "episodes_per_gpu": B,
            "steps": K, "warmup": W, "value": world * B * HORIZON * K / (total_ms / 1e3), "unit": "actions/s",
            "ms_per_step": total_ms / K, "gpu_launches_per_step": launches,
            "latency_ms": {"p50": pct(lat, 0.5), "p90": pct(lat, 0.9), "mean": statistics.fmean(lat), "min": min(lat),
@@ -305,12 +309,51 @@ def leg_latency(ctx, K, W, headline):
             "hbm_time_ms": t_hbm, "tensor_time_ms": ALG_FLOPS_STEP / (ctx.peaks["bf16_tflops"] * 1e12) * 1e3,
             "frac_of_hbm_roofline": t_hbm / pct(lat, 0.5), "target_frac": 1 / 1.5, "target_p50_ms": 1.5 * t_hbm,
             "alg_bytes_per_step": ALG_WEIGHT_BYTES_STEP, "peaks": ctx.peaks["source"]}
+    if headline and B == 1 and args.flow_steps == 1:
+        res["stages"] = stage_breakdown(ctx, ring)
     if headline or world == 1:
         hring = make_ring(cfg, B, min(8, len(ring)), ctx.dev, seed=4321 + rank, pinned=True)
         res["e2e"], host_out = timed_e2e_loop(ctx, hring, K, W, B)
         if not args.no_raw_frames:
             res["e2e_raw_frames"] = leg_raw_frames(ctx, K, W, B, host_out)
     return res
+
+
+# per-stage floors of one bs=1, S=1 control step (weights bytes / FLOPs of each stage)
+STAGE_ALG = {"siglip+projector": (0.830e9, 220.2e9), "gemma_prefill": (3.746e9, 1013.9e9),
+             "proprio+action_experts": (0.589e9 + 0.629e9, 3.3e9)}
+
+
+def stage_breakdown(ctx, ring, n=30):
+    """Time of each stage run ALONE under the real launch regime (engine option `stage_mask`: the step with only that
+    stage's kernels; results are meaningless, timings are not) beside its HBM / tensor floor.  The stages of a full step
+    overlap (the experts run on side streams under the prefill), so the parts do not add up to the step."""
+    import torch
+    eng, dev, peaks = ctx.model._engine, ctx.dev, ctx.peaks
+    out = {}
+    try:
+        for name, mask in (("siglip+projector", 1), ("gemma_prefill", 2), ("proprio+action_experts", 4)):
+            eng.set_option("stage_mask", mask)
+            with torch.inference_mode():
+                for i in range(4):
+                    ctx.step(ring[i % len(ring)])
+                torch.cuda.synchronize(dev)
+                ts = []
+                for i in range(n):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); ctx.step(ring[i % len(ring)]); b.record()
+                    torch.cuda.synchronize(dev)
+                    ts.append(a.elapsed_time(b))
+            by, fl = STAGE_ALG[name]
+            t_hbm = by / (peaks["hbm_gbs"] * 1e9) * 1e3
+            t_tc = fl / (peaks["bf16_tflops"] * 1e12) * 1e3
+            ms = statistics.median(ts)
+            out[name] = {"ms": ms, "hbm_floor_ms": t_hbm, "tensor_floor_ms": t_tc, "frac_of_floor": max(t_hbm, t_tc) / ms}
+    finally:
+        eng.set_option("stage_mask", 7)
+    out["note"] = ("each stage alone (stage_mask), p50 of %d launches incl. the input staging kernels; floors = SURVEY.md 8(d) "
+                   "bytes / measured copy bandwidth and FLOPs / measured burst bf16" % n)
+    return out
 
 
 def leg_raw_frames(ctx, K, W, B, host_out):
@@ -322,12 +365,13 @@ def leg_raw_frames(ctx, K, W, B, host_out):
     from blurr_b200 import synth
     from blurr_b200.episode import Episode
     cfg, dev, rank, world = ctx.cfg, ctx.dev, ctx.rank, ctx.world
-    stats = {"p01": [0.17, -0.21, -0.04, -3.1, -0.5, -1.2, 0.0], "p99": [0.45, 0.24, 0.28, 3.1, 0.6, 1.3, 1.0]}
+    dim = int(cfg.proprio_dim)      # 7 (Bridge) or 8 (Fractal)
+    stats = {"p01": ([0.17, -0.21, -0.04, -3.1, -0.5, -1.2, 0.0, -0.3])[:dim], "p99": ([0.45, 0.24, 0.28, 3.1, 0.6, 1.3, 1.0, 0.3])[:dim]}
     base = synth.synthetic_inputs(cfg, B, seed=99 + rank, dtype=torch.bfloat16, vary_text=B > 1)
     ep = Episode(ctx.model, base["input_ids"], base["attention_mask"], (480, 640), stats, "bound")
     g = torch.Generator().manual_seed(5 + rank)
     frames = [torch.randint(0, 256, (B, 480, 640, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
-    props = [(torch.rand((B, 7), generator=g, dtype=torch.float64) * 0.4).pin_memory() for _ in range(4)]
+    props = [(torch.rand((B, dim), generator=g, dtype=torch.float64) * 0.4).pin_memory() for _ in range(4)]
     noise = base["noise"].to(dev)
     with torch.inference_mode():
         def raw_step(i):
@@ -344,8 +388,8 @@ def leg_raw_frames(ctx, K, W, B, host_out):
         ctx.barrier()
     ep.close()
     raw = {"value": world * B * HORIZON * K / raw_s, "unit": "actions/s", "ms_per_step": raw_s * 1e3 / K,
-           "h2d_bytes_per_step": B * (480 * 640 * 3 + 7 * 8), "d2h_bytes_per_step": host_out.numel() * host_out.element_size(),
-           "observation": "480x640x3 uint8 frame + 7 float64 proprio per episode, pinned host memory",
+           "h2d_bytes_per_step": B * (480 * 640 * 3 + dim * 8), "d2h_bytes_per_step": host_out.numel() * host_out.element_size(),
+           "observation": f"480x640x3 uint8 frame + {dim} float64 proprio per episode, pinned host memory",
            "device_ops": "cv2.INTER_LANCZOS4-equivalent resize + VLAProcessor normalise + bf16 cast + normalize_bound (bit-exact)"}
     if rank == 0 and world == 1:
         raw["reference_host_preprocess"] = reference_host_preprocess_ms(cfg, base, B)
@@ -458,6 +502,8 @@ def run_ours(args):
     }
     if "step_roofline" in legs["latency"]:
         line["step_roofline"] = legs["latency"]["step_roofline"]
+    if "stages" in legs["latency"]:
+        line["stages"] = legs["latency"]["stages"]
     if "e2e_raw_frames" in legs["latency"]:
         line["e2e_raw_frames"] = legs["latency"]["e2e_raw_frames"]
     if "batched" in legs:
