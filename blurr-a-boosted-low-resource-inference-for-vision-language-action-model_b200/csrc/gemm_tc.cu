@@ -577,8 +577,9 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
 // B200 on the gate/up shape (tools/cta_timeline.py): main loop per tile 11.5 us against 15.4 us for one CTA per tile.
 // In the step (in-graph trace, same box): gate/up 46.3 -> 38.6 us, down 19.8 -> 19.6, o 11.3 -> 14.6, qkv 8.3 -> 8.9 —
 // the split-K GEMMs run one short tile per CTA, where the pair's longer set-up (cluster barrier, 2-SM TMEM
-// allocation) costs more than its main loop saves.  1 (default) = GeGLU only, 2 = every epilogue, 0 = never.
-static int g_pair_small = 1;
+// allocation) costs more than its main loop saves; once they were given token chunks (Run::plan_partial, bn_override != 0:
+// not served here) only down is left, where pairs win 2 us per layer.  1 = GeGLU only, 2 (default) = every epilogue, 0 = never.
+static int g_pair_small = 2;
 void gemm_set_pair_small(int mode) { g_pair_small = mode < 0 ? 0 : mode; }
 static bool gemm_pair_small_applies(const GemmCall& c) {
     if (g_pair_small == 0 || (g_pair_small == 1 && c.epi != EPI_GEGLU)) return false;
