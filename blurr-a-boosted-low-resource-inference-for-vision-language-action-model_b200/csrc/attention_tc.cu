@@ -1,6 +1,7 @@
-// Gemma joint-attention prefill on the tcgen05 tensor cores, for batched episodes
-// (joint_model.py:246-288; the mma.sync kernel of attention.cu stays the batch-1 path, where 144 small
-// CTAs beat 18 big ones).  At 64 episodes the mma.sync kernel is HMMA-bound (41 TFLOP/s, 15 % of the step).
+// Gemma joint-attention prefill and SigLIP self-attention on the tcgen05 tensor cores (joint_model.py:246-288,
+// siglip.py:133-152), at every batch size since round 2 (the mma.sync kernel of attention.cu keeps the few-query
+// launches of the experts and stays selectable with option attn_tc = 0).  At 64 episodes the mma.sync kernel is
+// HMMA-bound (41 TFLOP/s, 15 % of the step).
 //
 // One CTA = 128 (head, query) pairs of one sample.  All 8 query heads share the sample's single K/V head
 // (MQA), so the 2208 pairs of a sample form 18 row tiles that each read K and V exactly once.
@@ -70,16 +71,16 @@ __device__ __forceinline__ uint4* p_chunk(uint8_t* p_s, int row, int cidx) {
 }
 __device__ __forceinline__ float chunk_exp_sum(const uint4 c, float m) {
     const float2 a0 = unpack_bf16x2(c.x), a1 = unpack_bf16x2(c.y), a2 = unpack_bf16x2(c.z), a3 = unpack_bf16x2(c.w);
-    return ((__expf(a0.x - m) + __expf(a0.y - m)) + (__expf(a1.x - m) + __expf(a1.y - m))) +
-           ((__expf(a2.x - m) + __expf(a2.y - m)) + (__expf(a3.x - m) + __expf(a3.y - m)));
+    return ((exp_fast_f32(a0.x - m) + exp_fast_f32(a0.y - m)) + (exp_fast_f32(a1.x - m) + exp_fast_f32(a1.y - m))) +
+           ((exp_fast_f32(a2.x - m) + exp_fast_f32(a2.y - m)) + (exp_fast_f32(a3.x - m) + exp_fast_f32(a3.y - m)));
 }
 __device__ __forceinline__ uint4 chunk_probs(const uint4 c, float m, float inv_sum) {
     const float2 a0 = unpack_bf16x2(c.x), a1 = unpack_bf16x2(c.y), a2 = unpack_bf16x2(c.z), a3 = unpack_bf16x2(c.w);
     uint4 o;
-    o.x = pack_bf16x2(__expf(a0.x - m) * inv_sum, __expf(a0.y - m) * inv_sum);
-    o.y = pack_bf16x2(__expf(a1.x - m) * inv_sum, __expf(a1.y - m) * inv_sum);
-    o.z = pack_bf16x2(__expf(a2.x - m) * inv_sum, __expf(a2.y - m) * inv_sum);
-    o.w = pack_bf16x2(__expf(a3.x - m) * inv_sum, __expf(a3.y - m) * inv_sum);
+    o.x = pack_bf16x2(exp_fast_f32(a0.x - m) * inv_sum, exp_fast_f32(a0.y - m) * inv_sum);
+    o.y = pack_bf16x2(exp_fast_f32(a1.x - m) * inv_sum, exp_fast_f32(a1.y - m) * inv_sum);
+    o.z = pack_bf16x2(exp_fast_f32(a2.x - m) * inv_sum, exp_fast_f32(a2.y - m) * inv_sum);
+    o.w = pack_bf16x2(exp_fast_f32(a3.x - m) * inv_sum, exp_fast_f32(a3.y - m) * inv_sum);
     return o;
 }
 
@@ -235,22 +236,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
         uint32_t packed[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-            float s[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = col0 + g * 16 + i + e;
-                float v = bf16_round(__uint_as_float(r[i + e]));
-                v = v * 0.0625f;                                   // / sqrt(256): exact
-                v = bf16_round(v * (1.0f / 50.0f));
-                v = bf16_round(tanh_fast_f32(v));
-                v = bf16_round(v * 50.0f);
-                const float2 mv = unpack_bf16x2(mk[i >> 1]);
-                if (col < a.n_keys && row_valid) v = bf16_round(v + (e == 0 ? mv.x : mv.y));
-                else v = -INFINITY;
-                s[e] = v;
-                m = fmaxf(m, v);
-            }
-            packed[i >> 1] = pack_bf16x2(s[0], s[1]);
+            // two logits at a time: every rounding point of the chain is one packed conversion for the pair
+            const int col = col0 + g * 16 + i;
+            float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+            bf16_round2(v0, v1);
+            v0 *= 0.0625f; v1 *= 0.0625f;                          // / sqrt(256): exact
+            v0 *= (1.0f / 50.0f); v1 *= (1.0f / 50.0f);
+            bf16_round2(v0, v1);
+            v0 = tanh_fast_f32(v0); v1 = tanh_fast_f32(v1);
+            bf16_round2(v0, v1);
+            v0 *= 50.0f; v1 *= 50.0f;
+            bf16_round2(v0, v1);
+            const float2 mv = unpack_bf16x2(mk[i >> 1]);
+            v0 += mv.x; v1 += mv.y;
+            bf16_round2(v0, v1);
+            if (!(col < a.n_keys && row_valid)) v0 = -INFINITY;
+            if (!(col + 1 < a.n_keys && row_valid)) v1 = -INFINITY;
+            m = fmaxf(m, fmaxf(v0, v1));
+            packed[i >> 1] = pack_bf16x2(v0, v1);
         }
         const int cidx = (col0 + g * 16) >> 3;
         *p_chunk(p_s, row, cidx) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -548,7 +551,10 @@ int attn_take_timeout_flag() {
     return v;
 }
 
-static int g_attn_tc = -1;            // -1 automatic (batched episodes), 0 never, 1 whenever the shape allows
+// -1 automatic = whenever the shape allows, at any batch size (round 2: with cp.async Q staging, shared-space smem accesses
+// and the lean MUFU math the tcgen05 kernels are level with the mma.sync tile kernel at batch 1 - prefill stage 1.83 vs
+// 1.89 ms, SigLIP stage 1.35 vs 1.40 ms - and 3-4x faster for batched episodes); 0 = mma.sync kernels; 1 = same as -1
+static int g_attn_tc = -1;
 void attn_set_tc(int mode) { g_attn_tc = mode; }
 // Few-query attention (proprio: 1 query per sample, action: 4) on the tcgen05 kernel: the (head, query) pairs of a sample
 // are one 128-row tile.  Measured slower than the mma.sync tile kernel at batch 1 (per-CTA timeline, tools/attn_timeline.py:
@@ -565,14 +571,14 @@ bool attn_tc_applies(const JointAttnArgs& j) {
     if (g_attn_tc == 0) return false;
     const bool shape_ok = j.n_keys <= kTcKeys && j.n_slots >= 1 && j.q_per_sample >= 1 && j.n_heads >= 1;
     if (!shape_ok) return false;
-    return g_attn_tc == 1 || j.batch >= 8;
+    return true;
 }
 
 bool attn_tc_siglip_applies(int batch, int seq, int n_heads, int hidden) {
     if (g_attn_tc == 0) return false;
     const int hd = hidden / n_heads;
     if (seq > 256 || hd > 128 || (hd & 7) != 0) return false;
-    return g_attn_tc == 1 || batch >= 8;
+    return true;
 }
 
 cudaError_t launch_siglip_attention_tc(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq, int n_heads,

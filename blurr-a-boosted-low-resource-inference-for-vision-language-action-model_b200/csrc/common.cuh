@@ -48,13 +48,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(v);
 }
 
+// MUFU primitives without the denormal handling nvcc wraps around __expf / division (a compare, a predicated rescale and
+// a reconvergence point per call: the softmax of the tcgen05 attention kernel spent ~65 instructions per logit, half of
+// them there).  .ftz: results below 2^-126 flush to zero - irrelevant for exp(x - max) and for exp(2x) with |x| <= 15.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// exp(x) as __expf computes it (ex2.approx of x * log2(e)), minus the denormal path
+__device__ __forceinline__ float exp_fast_f32(float x) { return ex2_ftz(x * 1.4426950408889634f); }
+
 // tanh through one ex2 and one rcp (relative error ~2^-21 against tanhf's ~2^-23).  Every use rounds the
 // result to bf16 right away, so against tanhf it flips about one rounding in 2^12 - far inside the parity
 // tolerance - at a third of the instructions (the GELU / GeGLU epilogues and the batched softmax are ALU-bound).
+// Same bits as 1 - __fdividef(2, __expf(2x) + 1): the factors of two are exact.
 __device__ __forceinline__ float tanh_fast_f32(float x) {
     x = fminf(fmaxf(x, -15.f), 15.f);
-    const float e = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, e + 1.f);
+    const float e = ex2_ftz(x * 2.8853900817779268f);      // exp(2x)
+    return fmaf(-2.f, rcp_ftz(e + 1.f), 1.f);
 }
 
 // torch.nn.functional.gelu(x, approximate="tanh") on a bf16 tensor: computed in fp32 from the
