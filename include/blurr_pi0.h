@@ -132,10 +132,13 @@ int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const b
                            void* actions_out);
 
 /* Options: "use_cuda_graph" (default 1; replay of the step's kernels as a CUDA graph), "debug_taps" (default 0; implies eager launches),
+ * "chunked_splitk" (default 1: split-K GEMMs of 128..288 tokens also split the tokens across CTAs, chosen by a measured cost model),
  * "use_pdl" (default 1: programmatic dependent launch between the step's kernels; process-wide),
  * "num_inference_steps". */
 int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t value);
-/* Synchronises the stream and reports device-side input validation errors. */
+/* Synchronises the stream and reports (and clears) the device-side sticky error words: input validation (token id outside the
+ * embedding table, too many image tokens) and bounded pipeline waits that expired inside a GEMM / attention kernel.  A
+ * step that tripped one of them has already written NaN actions (the step's last kernel poisons them). */
 int blurr_pi0_check(blurr_pi0_t* h, void* cuda_stream);
 
 /* Debug / parity taps: copy a named internal buffer (bf16 unless noted) to `dst_dev`.
@@ -189,7 +192,11 @@ int blurr_op_normalize_proprio(void* cuda_stream, const double* raw, const doubl
  * size cap of the GEMM kernel), "gemm_use_2cta" (-1 automatic = CTA pairs for the GeGLU GEMM above 1024 tokens, 0, 1),
  * "gemm_large_t_mode" (above 1024 tokens: -1 automatic = persistent CTA pairs for every bf16 epilogue (GeGLU, GELU,
  * plain store), persistent single CTAs for fp32 partial / residual epilogues; 0 never persistent; 1 single-CTA
- * persistent for every epilogue; 2 and 3 = same as automatic), "attn_tc" (-1 automatic = tcgen05 attention from 8 episodes per GPU, 0 never, 1 always),
+ * persistent for every epilogue; 2 and 3 = same as automatic), "attn_tc" (-1 automatic = tcgen05 prefill / SigLIP attention whenever the shape allows, 0 never (mma.sync tile kernel), 1 = -1),
+ * "attn_tc_fewq" (1: the experts' few-query attention on the tcgen05 kernel too; default 0, measured slower at batch 1),
+ * "gemm_pair_small" (257..288 tokens: 0 one CTA per weight tile, 1 persistent CTA pairs for GeGLU only, 2 (default) for every epilogue),
+ * "gemm_cta_trace" / "attn_cta_trace" (device pointer to [n_cta][8] u64, 0 = off: per-CTA %globaltimer timeline), "op_gemm_bn" (token chunk
+ * width used by blurr_op_gemm*, 0 = automatic),
  * "gemm_pair_band" (persistent pairs: weight tile pairs per raster band, 0 = automatic), "gemm_pair_policy" (L2
  * hints above 1024 tokens: -1 automatic = 1; 0 weights evict_first / tokens evict_last; 1 both evict_normal; 2 weights
  * evict_last / tokens evict_first),
