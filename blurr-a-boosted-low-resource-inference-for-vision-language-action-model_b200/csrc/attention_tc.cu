@@ -26,7 +26,8 @@ namespace blurr {
 static __device__ int g_attn_timeout_flag = 0;
 
 // Per-CTA timeline for tuning (global option "attn_cta_trace" = device pointer to [n_cta][8] u64, 0 = off): %globaltimer at
-// 0 entry, 1 past the dependency wait, 2 Q staged, 3 S complete, 4 probabilities written, 5 V landed, 6 O complete, 7 stored.
+// 0 entry, 1 softmax pass 2 (sum of exp) done, 2 Q staged, 3 S complete, 4 probabilities written, 5 softmax pass 1 (rounding
+// chain, row max) done, 6 O complete, 7 stored.
 static __device__ unsigned long long* g_attn_cta_trace = nullptr;
 __device__ __forceinline__ void attn_stamp(int slot) {
     unsigned long long* t = g_attn_cta_trace;
@@ -132,7 +133,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     pdl_wait();
     pdl_trigger();
     trace_stamp(a.trace, 1);
-    attn_stamp(1);
 
     // ---- K tiles by TMA: k-block kb, chunk c -> [144 keys][64 dims] ----
     const int key_row0 = b * a.n_slots;
@@ -261,6 +261,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     }
     stat[half * 128 + row] = m;
     __syncthreads();
+    attn_stamp(5);      // pass 1 (rounding chain, logits, row max) done
     m = stat[row];
 #pragma unroll
     for (int pt = 1; pt < kTcParts; ++pt) m = fmaxf(m, stat[pt * 128 + row]);
@@ -271,6 +272,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant
     for (int c = 0; warp_live && c < kCols / 8; ++c) sum += chunk_exp_sum(*p_chunk(p_s, row, (col0 >> 3) + c), m);
     stat[half * 128 + row] = sum;
     __syncthreads();
+    attn_stamp(1);      // pass 2 (sum of exp) done
     sum = stat[row];
 #pragma unroll
     for (int pt = 1; pt < kTcParts; ++pt) sum += stat[pt * 128 + row];
