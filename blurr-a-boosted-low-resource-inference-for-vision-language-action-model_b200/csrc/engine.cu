@@ -126,6 +126,7 @@ struct TapBuf { void* ptr; size_t bytes; };
 
 static constexpr int kNumPos = 1024;     // RoPE table rows (position ids 0..1023)
 static constexpr int kNumSMs = 148;
+static constexpr int kTailOps = 2048;        // fused tails per step before the slabs are reused (10 flow steps x 18 layers x 3 ops < 2048)
 
 struct blurr_pi0 {
     blurr_pi0_config cfg;
@@ -167,6 +168,10 @@ struct blurr_pi0 {
     cudaEvent_t ev_fork = nullptr, ev_done_p = nullptr, ev_done_a = nullptr;
     std::vector<cudaEvent_t> ev_v, ev_p;
     int* d_err = nullptr;
+    int* tail_slabs = nullptr; int tail_next = 0;       // arrival counters + scratch of the fused GEMM tails (GemmTail::slab), one per op
+    // off by default: measured slower than the PDL-chained two-kernel path (action stage 1.04 vs 0.87 ms at one episode):
+    // fence + arrival atomic + a second L2 round trip cost more than a pre-launched consumer kernel
+    bool fuse_tails = false; int fuse_tail_max_tokens = 8;
     const int *flag_gemm = nullptr, *flag_attn = nullptr;    // sticky pipeline time-out words of the kernels (NaN-poison the actions)
     // options / bookkeeping
     bool use_graph = true, debug = false;
@@ -425,9 +430,10 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
         ok &= ev_ok;
     }
     h->d_err = static_cast<int*>(dalloc(h, 16));
+    h->tail_slabs = static_cast<int*>(dalloc(h, static_cast<size_t>(kTailOps) * kTailSlabWords * sizeof(int)));
     h->flag_gemm = gemm_timeout_flag_ptr();
     h->flag_attn = attn_timeout_flag_ptr();
-    ok &= h->ws && h->ws2 && h->ws3 && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
+    ok &= h->ws && h->ws2 && h->ws3 && h->d_err && h->tail_slabs && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
     if (!ok) {
         blurr_pi0_destroy(h);
         return fail(BLURR_ERR_CUDA, "blurr_pi0_create: device allocation failed");
@@ -733,7 +739,8 @@ struct Run {
     void wait(cudaEvent_t ev) {
         if (multi && rc == 0 && cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaStreamWaitEvent failed");
     }
-    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, int alt = 0) {
+    static constexpr int kFused = -2;     // gemm() return value: the consumer ran inside the GEMM kernel (GemmTail)
+    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, int alt = 0, GemmTail* tail = nullptr) {
         if (rc) return 1;
         float* ws = wsp(alt);
         const size_t ws_floats = alt ? h->ws2_floats : h->ws_floats;
@@ -759,21 +766,34 @@ struct Run {
             rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
             return 1;
         }
+        bool fused = false;
+        if (tail != nullptr && h->fuse_tails && T <= h->fuse_tail_max_tokens && !lin_mode) {
+            c.tail = tail;
+            if (gemm_tail_supported(c)) {
+                const GemmPlan pl = gemm_make_plan(T, L.Nw, L.K, c.splitk, EPI_PARTIAL, 0);
+                tail->slab = h->tail_slabs + static_cast<size_t>(h->tail_next++ % kTailOps) * kTailSlabWords;
+                if (tail->kind == TAIL_CONSUMER) { tail->consumer.partial = ws; tail->consumer.splitk = pl.splitk; tail->consumer.trace = nullptr; }
+                else { tail->rope.partial = ws; tail->rope.splitk = pl.splitk; tail->rope.trace = nullptr; }
+                fused = true;
+            } else {
+                c.tail = nullptr;
+            }
+        }
         std::string err;
         char nm[96];
-        snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", c.epi, T, L.Nw, L.K, c.splitk);
+        snprintf(nm, sizeof nm, "gemm%s[epi%d T%d N%d K%d S%d]", fused ? "+tail" : "", c.epi, T, L.Nw, L.K, c.splitk);
         c.trace = trace_slot(nm);
         prof_begin(nm);
         const int s = gemm_launch(st, c, &err);
         prof_end();
         ++h->launches;
         if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 1; }
+        if (fused) return kFused;
         return lin_mode ? 0 : s;
     }
-    void consumer(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
-                  float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
-                  bf16* xn_out, bool use_partial = true, int alt = 0) {
-        if (rc) return;
+    ConsumerArgs consumer_args(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
+                               float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
+                               bf16* xn_out, bool use_partial = true, int alt = 0) const {
         ConsumerArgs a{};
         a.partial = use_partial ? wsp(alt) : nullptr; a.splitk = splitk; a.T = T; a.N = N; a.ldp = ldp;
         a.bias = bias; a.add_mode = add_mode; a.res = res; a.ldr = ldr;
@@ -784,7 +804,30 @@ struct Run {
         a.pos = h->pos_emb; a.pos_rows = h->cfg.num_image_tokens; a.out_scale = out_scale;
         a.x_out = x_out; a.ldx = N; a.norm_mode = norm_mode; a.norm_w = nw; a.norm_b = nb; a.eps = eps;
         a.xn_out = xn_out; a.ldn = N;
+        return a;
+    }
+    void consumer(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
+                  float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
+                  bf16* xn_out, bool use_partial = true, int alt = 0) {
+        if (rc) return;
+        ConsumerArgs a = consumer_args(splitk, T, N, ldp, bias, add_mode, res, ldr, out_scale, x_out, norm_mode, nw, nb, eps,
+                                       xn_out, use_partial, alt);
         { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
+    }
+    // Split-K GEMM + its consumer.  Few-token GEMMs (the experts: 1 or 4 tokens per episode) carry the consumer as a
+    // fused tail of the GEMM kernel (one launch instead of two); everything else launches the consumer kernel.
+    void gemm_consumer(const Lin& L, const bf16* X, int T, int alt, int N, const bf16* bias, int add_mode, const bf16* res,
+                       int ldr, float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
+                       bf16* xn_out, bool gemm_bias = false) {
+        if (rc) return;
+        GemmTail tail{};
+        tail.kind = TAIL_CONSUMER;
+        tail.consumer = consumer_args(1, T, N, L.Nw, bias, add_mode, res, ldr, out_scale, x_out, norm_mode, nw, nb, eps, xn_out,
+                                      true, alt);
+        const bool can_fuse = N == L.Nw;
+        const int s = gemm(L, X, T, EPI_PARTIAL, nullptr, 0, gemm_bias, alt, can_fuse ? &tail : nullptr);
+        if (s == kFused) return;
+        consumer(s, T, N, L.Nw, bias, add_mode, res, ldr, out_scale, x_out, norm_mode, nw, nb, eps, xn_out, true, alt);
     }
     void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo, int alt) {
         if (rc) return;
@@ -884,25 +927,21 @@ struct StreamBufs {
 
 // One mixture's share of a joint layer (joint_model.py:24-129), split into its dependent phases so
 // that the same phase of two independent streams (VLM and proprio) can share a grid barrier.
-static int phase_qkv_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt, Lin* used) {
-    blurr_pi0* h = R.h;
+static Lin qkv_lin(blurr_pi0* h, int m, int l, bool kv_only) {
     const auto& c = h->cfg;
     MixLayer& L = h->mix[m].layers[l];
-    const int QW = c.num_heads * c.head_dim;
     Lin qkv = L.qkv;
     if (kv_only) {                      // last layer of vlm/proprio: only K and V are needed
+        const int QW = c.num_heads * c.head_dim;
         qkv.w = L.qkv.w + static_cast<size_t>(QW) * L.qkv.K;    // tile-packed: whole 128-row tiles are contiguous
         qkv.Nw = L.qkv.Nw - QW;
     }
-    *used = qkv;
-    return R.gemm(qkv, sb.xn, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
+    return qkv;
 }
-
-static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int s, const Lin& qkv, int alt) {
+static RopeKvArgs rope_args(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int s, const Lin& qkv, int alt) {
     blurr_pi0* h = R.h;
     const auto& c = h->cfg;
     MixtureW& M = h->mix[m];
-    if (R.rc) return;
     RopeKvArgs a{};
     a.partial = R.wsp(alt); a.splitk = s; a.T = B * sb.tokens_per_sample; a.ldp = qkv.Nw;
     if (s == 0) { a.lin = reinterpret_cast<const bf16*>(R.wsp(alt)); a.ldl = qkv.Nw; a.splitk = 1; }
@@ -913,7 +952,26 @@ static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool k
     const size_t layer_off = static_cast<size_t>(l) * h->max_batch * h->n_total * c.head_dim;
     a.k_cache = h->kcache + layer_off; a.v_cache = h->vcache + layer_off;
     a.n_slots = h->n_total; a.slot_base = sb.slot_base;
-    R.rope(a);
+    return a;
+}
+static int phase_qkv_gemm(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt, Lin* used) {
+    *used = qkv_lin(R.h, m, l, kv_only);
+    return R.gemm(*used, sb.xn, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
+}
+static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int s, const Lin& qkv, int alt) {
+    if (R.rc) return;
+    R.rope(rope_args(R, m, l, sb, B, kv_only, s, qkv, alt));
+}
+// q/k/v projection + RoPE + cache write; for the few-token expert streams RoPE runs as the GEMM kernel's fused tail
+static void phase_qkv_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt) {
+    if (R.rc) return;
+    const Lin qkv = qkv_lin(R.h, m, l, kv_only);
+    GemmTail tail{};
+    tail.kind = TAIL_ROPE;
+    tail.rope = rope_args(R, m, l, sb, B, kv_only, 1, qkv, alt);
+    const int s = R.gemm(qkv, sb.xn, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt, &tail);
+    if (s == Run::kFused || R.rc) return;
+    R.rope(rope_args(R, m, l, sb, B, kv_only, s, qkv, alt));
 }
 
 static void phase_attn(Run& R, int l, const StreamBufs& sb, int B, int n_keys, const bf16* mask, long long mbs,
@@ -958,18 +1016,20 @@ static void phase_post_mlp(Run& R, int m, int l, const StreamBufs& sb, int B, in
 // Layer l of one expert stream (mixture m, workspace `alt`), split at the point where it needs the
 // K/V of the streams before it.
 static void expert_layer_head(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt) {
-    Lin q;
-    const int s = phase_qkv_gemm(R, m, l, sb, B, kv_only, alt, &q);
-    phase_rope(R, m, l, sb, B, kv_only, s, q, alt);
+    phase_qkv_rope(R, m, l, sb, B, kv_only, alt);
 }
 static void expert_layer_tail(Run& R, int m, int l, const StreamBufs& sb, int B, int n_keys, const bf16* mask,
                               long long mbs, long long mrs, const bf16* next_norm, int alt) {
+    MixtureW& M = R.h->mix[m];
+    MixLayer& L = M.layers[l];
+    const int T = B * sb.tokens_per_sample;
+    const float eps = R.h->cfg.rms_norm_eps;
     phase_attn(R, l, sb, B, n_keys, mask, mbs, mrs, true);
-    const int o = phase_o_gemm(R, m, l, sb, B, alt);
-    phase_post_attn(R, m, l, sb, B, o, alt);
+    R.gemm_consumer(L.o, sb.ao, T, alt, M.hidden, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x, NORM_RMS_GEMMA,
+                    L.post_ln, nullptr, eps, sb.xn);
     phase_gate_up(R, m, l, sb, B);
-    const int d = phase_down(R, m, l, sb, B, alt);
-    phase_post_mlp(R, m, l, sb, B, d, next_norm, alt);
+    R.gemm_consumer(L.down, sb.hmid, T, alt, M.hidden, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
+                    next_norm ? NORM_RMS_GEMMA : NORM_NONE, next_norm, nullptr, eps, next_norm ? sb.xn : nullptr);
 }
 
 static void action_encode(Run& R, int B, int s) {
@@ -984,9 +1044,8 @@ static void action_encode(Run& R, int B, int s) {
     R.small_k(a1);
     int k = R.gemm(h->ae2, h->X2, Ta, EPI_PARTIAL, nullptr, 0, true, 2);
     R.bias_act(k, Ta, c.expert_hidden, h->ae2.Nw, h->ae2.bias, ACT_SILU, 1.0f, h->A1, c.expert_hidden, 2);
-    k = R.gemm(h->ae3, h->A1, Ta, EPI_PARTIAL, nullptr, 0, true, 2);
-    R.consumer(k, Ta, c.expert_hidden, h->ae3.Nw, h->ae3.bias, ADD_NONE, nullptr, 0, expert_norm, h->Ea,
-               NORM_RMS_GEMMA, h->mix[2].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Ean, true, 2);
+    R.gemm_consumer(h->ae3, h->A1, Ta, 2, c.expert_hidden, h->ae3.bias, ADD_NONE, nullptr, 0, expert_norm, h->Ea,
+                    NORM_RMS_GEMMA, h->mix[2].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Ean, true);
     R.tap("flow" + std::to_string(s) + ".action_embeds", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
 }
 
@@ -1246,6 +1305,15 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     else if (n == "profile") { h->profile = value != 0; if (value == 2) h->prof.clear(); }
     else if (n == "chunked_splitk") {
         h->chunked_splitk = value != 0;
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
+    else if (n == "fuse_tails") {              // 0: never; else the largest token count whose consumer rides in the GEMM kernel
+        h->fuse_tails = value != 0;
+        h->fuse_tail_max_tokens = value > 0 ? static_cast<int>(value) : 0;
         for (auto& kv : h->graphs) {
             cudaGraphExecDestroy(kv.second.exec);
             cudaGraphDestroy(kv.second.graph);

@@ -9,6 +9,8 @@
 
 namespace blurr {
 
+struct GemmTail;      // kernels.h
+
 enum GemmEpilogue {
     EPI_STORE = 0,    // out[t][n] = bf16(acc + bias[n])
     EPI_GELU = 1,     // out[t][n] = bf16(gelu_tanh(bf16(acc + bias[n])))
@@ -35,6 +37,7 @@ struct GemmCall {
     unsigned long long* trace;   // in-graph timeline slot (launch.cuh) or nullptr
     int w_static;             // 1: W was written before any kernel still in flight (engine weights), so the
                               // kernel may fetch it ahead of the programmatic-dependency wait
+    const GemmTail* tail;     // optional consumer fused behind an EPI_PARTIAL GEMM of <= 32 tokens (gemm_tail_supported)
 };
 
 // Device-side parameters of one GEMM (filled from a GemmPlan by gemm_launch / gemm_make_step_op).
@@ -71,6 +74,8 @@ struct GemmPlan {
 };
 
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override);
+// true when gemm_launch would run this call on the persistent few-token kernel, which can carry a fused tail
+bool gemm_tail_supported(const GemmCall& call);
 
 // Returns the number of split-K slices actually used (>= 1), or -1 with *err set.
 int gemm_launch(cudaStream_t stream, const GemmCall& call, std::string* err);
