@@ -168,6 +168,11 @@ struct blurr_pi0 {
     cudaEvent_t ev_fork = nullptr, ev_done_p = nullptr, ev_done_a = nullptr;
     std::vector<cudaEvent_t> ev_v, ev_p;
     int* d_err = nullptr;
+    // int8 fake-quant mode of the reference (QuantizedLinear.forward, int8_linear.py:72-83): the input of every quantised
+    // Linear is clamped to +-act_clip first.  Bits of act_clip_mask: 1 = proprio mixture (tied weights), 2 = action mixture,
+    // 3 = action encoder (the reference's swap skips the bare-Linear decoder and proprio encoder).  0 = off (every shipped config).
+    float act_clip = 0.f; int act_clip_mask = 0;
+    bf16* clip_action = nullptr;             // clamped copy of the action encoder's input (the flow state itself stays unclamped)
     int* tail_slabs = nullptr; int tail_next = 0;       // arrival counters + scratch of the fused GEMM tails (GemmTail::slab), one per op
     // off by default: measured slower than the PDL-chained two-kernel path (action stage 1.04 vs 0.87 ms at one episode):
     // fence + arrival atomic + a second L2 round trip cost more than a pre-launched consumer kernel
@@ -380,6 +385,7 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
     h->d_ppos = static_cast<int64_t*>(dalloc(h, Tp * 8));
     h->d_apos = static_cast<int64_t*>(dalloc(h, Ta * 8));
     h->d_proprios = bufb(Tp * c.proprio_dim);
+    h->clip_action = bufb(static_cast<size_t>(h->max_batch) * c.num_action_tokens * c.action_dim);
     h->d_action = bufb(Ta * c.action_dim);
     h->d_out = bufb(Ta * c.action_dim);
     h->d_mask_itp = bufb(static_cast<size_t>(B) * h->n_itp * ((h->n_itp + 7) / 8 * 8));
@@ -862,6 +868,12 @@ struct Run {
         { prof_begin("action_tail"); launched(launch_action_tail(st, a.xn, a.T, a.hidden, a.W, a.bias, a.action_dim, a.dt, a.action, a.vel_tap),
                       "action_tail"); prof_end(); }
     }
+    bool clips(int bit) const { return h->act_clip > 0.f && ((h->act_clip_mask >> bit) & 1); }
+    // torch.clamp(x, -clip, clip) in front of a quantised Linear (int8_linear.py:73-74); dst == src clamps in place
+    void clip_act(int bit, const bf16* src, bf16* dst, size_t n) {
+        if (rc || !clips(bit)) return;
+        { prof_begin("activation_clip"); launched(launch_clamp_copy(st, src, dst, static_cast<int>(n), 1, h->act_clip, nullptr, nullptr, nullptr), "activation_clip"); prof_end(); }
+    }
     void clamp(const ClampArgs& a) {
         if (rc) return;
         { prof_begin("clamp"); launched(launch_clamp_copy(st, a.src, a.dst, a.n, a.do_clamp, a.clip, h->d_err, h->flag_gemm, h->flag_attn), "clamp"); prof_end(); }
@@ -1016,6 +1028,7 @@ static void phase_post_mlp(Run& R, int m, int l, const StreamBufs& sb, int B, in
 // Layer l of one expert stream (mixture m, workspace `alt`), split at the point where it needs the
 // K/V of the streams before it.
 static void expert_layer_head(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt) {
+    R.clip_act(m, sb.xn, sb.xn, static_cast<size_t>(B) * sb.tokens_per_sample * R.h->mix[m].hidden);     // q/k/v_proj input
     phase_qkv_rope(R, m, l, sb, B, kv_only, alt);
 }
 static void expert_layer_tail(Run& R, int m, int l, const StreamBufs& sb, int B, int n_keys, const bf16* mask,
@@ -1025,9 +1038,12 @@ static void expert_layer_tail(Run& R, int m, int l, const StreamBufs& sb, int B,
     const int T = B * sb.tokens_per_sample;
     const float eps = R.h->cfg.rms_norm_eps;
     phase_attn(R, l, sb, B, n_keys, mask, mbs, mrs, true);
+    R.clip_act(m, sb.ao, sb.ao, static_cast<size_t>(T) * L.o.K);                  // o_proj input
     R.gemm_consumer(L.o, sb.ao, T, alt, M.hidden, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x, NORM_RMS_GEMMA,
                     L.post_ln, nullptr, eps, sb.xn);
+    R.clip_act(m, sb.xn, sb.xn, static_cast<size_t>(T) * M.hidden);              // gate/up_proj input
     phase_gate_up(R, m, l, sb, B);
+    R.clip_act(m, sb.hmid, sb.hmid, static_cast<size_t>(T) * M.inter);           // down_proj input
     R.gemm_consumer(L.down, sb.hmid, T, alt, M.hidden, nullptr, ADD_RESIDUAL, sb.x, M.hidden, 1.0f, sb.x,
                     next_norm ? NORM_RMS_GEMMA : NORM_NONE, next_norm, nullptr, eps, next_norm ? sb.xn : nullptr);
 }
@@ -1038,12 +1054,16 @@ static void action_encode(Run& R, int B, int s) {
     const auto& c = h->cfg;
     const int Ta = B * c.num_action_tokens;
     const float expert_norm = __bfloat162float(__float2bfloat16(static_cast<float>(std::sqrt(static_cast<double>(c.expert_hidden)))));
-    SmallKArgs a1{h->d_action, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f, h->X2,
+    const bf16* act_in = h->d_action;
+    if (R.clips(3)) { R.clip_act(3, h->d_action, h->clip_action, static_cast<size_t>(Ta) * c.action_dim); act_in = h->clip_action; }
+    SmallKArgs a1{act_in, Ta, c.action_dim, h->ae1_w, h->ae1_b, c.expert_hidden, 1.0f, h->X2,
                   2 * c.expert_hidden, c.expert_hidden, h->time_table + static_cast<size_t>(s) * c.expert_hidden,
                   c.expert_hidden};
     R.small_k(a1);
+    R.clip_act(3, h->X2, h->X2, static_cast<size_t>(Ta) * 2 * c.expert_hidden);
     int k = R.gemm(h->ae2, h->X2, Ta, EPI_PARTIAL, nullptr, 0, true, 2);
     R.bias_act(k, Ta, c.expert_hidden, h->ae2.Nw, h->ae2.bias, ACT_SILU, 1.0f, h->A1, c.expert_hidden, 2);
+    R.clip_act(3, h->A1, h->A1, static_cast<size_t>(Ta) * c.expert_hidden);
     R.gemm_consumer(h->ae3, h->A1, Ta, 2, c.expert_hidden, h->ae3.bias, ADD_NONE, nullptr, 0, expert_norm, h->Ea,
                     NORM_RMS_GEMMA, h->mix[2].layers[0].in_ln, nullptr, c.rms_norm_eps, h->Ean, true);
     R.tap("flow" + std::to_string(s) + ".action_embeds", h->Ea, static_cast<size_t>(Ta) * c.expert_hidden * 2);
@@ -1305,6 +1325,16 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
     else if (n == "profile") { h->profile = value != 0; if (value == 2) h->prof.clear(); }
     else if (n == "chunked_splitk") {
         h->chunked_splitk = value != 0;
+        for (auto& kv : h->graphs) {
+            cudaGraphExecDestroy(kv.second.exec);
+            cudaGraphDestroy(kv.second.graph);
+        }
+        h->graphs.clear();
+    }
+    else if (n == "activation_clip_bits" || n == "activation_clip_mask") {
+        // the reference's int8 fake-quant mode: value = the float32 bit pattern of the clip (0 = off) / the module mask
+        if (n == "activation_clip_mask") h->act_clip_mask = static_cast<int>(value);
+        else { const uint32_t bits = static_cast<uint32_t>(value); float f; memcpy(&f, &bits, 4); h->act_clip = f; }
         for (auto& kv : h->graphs) {
             cudaGraphExecDestroy(kv.second.exec);
             cudaGraphDestroy(kv.second.graph);

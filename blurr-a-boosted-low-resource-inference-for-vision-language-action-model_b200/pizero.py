@@ -297,13 +297,57 @@ class PiZero(nn.Module):
         self._bump()
 
     def enable_action_quantization(self):
-        """No-op when `action_quantization.mode` is null, as with every shipped config
-        (pizero.py:274-280); the int8 fake-quant modes are not built."""
+        """pizero.py:274-321.  No-op when `action_quantization.mode` is null (every shipped config).  Modes "int8" /
+        "int8_cached" are the reference's *fake* quantisation (int8_linear.py:20-100): each Linear of the action
+        mixture and the action encoder (the calls on the bare-Linear `action_decoder` / `proprio_encoder` swap nothing,
+        `quantize_module_int8` only replaces children, :94-100) gets per-output-channel symmetric int8 weights
+        that `forward` de-quantises back to the activation dtype before a plain `F.linear`, after clamping its input
+        to +-activation_clip.  Here the de-quantised weights replace the bf16 ones at upload time (same bits as the
+        reference's per-call de-quantisation) and the engine clamps the inputs of those GEMMs (option
+        "activation_clip_bits").  "bnb_int8" needs bitsandbytes, which neither this image nor the reference's
+        requirements carry."""
+        if self._action_quant_enabled:
+            return
         cfg = self.action_quant_config or {}
         mode = str(_cfg_get(cfg, "mode", "") or "").lower()
         if mode in {"", "none"}:
             return
-        raise NotImplementedError(f"action_quantization.mode={mode!r} is not supported by the B200 path")
+        if mode == "bnb_int8":
+            raise NotImplementedError("action_quantization.mode='bnb_int8' needs bitsandbytes (absent)")
+        if mode not in {"int8", "int8_cached"}:
+            return                                  # the reference ignores unknown modes too (:319-320)
+        clip = _cfg_get(cfg, "activation_clip", None)
+        cache_fp = bool(_cfg_get(cfg, "cache_fp_weight", False))
+        fp_dtype = getattr(torch, str(_cfg_get(cfg, "fp_dtype", "bfloat16")), torch.bfloat16)
+        mixtures = self.joint_model.mixtures
+        roots = [mixtures["action"], self.action_encoder, self.action_decoder, self.proprio_encoder]
+        seen = set()
+        with torch.no_grad():
+            for root in roots:
+                for m in root.modules():
+                    if m is root or not isinstance(m, nn.Linear) or id(m) in seen:     # children only, like the reference
+                        continue
+                    seen.add(id(m))
+                    w32 = m.weight.detach().to(torch.float32)
+                    scale = w32.abs().amax(dim=1, keepdim=True).clamp(min=1e-6) / 127.0
+                    q = torch.clamp((w32 / scale).round(), -128, 127).to(torch.int8)
+                    deq = q.to(torch.float32) * scale
+                    if cache_fp:
+                        deq = deq.to(fp_dtype)
+                    m.weight.data = deq.to(m.weight.dtype)
+        object.__setattr__(self, "_activation_clip", float(clip) if clip is not None else None)
+        self._action_quant_enabled = True
+        self._bump()
+
+    def _activation_clip_options(self):
+        """(float32 bits of the bf16-rounded clip, module mask) for the engine; (0, 0) when off."""
+        clip = getattr(self, "_activation_clip", None)
+        if not self._action_quant_enabled or clip is None:
+            return 0, 0
+        c = torch.tensor(clip, dtype=torch.bfloat16).float()        # torch.clamp casts the scalar to the tensor dtype
+        bits = int(c.view(torch.int32).item()) & 0xFFFFFFFF
+        tied = self.joint_model.mixtures["proprio"] is self.joint_model.mixtures["action"]
+        return bits, (1 << 2) | (1 << 3) | ((1 << 1) if tied else 0)
 
     def build_text_cache(self):
         raise NotImplementedError("text generation is outside the control-step path")
@@ -494,6 +538,9 @@ class _Engine:
             raise
         self.set_option("debug_taps", int(model._debug_taps))
         self.set_option("use_cuda_graph", int(model._use_cuda_graph))
+        bits, mask = model._activation_clip_options()
+        self.set_option("activation_clip_mask", mask)
+        self.set_option("activation_clip_bits", bits)
 
     def _upload(self, model: PiZero):
         sd = model.state_dict()

@@ -8,10 +8,11 @@ Mirrors `third_party/open_pi_zero/src/agent/env_adapter/simpler.py`:
     axis-angle, gripper post-processing;
   * `BridgeSimplerAdapter.postprocess_gripper` (:181-186): binarise to -1 / +1;
   * `EDRSimplerAdapter.postprocess_gripper` (:221-252) with its sticky-gripper state (`reset`, :197-202).
-`euler2axangle` restates transforms3d 0.4 (`euler.euler2quat(axes="sxyz")` + `quaternions.quat2axangle`); that
-package is not in the reference tree nor in this image, so its parity is checked against scipy's rotation
-vectors instead (tests/test_postprocess.py) — PARITY UNPINNED for that function; the de-normalisers are
-pinned against the reference's own `BaseEnvAdapter`.
+`euler2axangle` restates the transforms3d functions the reference vendors in `src/utils/geometry.py:261-291,
+294-363,366-434` (`euler2quat(axes="sxyz")` + `quat2axangle`).  Parity is pinned: bit-exact against that file and
+against golden vectors generated from it (tests/golden/postprocess_golden.json), and the whole `postprocess` incl. the
+sticky-gripper state machine is bit-exact against the reference's `BridgeSimplerAdapter` / `EDRSimplerAdapter` objects
+(tests/test_postprocess.py).
 """
 
 from __future__ import annotations

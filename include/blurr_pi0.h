@@ -136,6 +136,9 @@ int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const b
  * "fuse_tails" (default 0 = separate kernels; N in 1..8: a split-K GEMM of at most N token rows - the experts' projections at one
  * or two episodes - carries its consumer (bias/residual/RMSNorm, or RoPE + cache write) as tails run by the last CTA to finish each
  * weight tile; bit-identical results, 37 fewer launches per flow step, measured SLOWER than the PDL-chained kernels),
+ * "activation_clip_bits" / "activation_clip_mask" (default 0 / 0: the reference's int8 fake-quant mode, int8_linear.py:72-83 - the float32
+ * bit pattern of the clamp applied to the inputs of the swapped Linears, and which modules: bit 1 proprio mixture (tied weights), bit 2
+ * action mixture, bit 3 action encoder; the de-quantised weights arrive through blurr_pi0_set_weight like any others),
  * "use_pdl" (default 1: programmatic dependent launch between the step's kernels; process-wide),
  * "num_inference_steps". */
 int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t value);

@@ -313,6 +313,32 @@ def test_fused_gemm_tails_equal_separate_kernels(batch):
     assert (b.float() - ref.float()).abs().max().item() <= 1e-2
 
 
+@pytest.mark.parametrize("mode,clip,tied", [("int8", None, False), ("int8_cached", 1.0, False), ("int8", 0.5, True)])
+def test_int8_fake_quant_mode(mode, clip, tied):
+    """`enable_action_quantization` (pizero.py:274-321): the de-quantised int8 weights are uploaded and the engine clamps
+    the inputs of the swapped Linears; checked against the oracle's restatement, which tests/test_oracle_vs_reference.py
+    pins bit-identical to the unmodified reference in these modes."""
+    cfg = shrink_config(bridge_config(2), 2, 3)
+    cfg.action_quantization = dict(mode=mode, activation_clip=clip, cache_fp_weight=(mode == "int8_cached"), fp_dtype="bfloat16")
+    model, sd, inp = _setup(cfg, 2)
+    plain = _run(model, inp)
+    if tied:
+        model.tie_action_proprio_weights()
+        sd = {k: (sd[k.replace(".proprio.", ".action.")] if ".mixtures.proprio." in k else v) for k, v in sd.items()}
+    model.enable_action_quantization()
+    assert model._action_quant_enabled
+    got = _run(model, inp)
+    sd_q = O.quantize_state_dict_int8(sd, cache_fp_weight=(mode == "int8_cached"), fp_dtype=torch.bfloat16, tied=tied)
+    with O.int8_fake_quant(clip, tied=tied):
+        ref = _oracle(sd_q, cfg, inp)
+    ref_plain = _oracle(sd, cfg, inp)
+    err = (got.float() - ref.float()).abs().max().item()
+    moved = (ref.float() - ref_plain.float()).abs().max().item()
+    print(f"{mode} clip={clip} tied={tied}: max_abs vs quantised oracle {err:.3e}; quantisation moved the actions by {moved:.3e}")
+    assert err <= 1e-2 and not torch.equal(got, plain)
+    assert moved > err or moved > 0        # the mode really changes the arithmetic and we follow it
+
+
 def test_shrunk_fractal_ten_steps():
     """Config 3: proprio_dim 8, 10 Euler steps with bf16 `t` accumulation, same injected noise."""
     cfg = shrink_config(fractal_config(10), 2, 3)

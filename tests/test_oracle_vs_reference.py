@@ -42,6 +42,30 @@ def test_infer_action_bit_identical(dtype, steps, fractal):
         assert torch.equal(t, or_taps[name]), name
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode,clip,cache_fp", [("int8", None, False), ("int8", 1.0, False), ("int8_cached", 0.75, True)])
+def test_int8_fake_quant_mode_bit_identical(dtype, mode, clip, cache_fp):
+    """`enable_action_quantization` (pizero.py:274-321, int8_linear.py) on the unmodified reference against the oracle's
+    restatement (weights de-quantised up front, inputs of the swapped Linears clamped)."""
+    cfg = shrink_config(bridge_config(2), 2, 2)
+    cfg.action_quantization = dict(mode=mode, activation_clip=clip, cache_fp_weight=cache_fp, fp_dtype="bfloat16")
+    sd = synth.synthetic_state_dict(cfg, 0, torch.float32)
+    model = _ref_model(cfg, sd, dtype)
+    sd_t = {k: v.clone() for k, v in model.state_dict().items()}
+    model.enable_action_quantization()
+    assert model._action_quant_enabled
+    inp = synth.synthetic_inputs(cfg, 2, dtype=dtype, vary_text=True)
+    with torch.inference_mode():
+        with ref_harness.patched_randn(inp["noise"]):
+            a_ref = model(**{k: (v.clone() if k == "pixel_values" else v) for k, v in synth.call_args(inp).items()})
+        sd_q = O.quantize_state_dict_int8(sd_t, cache_fp_weight=cache_fp, fp_dtype=torch.bfloat16)
+        with O.int8_fake_quant(clip):
+            a_or = O.infer_action(sd_q, cfg, **synth.call_args(inp), noise=inp["noise"])
+        a_plain = O.infer_action(sd_t, cfg, **synth.call_args(inp), noise=inp["noise"])
+    assert torch.equal(a_ref, a_or)
+    assert not torch.equal(a_or, a_plain)          # the mode really changes the arithmetic
+
+
 def test_infer_action_naive_bit_identical_and_self_consistent():
     cfg = shrink_config(bridge_config(2), 2, 2)
     sd = synth.synthetic_state_dict(cfg, 0, torch.float32)

@@ -1,7 +1,8 @@
 """Action post-processing, CPU only: de-normalisers against the reference's own
-BaseEnvAdapter (when /root/reference is mounted) and fixed numbers; euler -> axis-angle against scipy's
-rotation vectors (transforms3d is not available: parity unpinned for that function); gripper logic against
-hand-written expectations of simpler.py:181-186,221-252."""
+BaseEnvAdapter (when /root/reference is mounted) and fixed numbers; euler -> axis-angle BIT-EXACT against the
+reference's vendored transforms3d functions (src/utils/geometry.py:261-291) - directly when the reference is mounted,
+and through tests/golden/postprocess_golden.json (generated from it by make_postprocess_golden.py) everywhere - plus
+scipy's rotation vectors as an independent check; gripper logic against simpler.py:181-186,221-252."""
 
 import os
 import sys
@@ -46,6 +47,67 @@ def test_euler_to_axis_angle_matches_scipy_rotation_vectors():
         assert np.allclose(Rotation.from_rotvec(got).as_matrix(), Rotation.from_rotvec(ref).as_matrix(), atol=2e-8)
         assert abs(np.linalg.norm(ax) - 1.0) < 1e-12 and 0.0 <= ang <= 2 * np.pi
     assert PP.euler2axangle(0.0, 0.0, 0.0)[1] == 0.0
+
+
+def test_euler_to_axis_angle_bit_exact_with_reference_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "postprocess_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 100
+    for c in cases:
+        rpy = [float.fromhex(v) for v in c["rpy"]]
+        ax, ang = PP.euler2axangle(*rpy)
+        want_ang = float.fromhex(c["angle"])
+        assert [float(v) for v in ax] == [float.fromhex(v) for v in c["axis"]], (rpy, ax)
+        assert ang == want_ang or (np.isnan(ang) and np.isnan(want_ang)), (rpy, ang)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+def test_euler_to_axis_angle_bit_exact_with_reference_geometry():
+    sys.path.insert(0, REF)
+    from src.utils.geometry import euler2axangle as ref_euler2axangle
+    rng = np.random.default_rng(7)
+    for rpy in np.concatenate([rng.uniform(-3.2, 3.2, (500, 3)), rng.uniform(-0.1, 0.1, (200, 3)), np.zeros((1, 3))]):
+        ax, ang = PP.euler2axangle(*rpy)
+        rax, rang = ref_euler2axangle(*rpy)
+        assert np.array_equal(ax, rax) and ang == rang, rpy
+
+
+def _reference_adapters():
+    """The reference's adapter classes, imported unmodified; `simpler_env` (absent here, only used by the
+    observation side) is stubbed, and the constructors (tokenizer download) are bypassed."""
+    import types
+    sys.path.insert(0, REF)
+    if "simpler_env" not in sys.modules:
+        pkg = types.ModuleType("simpler_env")
+        for name in ("simpler_env.utils", "simpler_env.utils.env", "simpler_env.utils.env.observation_utils"):
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["simpler_env"] = pkg
+        sys.modules["simpler_env.utils.env.observation_utils"].get_image_from_maniskill2_obs_dict = lambda *a, **k: None
+    from src.agent.env_adapter.simpler import BridgeSimplerAdapter, EDRSimplerAdapter
+    return BridgeSimplerAdapter, EDRSimplerAdapter
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+@pytest.mark.parametrize("kind,norm", [("bridge", "bound"), ("fractal", "bound"), ("fractal", "gaussian")])
+def test_postprocess_matches_reference_adapters(kind, norm):
+    """Whole `postprocess` (simpler.py:100-141) incl. the sticky gripper state machine over 40 control steps of
+    4-action chunks: bit-exact with the reference's adapter objects."""
+    Bridge, EDR = _reference_adapters()
+    cls = Bridge if kind == "bridge" else EDR
+    ref = cls.__new__(cls)
+    ref.action_normalization_type = norm
+    ref.dataset_statistics = {"action": STATS}
+    if kind == "fractal":
+        ref.sticky_gripper_num_repeat = 15
+        ref.reset()
+    ours = PP.ActionPostprocessor(STATS, kind, action_normalization_type=norm)
+    rng = np.random.default_rng(3)
+    for step in range(40):
+        chunk = rng.uniform(-1.0, 1.0, (4, 7)).astype(np.float32)
+        chunk[:, -1] = rng.uniform(0.0, 1.0, 4) if step % 3 else rng.choice([0.0, 1.0], 4)
+        a, b = ours.postprocess(chunk), ref.postprocess(chunk)
+        assert a.dtype == b.dtype and np.array_equal(a, b), (kind, norm, step)
 
 
 def test_bridge_and_fractal_gripper_rules():
