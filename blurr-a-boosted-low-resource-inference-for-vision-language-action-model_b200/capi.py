@@ -45,6 +45,19 @@ class Pi0ConfigC(C.Structure):
     ]
 
 
+class LlmConfigC(C.Structure):
+    """`blurr_llm_config` (include/blurr_llm.h)."""
+
+    _fields_ = [
+        ("abi_version", C.c_int32), ("num_layers", C.c_int32), ("hidden", C.c_int32), ("num_heads", C.c_int32),
+        ("num_kv_heads", C.c_int32), ("head_dim", C.c_int32), ("intermediate", C.c_int32), ("vocab", C.c_int32),
+        ("max_positions", C.c_int32), ("rms_eps", C.c_float),
+    ]
+
+
+LLM_ABI_VERSION = 1
+
+
 class Pi0InputsC(C.Structure):
     """`blurr_pi0_inputs` (include/blurr_pi0.h)."""
 
@@ -107,6 +120,19 @@ _SIGNATURES = [
     ("blurr_op_joint_attention", C.c_int,
      [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
       C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    # include/blurr_llm.h
+    ("blurr_llm_create", C.c_int, [C.POINTER(LlmConfigC), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("blurr_llm_destroy", None, [C.c_void_p]),
+    ("blurr_llm_set_weight", C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    ("blurr_llm_set_rope_table", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    ("blurr_llm_finalize", C.c_int, [C.c_void_p]),
+    ("blurr_llm_embed", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("blurr_llm_generate", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("blurr_llm_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    ("blurr_llm_check", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("blurr_llm_last_launch_count", C.c_int64, [C.c_void_p]),
+    ("blurr_llm_weight_bytes_per_token", C.c_int64, [C.c_void_p]),
 ]
 DECLARED_SYMBOLS = [s[0] for s in _SIGNATURES]
 

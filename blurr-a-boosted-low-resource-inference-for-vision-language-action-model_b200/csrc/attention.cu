@@ -23,7 +23,7 @@
 
 namespace blurr {
 
-template <int HD_PAD, int BM, bool GEMMA>
+template <int HD_PAD, int BM, int GEMMA>
 __global__ void __launch_bounds__(kAttnThreads) attn_mma_kernel(const AttnMmaArgs a) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
     trace_stamp(a.trace, 0);
@@ -77,7 +77,7 @@ AttnMmaArgs make_fewq_attn_args(const JointAttnArgs& j) {
 
 static constexpr size_t kAttnSmemMax = 215 * 1024;
 
-template <int HD_PAD, int BM, bool GEMMA>
+template <int HD_PAD, int BM, int GEMMA>
 static cudaError_t launch_attn(cudaStream_t stream, const AttnMmaArgs& a, int rows, int heads, int batch) {
     const size_t smem = attn_smem_bytes<HD_PAD, BM>(a.n_keys);
     static bool attr = false;
@@ -144,6 +144,31 @@ cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs
     const int pairs = j.n_heads * j.q_per_sample;
     if (attn_tile_rows(pairs, 1, j.batch, 32) == 16) return launch_attn<256, 16, true>(stream, a, pairs, 1, j.batch);
     return launch_attn<256, 32, true>(stream, a, pairs, 1, j.batch);
+}
+
+// Llama-style multi-head attention over a token-major KV cache (llm_engine.cu): head_dim 128 (or 64), one K/V head per
+// query head, causal by position.  Prefill (many query rows) and decode (one row per sequence) share the kernel.
+cudaError_t launch_mha_attention(cudaStream_t stream, const MhaAttnArgs& m) {
+    if (m.n_keys > kAttnMaxBlocks * kBK || m.n_kv_heads != m.n_heads) return cudaErrorInvalidValue;
+    AttnMmaArgs a{};
+    const int width = m.n_heads * m.head_dim;
+    a.q = m.q; a.ldq = width; a.q_col0 = 0; a.q_per_sample = m.q_per_sample;
+    a.k = m.k_cache; a.ldk = width; a.k_col0 = 0; a.kv_per_sample = m.n_slots;
+    a.v = m.v_cache; a.ldv = width; a.v_col0 = 0;
+    a.out = m.out; a.ldo = width; a.o_col0 = 0;
+    a.hd = m.head_dim; a.head_stride_q = m.head_dim; a.head_stride_kv = m.head_dim; a.n_keys = m.n_keys;
+    a.scale = m.scale; a.mask = nullptr; a.q_row_offset = m.q_pos0; a.trace = m.trace;
+    const int bm = attn_tile_rows(m.q_per_sample, m.n_heads, m.batch, 64);
+    if (m.head_dim == 128) {
+        if (bm == 16) return launch_attn<128, 16, 2>(stream, a, m.q_per_sample, m.n_heads, m.batch);
+        if (bm == 32) return launch_attn<128, 32, 2>(stream, a, m.q_per_sample, m.n_heads, m.batch);
+        return launch_attn<128, 64, 2>(stream, a, m.q_per_sample, m.n_heads, m.batch);
+    }
+    if (m.head_dim == 64) {
+        if (bm == 16) return launch_attn<64, 16, 2>(stream, a, m.q_per_sample, m.n_heads, m.batch);
+        return launch_attn<64, 32, 2>(stream, a, m.q_per_sample, m.n_heads, m.batch);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace blurr

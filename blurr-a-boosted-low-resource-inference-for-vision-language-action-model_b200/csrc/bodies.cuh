@@ -155,17 +155,22 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
     }
     if (a.norm_mode == NORM_NONE || a.xn_out == nullptr) return;
 
-    if (a.norm_mode == NORM_RMS_GEMMA) {
+    if (a.norm_mode == NORM_RMS_GEMMA || a.norm_mode == NORM_RMS_LLAMA) {
         const float ms = block_sum<THREADS>(lsq, red) / static_cast<float>(a.N);
         const float r = rsqrtf(ms + a.eps);
+        const bool llama = a.norm_mode == NORM_RMS_LLAMA;
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             const int v = threadIdx.x + i * THREADS;
             if (v >= nvec) continue;
             const int n = v << 2;
             const float4 w = load_bf16x4(a.norm_w + n);
-            const float4 y = make_float4((x[i].x * r) * (1.0f + w.x), (x[i].y * r) * (1.0f + w.y),
-                                         (x[i].z * r) * (1.0f + w.z), (x[i].w * r) * (1.0f + w.w));
+            // Gemma: (x * rstd) * (1 + w) in fp32, one rounding.  Llama (HF LlamaRMSNorm.forward): weight * (x * rstd).to(bf16)
+            const float4 y = llama
+                ? make_float4(w.x * bf16_round(x[i].x * r), w.y * bf16_round(x[i].y * r), w.z * bf16_round(x[i].z * r),
+                              w.w * bf16_round(x[i].w * r))
+                : make_float4((x[i].x * r) * (1.0f + w.x), (x[i].y * r) * (1.0f + w.y),
+                              (x[i].z * r) * (1.0f + w.z), (x[i].w * r) * (1.0f + w.w));
             store_bf16x4(a.xn_out + static_cast<size_t>(t) * a.ldn + n, y);
         }
     } else {
@@ -418,7 +423,9 @@ __device__ __forceinline__ void load_rows_async(bf16* dst, const bf16* src, int 
 // (output).  All K blocks are requested at once (one cp.async group per 64-key block) and consumed
 // as they land; the V blocks are requested into the same buffers as soon as the logits are done, so
 // their latency hides behind the softmax.
-template <int HD_PAD, int BM, bool GEMMA>
+// MODE: 0 = logits * scale (SigLIP), 1 = Gemma chain (1/16, soft-clamp, additive mask), 2 = logits * scale with the
+// causal mask computed from positions (Llama-style MHA: query row r sits at key position q_row_offset + r)
+template <int HD_PAD, int BM, int MODE>
 __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* smem_attn, const int qt, const int h,
                                               const int b) {
     // BM query rows per tile: 16 at batch 1 (most tiles, least latency), 32/64 for batched episodes
@@ -510,7 +517,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
                 const int kcol = kb * kBK + wc * KPW + nt * 8 + (lane & 3) * 2;
                 float s0 = bf16_round(acc[nt][half * 2 + 0]);
                 float s1 = bf16_round(acc[nt][half * 2 + 1]);
-                if (GEMMA) {
+                if (MODE == 1) {
                     s0 = s0 * 0.0625f;                           // / sqrt(256): exact, stays a bf16 value
                     s1 = s1 * 0.0625f;
                     const float inv50 = 1.0f / 50.0f;            // ATen: a * (1 / b) for a scalar divisor
@@ -531,6 +538,12 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
                 } else {
                     s0 = bf16_round(s0 * a.scale);
                     s1 = bf16_round(s1 * a.scale);
+                    if (MODE == 2) {
+                        // HF adds finfo.min above the diagonal; after the fp32 softmax that is a zero, like -inf here
+                        const int qpos = a.q_row_offset + q_row0 + r;
+                        if (kcol > qpos) s0 = -INFINITY;
+                        if (kcol + 1 > qpos) s1 = -INFINITY;
+                    }
                 }
                 *reinterpret_cast<uint32_t*>(Ls + r * ldl + kcol) = pack_bf16x2(s0, s1);
             }

@@ -85,6 +85,8 @@ __device__ __forceinline__ float gelu_tanh_f32(float x) {
 }
 
 __device__ __forceinline__ float silu_f32(float x) { return x / (1.0f + expf(-x)); }
+// gate activation of the GLU epilogue: 0 = tanh GELU (Gemma GeGLU), 1 = SiLU (Llama SwiGLU)
+__device__ __forceinline__ float glu_act_f32(float x, int act) { return act == 1 ? silu_f32(x) : gelu_tanh_f32(x); }
 
 // ---------------------------------------------------------------------------
 // shared-memory address / misc

@@ -76,8 +76,8 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, uint8_t* s
                 for (int j = 0; j < 2; ++j) {
                     const float2 a0 = unpack_bf16x2(lo.u[2 * j]), a1 = unpack_bf16x2(lo.u[2 * j + 1]);
                     const float2 b0 = unpack_bf16x2(hi.u[2 * j]), b1 = unpack_bf16x2(hi.u[2 * j + 1]);
-                    o.u[j] = pack_bf16x2(bf16_round(gelu_tanh_f32(a0.x)) * a0.y, bf16_round(gelu_tanh_f32(a1.x)) * a1.y);
-                    o.u[2 + j] = pack_bf16x2(bf16_round(gelu_tanh_f32(b0.x)) * b0.y, bf16_round(gelu_tanh_f32(b1.x)) * b1.y);
+                    o.u[j] = pack_bf16x2(bf16_round(glu_act_f32(a0.x, p.glu_act)) * a0.y, bf16_round(glu_act_f32(a1.x, p.glu_act)) * a1.y);
+                    o.u[2 + j] = pack_bf16x2(bf16_round(glu_act_f32(b0.x, p.glu_act)) * b0.y, bf16_round(glu_act_f32(b1.x, p.glu_act)) * b1.y);
                 }
                 *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + bx * (kBlockM / 2) +
                                            ch * 8) = o;
@@ -419,7 +419,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                         if (EPI == EPI_GEGLU) {
                             const float v = bf16_round(__uint_as_float(r[i]));
                             const float up = __shfl_down_sync(0xffffffffu, v, 1);
-                            if ((lane & 1) == 0) stg[t * OUTW + (nl >> 1)] = f2bf(bf16_round(gelu_tanh_f32(v)) * up);
+                            if ((lane & 1) == 0) stg[t * OUTW + (nl >> 1)] = f2bf(bf16_round(glu_act_f32(v, p.glu_act)) * up);
                         } else {
                             float v = bf16_round(__uint_as_float(r[i]) + bias);
                             if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
@@ -461,7 +461,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                         const float v = bf16_round(__uint_as_float(r[i]));
                         const float up = __shfl_down_sync(0xffffffffu, v, 1);
                         if ((lane & 1) == 0 && tb + i < p.T)
-                            dst[static_cast<size_t>(i) * p.ldo] = f2bf(bf16_round(gelu_tanh_f32(v)) * up);
+                            dst[static_cast<size_t>(i) * p.ldo] = f2bf(bf16_round(glu_act_f32(v, p.glu_act)) * up);
                     }
                 } else {
                     bf16* dst = p.out + static_cast<size_t>(tb) * p.ldo + n0 + nl;
@@ -829,7 +829,7 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                         const float v0 = bf16_round(__uint_as_float(r[i])), v1 = bf16_round(__uint_as_float(r[i + 1]));
                         const float recv = __shfl_xor_sync(0xffffffffu, (lane & 1) ? v0 : v1, 1);
                         const float gate = (lane & 1) ? recv : v0, up = (lane & 1) ? v1 : recv;
-                        stg[(g * 16 + i + (lane & 1)) * OUTW + (nl >> 1)] = f2bf(bf16_round(gelu_tanh_f32(gate)) * up);
+                        stg[(g * 16 + i + (lane & 1)) * OUTW + (nl >> 1)] = f2bf(bf16_round(glu_act_f32(gate, p.glu_act)) * up);
                     }
                 } else if (EPI == EPI_GELU) {
 #pragma unroll
@@ -885,8 +885,8 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                     for (int j = 0; j < 2; ++j) {
                         const float2 a0 = unpack_bf16x2(lo.u[2 * j]), a1 = unpack_bf16x2(lo.u[2 * j + 1]);
                         const float2 b0 = unpack_bf16x2(hi.u[2 * j]), b1 = unpack_bf16x2(hi.u[2 * j + 1]);
-                        o.u[j] = pack_bf16x2(bf16_round(gelu_tanh_f32(a0.x)) * a0.y, bf16_round(gelu_tanh_f32(a1.x)) * a1.y);
-                        o.u[2 + j] = pack_bf16x2(bf16_round(gelu_tanh_f32(b0.x)) * b0.y, bf16_round(gelu_tanh_f32(b1.x)) * b1.y);
+                        o.u[j] = pack_bf16x2(bf16_round(glu_act_f32(a0.x, p.glu_act)) * a0.y, bf16_round(glu_act_f32(a1.x, p.glu_act)) * a1.y);
+                        o.u[2 + j] = pack_bf16x2(bf16_round(glu_act_f32(b0.x, p.glu_act)) * b0.y, bf16_round(glu_act_f32(b1.x, p.glu_act)) * b1.y);
                     }
                     *reinterpret_cast<bf16x8*>(p.out + static_cast<size_t>(t0 + t) * p.ldo + col_base + ch * 8) = o;
                 }

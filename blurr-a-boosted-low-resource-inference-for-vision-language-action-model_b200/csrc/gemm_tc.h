@@ -37,6 +37,7 @@ struct GemmCall {
     unsigned long long* trace;   // in-graph timeline slot (launch.cuh) or nullptr
     int w_static;             // 1: W was written before any kernel still in flight (engine weights), so the
                               // kernel may fetch it ahead of the programmatic-dependency wait
+    int glu_act;              // EPI_GEGLU: gate activation, 0 = tanh GELU (Gemma), 1 = SiLU (Llama SwiGLU)
     const GemmTail* tail;     // optional consumer fused behind an EPI_PARTIAL GEMM of <= 32 tokens (gemm_tail_supported)
 };
 
@@ -63,6 +64,7 @@ struct GemmDev {
     int acc_stride;   // TMEM columns between them
     int staging_bytes; // persistent kernel: bf16 output staging tile behind the ring (0 = direct epilogue)
     int l2_policy;    // persistent pairs: 0 = weights evict_first / tokens evict_last, 1 = both evict_normal, 2 = weights evict_last / tokens evict_first
+    int glu_act;      // EPI_GEGLU gate activation (GemmCall::glu_act)
     int band;         // persistent pairs: weight tile pairs per raster band (the band sweeps every token tile before the next one starts)
 };
 

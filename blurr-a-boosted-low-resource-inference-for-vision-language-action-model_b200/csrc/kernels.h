@@ -15,7 +15,7 @@ typedef __nv_bfloat16 bf16;
 // the following normalisation in one pass over the row.
 // ---------------------------------------------------------------------------
 enum AddMode { ADD_NONE = 0, ADD_RESIDUAL = 1, ADD_POSEMB = 2 };
-enum NormMode { NORM_NONE = 0, NORM_RMS_GEMMA = 1, NORM_LAYERNORM = 2 };
+enum NormMode { NORM_NONE = 0, NORM_RMS_GEMMA = 1, NORM_LAYERNORM = 2, NORM_RMS_LLAMA = 3 };   // Llama: bf16(w * bf16(x * rstd))
 
 struct ConsumerArgs {
     const float* partial;   // [splitk][T][ldp] fp32 or nullptr (then x = res)
@@ -176,6 +176,45 @@ struct GemmTail {
     ConsumerArgs consumer;  // TAIL_CONSUMER: add_mode NONE / RESIDUAL, norm NONE / RMS_GEMMA, N = the GEMM's width <= 31 tiles
     RopeKvArgs rope;        // TAIL_ROPE: (n_heads + 2) * 256 == the GEMM's width
 };
+
+// ---------------------------------------------------------------------------
+// Llama-shaped decoder (llm_engine.cu / llm_kernels.cu): the OpenVLA-7B-shaped path
+// ---------------------------------------------------------------------------
+struct MhaAttnArgs {
+    const bf16* q;            // [B * q_per_sample][n_heads * head_dim]
+    int q_per_sample, q_pos0; // query row r of a sequence sits at key position q_pos0 + r (causal)
+    const bf16* k_cache;      // [B][n_slots][n_kv_heads * head_dim], token-major
+    const bf16* v_cache;
+    int n_slots, n_keys;
+    int batch, n_heads, n_kv_heads, head_dim;
+    float scale;              // head_dim ** -0.5
+    bf16* out;                // [B * q_per_sample][n_heads * head_dim]
+    unsigned long long* trace;
+};
+cudaError_t launch_mha_attention(cudaStream_t stream, const MhaAttnArgs& a);
+
+// q/k/v projection output -> RoPE (HF apply_rotary_pos_emb, rotate_half over head_dim / 2) -> q buffer and KV cache
+struct RopeMhaArgs {
+    const float* partial; int splitk;   // fp32 split-K partials [splitk][T][ldp] ...
+    const bf16* lin; int ldl;           // ... or the bf16 linear output
+    int T, ldp;
+    int n_heads, n_kv_heads, head_dim;  // columns: q heads | k heads | v heads
+    int tokens_per_seq, pos0;           // token t -> sequence t / tokens_per_seq, position pos0 + t % tokens_per_seq
+    const float* cos_table; const float* sin_table; int n_pos;   // [n_pos][head_dim / 2], values already rounded to bf16
+    bf16* q_out;                        // [T][n_heads * head_dim]
+    bf16* k_cache; bf16* v_cache; int n_slots;      // [B][n_slots][n_kv_heads * head_dim]
+};
+cudaError_t launch_rope_mha(cudaStream_t stream, const RopeMhaArgs& a);
+// rows[i] = table[ids[i]] (token embedding); ids outside [0, vocab) set *err_flag and read row 0
+cudaError_t launch_embed_rows(cudaStream_t stream, const int64_t* ids, int n, const bf16* table, long long vocab, int width,
+                              bf16* out, int* err_flag);
+// dst[b] = src[(b * rows_per_seq + row) ] (the last prompt position of every sequence)
+cudaError_t launch_gather_rows(cudaStream_t stream, const bf16* src, int batch, int rows_per_seq, int row, int width, bf16* dst);
+// ids[b] = argmax over logits[b][0..vocab) (lowest index among equal maxima, like torch.argmax on CPU)
+cudaError_t launch_argmax_rows(cudaStream_t stream, const bf16* logits, int batch, int ld, int vocab, int64_t* ids,
+                               int64_t* ids_copy, int copy_stride);
+// few-token GLU from the split-K partials of a gate/up projection with interleaved rows; act: 0 tanh GELU, 1 SiLU
+cudaError_t launch_glu_partial(cudaStream_t stream, const float* partial, int splitk, int T, int Nw, int act, bf16* out, int ldo);
 
 // argument bundles of the small single-purpose kernels (engine.cu builds them once per op)
 struct EmbedMergeArgs {

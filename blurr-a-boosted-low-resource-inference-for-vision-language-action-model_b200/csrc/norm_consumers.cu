@@ -52,7 +52,9 @@ cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a) {
         if (a.N == 4 * 512) return launch_kernel(consumer_stream_kernel<2, kRowThreads>, dim3(grid), dim3(kRowThreads), 0, stream, a);
         if (a.N == 4 * 256) return launch_kernel(consumer_stream_kernel<1, kRowThreads>, dim3(grid), dim3(kRowThreads), 0, stream, a);
     }
-    if ((a.N & 3) || a.N > 2 * 4 * kRowThreads || (a.ldp & 3)) return cudaErrorInvalidValue;
+    if ((a.N & 3) || a.N > 2 * 4 * 512 || (a.ldp & 3)) return cudaErrorInvalidValue;
+    if (a.N > 2 * 4 * kRowThreads)      // Llama-2-7B's 4096 columns: two 4-column groups per thread on 512 threads
+        return launch_kernel(consumer_kernel<2, 512>, dim3(a.T), dim3(512), 0, stream, a);
     // exact fits: every thread owns the same number of 4-column groups (1152 columns on 256 threads left 7/8 of
     // the CTA idle in the second pass and cost an occupancy-limiting 46 registers)
     if (a.N == 4 * 288) return launch_kernel(consumer_kernel<1, 288>, dim3(a.T), dim3(288), 0, stream, a);

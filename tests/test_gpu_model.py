@@ -334,8 +334,16 @@ def test_int8_fake_quant_mode(mode, clip, tied):
     ref_plain = _oracle(sd, cfg, inp)
     err = (got.float() - ref.float()).abs().max().item()
     moved = (ref.float() - ref_plain.float()).abs().max().item()
-    print(f"{mode} clip={clip} tied={tied}: max_abs vs quantised oracle {err:.3e}; quantisation moved the actions by {moved:.3e}")
-    assert err <= 1e-2 and not torch.equal(got, plain)
+    with O.int8_fake_quant(clip, tied=tied):
+        ref32 = _oracle_fp32(sd_q, cfg, inp, {})         # fp32 run of the same quantised bf16 model: the tie-breaker
+    e_ours = (got.float() - ref32).abs().max().item()
+    e_ref = (ref.float() - ref32).abs().max().item()
+    print(f"{mode} clip={clip} tied={tied}: max_abs vs quantised oracle {err:.3e} (vs fp32: ours {e_ours:.3e}, bf16 oracle "
+          f"{e_ref:.3e}); quantisation moved the actions by {moved:.3e}")
+    # the hard clamp in front of every Linear amplifies bf16 rounding differences: 1e-2, or no further from the fp32
+    # run than the bf16 oracle itself is
+    assert not torch.equal(got, plain)
+    assert err <= 1e-2 or e_ours <= 1.5 * e_ref + 2 ** -8
     assert moved > err or moved > 0        # the mode really changes the arithmetic and we follow it
 
 

@@ -20,8 +20,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     lib = capi.load_library()
     assert lib.blurr_abi_version() == capi.ABI_VERSION
-    header = open(os.path.join(ROOT, "include", "blurr_pi0.h")).read()
-    declared = set(re.findall(r"\b(blurr_[a-z0-9_]+)\s*\(", header))
+    declared = set()
+    for name in ("blurr_pi0.h", "blurr_llm.h"):
+        header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", name)).read(), flags=re.S)
+        declared |= set(re.findall(r"\b(blurr_[a-z0-9_]+)\s*\(", header))
     declared -= {"blurr_status", "blurr_dtype"}
     assert declared == set(capi.DECLARED_SYMBOLS)
     for name in declared:
@@ -37,6 +39,44 @@ def test_config_struct_matches_header_field_order():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"([a-z_0-9]+)(?:\[4\])?\s*[;,]", body)
     assert [f[0] for f in capi.Pi0InputsC._fields_] == names
+
+
+def test_llm_config_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "blurr_llm.h")).read()
+    body = header[header.index("typedef struct blurr_llm_config {"):header.index("} blurr_llm_config;")]
+    fields = re.findall(r"^\s+(?:int32_t|int64_t|float)\s+([a-z_0-9]+);", body, flags=re.M)
+    assert fields == [f[0] for f in capi.LlmConfigC._fields_]
+
+
+def test_llm_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from blurr_b200 import openvla
+    with pytest.raises(capi.BlurrError, match="no CUDA device"):
+        openvla.LlamaDecoder(openvla.openvla_7b_config(), "cuda:0")
+
+
+def test_openvla_action_detokenizer_and_rope_tables():
+    """`predict_action`'s tail (bins on [-1, 1], q01/q99 de-normalisation) and the RoPE tables against transformers'
+    LlamaRotaryEmbedding on CPU."""
+    import numpy as np
+    from blurr_b200 import openvla
+    d = openvla.ActionDetokenizer(vocab_size=32000, n_bins=256)
+    ids = np.array([31999, 31998, 31745, 31744, 31000, 5])
+    centers = (np.linspace(-1, 1, 256)[:-1] + np.linspace(-1, 1, 256)[1:]) / 2
+    assert np.array_equal(d.normalized(ids), centers[[0, 1, 254, 254, 254, 254]])
+    q01, q99 = np.array([-0.5, 0.0]), np.array([0.5, 2.0])
+    out = d.actions(np.array([31999, 31745]), q01, q99, mask=np.array([True, False]))
+    assert np.allclose(out, [0.5 * (centers[0] + 1) * 1.0 - 0.5, centers[254]])
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+    rot = LlamaRotaryEmbedding(LlamaConfig(hidden_size=256, num_attention_heads=2, head_dim=128, rope_theta=10000.0))
+    assert torch.equal(rot.inv_freq, openvla.default_inv_freq(128, 10000.0, "cpu"))
+    x = torch.zeros((1, 40, 256), dtype=torch.bfloat16)
+    cos, sin = rot(x, torch.arange(40)[None, :])
+    c2, s2 = openvla.rope_tables(rot.inv_freq, 40)
+    assert torch.equal(cos[0, :, :64].float(), c2) and torch.equal(sin[0, :, :64].float(), s2)
+    assert torch.equal(cos[0, :, 64:], cos[0, :, :64])
 
 
 def test_create_fails_loudly_without_gpu():
