@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["auto", "latency", "batched"], default="auto",
+    ap.add_argument("--workload", choices=["auto", "latency", "batched", "openvla"], default="auto",
                     help="headline measurement (see the module docstring)")
     ap.add_argument("--batch", type=int, default=1, help="episodes per GPU of the latency measurement")
     ap.add_argument("--batched", type=int, default=64, help="episodes per GPU of the batched measurement (0 = skip)")
@@ -461,6 +461,8 @@ def leg_batched(ctx, K, W, headline):
 
 def run_ours(args):
     import torch
+    if args.workload == "openvla":
+        return run_openvla(args)
     ctx = Ctx(args)
     world, rank = ctx.world, ctx.rank
     visible = torch.cuda.device_count()
@@ -522,6 +524,118 @@ def run_ours(args):
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_openvla(args):
+    """BASELINE.json configs[4]: OpenVLA-7B-shaped 7-token greedy action decode with a KV cache, batch 1 and 32 -
+    the Llama-2-7B-shaped language model behind include/blurr_llm.h on random-init weights and random projected patch
+    embeddings (the vision backbone is not part of this leg).  One "step" = one predict_action's language-model work:
+    prefill of 1 + 256 + 24 prompt positions, then 7 greedy tokens.  Prints its own JSON line (metric
+    openvla7b_shaped_action_chunks_per_sec)."""
+    import torch
+    from blurr_b200 import openvla
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    peaks = measured_peaks()
+    cfg = openvla.openvla_7b_config()
+    prompt, n_new = 1 + 256 + 24, 7
+    K, W = min(args.steps, 50), max(args.warmup, 3)
+    dec = openvla.LlamaDecoder(cfg, dev, max_batch=32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    # weights layer by layer: the 13.5 GB state_dict never exists twice
+    one = openvla.LlamaShapedConfig(**{**cfg.__dict__, "num_layers": 1})
+    for l in range(cfg.num_layers):
+        sd = openvla.synthetic_llama_state_dict(one, dev, seed=l)
+        for k, v in sd.items():
+            if k.startswith("model.layers.0."):
+                dec.set_weight(k.replace("model.layers.0.", f"model.layers.{l}."), v)
+            elif l == 0:
+                dec.set_weight(k, v)
+        del sd
+    cos, sin = openvla.rope_tables(openvla.default_inv_freq(cfg.head_dim, cfg.rope_theta, dev), cfg.max_positions)
+    torch.cuda.synchronize()
+    import ctypes as C
+    from blurr_b200 import capi
+    capi.check(dec.lib.blurr_llm_set_rope_table(dec.handle, C.c_void_p(cos.data_ptr()), C.c_void_p(sin.data_ptr()), cfg.max_positions))
+    capi.check(dec.lib.blurr_llm_finalize(dec.handle))
+    hbm = peaks["hbm_gbs"]
+    out = {}
+    for B in (1, 32):
+        ring = [(torch.randn((B, prompt, cfg.hidden), device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(4)]
+        host = [r.cpu().pin_memory() for r in ring]
+        res = {}
+        for label, n in (("prefill_plus_1", 1), ("predict_action", n_new)):
+            for i in range(W):
+                dec.generate(ring[i % 4], n)
+            dec.check()
+            sampler = ClockSampler(0) if (label == "predict_action" and B == 1) else None
+            if sampler:
+                sampler.start()
+                t0 = time.perf_counter()
+                while sampler.count() < 3 and time.perf_counter() - t0 < 3.0:
+                    dec.generate(ring[0], n)
+                    torch.cuda.synchronize()
+                sampler.mark()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+            evs[0].record()
+            for i in range(K):
+                dec.generate(ring[i % 4], n)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            dec.check()
+            lat = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(K))
+            res[label] = {"ms_p50": lat[len(lat) // 2], "ms_mean": evs[0].elapsed_time(evs[K]) / K, "launches": dec.last_launch_count}
+            if sampler:
+                res["clocks"] = sampler.stop()
+        # end to end: pinned host prompt embeddings -> device -> generate -> token ids on the host
+        ids_host = torch.empty((B, n_new), dtype=torch.int64).pin_memory()
+        stage = torch.empty_like(ring[0])
+        t_e2e = []
+        for i in range(W + K):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            stage.copy_(host[i % 4], non_blocking=True)
+            ids = dec.generate(stage, n_new)
+            ids_host.copy_(ids, non_blocking=True)
+            torch.cuda.synchronize()
+            if i >= W:
+                t_e2e.append((time.perf_counter() - t0) * 1e3)
+        t_e2e.sort()
+        per_tok = (res["predict_action"]["ms_mean"] - res["prefill_plus_1"]["ms_mean"]) / (n_new - 1)
+        wb = dec.weight_bytes_per_token
+        res.update({
+            "batch": B, "prompt_positions": prompt, "new_tokens": n_new,
+            "decode_ms_per_token": per_tok,
+            "decode_weight_stream": {"bytes_per_token": wb, "achieved_gbps": wb / per_tok / 1e6, "peak_gbps": hbm,
+                                     "frac": wb / per_tok / 1e6 / hbm, "hbm_floor_ms": wb / hbm / 1e6},
+            "action_chunks_per_sec": B * 1e3 / res["predict_action"]["ms_mean"],
+            "e2e": {"ms_p50": t_e2e[len(t_e2e) // 2], "action_chunks_per_sec": B * 1e3 / (sum(t_e2e) / len(t_e2e)),
+                    "h2d_bytes_per_step": stage.numel() * 2, "d2h_bytes_per_step": ids_host.numel() * 8},
+        })
+        out[f"bs{B}"] = res
+    head = out["bs1"]
+    line = {
+        "metric": "openvla7b_shaped_action_chunks_per_sec", "value": head["action_chunks_per_sec"], "unit": "action chunks/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": head["predict_action"]["ms_mean"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (random-init Llama-2-7B-shaped weights, random projected patch embeddings)",
+        "config": {"workload": "openvla7b_shaped_bs1_7_token_decode (BASELINE.json configs[4]; language model only)",
+                   "prompt_positions": prompt, "new_tokens": n_new, "layers": cfg.num_layers, "hidden": cfg.hidden,
+                   "l2": "inputs larger than L2: every token streams 13.2 GB of weights", "cuda_graph": True},
+        "e2e": {"value": head["e2e"]["action_chunks_per_sec"], "unit": "action chunks/s",
+                "h2d_bytes_per_step": head["e2e"]["h2d_bytes_per_step"], "d2h_bytes_per_step": head["e2e"]["d2h_bytes_per_step"]},
+        "gpu_launches": head["predict_action"]["launches"] * K, "gpu_launches_per_step": head["predict_action"]["launches"],
+        "clocks": head.get("clocks"),
+        "roofline": {"bound": "hbm", "achieved": head["decode_weight_stream"]["achieved_gbps"], "peak": hbm, "unit": "GB/s",
+                     "frac": head["decode_weight_stream"]["frac"], "traffic": None,
+                     "kernel": "one decode step (all weight-streaming GEMMs of a token)", "peak_source": peaks["source"]},
+        "parity": "pinned against transformers 5.5 LlamaForCausalLM (tests/test_gpu_llm.py); unpinned against the reference's remote code",
+        "openvla": out,
+    }
+    print(json.dumps(line), flush=True)
+    dec.close()
+    return 0
 
 
 def ncu_traffic_bytes():

@@ -440,7 +440,9 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
     constexpr int CH = HD_PAD / 8;              // 16-byte chunks per row that carry data
     constexpr int LDS_MIN = WC * NP_PV * 16 > HD_PAD ? WC * NP_PV * 16 : HD_PAD;
     constexpr int LDS = LDS_MIN + 8;            // smem row stride (elements), conflict-free for ldmatrix
-    const int nkb = (a.n_keys + kBK - 1) / kBK;
+    // causal (MODE 2): keys past the tile's last query position are masked for every row - never load them
+    const int n_keys_tile = MODE == 2 ? min(a.n_keys, a.q_row_offset + qt * BM + BM) : a.n_keys;
+    const int nkb = (n_keys_tile + kBK - 1) / kBK;
     const int ldl = nkb * kBK + 8;              // logit row stride (elements)
     bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
     bf16* KVs = Qs + BM * LDS;                  // nkb buffers of [64][LDS]
@@ -470,7 +472,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
         cp_async_16(Qs + r * LDS + c * 8, g, valid);
     }
     for (int kb = 0; kb < nkb; ++kb) {
-        load_rows_async<LDS, CH>(KVs + kb * kBK * LDS, kbase, a.ldk, kb * kBK, kBK, a.n_keys, a.hd);
+        load_rows_async<LDS, CH>(KVs + kb * kBK * LDS, kbase, a.ldk, kb * kBK, kBK, n_keys_tile, a.hd);
         cp_async_commit();
     }
 
@@ -532,8 +534,8 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
                         const int mr = a.mqa_nq > 0 ? qr % a.mqa_nq : qr;
                         const bf16* mrow = a.mask + static_cast<size_t>(b) * a.mask_bstride +
                                            static_cast<size_t>(a.q_row_offset + mr) * a.mask_rstride;
-                        if (kcol < a.n_keys) s0 = bf16_round(s0 + bf2f(mrow[kcol]));
-                        if (kcol + 1 < a.n_keys) s1 = bf16_round(s1 + bf2f(mrow[kcol + 1]));
+                        if (kcol < n_keys_tile) s0 = bf16_round(s0 + bf2f(mrow[kcol]));
+                        if (kcol + 1 < n_keys_tile) s1 = bf16_round(s1 + bf2f(mrow[kcol + 1]));
                     }
                 } else {
                     s0 = bf16_round(s0 * a.scale);
@@ -553,7 +555,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
 
     // V blocks into the same buffers; the softmax below runs while they arrive
     for (int kb = 0; kb < nkb; ++kb) {
-        load_rows_async<LDS, CH>(KVs + kb * kBK * LDS, vbase, a.ldv, kb * kBK, kBK, a.n_keys, a.hd);
+        load_rows_async<LDS, CH>(KVs + kb * kBK * LDS, vbase, a.ldv, kb * kBK, kBK, n_keys_tile, a.hd);
         cp_async_commit();
     }
 
@@ -566,7 +568,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
 #pragma unroll
         for (int i = 0; i < PER_LANE; ++i) {
             const int c = lane + i * 32;
-            x[i] = (c < a.n_keys) ? bf2f(lrow[c]) : -INFINITY;
+            x[i] = (c < n_keys_tile) ? bf2f(lrow[c]) : -INFINITY;
             m = fmaxf(m, x[i]);
         }
         m = warp_max(m);
@@ -574,7 +576,7 @@ __device__ __forceinline__ void attn_mma_body(const AttnMmaArgs& a, uint8_t* sme
 #pragma unroll
         for (int i = 0; i < PER_LANE; ++i) {
             const int c = lane + i * 32;
-            x[i] = (c < a.n_keys) ? expf(x[i] - m) : 0.f;
+            x[i] = (c < n_keys_tile) ? expf(x[i] - m) : 0.f;
             sum += x[i];
         }
         sum = warp_sum(sum);

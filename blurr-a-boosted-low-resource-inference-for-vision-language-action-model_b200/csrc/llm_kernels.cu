@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) rope_mha_kernel(const RopeMhaArgs a) {
     const int n_v = (a.n_kv_heads * a.head_dim) >> 2;
     const size_t sstride = static_cast<size_t>(a.T) * a.ldp;
     const size_t cache_row = (static_cast<size_t>(seq) * a.n_slots + pos) * (a.n_kv_heads * a.head_dim);
-    for (int it = threadIdx.x; it < n_rot + n_v; it += blockDim.x) {
+    for (int it = blockIdx.y * blockDim.x + threadIdx.x; it < n_rot + n_v; it += gridDim.y * blockDim.x) {
         if (it < n_rot) {
             const int h = it / gpr, j = (it - h * gpr) << 2;
             const int col = h * a.head_dim + j;           // q heads then k heads are contiguous in the projection
@@ -63,9 +63,131 @@ __global__ void __launch_bounds__(256) rope_mha_kernel(const RopeMhaArgs a) {
     }
 }
 
+// Decode attention: ONE query row per (sequence, head) against that head's cached keys - pure K/V streaming (2 * n_keys *
+// head_dim * 2 bytes per CTA), so no tensor cores: a group of HD / 8 lanes owns one key (16-byte loads, 4 keys in flight
+// per group), scores and probabilities live in shared memory, the P.V sum is reduced across groups at the end.
+// Rounding chain of HF eager attention: bf16(q.k) * scale -> bf16, fp32 softmax -> bf16, fp32 accumulate -> bf16.
+template <int HD>
+__global__ void __launch_bounds__(256) mha_decode_kernel(const MhaAttnArgs a) {
+    constexpr int LPK = HD / 8;                 // lanes per key
+    constexpr int GROUPS = 256 / LPK;           // keys in flight per pass
+    __shared__ float sc[320];
+    __shared__ float red[8];
+    __shared__ float part[GROUPS][HD + 4];
+    pdl_wait();
+    pdl_trigger();
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int width = a.n_heads * HD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = threadIdx.x / LPK, gl = threadIdx.x % LPK;
+    const bf16* qp = a.q + static_cast<size_t>(b) * width + h * HD + gl * 8;
+    const uint4 qraw = *reinterpret_cast<const uint4*>(qp);
+    float q[8];
+    {
+        const uint32_t w[4] = {qraw.x, qraw.y, qraw.z, qraw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { q[2 * e] = __uint_as_float(w[e] << 16); q[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+    }
+    const size_t row0 = static_cast<size_t>(b) * a.n_slots;
+    const bf16* kbase = a.k_cache + row0 * width + h * HD + gl * 8;
+    const bf16* vbase = a.v_cache + row0 * width + h * HD + gl * 8;
+    const int n = a.n_keys;
+    // ---- scores ----
+    for (int k0 = group; k0 < n; k0 += 4 * GROUPS) {
+        uint4 kr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * GROUPS;
+            kr[u] = k < n ? __ldcg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(k) * width)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t w[4] = {kr[u].x, kr[u].y, kr[u].z, kr[u].w};
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                d = fmaf(q[2 * e], __uint_as_float(w[e] << 16), d);
+                d = fmaf(q[2 * e + 1], __uint_as_float(w[e] & 0xffff0000u), d);
+            }
+#pragma unroll
+            for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            const int k = k0 + u * GROUPS;
+            if (gl == 0 && k < n) sc[k] = bf16_round(bf16_round(d) * a.scale);
+        }
+    }
+    __syncthreads();
+    // ---- softmax (fp32) -> bf16 probabilities ----
+    float m = -INFINITY;
+    for (int k = threadIdx.x; k < n; k += 256) m = fmaxf(m, sc[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int k = threadIdx.x; k < n; k += 256) { const float e = expf(sc[k] - m); sc[k] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    for (int k = threadIdx.x; k < n; k += 256) sc[k] = bf16_round(sc[k] / sum);
+    __syncthreads();
+    // ---- O = P V ----
+    float o8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o8[e] = 0.f;
+    for (int k0 = group; k0 < n; k0 += 4 * GROUPS) {
+        uint4 vr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * GROUPS;
+            vr[u] = k < n ? __ldcg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(k) * width)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * GROUPS;
+            const float p = k < n ? sc[k] : 0.f;
+            const uint32_t w[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                o8[2 * e] = fmaf(p, __uint_as_float(w[e] << 16), o8[2 * e]);
+                o8[2 * e + 1] = fmaf(p, __uint_as_float(w[e] & 0xffff0000u), o8[2 * e + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[group][gl * 8 + e] = o8[e];
+    __syncthreads();
+    for (int d = threadIdx.x; d < HD; d += 256) {
+        float acc = 0.f;
+#pragma unroll 4
+        for (int g = 0; g < GROUPS; ++g) acc += part[g][d];
+        a.out[static_cast<size_t>(b) * width + h * HD + d] = f2bf(acc);
+    }
+}
+
+cudaError_t launch_mha_decode(cudaStream_t stream, const MhaAttnArgs& a) {
+    if (a.q_per_sample != 1 || a.n_keys > 320 || a.n_kv_heads != a.n_heads) return cudaErrorInvalidValue;
+    if (a.head_dim == 128) return launch_kernel(mha_decode_kernel<128>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a);
+    if (a.head_dim == 64) return launch_kernel(mha_decode_kernel<64>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a);
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_rope_mha(cudaStream_t stream, const RopeMhaArgs& a) {
     if ((a.head_dim & 7) || a.T <= 0) return cudaErrorInvalidValue;
-    return launch_kernel(rope_mha_kernel, dim3(a.T), dim3(256), 0, stream, a);
+    // one work item (4 rotation pairs / 4 value columns, all K slices) per thread: a decode step's single row still
+    // spreads over ~10 CTAs instead of looping in one (measured 19 -> 5 us per layer at one sequence)
+    const int items = (a.n_heads + a.n_kv_heads) * (a.head_dim >> 3) + ((a.n_kv_heads * a.head_dim) >> 2);
+    int gy = (items + 255) / 256;
+    if (a.T * gy > 148 * 8) gy = (148 * 8 + a.T - 1) / a.T;      // prefill: enough rows already
+    if (gy < 1) gy = 1;
+    return launch_kernel(rope_mha_kernel, dim3(a.T, gy), dim3(256), 0, stream, a);
 }
 
 __global__ void __launch_bounds__(256) embed_rows_kernel(const int64_t* ids, int n, const bf16* table, long long vocab,
@@ -112,9 +234,22 @@ __global__ void __launch_bounds__(1024) argmax_rows_kernel(const bf16* logits, i
     const bf16* row = logits + static_cast<size_t>(b) * ld;
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const int nvec = vec ? (vocab >> 3) : 0;
+    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+        const uint4 q = __ldcg(reinterpret_cast<const uint4*>(row) + c);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float v = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+            const int i = c * 8 + e;
+            if (v != v) continue;                               // NaN never wins
+            if (v > best || (v == best && i < best_i)) { best = v; best_i = i; }
+        }
+    }
+    for (int i = nvec * 8 + threadIdx.x; i < vocab; i += blockDim.x) {
         const float v = bf2f(row[i]);
-        if (v != v) continue;                                   // NaN never wins
+        if (v != v) continue;
         if (v > best || (v == best && i < best_i)) { best = v; best_i = i; }
     }
 #pragma unroll
