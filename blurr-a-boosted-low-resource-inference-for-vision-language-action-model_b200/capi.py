@@ -131,6 +131,7 @@ _SIGNATURES = [
      [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("blurr_llm_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     ("blurr_llm_check", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("blurr_llm_trace_report", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("blurr_llm_last_launch_count", C.c_int64, [C.c_void_p]),
     ("blurr_llm_weight_bytes_per_token", C.c_int64, [C.c_void_p]),
 ]

@@ -90,6 +90,22 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     __syncthreads();
     gemm_persistent<EPI>(p, &tmap_w, &tmap_x, sh, tmem_empty_bar, gx, gy, gz, blockIdx.x, gridDim.x, true);
     __syncthreads();
+    if (p.pf.len > 0 && warp == 0 && elect_one_sync()) {
+        // this CTA has no more weights to stream: L2 prefetch rider for the next GEMM (GemmPrefetch)
+        for (int it = blockIdx.x; it < p.pf.items; it += gridDim.x) {
+            const int bx = it % p.pf.gx, bz = it / p.pf.gx;
+            const unsigned off = static_cast<unsigned>(bz) * p.pf.slice_bytes;
+            if (off >= p.pf.tile_bytes) continue;
+            const unsigned slice = min(p.pf.slice_bytes, p.pf.tile_bytes - off);
+            if (p.pf.skip >= slice) continue;
+            const unsigned len = min(p.pf.len, slice - p.pf.skip);
+            const char* src = p.pf.base + static_cast<size_t>(bx) * p.pf.tile_bytes + off + p.pf.skip;
+            for (unsigned o = 0; o < len; o += 32768u) {
+                const unsigned n = min(32768u, len - o);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src + o), "r"(n) : "memory");
+            }
+        }
+    }
     if (EPI == EPI_PARTIAL && tail.kind != TAIL_NONE) {
         // one weight tile x K slice per CTA (gy == 1, gridDim.x == gx * gz): this CTA's partial stores are made visible
         // device-wide, then it arrives at its group's counter; the group's last arrival finishes the group (GemmTail).
@@ -582,7 +598,7 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     d.T = c.T; d.bn = bn; d.nt = 1; d.kb_total = kb_total; d.kb_per_split = kb_total;
     d.tmem_cols = 512; d.acc_bufs = 2; d.acc_stride = 256; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = nullptr;
-    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; if (c.prefetch) d.pf = *c.prefetch;
     d.staging_bytes = bn * (c.epi == EPI_GEGLU ? kBlockM / 2 : kBlockM) * 2;
     const int stage_bytes = kTileABytes + half * kBlockK * 2;
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
@@ -636,7 +652,7 @@ static int gemm_launch_pair_small(cudaStream_t stream, const GemmCall& c, std::s
     d.T = c.T; d.bn = bn; d.nt = 2; d.kb_total = kb_total; d.kb_per_split = kb_per_split;
     d.tmem_cols = 512; d.acc_bufs = 1; d.acc_stride = 0; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
-    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; if (c.prefetch) d.pf = *c.prefetch;
     d.staging_bytes = c.epi == EPI_PARTIAL ? 0 : ntok * kBlockM * 2;      // GeGLU is staged as raw gate / up values (one accumulator buffer)
     const int stage_bytes = kTileABytes + 2 * half * kBlockK * 2;
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
@@ -657,6 +673,27 @@ static int gemm_launch_pair_small(cudaStream_t stream, const GemmCall& c, std::s
     }
     if (e != cudaSuccess) { *err = std::string("gemm (persistent pairs, batch 1) launch failed: ") + cudaGetErrorString(e); return -1; }
     return splitk;
+}
+
+bool gemm_make_prefetch(const GemmCall& next, size_t budget_bytes, GemmPrefetch* out) {
+    *out = GemmPrefetch{};
+    if (!next.w_packed || !next.w_static || !g_persistent || next.T > kPersistentMaxTokens || next.bn_override != 0) return false;
+    if (next.epi != EPI_PARTIAL && next.epi != EPI_GEGLU && next.epi != EPI_STORE) return false;
+    const GemmPlan pl = gemm_make_plan(next.T, next.Nw, next.K, next.splitk, next.epi, 0);
+    if (!pl.valid || pl.cluster != 1 || pl.two_cta || pl.grid_y != 1) return false;
+    const int tiles = pl.grid_x * pl.splitk;
+    const int items = tiles < kTargetCtas ? tiles : kTargetCtas;
+    const int ring = pl.stages < pl.kb_per_split ? pl.stages : pl.kb_per_split;
+    out->base = reinterpret_cast<const char*>(next.W);
+    out->tile_bytes = static_cast<unsigned>(pl.kb_total) * kTileABytes;
+    out->slice_bytes = static_cast<unsigned>(pl.kb_per_split) * kTileABytes;
+    out->skip = static_cast<unsigned>(ring) * kTileABytes;
+    out->gx = pl.grid_x;
+    out->items = items;
+    size_t len = budget_bytes / static_cast<size_t>(items);
+    len &= ~static_cast<size_t>(kTileABytes - 1);        // whole 16 KB k-blocks
+    out->len = static_cast<unsigned>(len);
+    return out->len > 0 && out->skip < out->slice_bytes;
 }
 
 bool gemm_tail_supported(const GemmCall& c) {
@@ -703,7 +740,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     d.T = c.T; d.bn = pl.bn; d.nt = pl.nt; d.stages = pl.stages; d.kb_total = pl.kb_total;
     d.kb_per_split = pl.kb_per_split; d.tmem_cols = pl.tmem_cols; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
-    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act;
+    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; if (c.prefetch) d.pf = *c.prefetch;
     cudaError_t e;
     if (pl.two_cta) {
         CUtensorMap txh;

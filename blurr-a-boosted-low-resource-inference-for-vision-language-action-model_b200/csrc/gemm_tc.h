@@ -18,6 +18,19 @@ enum GemmEpilogue {
     EPI_PARTIAL = 3,  // partial[z][t][n] = fp32 partial sum of split-K slice z
 };
 
+// Rider of a weight-streaming GEMM: as each CTA runs out of work it asks L2 (cp.async.bulk.prefetch.L2) for the part of
+// the NEXT GEMM's weight stream that lies just past that GEMM's own shared-memory ring, so that HBM keeps streaming
+// through the small dependent kernels in between (consumer, RoPE, attention).  Filled by gemm_make_prefetch().
+struct GemmPrefetch {
+    const char* base;          // the next GEMM's tile-packed weights
+    unsigned tile_bytes;       // bytes of one 128-row weight tile (kb_total * 16 KB)
+    unsigned slice_bytes;      // bytes of one K slice of a tile
+    unsigned skip;             // leading bytes of a slice that the next GEMM fetches into shared memory before its dependency wait
+    unsigned len;              // bytes to prefetch per (tile, slice) work item
+    int gx;                    // weight tiles
+    int items;                 // first-round work items of the next GEMM (<= 148)
+};
+
 struct GemmCall {
     const __nv_bfloat16* W;   // row-major [Nw][K] (row stride ldw), or tile-packed (w_packed)
     int Nw, K, ldw;
@@ -38,6 +51,7 @@ struct GemmCall {
     int w_static;             // 1: W was written before any kernel still in flight (engine weights), so the
                               // kernel may fetch it ahead of the programmatic-dependency wait
     int glu_act;              // EPI_GEGLU: gate activation, 0 = tanh GELU (Gemma), 1 = SiLU (Llama SwiGLU)
+    const GemmPrefetch* prefetch;   // optional L2 prefetch rider for the next GEMM (few-token persistent kernel only)
     const GemmTail* tail;     // optional consumer fused behind an EPI_PARTIAL GEMM of <= 32 tokens (gemm_tail_supported)
 };
 
@@ -65,6 +79,7 @@ struct GemmDev {
     int staging_bytes; // persistent kernel: bf16 output staging tile behind the ring (0 = direct epilogue)
     int l2_policy;    // persistent pairs: 0 = weights evict_first / tokens evict_last, 1 = both evict_normal, 2 = weights evict_last / tokens evict_first
     int glu_act;      // EPI_GEGLU gate activation (GemmCall::glu_act)
+    GemmPrefetch pf;  // len == 0: none
     int band;         // persistent pairs: weight tile pairs per raster band (the band sweeps every token tile before the next one starts)
 };
 
@@ -76,6 +91,9 @@ struct GemmPlan {
 };
 
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override);
+// Prefetch rider description for `next` (a few-token EPI_PARTIAL / EPI_GEGLU call with tile-packed static weights):
+// `budget_bytes` spread over its first-round work items.  Returns false (len = 0) when `next` is not such a call.
+bool gemm_make_prefetch(const GemmCall& next, size_t budget_bytes, GemmPrefetch* out);
 // true when gemm_launch would run this call on the persistent few-token kernel, which can carry a fused tail
 bool gemm_tail_supported(const GemmCall& call);
 

@@ -203,6 +203,7 @@ struct RopeMhaArgs {
     const float* cos_table; const float* sin_table; int n_pos;   // [n_pos][head_dim / 2], values already rounded to bf16
     bf16* q_out;                        // [T][n_heads * head_dim]
     bf16* k_cache; bf16* v_cache; int n_slots;      // [B][n_slots][n_kv_heads * head_dim]
+    unsigned long long* trace;
 };
 cudaError_t launch_rope_mha(cudaStream_t stream, const RopeMhaArgs& a);
 // rows[i] = table[ids[i]] (token embedding); ids outside [0, vocab) set *err_flag and read row 0
@@ -214,7 +215,8 @@ cudaError_t launch_gather_rows(cudaStream_t stream, const bf16* src, int batch, 
 cudaError_t launch_argmax_rows(cudaStream_t stream, const bf16* logits, int batch, int ld, int vocab, int64_t* ids,
                                int64_t* ids_copy, int copy_stride);
 // few-token GLU from the split-K partials of a gate/up projection with interleaved rows; act: 0 tanh GELU, 1 SiLU
-cudaError_t launch_glu_partial(cudaStream_t stream, const float* partial, int splitk, int T, int Nw, int act, bf16* out, int ldo);
+cudaError_t launch_glu_partial(cudaStream_t stream, const float* partial, int splitk, int T, int Nw, int act, bf16* out, int ldo,
+                               unsigned long long* trace = nullptr);
 
 // argument bundles of the small single-purpose kernels (engine.cu builds them once per op)
 struct EmbedMergeArgs {

@@ -42,7 +42,9 @@ static int fail(int code, const std::string& msg) { return record_error(code, ms
 namespace {
 
 constexpr int kSMs = 148;
+constexpr int kTraceMax = 4096;
 constexpr int kMaxKeptLogits = 16;    // generated tokens whose logits blurr_llm_generate can return
+constexpr int kMidTokens = 288;       // up to here o / down run as chunked split-K (plan_mid_tokens)
 constexpr int kFewTokens = 32;        // at most this many token rows: split-K partials + consumers (weight streaming)
 
 struct Lin { bf16* w = nullptr; int Nw = 0, K = 0; };
@@ -83,6 +85,14 @@ struct blurr_llm {
     int64_t launches = 0, weight_bytes = 0;
     struct GraphEntry { cudaGraph_t graph; cudaGraphExec_t exec; int64_t launches; };
     std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
+    // in-graph timeline (option "trace"): every kernel stamps %globaltimer at entry / after its dependency wait / at exit
+    // option "l2_prefetch_mb": GemmPrefetch budget per decode GEMM.  Off by default - measured neutral (decode layer 97.0 us
+    // without, 97.1 / 98.6 us with 16 / 48 MB): the next GEMM's own pre-wait ring fetch (32 MB) already keeps HBM busy
+    // through the small kernel in front of it, and what the rider gains there the issuing GEMM loses at its tail.
+    size_t l2_prefetch_bytes = 0;
+    bool trace = false;
+    unsigned long long* trace_buf = nullptr;
+    std::vector<std::string> trace_labels;
 };
 
 static void* dalloc(blurr_llm* h, size_t bytes) {
@@ -158,6 +168,7 @@ extern "C" int blurr_llm_create(const blurr_llm_config* cfg, int device, int max
     size_t widest_nw = h->lm_head.Nw;
     if (widest_nw < static_cast<size_t>(2 * c.intermediate)) widest_nw = 2 * c.intermediate;
     h->ws_floats = 16 * static_cast<size_t>(kFewTokens) * widest_nw;
+    if (h->ws_floats < 4 * static_cast<size_t>(kMidTokens) * c.hidden) h->ws_floats = 4 * static_cast<size_t>(kMidTokens) * c.hidden;
     h->ws = static_cast<float*>(dalloc(h, h->ws_floats * 4));
     const size_t cache = static_cast<size_t>(c.num_layers) * max_batch * c.max_positions * KVW;
     h->kcache = bufb(cache); h->vcache = bufb(cache);
@@ -274,30 +285,78 @@ int pick_splitk(int tiles, int kb_total) {
     return best_s;
 }
 
+// 33..288 token rows (a single-sequence prefill): tokens split into `chunks` CTAs per weight tile x K slices, by the cost
+// model measured for the Pi-0 prefill (engine.cu Run::plan_partial, tools/sweep_splitk.py): >= 0.25 us per k-block per
+// CTA (0.40 when one CTA holds two 144-token chunks), the fp32 tile store, and the consumer's re-read of the slices.
+int plan_mid_tokens(int T, int Nw, int K, size_t ws_floats, int* bn_override) {
+    *bn_override = 0;
+    const int tiles = Nw / 128, kb = (K + 63) / 64;
+    double best_cost = 1e30;
+    int best_s = 1;
+    for (int chunks = 1; chunks <= 4; ++chunks) {
+        const int bn = ((T + chunks - 1) / chunks + 15) / 16 * 16;
+        if (chunks > 1 && bn < 64) break;
+        int sl = kSMs / (tiles * chunks);
+        if (sl < 1) break;
+        if (sl > kb / 2) sl = kb / 2 > 0 ? kb / 2 : 1;
+        if (sl > 16) sl = 16;
+        while (sl > 1 && static_cast<size_t>(sl) * T * Nw > ws_floats) --sl;
+        const int kb_per = (kb + sl - 1) / sl;
+        sl = (kb + kb_per - 1) / kb_per;
+        const double us_kb = (chunks == 1 && T > 256) ? 0.40 : 0.25;
+        const double tile_tokens = chunks == 1 ? (T > 256 ? 288 : (T + 15) / 16 * 16) : bn;
+        const double cost = kb_per * us_kb + 128.0 * tile_tokens * 4.0 / 55e3 + static_cast<double>(sl) * T * Nw * 4.0 / 6e6;
+        if (cost < best_cost) { best_cost = cost; best_s = sl; *bn_override = chunks == 1 ? 0 : bn; }
+    }
+    return best_s;
+}
+
 struct Run {
     blurr_llm* h;
     cudaStream_t st;
     int rc = 0;
 
+    unsigned long long* slot(const std::string& what) {
+        if (!h->trace || !h->trace_buf || h->trace_labels.size() >= static_cast<size_t>(kTraceMax)) return nullptr;
+        h->trace_labels.push_back(what);
+        return h->trace_buf + (h->trace_labels.size() - 1) * 4;
+    }
     void launched(cudaError_t e, const char* what) {
         ++h->launches;
         if (e != cudaSuccess && !rc) rc = fail(BLURR_ERR_CUDA, std::string(what) + " launch failed: " + cudaGetErrorString(e));
     }
     // Y = X W^T.  Few tokens: fp32 split-K partials in the workspace (returns the slice count); otherwise the bf16 linear
     // output in `out` (returns 0).  EPI_GEGLU: SwiGLU straight from the epilogue (out = HM).
-    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo) {
-        if (rc) return 0;
+    GemmCall make_call(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo) const {
         GemmCall c{};
         c.W = L.w; c.Nw = L.Nw; c.K = L.K; c.ldw = L.K; c.w_packed = 1;
         c.X = X; c.T = T; c.ldx = L.K;
         c.epi = epi; c.splitk = 1; c.glu_act = 1; c.w_static = 1;
         c.out = out; c.ldo = ldo;
         if (epi == EPI_PARTIAL) {
-            c.splitk = pick_splitk(L.Nw / 128, (L.K + 63) / 64);
+            c.splitk = T <= kFewTokens ? pick_splitk(L.Nw / 128, (L.K + 63) / 64)
+                                       : plan_mid_tokens(T, L.Nw, L.K, h->ws_floats, &c.bn_override);
             c.partial = h->ws;
-            if (static_cast<size_t>(c.splitk) * T * L.Nw > h->ws_floats) { rc = fail(BLURR_ERR_STATE, "split-K workspace too small"); return 0; }
+        }
+        return c;
+    }
+    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, const Lin* next = nullptr) {
+        if (rc) return 0;
+        GemmCall c = make_call(L, X, T, epi, out, ldo);
+        if (epi == EPI_PARTIAL && static_cast<size_t>(c.splitk) * T * L.Nw > h->ws_floats) {
+            rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
+            return 0;
+        }
+        // decode steps: as this GEMM's CTAs drain they ask L2 for the head of the next GEMM's weight stream
+        GemmPrefetch pf{};
+        if (next != nullptr && h->l2_prefetch_bytes > 0 && T <= kFewTokens) {
+            const GemmCall n = make_call(*next, nullptr, T, EPI_PARTIAL, nullptr, 0);
+            if (gemm_make_prefetch(n, h->l2_prefetch_bytes, &pf)) c.prefetch = &pf;
         }
         std::string err;
+        char nm[96];
+        snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", epi, T, L.Nw, L.K, c.splitk);
+        c.trace = slot(nm);
         const int s = gemm_launch(st, c, &err);
         ++h->launches;
         if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 0; }
@@ -315,49 +374,53 @@ struct Run {
         a.x_out = x_out; a.ldx = N;
         a.norm_mode = norm_w ? NORM_RMS_LLAMA : NORM_NONE; a.norm_w = norm_w; a.eps = h->cfg.rms_eps;
         a.xn_out = norm_w ? xn_out : nullptr; a.ldn = N;
+        a.trace = slot("consumer[T" + std::to_string(T) + "]");
         launched(launch_consumer(st, a), "consumer");
     }
 
     // One decoder layer over B sequences x Tq new tokens at positions pos0..pos0+Tq-1 (modeling_llama.py LlamaDecoderLayer)
-    void layer(int l, int B, int Tq, int pos0, const bf16* next_norm) {
+    void layer(int l, int B, int Tq, int pos0, const bf16* next_norm, const Lin* next_first) {
         const auto& c = h->cfg;
         Layer& L = h->layers[l];
         const int T = B * Tq, QW = c.num_heads * c.head_dim, KVW = c.num_kv_heads * c.head_dim;
         const bool few = T <= kFewTokens;
+        const bool part = few || T <= kMidTokens;       // o / down: few weight tiles, long K -> split-K partials + consumer
         const size_t cache_off = static_cast<size_t>(l) * h->max_batch * c.max_positions * KVW;
         // q/k/v projections + RoPE + cache append
-        int s = gemm(L.qkv, h->XN, T, few ? EPI_PARTIAL : EPI_STORE, h->LIN, L.qkv.Nw);
+        int s = gemm(L.qkv, h->XN, T, few ? EPI_PARTIAL : EPI_STORE, h->LIN, L.qkv.Nw, &L.o);
         RopeMhaArgs r{};
         if (few) { r.partial = h->ws; r.splitk = s; } else { r.lin = h->LIN; r.ldl = L.qkv.Nw; r.splitk = 1; }
         r.T = T; r.ldp = L.qkv.Nw; r.n_heads = c.num_heads; r.n_kv_heads = c.num_kv_heads; r.head_dim = c.head_dim;
         r.tokens_per_seq = Tq; r.pos0 = pos0; r.cos_table = h->cos_t; r.sin_table = h->sin_t; r.n_pos = h->n_pos;
         r.q_out = h->Q; r.k_cache = h->kcache + cache_off; r.v_cache = h->vcache + cache_off; r.n_slots = c.max_positions;
+        r.trace = slot("rope_mha");
         if (!rc) launched(launch_rope_mha(st, r), "rope_mha");
         // causal multi-head attention over the cache
         MhaAttnArgs m{};
         m.q = h->Q; m.q_per_sample = Tq; m.q_pos0 = pos0; m.k_cache = r.k_cache; m.v_cache = r.v_cache;
         m.n_slots = c.max_positions; m.n_keys = pos0 + Tq; m.batch = B; m.n_heads = c.num_heads; m.n_kv_heads = c.num_kv_heads;
         m.head_dim = c.head_dim; m.scale = static_cast<float>(std::pow(static_cast<double>(c.head_dim), -0.5)); m.out = h->AO;
+        m.trace = slot(Tq == 1 ? "mha_decode" : "mha_prefill");
         if (!rc) launched(launch_mha_attention(st, m), "mha_attention");
         // o_proj + residual + post-attention norm
-        s = gemm(L.o, h->AO, T, few ? EPI_PARTIAL : EPI_STORE, h->LIN, L.o.Nw);
-        consumer(few ? s : 0, few ? nullptr : h->LIN, T, c.hidden, L.o.Nw, h->X, h->X, L.post_ln, h->XN);
+        s = gemm(L.o, h->AO, T, part ? EPI_PARTIAL : EPI_STORE, h->LIN, L.o.Nw, &L.gu);
+        consumer(part ? s : 0, part ? nullptr : h->LIN, T, c.hidden, L.o.Nw, h->X, h->X, L.post_ln, h->XN);
         // SwiGLU MLP
         if (few) {
-            s = gemm(L.gu, h->XN, T, EPI_PARTIAL, nullptr, 0);
-            if (!rc) launched(launch_glu_partial(st, h->ws, s, T, L.gu.Nw, 1, h->HM, c.intermediate), "glu");
+            s = gemm(L.gu, h->XN, T, EPI_PARTIAL, nullptr, 0, &L.down);
+            if (!rc) launched(launch_glu_partial(st, h->ws, s, T, L.gu.Nw, 1, h->HM, c.intermediate, slot("glu")), "glu");
         } else {
             gemm(L.gu, h->XN, T, EPI_GEGLU, h->HM, c.intermediate);
         }
-        s = gemm(L.down, h->HM, T, few ? EPI_PARTIAL : EPI_STORE, h->LIN, L.down.Nw);
-        consumer(few ? s : 0, few ? nullptr : h->LIN, T, c.hidden, L.down.Nw, h->X, h->X, next_norm, h->XN);
+        s = gemm(L.down, h->HM, T, part ? EPI_PARTIAL : EPI_STORE, h->LIN, L.down.Nw, next_first);
+        consumer(part ? s : 0, part ? nullptr : h->LIN, T, c.hidden, L.down.Nw, h->X, h->X, next_norm, h->XN);
         (void)QW;
     }
 
     // final-normed rows [B][hidden] -> logits -> greedy token `step` of every sequence
     void head(const bf16* xn_rows, int B, int step, int n_new, bool keep_logits) {
         const auto& c = h->cfg;
-        const int s = gemm(h->lm_head, xn_rows, B, EPI_PARTIAL, nullptr, 0);
+        const int s = gemm(h->lm_head, xn_rows, B, EPI_PARTIAL, nullptr, 0, &h->layers[0].qkv);
         if (!rc) launched(launch_bias_act(st, h->ws, s, B, h->lm_head.Nw, h->lm_head.Nw, nullptr, ACT_NONE, 1.0f, h->LOGITS, h->lm_head.Nw), "logits");
         if (!rc) launched(launch_argmax_rows(st, h->LOGITS, B, h->lm_head.Nw, c.vocab, h->ids, h->out_ids + step, n_new), "argmax");
         if (keep_logits && !rc) {
@@ -373,16 +436,24 @@ void run_generate(Run& R, int B, int T, int n_new, bool keep_logits) {
     blurr_llm* h = R.h;
     const auto& c = h->cfg;
     const int L = c.num_layers;
+    if (h->trace && h->trace_buf) {
+        h->trace_labels.clear();
+        if (cudaMemsetAsync(h->trace_buf, 0xFF, static_cast<size_t>(kTraceMax) * 4 * sizeof(unsigned long long), R.st) != cudaSuccess)
+            R.rc = fail(BLURR_ERR_CUDA, "trace reset failed");
+    }
     // ---- prefill: X <- inputs_embeds, XN <- input norm of layer 0 ----
     R.consumer(0, nullptr, B * T, c.hidden, c.hidden, h->IN, h->X, h->layers[0].in_ln, h->XN);
-    for (int l = 0; l < L; ++l) R.layer(l, B, T, 0, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm);
+    for (int l = 0; l < L; ++l)
+        R.layer(l, B, T, 0, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm, l + 1 < L ? &h->layers[l + 1].qkv : &h->lm_head);
     if (!R.rc) R.launched(launch_gather_rows(R.st, h->XN, B, T, T - 1, c.hidden, h->LAST), "gather_last");
     R.head(h->LAST, B, 0, n_new, keep_logits);
     // ---- greedy decode: one token per sequence per step ----
     for (int i = 1; i < n_new; ++i) {
         if (!R.rc) R.launched(launch_embed_rows(R.st, h->ids, B, h->embed, c.vocab, c.hidden, h->X, h->d_err), "embed");
         R.consumer(0, nullptr, B, c.hidden, c.hidden, h->X, nullptr, h->layers[0].in_ln, h->XN);
-        for (int l = 0; l < L; ++l) R.layer(l, B, 1, T + i - 1, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm);
+        for (int l = 0; l < L; ++l)
+            R.layer(l, B, 1, T + i - 1, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm,
+                    l + 1 < L ? &h->layers[l + 1].qkv : &h->lm_head);
         R.head(h->XN, B, i, n_new, keep_logits);
     }
 }
@@ -453,6 +524,20 @@ extern "C" int blurr_llm_set_option(blurr_llm_t* h, const char* name, int64_t va
     if (!h || !name) return fail(BLURR_ERR_INVALID, "blurr_llm_set_option: null argument");
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
+    else if (n == "l2_prefetch_mb") {
+        h->l2_prefetch_bytes = value > 0 ? static_cast<size_t>(value) << 20 : 0;
+        for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); cudaGraphDestroy(kv.second.graph); }
+        h->graphs.clear();
+    }
+    else if (n == "trace") {
+        if (value != 0 && !h->trace_buf) {
+            h->trace_buf = static_cast<unsigned long long*>(dalloc(h, static_cast<size_t>(kTraceMax) * 4 * sizeof(unsigned long long)));
+            if (!h->trace_buf) return fail(BLURR_ERR_CUDA, "trace buffer allocation failed");
+        }
+        h->trace = value != 0;
+        for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); cudaGraphDestroy(kv.second.graph); }
+        h->graphs.clear();
+    }
     else return fail(BLURR_ERR_INVALID, "blurr_llm_set_option: unknown option " + n);
     return 0;
 }
@@ -469,6 +554,29 @@ extern "C" int blurr_llm_check(blurr_llm_t* h, void* cuda_stream) {
     }
     const int g = gemm_take_timeout_flag(), a = attn_take_timeout_flag();
     if (g > 0 || a > 0) return fail(BLURR_ERR_CUDA, "a bounded pipeline wait expired inside a GEMM / attention kernel");
+    return 0;
+}
+
+extern "C" int blurr_llm_trace_report(blurr_llm_t* h, char* buf, size_t buf_bytes) {
+    if (!h || !buf || buf_bytes == 0) return fail(BLURR_ERR_INVALID, "blurr_llm_trace_report: bad arguments");
+    if (!h->trace || !h->trace_buf) return fail(BLURR_ERR_STATE, "blurr_llm_trace_report: option trace is off");
+    LLM_CUDA_TRY(cudaDeviceSynchronize());
+    const size_t n = h->trace_labels.size();
+    std::vector<unsigned long long> host(n * 4);
+    if (n) LLM_CUDA_TRY(cudaMemcpy(host.data(), h->trace_buf, n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < n; ++i) if (host[i * 4] < t0) t0 = host[i * 4];
+    std::string out = "# idx start_us waited_us end_us label   (globaltimer, relative to the first kernel start)\n";
+    char line[256];
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned long long s = host[i * 4], w = host[i * 4 + 1], e = ~host[i * 4 + 2];
+        if (s == ~0ull) continue;
+        snprintf(line, sizeof line, "%zu %.3f %.3f %.3f %s\n", i, (s - t0) * 1e-3, w == ~0ull ? -1.0 : (w - t0) * 1e-3, (e - t0) * 1e-3,
+                 h->trace_labels[i].c_str());
+        out += line;
+    }
+    if (out.size() + 1 > buf_bytes) return fail(BLURR_ERR_INVALID, "blurr_llm_trace_report: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 

@@ -133,6 +133,11 @@ class LlamaDecoder:
     def set_option(self, name: str, value: int):
         capi.check(self.lib.blurr_llm_set_option(self.handle, name.encode(), int(value)))
 
+    def trace_report(self) -> str:
+        buf = C.create_string_buffer(1 << 20)
+        capi.check(self.lib.blurr_llm_trace_report(self.handle, buf, len(buf)))
+        return buf.value.decode()
+
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.blurr_llm_last_launch_count(self.handle))
