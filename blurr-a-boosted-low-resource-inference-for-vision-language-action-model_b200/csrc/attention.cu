@@ -122,8 +122,12 @@ cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld
 
 cudaError_t launch_joint_attention_prefill_tc(cudaStream_t stream, const JointAttnArgs& j, std::string* err);
 
+static bool prefill_stream_applies(const JointAttnArgs& j);
+static cudaError_t launch_prefill_stream(cudaStream_t stream, const JointAttnArgs& j);
+
 cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnArgs& j) {
     if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
+    if (prefill_stream_applies(j)) return launch_prefill_stream(stream, j);      // one or two episodes: streaming kernel
     if (attn_tc_applies(j)) {
         std::string err;
         return launch_joint_attention_prefill_tc(stream, j, &err);
@@ -134,7 +138,335 @@ cudaError_t launch_joint_attention_prefill(cudaStream_t stream, const JointAttnA
     return launch_attn<256, 32, true>(stream, a, j.q_per_sample, j.n_heads, j.batch);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Few-query joint attention as a streaming kernel (the experts: 1 proprio / 4 action queries per sample, 8 query heads
+// over ONE shared K/V head, <= 288 keys).  The tile kernel above spends its time in dependent phases (K blocks, logits,
+// V blocks into the same buffers, P.V): ~13 us for 0.6 MFLOP.  Here a CTA owns 8 (head, query) rows of one sample and
+// requests everything it will read at once:
+//  * K straight from global into mma.sync B fragments (no shared memory): the dot product does not care in which order
+//    the 256 dims are summed, so k-steps 2t / 2t+1 of lane (g, c) are DEFINED as dims 32t + 8c .. + 7 - one 16-byte load
+//    per lane per t for the key row g of its 8-key tile, and the same permutation for the query row's A fragments;
+//  * all of V into shared memory with cp.async (read back with ldmatrix.trans for P.V).
+// 18 warps x 2 key tiles x 8 keys = 288 keys.  Same rounding chain as attn_mma_body<256, ., 1> (joint_model.py:246-288):
+// bf16(q.k) / 16 -> bf16(/50) -> bf16(tanh) -> bf16(*50) -> bf16(+ mask) -> fp32 softmax -> bf16 -> P.V in fp32.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kFqWarps = 18;
+static constexpr int kFqThreads = kFqWarps * 32;
+static constexpr int kFqMaxKeys = kFqWarps * 16;                 // 288
+static constexpr int kFqRows = 8;
+static constexpr int kFqLdV = 256 + 8;                           // V row stride in shared memory (elements): conflict-free ldmatrix
+static constexpr int kFqLdP = kFqMaxKeys + 8;
+static constexpr size_t kFqSmem = static_cast<size_t>(kFqMaxKeys) * kFqLdV * 2 + kFqRows * kFqLdP * 4 + kFqRows * kFqLdP * 2;
+
+__global__ void __launch_bounds__(kFqThreads, 1) fewq_stream_kernel(const JointAttnArgs j) {
+    extern __shared__ __align__(16) uint8_t fq_smem[];
+    bf16* v_s = reinterpret_cast<bf16*>(fq_smem);                                                   // [288][264]
+    float* sc = reinterpret_cast<float*>(fq_smem + static_cast<size_t>(kFqMaxKeys) * kFqLdV * 2);   // [8][296] logits
+    bf16* p_s = reinterpret_cast<bf16*>(sc + kFqRows * kFqLdP);                                     // [8][296] probabilities
+    trace_stamp(j.trace, 0);
+    pdl_wait();
+    pdl_trigger();
+    trace_stamp(j.trace, 1);
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int nq = j.q_per_sample, rows_total = j.n_heads * nq, n = j.n_keys;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, c = lane & 3;
+    const bf16* kb = j.k_cache + static_cast<size_t>(b) * j.n_slots * 256;
+    const bf16* vb = j.v_cache + static_cast<size_t>(b) * j.n_slots * 256;
+    // ---- everything this CTA reads, requested up front ----
+    for (int i = threadIdx.x; i < kFqMaxKeys * 32; i += kFqThreads) {
+        const int key = i >> 5, ch = i & 31;
+        const bool valid = key < n;                           // rows past n_keys are zero-filled (their probabilities are 0)
+        cp_async_16(v_s + key * kFqLdV + ch * 8, valid ? vb + static_cast<size_t>(key) * 256 + ch * 8 : vb, valid);
+    }
+    cp_async_commit();
+    uint4 kr[2][8];
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+        const int key = (warp * 2 + t2) * 8 + g;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            kr[t2][t] = key < n ? __ldcg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * 256 + 32 * t + 8 * c))
+                                : make_uint4(0u, 0u, 0u, 0u);
+    }
+    // row g of this tile -> (head, query)
+    const int p = tile * kFqRows + g;
+    const bool row_valid = p < rows_total;
+    const int head = row_valid ? p / nq : 0, qi = row_valid ? p - head * nq : 0;
+    const bf16* qrow = j.q + (static_cast<size_t>(b) * nq + qi) * (j.n_heads * 256) + head * 256;
+    uint4 qr[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+        qr[t] = row_valid ? *reinterpret_cast<const uint4*>(qrow + 32 * t + 8 * c) : make_uint4(0u, 0u, 0u, 0u);
+    // ---- logits: 2 key tiles x 16 k-steps of m16n8k16 (rows 8..15 of A are zero) ----
+    const bf16* mrow = row_valid ? j.mask + static_cast<size_t>(b) * j.mask_bstride +
+                                       static_cast<size_t>(j.q_row_offset + qi) * j.mask_rstride
+                                 : nullptr;
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const uint32_t a0[4] = {qr[t].x, 0u, qr[t].y, 0u};
+            mma_bf16_16816(acc, a0, kr[t2][t].x, kr[t2][t].y);
+            const uint32_t a1[4] = {qr[t].z, 0u, qr[t].w, 0u};
+            mma_bf16_16816(acc, a1, kr[t2][t].z, kr[t2][t].w);
+        }
+        // acc[0], acc[1]: row g, keys key0 + 2c, + 1
+        const int key0 = (warp * 2 + t2) * 8 + 2 * c;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = key0 + e;
+            float s0 = bf16_round(acc[e]) * 0.0625f;          // / sqrt(256): exact
+            s0 = bf16_round(s0 * (1.0f / 50.0f));
+            s0 = bf16_round(tanhf(s0));
+            s0 = bf16_round(s0 * 50.0f);
+            if (mrow != nullptr && k < n) s0 = bf16_round(s0 + bf2f(mrow[k]));
+            sc[g * kFqLdP + k] = s0;
+        }
+    }
+    __syncthreads();
+    // ---- softmax: fp32 over the bf16 logits, probabilities rounded to bf16 ----
+    if (warp < kFqRows) {
+        const float* row = sc + warp * kFqLdP;
+        constexpr int PER_LANE = kFqMaxKeys / 32;            // 9
+        float x[PER_LANE];
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+            const int col = lane + i * 32;
+            x[i] = col < n ? row[col] : -INFINITY;
+            m = fmaxf(m, x[i]);
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+            const int col = lane + i * 32;
+            x[i] = col < n ? expf(x[i] - m) : 0.f;
+            sum += x[i];
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) p_s[warp * kFqLdP + lane + i * 32] = f2bf(x[i] / sum);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // ---- O = P V: warps 0..15 own 16 output dims each ----
+    if (warp < 16) {
+        float oacc[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+        const int dim0 = warp * 16;
+#pragma unroll 3
+        for (int ks = 0; ks < kFqMaxKeys / 16; ++ks) {
+            uint32_t pa[2];
+            // lanes 0..7: rows of the (keys ks*16 .. +7) matrix, lanes 8..15: the (+8 .. +15) matrix
+            ldmatrix_x2(pa, smem_u32(p_s + (lane & 7) * kFqLdP + ks * 16 + ((lane >> 3) & 1) * 8));
+            const uint32_t af[4] = {pa[0], 0u, pa[1], 0u};
+            uint32_t bfr[4];
+            const int mi = lane >> 3;
+            const int key = ks * 16 + (mi & 1) * 8 + (lane & 7);
+            const int dim = dim0 + (mi >> 1) * 8;
+            ldmatrix_x4_trans(bfr, smem_u32(v_s + key * kFqLdV + dim));
+            mma_bf16_16816(oacc[0], af, bfr[0], bfr[1]);
+            mma_bf16_16816(oacc[1], af, bfr[2], bfr[3]);
+        }
+        if (row_valid) {
+            bf16* orow = j.out + (static_cast<size_t>(b) * nq + qi) * (j.n_heads * 256) + head * 256 + dim0 + 2 * c;
+            *reinterpret_cast<uint32_t*>(orow) = pack_bf16x2(oacc[0][0], oacc[0][1]);
+            *reinterpret_cast<uint32_t*>(orow + 8) = pack_bf16x2(oacc[1][0], oacc[1][1]);
+        }
+    }
+    trace_stamp(j.trace, 2);
+}
+
+// The same streaming design for the PREFILL at one or two episodes (276 queries x 8 heads = 2208 rows per sample): a CTA owns
+// 16 rows = 2 queries x 8 heads (all heads share the K/V head, and rows of one query share a mask row), so 138 CTAs cover
+// a sample in ONE wave, each reading the sample's K (registers) and V (shared memory) once from L2 - 40 MB of L2 traffic
+// per layer, fine for a couple of samples, absurd for 64 (those keep the tcgen05 kernel, which reads K/V once per 128
+// rows).  A fragments come from a shared-memory copy of the 16 query rows whose columns are stored in the permuted order
+// of the K fragments (see fewq_stream_kernel), so a plain ldmatrix yields matching k indices.
+static constexpr int kPsRows = 16;
+static constexpr int kPsLdQ = 256 + 8;
+static constexpr size_t kPsSmem = static_cast<size_t>(kFqMaxKeys) * kFqLdV * 2 + kPsRows * kPsLdQ * 2 + kPsRows * kFqLdP * 4 +
+                                  kPsRows * kFqLdP * 2;
+
+__global__ void __launch_bounds__(kFqThreads, 1) prefill_stream_kernel(const JointAttnArgs j) {
+    extern __shared__ __align__(16) uint8_t ps_smem[];
+    bf16* v_s = reinterpret_cast<bf16*>(ps_smem);                                                   // [288][264]
+    bf16* q_s = v_s + static_cast<size_t>(kFqMaxKeys) * kFqLdV;                                     // [16][264], permuted columns
+    float* sc = reinterpret_cast<float*>(q_s + kPsRows * kPsLdQ);                                   // [16][296]
+    bf16* p_s = reinterpret_cast<bf16*>(sc + kPsRows * kFqLdP);                                     // [16][296]
+    trace_stamp(j.trace, 0);
+    pdl_wait();
+    pdl_trigger();
+    trace_stamp(j.trace, 1);
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int qps = j.q_per_sample, nh = j.n_heads, rows_total = nh * qps, n = j.n_keys;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, c = lane & 3;
+    const bf16* kb = j.k_cache + static_cast<size_t>(b) * j.n_slots * 256;
+    const bf16* vb = j.v_cache + static_cast<size_t>(b) * j.n_slots * 256;
+    for (int i = threadIdx.x; i < kFqMaxKeys * 32; i += kFqThreads) {
+        const int key = i >> 5, ch = i & 31;
+        const bool valid = key < n;
+        cp_async_16(v_s + key * kFqLdV + ch * 8, valid ? vb + static_cast<size_t>(key) * 256 + ch * 8 : vb, valid);
+    }
+    cp_async_commit();
+    uint4 kr[2][8];
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+        const int key = (warp * 2 + t2) * 8 + g;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            kr[t2][t] = key < n ? __ldcg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * 256 + 32 * t + 8 * c))
+                                : make_uint4(0u, 0u, 0u, 0u);
+    }
+    // query rows -> shared memory, dims (d, d + 1) of row r stored at the column the K fragments use for them
+    for (int i = threadIdx.x; i < kPsRows * 128; i += kFqThreads) {
+        const int r = i >> 7, d = (i & 127) << 1;
+        const int p = tile * kPsRows + r;
+        uint32_t val = 0u;
+        if (p < rows_total) {
+            const int query = p / nh, head = p - query * nh;
+            val = *reinterpret_cast<const uint32_t*>(j.q + (static_cast<size_t>(b) * qps + query) * (nh * 256) + head * 256 + d);
+        }
+        const int t = d >> 5, rr = d & 31, cc = rr >> 3, o = rr & 7;
+        const int col = (2 * t + (o >> 2)) * 16 + 2 * cc + ((o & 2) ? 8 : 0);
+        *reinterpret_cast<uint32_t*>(q_s + r * kPsLdQ + col) = val;
+    }
+    __syncthreads();
+    // rows g and g + 8 of this tile
+    const bf16* mrow[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int p = tile * kPsRows + g + hh * 8;
+        mrow[hh] = p < rows_total ? j.mask + static_cast<size_t>(b) * j.mask_bstride +
+                                        static_cast<size_t>(j.q_row_offset + p / nh) * j.mask_rstride
+                                  : nullptr;
+    }
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+            uint32_t af[4];
+            ldmatrix_x4(af, smem_u32(q_s + (lane & 15) * kPsLdQ + ks * 16 + (lane >> 4) * 8));
+            const uint4 kk = kr[t2][ks >> 1];
+            if (ks & 1) mma_bf16_16816(acc, af, kk.z, kk.w);
+            else mma_bf16_16816(acc, af, kk.x, kk.y);
+        }
+        const int key0 = (warp * 2 + t2) * 8 + 2 * c;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = key0 + e;
+                float s0 = bf16_round(acc[hh * 2 + e]) * 0.0625f;
+                s0 = bf16_round(s0 * (1.0f / 50.0f));
+                s0 = bf16_round(tanhf(s0));
+                s0 = bf16_round(s0 * 50.0f);
+                if (mrow[hh] != nullptr && k < n) s0 = bf16_round(s0 + bf2f(mrow[hh][k]));
+                sc[(g + hh * 8) * kFqLdP + k] = s0;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp < kPsRows) {
+        const float* row = sc + warp * kFqLdP;
+        constexpr int PER_LANE = kFqMaxKeys / 32;
+        float x[PER_LANE];
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+            const int col = lane + i * 32;
+            x[i] = col < n ? row[col] : -INFINITY;
+            m = fmaxf(m, x[i]);
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+            const int col = lane + i * 32;
+            x[i] = col < n ? expf(x[i] - m) : 0.f;
+            sum += x[i];
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) p_s[warp * kFqLdP + lane + i * 32] = f2bf(x[i] / sum);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (warp < 16) {
+        float oacc[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+        const int dim0 = warp * 16;
+#pragma unroll 3
+        for (int ks = 0; ks < kFqMaxKeys / 16; ++ks) {
+            uint32_t af[4];
+            ldmatrix_x4(af, smem_u32(p_s + (lane & 15) * kFqLdP + ks * 16 + (lane >> 4) * 8));
+            uint32_t bfr[4];
+            const int mi = lane >> 3;
+            const int key = ks * 16 + (mi & 1) * 8 + (lane & 7);
+            const int dim = dim0 + (mi >> 1) * 8;
+            ldmatrix_x4_trans(bfr, smem_u32(v_s + key * kFqLdV + dim));
+            mma_bf16_16816(oacc[0], af, bfr[0], bfr[1]);
+            mma_bf16_16816(oacc[1], af, bfr[2], bfr[3]);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int p = tile * kPsRows + g + hh * 8;
+            if (p >= rows_total) continue;
+            const int query = p / nh, head = p - query * nh;
+            bf16* orow = j.out + (static_cast<size_t>(b) * qps + query) * (nh * 256) + head * 256 + dim0 + 2 * c;
+            *reinterpret_cast<uint32_t*>(orow) = pack_bf16x2(oacc[0][hh * 2], oacc[0][hh * 2 + 1]);
+            *reinterpret_cast<uint32_t*>(orow + 8) = pack_bf16x2(oacc[1][hh * 2], oacc[1][hh * 2 + 1]);
+        }
+    }
+    trace_stamp(j.trace, 2);
+}
+
+static int g_prefill_stream = 1;
+void attn_set_prefill_stream(int on) { g_prefill_stream = on; }
+static bool prefill_stream_applies(const JointAttnArgs& j) {
+    if (!g_prefill_stream || j.n_keys > kFqMaxKeys || j.mask == nullptr) return false;
+    const long tiles = (static_cast<long>(j.n_heads) * j.q_per_sample + kPsRows - 1) / kPsRows;
+    return tiles * j.batch <= 2 * 148;          // every CTA re-reads the sample's K/V from L2: only worth it within two waves
+}
+static cudaError_t launch_prefill_stream(cudaStream_t stream, const JointAttnArgs& j) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(prefill_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPsSmem));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int rows = j.n_heads * j.q_per_sample;
+    return launch_kernel(prefill_stream_kernel, dim3((rows + kPsRows - 1) / kPsRows, j.batch), dim3(kFqThreads), kPsSmem, stream, j);
+}
+
+static int g_fewq_stream = 1;
+void attn_set_fewq_stream(int on) { g_fewq_stream = on; }
+
+static cudaError_t launch_fewq_stream(cudaStream_t stream, const JointAttnArgs& j) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(fewq_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFqSmem));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int rows = j.n_heads * j.q_per_sample;
+    return launch_kernel(fewq_stream_kernel, dim3((rows + kFqRows - 1) / kFqRows, j.batch), dim3(kFqThreads), kFqSmem, stream, j);
+}
+
 cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs& j) {
+    if (g_fewq_stream && j.n_keys <= kFqMaxKeys && j.mask != nullptr) return launch_fewq_stream(stream, j);
     if (j.n_keys > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
     if (attn_tc_fewq_applies(j)) {
         std::string err;

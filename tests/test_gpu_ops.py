@@ -271,18 +271,53 @@ def test_joint_attention_prefill_tcgen05(batch, scale):
     cnts = ([268, 261, 276, 258] * 3)[:batch]
     mask = _block_mask(batch, 277, 277, cnts, 0)
     try:
+        capi.check(lib.blurr_set_global_option(b"attn_prefill_stream", 0))
         capi.check(lib.blurr_set_global_option(b"attn_tc", 0))
         base = op_joint_attention(False, q, 276, 0, kc, vc, n_keys, mask, batch, n_heads)
         capi.check(lib.blurr_set_global_option(b"attn_tc", 1))
         got = op_joint_attention(False, q, 276, 0, kc, vc, n_keys, mask, batch, n_heads)
     finally:
         capi.check(lib.blurr_set_global_option(b"attn_tc", -1))
+        capi.check(lib.blurr_set_global_option(b"attn_prefill_stream", 1))
     ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], mask[:, :276], n_heads)
     print(report(f"joint_prefill tcgen05 B={batch} scale={scale}", got, ref))
     print(report("  vs mma.sync kernel", got, base))
     assert (got.float() - ref.float()).abs().max().item() <= 0.05
     assert (got.float() - base.float()).abs().max().item() <= 0.05
     assert ((got.float() - base.float()).abs() > 0).float().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("batch,scale,qps", [(1, 1.0, 276), (2, 2.0, 276), (2, 6.0, 276), (1, 3.0, 37)])
+def test_joint_attention_prefill_stream(batch, scale, qps):
+    """The one-or-two-episode prefill kernel (16 rows = 2 queries x 8 heads per CTA, K straight into permuted mma.sync
+    fragments, V in shared memory) against the torch restatement and the mma.sync tile kernel: same rounding points,
+    the 256 dims of a dot product are only summed in another order."""
+    lib = capi.load_library()
+    n_heads, n_keys, slots = 8, 277, 281
+    q = _rand((batch * qps, n_heads * 256), scale, 53)
+    kc = _rand((batch, slots, 256), scale, 54)
+    vc = _rand((batch, slots, 256), 1.0, 55)
+    mask = _block_mask(batch, 277, 277, [268, 261][:batch], 0)
+    try:
+        capi.check(lib.blurr_set_global_option(b"attn_prefill_stream", 0))
+        capi.check(lib.blurr_set_global_option(b"attn_tc", 0))
+        base = op_joint_attention(False, q, qps, 0, kc, vc, n_keys, mask, batch, n_heads)
+        capi.check(lib.blurr_set_global_option(b"attn_prefill_stream", 1))
+        got = op_joint_attention(False, q, qps, 0, kc, vc, n_keys, mask, batch, n_heads)
+    finally:
+        capi.check(lib.blurr_set_global_option(b"attn_tc", -1))
+        capi.check(lib.blurr_set_global_option(b"attn_prefill_stream", 1))
+    ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], mask[:, :qps], n_heads)
+    print(report(f"joint_prefill stream B={batch} scale={scale} qps={qps}", got, ref))
+    print(report("  vs mma.sync kernel", got, base))
+    assert (got.float() - ref.float()).abs().max().item() <= 0.05
+    # against the other kernel: a logit that lands on a bf16 rounding boundary may round the other way (the dims are
+    # summed in another order); with peaked softmaxes (scale 6) one such flip moves an output row visibly, so the bound
+    # there is on how many elements differ at all, not on the largest one
+    d = (got.float() - base.float()).abs()
+    assert (d > 0).float().mean().item() < 0.01 and d.mean().item() < 1e-4
+    if scale <= 3.0:
+        assert d.max().item() <= 0.05
 
 
 @pytest.mark.parametrize("qps,row0,n_keys,batch", [(1, 276, 277, 2), (4, 0, 281, 2), (4, 0, 281, 160)])
@@ -302,12 +337,18 @@ def test_joint_attention_fewq(qps, row0, n_keys, batch):
     ref = _joint_ref(q, kc[:, :n_keys], vc[:, :n_keys], rows, n_heads)
     outs = {}
     try:
-        for mode in (0, 1):        # 0: mma.sync tile kernel, 1: the tcgen05 kernel (one 128-row tile of (head, query) pairs per sample)
-            capi.check(lib.blurr_set_global_option(b"attn_tc_fewq", mode))
+        # "stream": the default streaming kernel (K rows in registers, V in shared memory, FMA dot products);
+        # 0: mma.sync tile kernel; 1: the tcgen05 kernel (one 128-row tile of (head, query) pairs per sample)
+        for mode in ("stream", 0, 1):
+            capi.check(lib.blurr_set_global_option(b"attn_fewq_stream", 1 if mode == "stream" else 0))
+            capi.check(lib.blurr_set_global_option(b"attn_tc_fewq", mode if mode != "stream" else 0))
             outs[mode] = op_joint_attention(True, q, qps, row0, kc, vc, n_keys, mask, batch, n_heads)
-            print(report(f"joint_fewq qps={qps} tcgen05={mode}", outs[mode], ref))
+            print(report(f"joint_fewq qps={qps} kernel={mode}", outs[mode], ref))
             assert (outs[mode].float() - ref.float()).abs().max().item() <= 0.05
     finally:
         capi.check(lib.blurr_set_global_option(b"attn_tc_fewq", -1))
+        capi.check(lib.blurr_set_global_option(b"attn_fewq_stream", 1))
+    ds = (outs["stream"].float() - outs[0].float()).abs()
+    assert ds.max().item() <= 0.05 and (ds > 0).float().mean().item() < 0.05
     d = (outs[0].float() - outs[1].float()).abs()
     assert d.max().item() <= 0.05 and (d > 0).float().mean().item() < 0.05
