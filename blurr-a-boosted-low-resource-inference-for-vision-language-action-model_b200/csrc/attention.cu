@@ -105,10 +105,18 @@ bool attn_tc_siglip_applies(int batch, int seq, int n_heads, int hidden);
 cudaError_t launch_siglip_attention_tc(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq, int n_heads,
                                        int hidden, bf16* out, int ld_out, unsigned long long* trace);
 
+static bool siglip_stream_applies(const AttnMmaArgs& a, int seq, int n_heads, int batch);
+static cudaError_t launch_siglip_stream(cudaStream_t stream, const AttnMmaArgs& a, int seq, int n_heads, int batch);
+
 cudaError_t launch_siglip_attention(cudaStream_t stream, const bf16* qkv, int ld_qkv, int batch, int seq,
                                     int n_heads, int hidden, bf16* out, int ld_out, unsigned long long* trace) {
     const int hd = hidden / n_heads;
     if (hd > 80 || seq > kAttnMaxBlocks * kBK) return cudaErrorInvalidValue;
+    {
+        AttnMmaArgs sa = make_siglip_attn_args(qkv, ld_qkv, seq, n_heads, hidden, out, ld_out);
+        sa.trace = trace;
+        if (siglip_stream_applies(sa, seq, n_heads, batch)) return launch_siglip_stream(stream, sa, seq, n_heads, batch);
+    }
     if (attn_tc_siglip_applies(batch, seq, n_heads, hidden))
         return launch_siglip_attention_tc(stream, qkv, ld_qkv, batch, seq, n_heads, hidden, out, ld_out, trace);
     AttnMmaArgs a = make_siglip_attn_args(qkv, ld_qkv, seq, n_heads, hidden, out, ld_out);
@@ -449,6 +457,172 @@ static cudaError_t launch_prefill_stream(cudaStream_t stream, const JointAttnArg
     }
     const int rows = j.n_heads * j.q_per_sample;
     return launch_kernel(prefill_stream_kernel, dim3((rows + kPsRows - 1) / kPsRows, j.batch), dim3(kFqThreads), kPsSmem, stream, j);
+}
+
+// SigLIP self-attention (siglip.py:133-152) at one or two images, the same streaming design: a CTA owns 32 query rows of
+// one head (8 tiles x 16 heads = 128 CTAs per image: one wave), its 8 warps take 32 keys each straight into permuted
+// B fragments (head_dim 72 = dims 0..63 in two 16-byte steps + one more that only lane column 0 fills), V (256 x 72) goes
+// to shared memory with cp.async, the logits are bf16(bf16(q.k) * scale), fp32 softmax, bf16 P, P.V by mma.sync.
+static constexpr int kSsThreads = 256;
+static constexpr int kSsRows = 32;
+static constexpr int kSsKeys = 256;
+static constexpr int kSsLdV = 96 + 8;         // up to 96 head dims
+static constexpr int kSsLdQ = 96 + 8;
+static constexpr int kSsLdP = kSsKeys + 8;
+static constexpr size_t kSsSmem = static_cast<size_t>(kSsKeys) * kSsLdV * 2 + kSsRows * kSsLdQ * 2 + kSsRows * kSsLdP * 4 + kSsRows * kSsLdP * 2;
+
+__global__ void __launch_bounds__(kSsThreads) siglip_stream_kernel(const AttnMmaArgs a) {
+    extern __shared__ __align__(16) uint8_t ss_smem[];
+    bf16* v_s = reinterpret_cast<bf16*>(ss_smem);                                    // [256][104]
+    bf16* q_s = v_s + kSsKeys * kSsLdV;                                              // [32][104], permuted columns
+    float* sc = reinterpret_cast<float*>(q_s + kSsRows * kSsLdQ);                    // [32][264]
+    bf16* p_s = reinterpret_cast<bf16*>(sc + kSsRows * kSsLdP);                      // [32][264]
+    trace_stamp(a.trace, 0);
+    pdl_wait();
+    pdl_trigger();
+    trace_stamp(a.trace, 1);
+    const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int n = a.n_keys, hd = a.hd, rows_total = a.q_per_sample;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, c = lane & 3;
+    const bf16* qbase = a.q + static_cast<size_t>(b) * a.q_per_sample * a.ldq + a.q_col0 + h * a.head_stride_q;
+    const bf16* kbase = a.k + static_cast<size_t>(b) * a.kv_per_sample * a.ldk + a.k_col0 + h * a.head_stride_kv;
+    const bf16* vbase = a.v + static_cast<size_t>(b) * a.kv_per_sample * a.ldv + a.v_col0 + h * a.head_stride_kv;
+    const int vch = hd >> 3;                                   // 16-byte chunks per V row (9)
+    for (int i = threadIdx.x; i < kSsKeys * 12; i += kSsThreads) {
+        const int key = i / 12, ch = i - key * 12;
+        const bool valid = key < n && ch < vch;                // the rest is zero-filled: padded dims / keys contribute 0
+        cp_async_16(v_s + key * kSsLdV + ch * 8, valid ? vbase + static_cast<size_t>(key) * a.ldv + ch * 8 : vbase, valid);
+    }
+    cp_async_commit();
+    uint4 kr[4][3];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int key = warp * 32 + nt * 8 + g;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int d = 32 * t + 8 * c;
+            kr[nt][t] = (key < n && d < hd) ? __ldcg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(key) * a.ldk + d))
+                                            : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    for (int i = threadIdx.x; i < kSsRows * 48; i += kSsThreads) {
+        const int r = i / 48, d = (i - r * 48) << 1;
+        const int row = tile * kSsRows + r;
+        uint32_t val = 0u;
+        if (row < rows_total && d < hd) val = *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(row) * a.ldq + d);
+        const int t = d >> 5, rr = d & 31, cc = rr >> 3, o = rr & 7;
+        const int col = (2 * t + (o >> 2)) * 16 + 2 * cc + ((o & 2) ? 8 : 0);
+        *reinterpret_cast<uint32_t*>(q_s + r * kSsLdQ + col) = val;
+    }
+    __syncthreads();
+    // ---- logits: 2 row tiles x 4 key tiles x 6 k-steps ----
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        uint32_t af[6][4];
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks)
+            ldmatrix_x4(af[ks], smem_u32(q_s + (mt * 16 + (lane & 15)) * kSsLdQ + ks * 16 + (lane >> 4) * 8));
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks) {
+                const uint4 kk = kr[nt][ks >> 1];
+                if (ks & 1) mma_bf16_16816(acc, af[ks], kk.z, kk.w);
+                else mma_bf16_16816(acc, af[ks], kk.x, kk.y);
+            }
+            const int key0 = warp * 32 + nt * 8 + 2 * c;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    sc[(mt * 16 + g + hh * 8) * kSsLdP + key0 + e] = bf16_round(bf16_round(acc[hh * 2 + e]) * a.scale);
+        }
+    }
+    __syncthreads();
+    // ---- softmax: 4 rows per warp ----
+    for (int rr = 0; rr < kSsRows / 8; ++rr) {
+        const int r = warp * (kSsRows / 8) + rr;
+        const float* row = sc + r * kSsLdP;
+        float x[kSsKeys / 32];
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kSsKeys / 32; ++i) {
+            const int col = lane + i * 32;
+            x[i] = col < n ? row[col] : -INFINITY;
+            m = fmaxf(m, x[i]);
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSsKeys / 32; ++i) {
+            const int col = lane + i * 32;
+            x[i] = col < n ? expf(x[i] - m) : 0.f;
+            sum += x[i];
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int i = 0; i < kSsKeys / 32; ++i) p_s[r * kSsLdP + lane + i * 32] = f2bf(x[i] / sum);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // ---- O = P V: warp -> row tile (warp & 1), output 8-dim tiles (warp >> 1) + 4 i ----
+    {
+        const int mt = warp & 1;
+        const int n_tiles = (hd + 7) >> 3;
+        float oacc[3][4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+#pragma unroll 4
+        for (int ks = 0; ks < kSsKeys / 16; ++ks) {
+            uint32_t af[4];
+            ldmatrix_x4(af, smem_u32(p_s + (mt * 16 + (lane & 15)) * kSsLdP + ks * 16 + (lane >> 4) * 8));
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int nt = (warp >> 1) + 4 * i;
+                if (nt >= n_tiles) continue;                       // warp-uniform
+                uint32_t bfr[2];
+                // x2.trans: lanes 0..7 -> keys ks*16 .. +7, lanes 8..15 -> keys +8 .. +15 of dim tile nt
+                ldmatrix_x2_trans(bfr, smem_u32(v_s + (ks * 16 + (lane & 15)) * kSsLdV + nt * 8));
+                mma_bf16_16816(oacc[i], af, bfr[0], bfr[1]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int nt = (warp >> 1) + 4 * i;
+            if (nt >= n_tiles) continue;
+            const int dim = nt * 8 + 2 * c;
+            if (dim >= hd) continue;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int row = tile * kSsRows + mt * 16 + g + hh * 8;
+                if (row >= rows_total) continue;
+                bf16* dst = a.out + static_cast<size_t>(b) * a.q_per_sample * a.ldo + static_cast<size_t>(row) * a.ldo + a.o_col0 +
+                            h * a.head_stride_q + dim;
+                *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(oacc[i][hh * 2], oacc[i][hh * 2 + 1]);
+            }
+        }
+    }
+    trace_stamp(a.trace, 2);
+}
+
+static int g_siglip_stream = 1;
+void attn_set_siglip_stream(int on) { g_siglip_stream = on; }
+static bool siglip_stream_applies(const AttnMmaArgs& a, int seq, int n_heads, int batch) {
+    if (!g_siglip_stream || seq > kSsKeys || a.hd > 96 || (a.hd & 7)) return false;
+    return static_cast<long>((seq + kSsRows - 1) / kSsRows) * n_heads * batch <= 2 * 148;
+}
+static cudaError_t launch_siglip_stream(cudaStream_t stream, const AttnMmaArgs& a, int seq, int n_heads, int batch) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(siglip_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSsSmem));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    return launch_kernel(siglip_stream_kernel, dim3((seq + kSsRows - 1) / kSsRows, n_heads, batch), dim3(kSsThreads), kSsSmem, stream, a);
 }
 
 static int g_fewq_stream = 1;

@@ -115,6 +115,7 @@ bool attn_tc_applies(const JointAttnArgs& a);
 void attn_set_tc_fewq(int mode);                 // few-query attention on the tcgen05 kernel: 1 on, 0 / -1 off (default: measured slower at batch 1)
 bool attn_tc_fewq_applies(const JointAttnArgs& a);
 void attn_set_prefill_stream(int on);           // prefill attention of <= 2 waves of 16-row tiles as the streaming kernel (default 1)
+void attn_set_siglip_stream(int on);            // SigLIP attention of <= 2 waves of 32-row tiles as the streaming kernel (default 1)
 void attn_set_fewq_stream(int on);              // few-query attention as the streaming kernel (default 1) vs the mma.sync tile kernel
 int attn_take_timeout_flag();
 int attn_set_cta_trace(void* dev_ptr);          // per-CTA timeline of the tcgen05 attention kernel (attention_tc.cu)

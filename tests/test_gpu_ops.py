@@ -187,6 +187,34 @@ def test_siglip_attention(batch):
     assert (got.float() - ref.float()).abs().max().item() <= 0.03
 
 
+@pytest.mark.parametrize("batch,seq,scale", [(1, 256, 1.0), (2, 256, 3.0), (1, 200, 1.0)])
+def test_siglip_attention_stream(batch, seq, scale):
+    """SigLIP attention of one or two images as the streaming kernel (32 query rows of one head per CTA, K straight into
+    permuted mma.sync fragments, V in shared memory) against the torch restatement and the mma.sync tile kernel."""
+    lib = capi.load_library()
+    heads, hidden = 16, 1152
+    hd = hidden // heads
+    qkv = _rand((batch * seq, 3 * hidden), scale, 62)
+    try:
+        capi.check(lib.blurr_set_global_option(b"attn_siglip_stream", 0))
+        capi.check(lib.blurr_set_global_option(b"attn_tc", 0))
+        base = op_siglip_attention(qkv, batch, seq, heads, hidden)
+        capi.check(lib.blurr_set_global_option(b"attn_siglip_stream", 1))
+        got = op_siglip_attention(qkv, batch, seq, heads, hidden)
+    finally:
+        capi.check(lib.blurr_set_global_option(b"attn_tc", -1))
+        capi.check(lib.blurr_set_global_option(b"attn_siglip_stream", 1))
+    q, k, v = [t.view(batch, seq, heads, hd).transpose(1, 2) for t in qkv.view(batch, seq, 3 * hidden).split(hidden, -1)]
+    w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
+    w = torch.softmax(w, dim=-1, dtype=torch.float32).to(torch.bfloat16)
+    ref = torch.matmul(w, v).transpose(1, 2).contiguous().view(batch * seq, hidden)
+    print(report(f"siglip_attention stream B={batch} seq={seq} scale={scale}", got, ref))
+    print(report("  vs mma.sync kernel", got, base))
+    assert (got.float() - ref.float()).abs().max().item() <= 0.03 * scale
+    d = (got.float() - base.float()).abs()
+    assert d.max().item() <= 0.03 * scale and (d > 0).float().mean().item() < 0.05
+
+
 @pytest.mark.parametrize("batch", [1, 3, 9])
 def test_siglip_attention_tcgen05(batch):
     """Batched-episode SigLIP attention on tcgen05 (head_dim 72 zero-padded to 128 inside the Q tile) against
@@ -196,12 +224,14 @@ def test_siglip_attention_tcgen05(batch):
     hd = hidden // heads
     qkv = _rand((batch * seq, 3 * hidden), 1.0, 52)
     try:
+        capi.check(lib.blurr_set_global_option(b"attn_siglip_stream", 0))
         capi.check(lib.blurr_set_global_option(b"attn_tc", 0))
         base = op_siglip_attention(qkv, batch, seq, heads, hidden)
         capi.check(lib.blurr_set_global_option(b"attn_tc", 1))
         got = op_siglip_attention(qkv, batch, seq, heads, hidden)
     finally:
         capi.check(lib.blurr_set_global_option(b"attn_tc", -1))
+        capi.check(lib.blurr_set_global_option(b"attn_siglip_stream", 1))
     q, k, v = [t.view(batch, seq, heads, hd).transpose(1, 2) for t in qkv.view(batch, seq, 3 * hidden).split(hidden, -1)]
     w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
     w = torch.softmax(w, dim=-1, dtype=torch.float32).to(torch.bfloat16)
