@@ -369,6 +369,12 @@ class PiZero(nn.Module):
     def _bump(self):
         object.__setattr__(self, "_weights_version", self._weights_version + 1)
 
+    def refresh_weights(self):
+        """Call after editing parameters in place (`p.data.copy_(...)`, an optimiser step, ...): the engine holds a repacked
+        copy of the weights that only `.to()`, `load_state_dict`, `tie_action_proprio_weights` and
+        `enable_action_quantization` invalidate on their own; the next call re-uploads."""
+        self._bump()
+
     def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .bfloat16()
         out = super()._apply(fn, *args, **kwargs)
         self._bump()

@@ -347,6 +347,23 @@ def test_int8_fake_quant_mode(mode, clip, tied):
     assert moved > err or moved > 0        # the mode really changes the arithmetic and we follow it
 
 
+def test_refresh_weights_after_in_place_edit():
+    """The engine keeps a repacked copy of the weights: an in-place parameter edit is picked up after refresh_weights()."""
+    cfg = shrink_config(bridge_config(1), 2, 3)
+    model, sd, inp = _setup(cfg, 1)
+    a = _run(model, inp)
+    with torch.no_grad():
+        model.action_decoder.weight.mul_(0.5)
+    stale = _run(model, inp)
+    assert torch.equal(a, stale)                  # documented: not seen until the caller says so
+    model.refresh_weights()
+    b = _run(model, inp)
+    sd2 = dict(sd)
+    sd2["action_decoder.weight"] = sd["action_decoder.weight"] * 0.5
+    ref = _oracle(sd2, cfg, inp)
+    assert not torch.equal(a, b) and (b.float() - ref.float()).abs().max().item() <= 1e-2
+
+
 def test_shrunk_fractal_ten_steps():
     """Config 3: proprio_dim 8, 10 Euler steps with bf16 `t` accumulation, same injected noise."""
     cfg = shrink_config(fractal_config(10), 2, 3)
