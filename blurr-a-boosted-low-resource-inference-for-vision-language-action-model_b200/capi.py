@@ -58,6 +58,19 @@ class LlmConfigC(C.Structure):
 LLM_ABI_VERSION = 1
 
 
+class VitConfigC(C.Structure):
+    """`blurr_vit_config` (include/blurr_vit.h)."""
+
+    _fields_ = [
+        ("abi_version", C.c_int32), ("num_layers", C.c_int32), ("hidden", C.c_int32), ("num_heads", C.c_int32),
+        ("mlp_dim", C.c_int32), ("image_size", C.c_int32), ("patch_size", C.c_int32), ("num_prefix_tokens", C.c_int32),
+        ("use_layerscale", C.c_int32), ("gelu_erf", C.c_int32), ("ln_eps", C.c_float),
+    ]
+
+
+VIT_ABI_VERSION = 1
+
+
 class Pi0InputsC(C.Structure):
     """`blurr_pi0_inputs` (include/blurr_pi0.h)."""
 
@@ -134,6 +147,17 @@ _SIGNATURES = [
     ("blurr_llm_trace_report", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("blurr_llm_last_launch_count", C.c_int64, [C.c_void_p]),
     ("blurr_llm_weight_bytes_per_token", C.c_int64, [C.c_void_p]),
+    # include/blurr_vit.h
+    ("blurr_vit_create", C.c_int, [C.POINTER(VitConfigC), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("blurr_vit_destroy", None, [C.c_void_p]),
+    ("blurr_vit_set_weight", C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    ("blurr_vit_finalize", C.c_int, [C.c_void_p]),
+    ("blurr_vit_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int]),
+    ("blurr_vit_last_launch_count", C.c_int64, [C.c_void_p]),
+    ("blurr_mlp_create", C.c_int, [C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("blurr_mlp_destroy", None, [C.c_void_p]),
+    ("blurr_mlp_set_weight", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("blurr_mlp_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
 ]
 DECLARED_SYMBOLS = [s[0] for s in _SIGNATURES]
 

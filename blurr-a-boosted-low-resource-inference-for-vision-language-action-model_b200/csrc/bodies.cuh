@@ -109,6 +109,7 @@ template <int VPT, int THREADS = kRowThreads, bool PRELOADED = false>
 __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t, const ConsumerRowIn<VPT>* pre = nullptr) {
     __shared__ float red[(THREADS + 31) / 32];
     const int nvec = a.N >> 2;
+    const int to = a.row_group > 0 ? t + (t / a.row_group) * a.row_extra + a.row_offset : t;     // output row
     float4 x[VPT];
     float lsum = 0.f, lsq = 0.f;
 #pragma unroll
@@ -135,6 +136,11 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
             if (a.out_scale != 1.0f)
                 val = make_float4(bf16_round(val.x * a.out_scale), bf16_round(val.y * a.out_scale),
                                   bf16_round(val.z * a.out_scale), bf16_round(val.w * a.out_scale));
+            if (a.col_scale != nullptr) {
+                const float4 gsc = load_bf16x4(a.col_scale + n);
+                val = make_float4(bf16_round(val.x * gsc.x), bf16_round(val.y * gsc.y), bf16_round(val.z * gsc.z),
+                                  bf16_round(val.w * gsc.w));
+            }
             if (a.add_mode == ADD_RESIDUAL) {
                 const float4 r = PRELOADED ? unpack_bf16x4(pre->add[i]) : load_bf16x4(a.res + static_cast<size_t>(t) * a.ldr + n);
                 val = make_float4(bf16_round(r.x + val.x), bf16_round(r.y + val.y), bf16_round(r.z + val.z),
@@ -148,7 +154,7 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
         } else {
             val = load_bf16x4(a.res + static_cast<size_t>(t) * a.ldr + n);
         }
-        if (a.x_out != nullptr) store_bf16x4(a.x_out + static_cast<size_t>(t) * a.ldx + n, val);
+        if (a.x_out != nullptr) store_bf16x4(a.x_out + static_cast<size_t>(to) * a.ldx + n, val);
         x[i] = val;
         lsum += (val.x + val.y) + (val.z + val.w);
         lsq += (val.x * val.x + val.y * val.y) + (val.z * val.z + val.w * val.w);
@@ -171,7 +177,7 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
                               w.w * bf16_round(x[i].w * r))
                 : make_float4((x[i].x * r) * (1.0f + w.x), (x[i].y * r) * (1.0f + w.y),
                               (x[i].z * r) * (1.0f + w.z), (x[i].w * r) * (1.0f + w.w));
-            store_bf16x4(a.xn_out + static_cast<size_t>(t) * a.ldn + n, y);
+            store_bf16x4(a.xn_out + static_cast<size_t>(to) * a.ldn + n, y);
         }
     } else {
         const float mean = block_sum<THREADS>(lsum, red) / static_cast<float>(a.N);
@@ -193,7 +199,7 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
             const float4 w = load_bf16x4(a.norm_w + n), b = load_bf16x4(a.norm_b + n);
             const float4 y = make_float4((x[i].x - mean) * rstd * w.x + b.x, (x[i].y - mean) * rstd * w.y + b.y,
                                          (x[i].z - mean) * rstd * w.z + b.z, (x[i].w - mean) * rstd * w.w + b.w);
-            store_bf16x4(a.xn_out + static_cast<size_t>(t) * a.ldn + n, y);
+            store_bf16x4(a.xn_out + static_cast<size_t>(to) * a.ldn + n, y);
         }
     }
 }

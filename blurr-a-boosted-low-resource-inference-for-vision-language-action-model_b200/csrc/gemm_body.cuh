@@ -242,7 +242,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float v = bf16_round(__uint_as_float(r[i]) + bias);
-                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
                     tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
                 }
             }
@@ -422,7 +422,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                             if ((lane & 1) == 0) stg[t * OUTW + (nl >> 1)] = f2bf(bf16_round(glu_act_f32(v, p.glu_act)) * up);
                         } else {
                             float v = bf16_round(__uint_as_float(r[i]) + bias);
-                            if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                            if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
                             stg[t * OUTW + nl] = f2bf(v);
                         }
                     }
@@ -468,7 +468,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float v = bf16_round(__uint_as_float(r[i]) + bias);
-                        if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                        if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
                         if (tb + i < p.T) dst[static_cast<size_t>(i) * p.ldo] = f2bf(v);
                     }
                 }
@@ -593,7 +593,7 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float v = bf16_round(__uint_as_float(r[i]) + bias);
-                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
                     tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
                 }
             }
@@ -834,7 +834,7 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                 } else if (EPI == EPI_GELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float v = gelu_tanh_f32(bf16_round(__uint_as_float(r[i]) + bias));
+                        const float v = gelu_sel_f32(bf16_round(__uint_as_float(r[i]) + bias), p.glu_act);
                         stg[(g * 16 + i) * kBlockM + nl] = f2bf(v);
                     }
                 } else {

@@ -91,6 +91,9 @@ struct GemmPlan {
 };
 
 GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_override);
+// K slices (return value) and tokens per chunk (*bn_override, 0 = one CTA holds all rows) for an EPI_PARTIAL GEMM of
+// 33..288 rows, from the measured cost model (tools/sweep_splitk.py)
+int gemm_plan_chunked_splitk(int T, int Nw, int K, size_t ws_floats, int* bn_override);
 // Prefetch rider description for `next` (a few-token EPI_PARTIAL / EPI_GEGLU call with tile-packed static weights):
 // `budget_bytes` spread over its first-round work items.  Returns false (len = 0) when `next` is not such a call.
 bool gemm_make_prefetch(const GemmCall& next, size_t budget_bytes, GemmPrefetch* out);

@@ -40,11 +40,17 @@ struct ConsumerArgs {
     // written by the GEMM's store epilogue - half the bytes of the fp32 partial and no bias pass here
     const bf16* lin;        // [T][ldl] or nullptr
     int ldl;
+    const bf16* col_scale;  // [N] or nullptr: per-column scale applied as bf16(x * g) after the bias (DINOv2 LayerScale)
+    // output row map (0 = identity): row t is written to row t + (t / row_group) * row_extra + row_offset of x_out / xn_out
+    // (ViT prefix tokens: the 256 patch rows of sample b land behind that sample's cls / register rows)
+    int row_group, row_extra, row_offset;
 };
 cudaError_t launch_consumer(cudaStream_t stream, const ConsumerArgs& a);
 
 // Element-wise finish without a norm: out = act(bf16(sum + bias)) * scale
 enum ActMode { ACT_NONE = 0, ACT_SILU = 1 };
+// GemmCall::glu_act also selects the EPI_GELU flavour: 0 tanh approximation (SigLIP, Gemma), 2 exact erf (DINOv2, nn.GELU())
+enum GeluKind { GELU_TANH = 0, GELU_ERF = 2 };
 cudaError_t launch_bias_act(cudaStream_t stream, const float* partial, int splitk, int T, int N, int ldp,
                             const bf16* bias, int act, float scale, bf16* out, int ldo);
 
@@ -220,6 +226,10 @@ cudaError_t launch_argmax_rows(cudaStream_t stream, const bf16* logits, int batc
 // few-token GLU from the split-K partials of a gate/up projection with interleaved rows; act: 0 tanh GELU, 1 SiLU
 cudaError_t launch_glu_partial(cudaStream_t stream, const float* partial, int splitk, int T, int Nw, int act, bf16* out, int ldo,
                                unsigned long long* trace = nullptr);
+
+// dst[(b * rows + r) * ldd + c] = src[(b * src_rows_per_sample + row0 + r) * lds + c]  (patch-token features of a ViT)
+cudaError_t launch_copy_rows(cudaStream_t stream, const bf16* src, int batch, int src_rows_per_sample, int row0, int rows, int width,
+                             int lds, bf16* dst, int ldd);
 
 // argument bundles of the small single-purpose kernels (engine.cu builds them once per op)
 struct EmbedMergeArgs {

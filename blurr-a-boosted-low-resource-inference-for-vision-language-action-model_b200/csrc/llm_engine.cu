@@ -285,32 +285,6 @@ int pick_splitk(int tiles, int kb_total) {
     return best_s;
 }
 
-// 33..288 token rows (a single-sequence prefill): tokens split into `chunks` CTAs per weight tile x K slices, by the cost
-// model measured for the Pi-0 prefill (engine.cu Run::plan_partial, tools/sweep_splitk.py): >= 0.25 us per k-block per
-// CTA (0.40 when one CTA holds two 144-token chunks), the fp32 tile store, and the consumer's re-read of the slices.
-int plan_mid_tokens(int T, int Nw, int K, size_t ws_floats, int* bn_override) {
-    *bn_override = 0;
-    const int tiles = Nw / 128, kb = (K + 63) / 64;
-    double best_cost = 1e30;
-    int best_s = 1;
-    for (int chunks = 1; chunks <= 4; ++chunks) {
-        const int bn = ((T + chunks - 1) / chunks + 15) / 16 * 16;
-        if (chunks > 1 && bn < 64) break;
-        int sl = kSMs / (tiles * chunks);
-        if (sl < 1) break;
-        if (sl > kb / 2) sl = kb / 2 > 0 ? kb / 2 : 1;
-        if (sl > 16) sl = 16;
-        while (sl > 1 && static_cast<size_t>(sl) * T * Nw > ws_floats) --sl;
-        const int kb_per = (kb + sl - 1) / sl;
-        sl = (kb + kb_per - 1) / kb_per;
-        const double us_kb = (chunks == 1 && T > 256) ? 0.40 : 0.25;
-        const double tile_tokens = chunks == 1 ? (T > 256 ? 288 : (T + 15) / 16 * 16) : bn;
-        const double cost = kb_per * us_kb + 128.0 * tile_tokens * 4.0 / 55e3 + static_cast<double>(sl) * T * Nw * 4.0 / 6e6;
-        if (cost < best_cost) { best_cost = cost; best_s = sl; *bn_override = chunks == 1 ? 0 : bn; }
-    }
-    return best_s;
-}
-
 struct Run {
     blurr_llm* h;
     cudaStream_t st;
@@ -335,7 +309,7 @@ struct Run {
         c.out = out; c.ldo = ldo;
         if (epi == EPI_PARTIAL) {
             c.splitk = T <= kFewTokens ? pick_splitk(L.Nw / 128, (L.K + 63) / 64)
-                                       : plan_mid_tokens(T, L.Nw, L.K, h->ws_floats, &c.bn_override);
+                                       : gemm_plan_chunked_splitk(T, L.Nw, L.K, h->ws_floats, &c.bn_override);
             c.partial = h->ws;
         }
         return c;

@@ -69,6 +69,23 @@ cudaError_t launch_action_tail(cudaStream_t stream, const bf16* xn, int T, int h
                          b, action_dim, dt, action, velocity_tap);
 }
 
+__global__ void __launch_bounds__(256) copy_rows_kernel(const bf16* src, int src_rows_per_sample, int row0, int rows, int width,
+                                                        int lds, bf16* dst, int ldd) {
+    pdl_wait();
+    pdl_trigger();
+    const int r = blockIdx.x, b = blockIdx.y;
+    const uint4* s = reinterpret_cast<const uint4*>(src + (static_cast<size_t>(b) * src_rows_per_sample + row0 + r) * lds);
+    uint4* d = reinterpret_cast<uint4*>(dst + (static_cast<size_t>(b) * rows + r) * ldd);
+    for (int i = threadIdx.x; i < width / 8; i += blockDim.x) d[i] = s[i];
+}
+
+cudaError_t launch_copy_rows(cudaStream_t stream, const bf16* src, int batch, int src_rows_per_sample, int row0, int rows, int width,
+                             int lds, bf16* dst, int ldd) {
+    if ((width & 7) || (lds & 7) || (ldd & 7)) return cudaErrorInvalidValue;
+    return launch_kernel(copy_rows_kernel, dim3(rows, batch), dim3(256), 0, stream, src, src_rows_per_sample, row0, rows, width, lds,
+                         dst, ldd);
+}
+
 // Last kernel of a control step.  `flags` are the device-side sticky error words of the step (GEMM / attention pipeline
 // time-outs, input validation): if any is set the step's results are not trustworthy, so the actions leave as NaN —
 // a robot loop that never calls blurr_pi0_check() still cannot act on garbage (the reference would have raised).

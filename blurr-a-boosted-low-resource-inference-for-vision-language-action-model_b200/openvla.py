@@ -211,3 +211,229 @@ def synthetic_llama_state_dict(cfg: LlamaShapedConfig, device, seed: int = 0, dt
     sd["model.norm.weight"] = torch.ones(cfg.hidden, device=device, dtype=dtype)
     sd["lm_head.weight"] = w(cfg.vocab, cfg.hidden)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Vision side: generic ViT towers + projector (include/blurr_vit.h)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class VitShapedConfig:
+    num_layers: int            # blocks to RUN (OpenVLA takes the second-to-last block's output: depth - 1)
+    hidden: int
+    num_heads: int
+    mlp_dim: int
+    num_prefix_tokens: int = 0
+    use_layerscale: bool = False
+    gelu_erf: bool = False
+    image_size: int = 224
+    patch_size: int = 14
+    ln_eps: float = 1e-6
+
+
+def dinov2_large_reg4_config(depth: int = 24) -> VitShapedConfig:
+    """`vit_large_patch14_reg4_dinov2` at 224 px: 24 blocks, 1024 wide, cls + 4 registers, LayerScale, exact GELU."""
+    return VitShapedConfig(num_layers=depth - 1, hidden=1024, num_heads=16, mlp_dim=4096, num_prefix_tokens=5,
+                           use_layerscale=True, gelu_erf=True)
+
+
+def siglip_so400m_config(depth: int = 27) -> VitShapedConfig:
+    """`vit_so400m_patch14_siglip_224`: 27 blocks, 1152 wide, no prefix tokens, tanh GELU."""
+    return VitShapedConfig(num_layers=depth - 1, hidden=1152, num_heads=16, mlp_dim=4304)
+
+
+class VitEncoder:
+    """One ViT tower on one B200 through `include/blurr_vit.h`; `forward` returns the patch-token features."""
+
+    def __init__(self, cfg: VitShapedConfig, device, max_batch: int = 1):
+        self.lib = capi.load_library()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.max_batch = max_batch
+        self.handle = C.c_void_p()
+        c = capi.VitConfigC(capi.VIT_ABI_VERSION, cfg.num_layers, cfg.hidden, cfg.num_heads, cfg.mlp_dim, cfg.image_size,
+                            cfg.patch_size, cfg.num_prefix_tokens, int(cfg.use_layerscale), int(cfg.gelu_erf), cfg.ln_eps)
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        capi.check(self.lib.blurr_vit_create(C.byref(c), index, max_batch, C.byref(self.handle)))
+        self.n_patches = (cfg.image_size // cfg.patch_size) ** 2
+
+    def set_weight(self, key: str, tensor: torch.Tensor):
+        t = tensor.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+        torch.cuda.current_stream(self.device).synchronize()
+        shape = (C.c_int64 * t.dim())(*t.shape)
+        capi.check(self.lib.blurr_vit_set_weight(self.handle, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+
+    def finalize(self):
+        capi.check(self.lib.blurr_vit_finalize(self.handle))
+
+    @classmethod
+    def from_hf_dinov2(cls, model, device, max_batch: int = 1, num_layers: Optional[int] = None) -> "VitEncoder":
+        """From a transformers `Dinov2WithRegistersModel` (image_size 224 so that its position embeddings are native)."""
+        hc = model.config
+        depth = hc.num_hidden_layers
+        cfg = VitShapedConfig(num_layers=num_layers or depth - 1, hidden=hc.hidden_size, num_heads=hc.num_attention_heads,
+                              mlp_dim=int(hc.hidden_size * hc.mlp_ratio), num_prefix_tokens=1 + hc.num_register_tokens,
+                              use_layerscale=True, gelu_erf=True, image_size=hc.image_size, patch_size=hc.patch_size,
+                              ln_eps=hc.layer_norm_eps)
+        self = cls(cfg, device, max_batch)
+        sd = {k: v.to(torch.bfloat16) for k, v in model.state_dict().items()}
+        e = "embeddings."
+        self.set_weight("patch.weight", sd[e + "patch_embeddings.projection.weight"].flatten(1))
+        self.set_weight("patch.bias", sd[e + "patch_embeddings.projection.bias"])
+        pos = sd[e + "position_embeddings"][0]
+        self.set_weight("pos", pos[1:])
+        prefix = torch.cat([sd[e + "cls_token"][0] + pos[:1], sd[e + "register_tokens"][0]], dim=0)     # bf16 add, like HF
+        self.set_weight("prefix", prefix)
+        for l in range(cfg.num_layers):
+            p, q = f"encoder.layer.{l}.", f"layers.{l}."
+            for a, b in (("norm1", "ln1"), ("norm2", "ln2"), ("mlp.fc1", "fc1"), ("mlp.fc2", "fc2"),
+                         ("attention.attention.query", "q"), ("attention.attention.key", "k"),
+                         ("attention.attention.value", "v"), ("attention.output.dense", "o")):
+                self.set_weight(q + b + ".weight", sd[p + a + ".weight"])
+                self.set_weight(q + b + ".bias", sd[p + a + ".bias"])
+            self.set_weight(q + "ls1", sd[p + "layer_scale1.lambda1"])
+            self.set_weight(q + "ls2", sd[p + "layer_scale2.lambda1"])
+        self.finalize()
+        return self
+
+    @classmethod
+    def from_hf_siglip(cls, model, device, max_batch: int = 1, num_layers: Optional[int] = None) -> "VitEncoder":
+        """From a transformers `SiglipVisionModel`."""
+        hc = model.config
+        cfg = VitShapedConfig(num_layers=num_layers or hc.num_hidden_layers - 1, hidden=hc.hidden_size,
+                              num_heads=hc.num_attention_heads, mlp_dim=hc.intermediate_size, image_size=hc.image_size,
+                              patch_size=hc.patch_size, ln_eps=hc.layer_norm_eps)
+        self = cls(cfg, device, max_batch)
+        sd = {k: v.to(torch.bfloat16) for k, v in model.state_dict().items()}
+        e = "vision_model.embeddings."
+        self.set_weight("patch.weight", sd[e + "patch_embedding.weight"].flatten(1))
+        self.set_weight("patch.bias", sd[e + "patch_embedding.bias"])
+        self.set_weight("pos", sd[e + "position_embedding.weight"])
+        for l in range(cfg.num_layers):
+            p, q = f"vision_model.encoder.layers.{l}.", f"layers.{l}."
+            for a, b in (("layer_norm1", "ln1"), ("layer_norm2", "ln2"), ("mlp.fc1", "fc1"), ("mlp.fc2", "fc2"),
+                         ("self_attn.q_proj", "q"), ("self_attn.k_proj", "k"), ("self_attn.v_proj", "v"),
+                         ("self_attn.out_proj", "o")):
+                self.set_weight(q + b + ".weight", sd[p + a + ".weight"])
+                self.set_weight(q + b + ".bias", sd[p + a + ".bias"])
+        self.finalize()
+        return self
+
+    @classmethod
+    def synthetic(cls, cfg: VitShapedConfig, device, max_batch: int = 1, seed: int = 0) -> "VitEncoder":
+        """Random-init tower of the given shape (benchmarks)."""
+        self = cls(cfg, device, max_batch)
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        H = cfg.hidden
+
+        def w(*shape, std=0.02):
+            return (torch.randn(shape, device=device, generator=g) * std).to(torch.bfloat16)
+
+        self.set_weight("patch.weight", w(H, 3 * cfg.patch_size ** 2))
+        self.set_weight("patch.bias", w(H))
+        self.set_weight("pos", w(self.n_patches, H))
+        if cfg.num_prefix_tokens:
+            self.set_weight("prefix", w(cfg.num_prefix_tokens, H))
+        ones = torch.ones(H, device=device, dtype=torch.bfloat16)
+        for l in range(cfg.num_layers):
+            q = f"layers.{l}."
+            for name, (n, k) in (("q", (H, H)), ("k", (H, H)), ("v", (H, H)), ("o", (H, H)), ("fc1", (cfg.mlp_dim, H)),
+                                 ("fc2", (H, cfg.mlp_dim))):
+                self.set_weight(q + name + ".weight", w(n, k))
+                self.set_weight(q + name + ".bias", w(n))
+            for name in ("ln1", "ln2"):
+                self.set_weight(q + name + ".weight", ones)
+                self.set_weight(q + name + ".bias", torch.zeros_like(ones))
+            if cfg.use_layerscale:
+                self.set_weight(q + "ls1", ones)
+                self.set_weight(q + "ls2", ones)
+        self.finalize()
+        return self
+
+    def forward(self, pixel_values: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pixel_values bf16 [B, 3, 224, 224] -> bf16 [B, n_patches, hidden] (or the first `hidden` columns of `out`)."""
+        if pixel_values.dtype != torch.bfloat16 or pixel_values.device.type != "cuda" or pixel_values.dim() != 4:
+            raise ValueError("pixel_values must be a bf16 CUDA tensor [B, 3, H, W]")
+        B = pixel_values.shape[0]
+        if out is None:
+            out = torch.empty((B, self.n_patches, self.cfg.hidden), device=self.device, dtype=torch.bfloat16)
+        if out.stride(-1) != 1 or out.stride(0) != self.n_patches * out.stride(1):
+            raise ValueError("out must be [B, n_patches, >= hidden] with contiguous rows")
+        strides = (C.c_int64 * 4)(*pixel_values.stride())
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(self.lib.blurr_vit_forward(self.handle, C.c_void_p(stream), B, C.c_void_p(pixel_values.data_ptr()), strides,
+                                              C.c_void_p(out.data_ptr()), out.stride(1)))
+        return out
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.blurr_vit_last_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.blurr_vit_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MlpProjector:
+    """OpenVLA's fused-backbone projector: Linear -> GELU -> Linear -> GELU -> Linear (exact GELU), `include/blurr_vit.h`."""
+
+    def __init__(self, dims, device, max_rows: int):
+        self.lib = capi.load_library()
+        self.dims = list(dims)
+        self.device = torch.device(device)
+        self.handle = C.c_void_p()
+        arr = (C.c_int32 * len(self.dims))(*self.dims)
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        capi.check(self.lib.blurr_mlp_create(arr, len(self.dims) - 1, index, max_rows, C.byref(self.handle)))
+
+    def set_layer(self, i: int, weight: torch.Tensor, bias: torch.Tensor):
+        w = weight.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+        b = bias.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+        assert tuple(w.shape) == (self.dims[i + 1], self.dims[i]) and tuple(b.shape) == (self.dims[i + 1],)
+        torch.cuda.current_stream(self.device).synchronize()
+        capi.check(self.lib.blurr_mlp_set_weight(self.handle, i, C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr())))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x bf16 [..., dims[0]] contiguous -> bf16 [..., dims[-1]]."""
+        x2 = x.reshape(-1, self.dims[0])
+        if not x2.is_contiguous() or x2.dtype != torch.bfloat16:
+            raise ValueError("x must be contiguous bf16")
+        y = torch.empty((x2.shape[0], self.dims[-1]), device=self.device, dtype=torch.bfloat16)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(self.lib.blurr_mlp_forward(self.handle, C.c_void_p(stream), x2.shape[0], C.c_void_p(x2.data_ptr()),
+                                              self.dims[0], C.c_void_p(y.data_ptr()), self.dims[-1]))
+        return y.reshape(*x.shape[:-1], self.dims[-1])
+
+    def close(self):
+        if self.handle:
+            self.lib.blurr_mlp_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FusedVisionBackbone:
+    """DINOv2 + SigLIP towers on the same image, patch features concatenated (DINOv2 first, as in Prismatic's
+    `dinosiglip` backbone) and projected to the language model's width."""
+
+    def __init__(self, dino: VitEncoder, siglip: VitEncoder, projector: MlpProjector):
+        self.dino, self.siglip, self.projector = dino, siglip, projector
+        self.width = dino.cfg.hidden + siglip.cfg.hidden
+
+    def forward(self, pixel_values_dino: torch.Tensor, pixel_values_siglip: torch.Tensor) -> torch.Tensor:
+        B = pixel_values_dino.shape[0]
+        feats = torch.empty((B, self.dino.n_patches, self.width), device=pixel_values_dino.device, dtype=torch.bfloat16)
+        self.dino.forward(pixel_values_dino, out=feats)
+        self.siglip.forward(pixel_values_siglip, out=feats[:, :, self.dino.cfg.hidden:])
+        return self.projector.forward(feats)

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = capi.load_library()
     assert lib.blurr_abi_version() == capi.ABI_VERSION
     declared = set()
-    for name in ("blurr_pi0.h", "blurr_llm.h"):
+    for name in ("blurr_pi0.h", "blurr_llm.h", "blurr_vit.h"):
         header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", name)).read(), flags=re.S)
         declared |= set(re.findall(r"\b(blurr_[a-z0-9_]+)\s*\(", header))
     declared -= {"blurr_status", "blurr_dtype"}
@@ -46,6 +46,13 @@ def test_llm_config_struct_matches_header_field_order():
     body = header[header.index("typedef struct blurr_llm_config {"):header.index("} blurr_llm_config;")]
     fields = re.findall(r"^\s+(?:int32_t|int64_t|float)\s+([a-z_0-9]+);", body, flags=re.M)
     assert fields == [f[0] for f in capi.LlmConfigC._fields_]
+
+
+def test_vit_config_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "blurr_vit.h")).read()
+    body = header[header.index("typedef struct blurr_vit_config {"):header.index("} blurr_vit_config;")]
+    fields = re.findall(r"^\s+(?:int32_t|int64_t|float)\s+([a-z_0-9]+);", body, flags=re.M)
+    assert fields == [f[0] for f in capi.VitConfigC._fields_]
 
 
 def test_llm_create_fails_loudly_without_gpu():
