@@ -560,11 +560,50 @@ def run_openvla(args):
     capi.check(dec.lib.blurr_llm_set_rope_table(dec.handle, C.c_void_p(cos.data_ptr()), C.c_void_p(sin.data_ptr()), cfg.max_positions))
     capi.check(dec.lib.blurr_llm_finalize(dec.handle))
     hbm = peaks["hbm_gbs"]
+    # vision side: full-depth DINOv2-L/14 (reg4) + SigLIP-so400m/14 towers (second-to-last block) and the 3-layer projector
+    dino = openvla.VitEncoder.synthetic(openvla.dinov2_large_reg4_config(), dev, max_batch=32, seed=100)
+    sig = openvla.VitEncoder.synthetic(openvla.siglip_so400m_config(), dev, max_batch=32, seed=101)
+    proj = openvla.MlpProjector([2176, 8704, 4096, 4096], dev, max_rows=32 * 256)
+    for i, (n_out, n_in) in enumerate(((8704, 2176), (4096, 8704), (4096, 4096))):
+        proj.set_layer(i, (torch.randn((n_out, n_in), device=dev, generator=g) * 0.02).to(torch.bfloat16),
+                       torch.zeros(n_out, device=dev, dtype=torch.bfloat16))
+    fused = openvla.FusedVisionBackbone(dino, sig, proj)
+    n_text = prompt - 1 - 256
     out = {}
     for B in (1, 32):
         ring = [(torch.randn((B, prompt, cfg.hidden), device=dev, generator=g) * 0.5).to(torch.bfloat16) for _ in range(4)]
         host = [r.cpu().pin_memory() for r in ring]
         res = {}
+        # vision towers + projector alone
+        px = (torch.rand((B, 3, 224, 224), device=dev, generator=g) * 2 - 1).to(torch.bfloat16)
+        ids_prompt = torch.randint(3, cfg.vocab - 100, (B, 1 + n_text), device=dev, generator=g)
+        for _ in range(W):
+            fused.forward(px, px)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        evs[0].record()
+        for i in range(K):
+            fused.forward(px, px)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        lat = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(K))
+        res["vision_towers_and_projector"] = {"ms_p50": lat[len(lat) // 2], "launches": dino.last_launch_count + sig.last_launch_count + 4}
+
+        def full_step():
+            patch = fused.forward(px, px)
+            return dec.generate(openvla.build_prompt_embeds(dec, ids_prompt, patch), n_new)
+        for _ in range(W):
+            full_step()
+        dec.check()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        evs[0].record()
+        for i in range(K):
+            full_step()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        dec.check()
+        lat = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(K))
+        res["predict_action_full"] = {"ms_p50": lat[len(lat) // 2], "ms_mean": evs[0].elapsed_time(evs[K]) / K,
+                                      "note": "pixels -> DINOv2 + SigLIP -> projector -> [BOS] + 256 patches + prompt tokens -> 7 greedy tokens"}
         for label, n in (("prefill_plus_1", 1), ("predict_action", n_new)):
             for i in range(W):
                 dec.generate(ring[i % 4], n)
@@ -610,6 +649,7 @@ def run_openvla(args):
             "decode_weight_stream": {"bytes_per_token": wb, "achieved_gbps": wb / per_tok / 1e6, "peak_gbps": hbm,
                                      "frac": wb / per_tok / 1e6 / hbm, "hbm_floor_ms": wb / hbm / 1e6},
             "action_chunks_per_sec": B * 1e3 / res["predict_action"]["ms_mean"],
+            "action_chunks_per_sec_full_model": B * 1e3 / res["predict_action_full"]["ms_mean"],
             "e2e": {"ms_p50": t_e2e[len(t_e2e) // 2], "action_chunks_per_sec": B * 1e3 / (sum(t_e2e) / len(t_e2e)),
                     "h2d_bytes_per_step": stage.numel() * 2, "d2h_bytes_per_step": ids_host.numel() * 8},
         })
@@ -620,7 +660,8 @@ def run_openvla(args):
         "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": head["predict_action"]["ms_mean"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (random-init Llama-2-7B-shaped weights, random projected patch embeddings)",
-        "config": {"workload": "openvla7b_shaped_bs1_7_token_decode (BASELINE.json configs[4]; language model only)",
+        "config": {"workload": "openvla7b_shaped_bs1_7_token_decode (BASELINE.json configs[4]; headline value = language model, "
+                               "openvla.bs*.predict_action_full = with the DINOv2 + SigLIP towers and the projector)",
                    "prompt_positions": prompt, "new_tokens": n_new, "layers": cfg.num_layers, "hidden": cfg.hidden,
                    "l2": "inputs larger than L2: every token streams 13.2 GB of weights", "cuda_graph": True},
         "e2e": {"value": head["e2e"]["action_chunks_per_sec"], "unit": "action chunks/s",
