@@ -613,6 +613,7 @@ static int g_siglip_stream = 1;
 void attn_set_siglip_stream(int on) { g_siglip_stream = on; }
 static bool siglip_stream_applies(const AttnMmaArgs& a, int seq, int n_heads, int batch) {
     if (!g_siglip_stream || seq > kSsKeys || a.hd > 96 || (a.hd & 7)) return false;
+    if (g_siglip_stream == 2) return true;          // experiments: at any batch size
     return static_cast<long>((seq + kSsRows - 1) / kSsRows) * n_heads * batch <= 2 * 148;
 }
 static cudaError_t launch_siglip_stream(cudaStream_t stream, const AttnMmaArgs& a, int seq, int n_heads, int batch) {
