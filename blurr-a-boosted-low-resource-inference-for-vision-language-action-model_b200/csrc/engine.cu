@@ -1415,6 +1415,7 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "attn_fewq_stream") attn_set_fewq_stream(static_cast<int>(value));
     else if (n == "attn_prefill_stream") attn_set_prefill_stream(static_cast<int>(value));
     else if (n == "attn_siglip_stream") attn_set_siglip_stream(static_cast<int>(value));
+    else if (n == "attn_mha_prefill_stream") attn_set_mha_prefill_stream(static_cast<int>(value));
     else if (n == "attn_cta_trace") { if (attn_set_cta_trace(reinterpret_cast<void*>(static_cast<intptr_t>(value)))) return fail(BLURR_ERR_CUDA, "attn_cta_trace: cudaMemcpyToSymbol failed"); }
     else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
     else if (n == "gemm_pair_band") gemm_set_pair_band(static_cast<int>(value));

@@ -122,6 +122,7 @@ void attn_set_tc_fewq(int mode);                 // few-query attention on the t
 bool attn_tc_fewq_applies(const JointAttnArgs& a);
 void attn_set_prefill_stream(int on);           // prefill attention of <= 2 waves of 16-row tiles as the streaming kernel (default 1)
 void attn_set_siglip_stream(int on);            // SigLIP attention of <= 2 waves of 32-row tiles as the streaming kernel (default 1)
+void attn_set_mha_prefill_stream(int on);       // Llama-shaped prefill attention: one CTA per (sequence, head); default 0 = the tile kernel
 void attn_set_fewq_stream(int on);              // few-query attention as the streaming kernel (default 1) vs the mma.sync tile kernel
 int attn_take_timeout_flag();
 int attn_set_cta_trace(void* dev_ptr);          // per-CTA timeline of the tcgen05 attention kernel (attention_tc.cu)
