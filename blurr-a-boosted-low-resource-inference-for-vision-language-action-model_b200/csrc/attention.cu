@@ -211,6 +211,15 @@ __global__ void __launch_bounds__(kFqThreads, 1) fewq_stream_kernel(const JointA
     const bf16* mrow = row_valid ? j.mask + static_cast<size_t>(b) * j.mask_bstride +
                                        static_cast<size_t>(j.q_row_offset + qi) * j.mask_rstride
                                  : nullptr;
+    // the additive mask values of this lane's logits, requested with everything else (not after the MMAs)
+    float mk[2][2];
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = (warp * 2 + t2) * 8 + 2 * c + e;
+            mk[t2][e] = (mrow != nullptr && k < n) ? bf2f(mrow[k]) : 0.f;
+        }
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kFqThreads, 1) fewq_stream_kernel(const JointA
             s0 = bf16_round(s0 * (1.0f / 50.0f));
             s0 = bf16_round(tanhf(s0));
             s0 = bf16_round(s0 * 50.0f);
-            if (mrow != nullptr && k < n) s0 = bf16_round(s0 + bf2f(mrow[k]));
+            if (mrow != nullptr && k < n) s0 = bf16_round(s0 + mk[t2][e]);
             sc[g * kFqLdP + k] = s0;
         }
     }
@@ -334,6 +343,25 @@ __global__ void __launch_bounds__(kFqThreads, 1) prefill_stream_kernel(const Joi
             kr[t2][t] = key < n ? __ldcg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * 256 + 32 * t + 8 * c))
                                 : make_uint4(0u, 0u, 0u, 0u);
     }
+    // rows g and g + 8 of this tile
+    const bf16* mrow[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int p = tile * kPsRows + g + hh * 8;
+        mrow[hh] = p < rows_total ? j.mask + static_cast<size_t>(b) * j.mask_bstride +
+                                        static_cast<size_t>(j.q_row_offset + p / nh) * j.mask_rstride
+                                  : nullptr;
+    }
+    float mk[2][2][2];                 // [key tile][row half][key]: requested before the MMAs
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = (warp * 2 + t2) * 8 + 2 * c + e;
+                mk[t2][hh][e] = (mrow[hh] != nullptr && k < n) ? bf2f(mrow[hh][k]) : 0.f;
+            }
     // query rows -> shared memory, dims (d, d + 1) of row r stored at the column the K fragments use for them
     for (int i = threadIdx.x; i < kPsRows * 128; i += kFqThreads) {
         const int r = i >> 7, d = (i & 127) << 1;
@@ -348,15 +376,6 @@ __global__ void __launch_bounds__(kFqThreads, 1) prefill_stream_kernel(const Joi
         *reinterpret_cast<uint32_t*>(q_s + r * kPsLdQ + col) = val;
     }
     __syncthreads();
-    // rows g and g + 8 of this tile
-    const bf16* mrow[2];
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        const int p = tile * kPsRows + g + hh * 8;
-        mrow[hh] = p < rows_total ? j.mask + static_cast<size_t>(b) * j.mask_bstride +
-                                        static_cast<size_t>(j.q_row_offset + p / nh) * j.mask_rstride
-                                  : nullptr;
-    }
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -378,7 +397,7 @@ __global__ void __launch_bounds__(kFqThreads, 1) prefill_stream_kernel(const Joi
                 s0 = bf16_round(s0 * (1.0f / 50.0f));
                 s0 = bf16_round(tanhf(s0));
                 s0 = bf16_round(s0 * 50.0f);
-                if (mrow[hh] != nullptr && k < n) s0 = bf16_round(s0 + bf2f(mrow[hh][k]));
+                if (mrow[hh] != nullptr && k < n) s0 = bf16_round(s0 + mk[t2][hh][e]);
                 sc[(g + hh * 8) * kFqLdP + k] = s0;
             }
         }

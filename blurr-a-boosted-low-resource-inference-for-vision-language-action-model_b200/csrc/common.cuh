@@ -85,10 +85,8 @@ __device__ __forceinline__ float gelu_tanh_f32(float x) {
 }
 
 __device__ __forceinline__ float silu_f32(float x) { return x / (1.0f + expf(-x)); }
-// EPI_GELU flavour (GemmCall::glu_act): 0 tanh approximation, 2 exact erf (nn.GELU() default)
-__device__ __forceinline__ float gelu_sel_f32(float x, int kind) {
-    return kind == 2 ? 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)) : gelu_tanh_f32(x);
-}
+// exact GELU (nn.GELU() default); the tanh flavour is gelu_tanh_f32.  Chosen at compile time (EPI_GELU / EPI_GELU_ERF).
+__device__ __forceinline__ float gelu_erf_f32(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // gate activation of the GLU epilogue: 0 = tanh GELU (Gemma GeGLU), 1 = SiLU (Llama SwiGLU)
 __device__ __forceinline__ float glu_act_f32(float x, int act) { return act == 1 ? silu_f32(x) : gelu_tanh_f32(x); }
 

@@ -242,7 +242,8 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float v = bf16_round(__uint_as_float(r[i]) + bias);
-                    if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
+                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    if (EPI == EPI_GELU_ERF) v = gelu_erf_f32(v);
                     tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
                 }
             }
@@ -422,7 +423,8 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
                             if ((lane & 1) == 0) stg[t * OUTW + (nl >> 1)] = f2bf(bf16_round(glu_act_f32(v, p.glu_act)) * up);
                         } else {
                             float v = bf16_round(__uint_as_float(r[i]) + bias);
-                            if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
+                            if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    if (EPI == EPI_GELU_ERF) v = gelu_erf_f32(v);
                             stg[t * OUTW + nl] = f2bf(v);
                         }
                     }
@@ -468,7 +470,8 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float v = bf16_round(__uint_as_float(r[i]) + bias);
-                        if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
+                        if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    if (EPI == EPI_GELU_ERF) v = gelu_erf_f32(v);
                         if (tb + i < p.T) dst[static_cast<size_t>(i) * p.ldo] = f2bf(v);
                     }
                 }
@@ -593,7 +596,8 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float v = bf16_round(__uint_as_float(r[i]) + bias);
-                    if (EPI == EPI_GELU) v = gelu_sel_f32(v, p.glu_act);
+                    if (EPI == EPI_GELU) v = gelu_tanh_f32(v);
+                    if (EPI == EPI_GELU_ERF) v = gelu_erf_f32(v);
                     tile[(g * 16 + i) * kBlockM + nl] = f2bf(v);
                 }
             }
@@ -831,10 +835,11 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
                         const float gate = (lane & 1) ? recv : v0, up = (lane & 1) ? v1 : recv;
                         stg[(g * 16 + i + (lane & 1)) * OUTW + (nl >> 1)] = f2bf(bf16_round(glu_act_f32(gate, p.glu_act)) * up);
                     }
-                } else if (EPI == EPI_GELU) {
+                } else if (EPI == EPI_GELU || EPI == EPI_GELU_ERF) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float v = gelu_sel_f32(bf16_round(__uint_as_float(r[i]) + bias), p.glu_act);
+                        const float x0 = bf16_round(__uint_as_float(r[i]) + bias);
+                        const float v = EPI == EPI_GELU_ERF ? gelu_erf_f32(x0) : gelu_tanh_f32(x0);
                         stg[(g * 16 + i) * kBlockM + nl] = f2bf(v);
                     }
                 } else {

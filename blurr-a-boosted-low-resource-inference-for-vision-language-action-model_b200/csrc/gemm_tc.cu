@@ -616,7 +616,7 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     cudaError_t e;
     switch (c.epi) {
         case EPI_GEGLU: e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
-        case EPI_GELU:  e = launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
+        case EPI_GELU:    e = c.glu_act == 2 ? launch_pairp<EPI_GELU_ERF>(stream, n_pairs, smem, tw, txh, d, gxp, gy) : launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
         default:        e = launch_pairp<EPI_STORE>(stream, n_pairs, smem, tw, txh, d, gxp, gy); break;
     }
     if (e != cudaSuccess) { *err = std::string("gemm (persistent pairs) launch failed: ") + cudaGetErrorString(e); return -1; }
@@ -667,7 +667,7 @@ static int gemm_launch_pair_small(cudaStream_t stream, const GemmCall& c, std::s
     cudaError_t e;
     switch (c.epi) {
         case EPI_GEGLU:   e = launch_pairp<EPI_GEGLU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
-        case EPI_GELU:    e = launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
+        case EPI_GELU:    e = c.glu_act == 2 ? launch_pairp<EPI_GELU_ERF>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256) : launch_pairp<EPI_GELU>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
         case EPI_PARTIAL: e = launch_pairp<EPI_PARTIAL>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
         default:          e = launch_pairp<EPI_STORE>(stream, n_pairs, smem, tw, txh, d, gxp, 1, splitk, kGemmThreads + 256); break;
     }
@@ -773,7 +773,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         if (get_tmap(c.X, c.T, c.K, c.ldx, pl.bn / 2, &txh, err)) return -1;
         switch (c.epi) {
             case EPI_STORE:   e = launch_epi2<EPI_STORE>(stream, pl, tw, txh, d); break;
-            case EPI_GELU:    e = launch_epi2<EPI_GELU>(stream, pl, tw, txh, d); break;
+            case EPI_GELU:    e = c.glu_act == 2 ? launch_epi2<EPI_GELU_ERF>(stream, pl, tw, txh, d) : launch_epi2<EPI_GELU>(stream, pl, tw, txh, d); break;
             case EPI_GEGLU:   e = launch_epi2<EPI_GEGLU>(stream, pl, tw, txh, d); break;
             case EPI_PARTIAL: e = launch_epi2<EPI_PARTIAL>(stream, pl, tw, txh, d); break;
             default: *err = "gemm_launch: bad epilogue"; return -1;
@@ -799,7 +799,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     if (large_dbuf || (g_persistent && pl.cluster == 1 && pl.nt * pl.bn <= kPersistentMaxTokens && c.epi != EPI_GEGLU)) {
         switch (c.epi) {
             case EPI_STORE:   e = launch_epip<EPI_STORE>(stream, pl, tw, tx, d); break;
-            case EPI_GELU:    e = launch_epip<EPI_GELU>(stream, pl, tw, tx, d); break;
+            case EPI_GELU:    e = c.glu_act == 2 ? launch_epip<EPI_GELU_ERF>(stream, pl, tw, tx, d) : launch_epip<EPI_GELU>(stream, pl, tw, tx, d); break;
             case EPI_GEGLU:   e = launch_epip<EPI_GEGLU>(stream, pl, tw, tx, d); break;
             case EPI_PARTIAL: e = launch_epip<EPI_PARTIAL>(stream, pl, tw, tx, d, c.tail); break;
             default: *err = "gemm_launch: bad epilogue"; return -1;
@@ -809,7 +809,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     }
     switch (c.epi) {
         case EPI_STORE:   e = launch_epi<EPI_STORE>(stream, pl, tw, tx, txs, d); break;
-        case EPI_GELU:    e = launch_epi<EPI_GELU>(stream, pl, tw, tx, txs, d); break;
+        case EPI_GELU:    e = c.glu_act == 2 ? launch_epi<EPI_GELU_ERF>(stream, pl, tw, tx, txs, d) : launch_epi<EPI_GELU>(stream, pl, tw, tx, txs, d); break;
         case EPI_GEGLU:   e = launch_epi<EPI_GEGLU>(stream, pl, tw, tx, txs, d); break;
         case EPI_PARTIAL: e = launch_epi<EPI_PARTIAL>(stream, pl, tw, tx, txs, d); break;
         default: *err = "gemm_launch: bad epilogue"; return -1;

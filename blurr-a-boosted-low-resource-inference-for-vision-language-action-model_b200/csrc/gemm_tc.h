@@ -16,6 +16,8 @@ enum GemmEpilogue {
     EPI_GELU = 1,     // out[t][n] = bf16(gelu_tanh(bf16(acc + bias[n])))
     EPI_GEGLU = 2,    // weight rows interleaved 64 gate / 64 up per 128-row tile; out width Nw/2
     EPI_PARTIAL = 3,  // partial[z][t][n] = fp32 partial sum of split-K slice z
+    EPI_GELU_ERF = 4, // EPI_GELU with the exact erf GELU (nn.GELU()); callers pass EPI_GELU + glu_act = 2, gemm_launch picks this
+                      // instantiation - a runtime switch inside the epilogue cost the tanh flavour 3.4 us per SigLIP fc1 launch
 };
 
 // Rider of a weight-streaming GEMM: as each CTA runs out of work it asks L2 (cp.async.bulk.prefetch.L2) for the part of
