@@ -200,6 +200,11 @@ int blurr_op_normalize_proprio(void* cuda_stream, const double* raw, const doubl
  * plain store), persistent single CTAs for fp32 partial / residual epilogues; 0 never persistent; 1 single-CTA
  * persistent for every epilogue; 2 and 3 = same as automatic), "attn_tc" (-1 automatic = tcgen05 prefill / SigLIP attention whenever the shape allows, 0 never (mma.sync tile kernel), 1 = -1),
  * "attn_tc_fewq" (1: the experts' few-query attention on the tcgen05 kernel too; default 0, measured slower at batch 1),
+ * "attn_prefill_stream", "attn_fewq_stream", "attn_siglip_stream" (default 1: at one or two episodes the prefill, the experts'
+ * few-query and the SigLIP attention run as the streaming mma.sync kernels of csrc/attention.cu - K straight into permuted
+ * fragments, V in shared memory, every load requested up front; 0: the tile / tcgen05 kernels; attn_siglip_stream = 2 forces
+ * the streaming kernel at any batch size, measured slower), "attn_mha_prefill_stream" (Llama-shaped prefill attention as one
+ * CTA per (sequence, head); default 0),
  * "gemm_pair_small" (257..288 tokens: 0 one CTA per weight tile, 1 persistent CTA pairs for GeGLU only, 2 (default) for every epilogue),
  * "gemm_cta_trace" / "attn_cta_trace" (device pointer to [n_cta][8] u64, 0 = off: per-CTA %globaltimer timeline), "op_gemm_bn" (token chunk
  * width used by blurr_op_gemm*, 0 = automatic),
