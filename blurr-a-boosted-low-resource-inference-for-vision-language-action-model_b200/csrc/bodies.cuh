@@ -112,6 +112,26 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
     const int to = a.row_group > 0 ? t + (t / a.row_group) * a.row_extra + a.row_offset : t;     // output row
     float4 x[VPT];
     float lsum = 0.f, lsq = 0.f;
+    // Everything that does not depend on the partial sums is requested first - residual / position row, norm weights -
+    // so the row costs one round trip to L2 plus the reduction instead of three dependent ones (the kernel is latency-bound).
+    const bool want_norm = a.norm_mode != NORM_NONE && a.xn_out != nullptr;
+    const bool from_res = a.partial == nullptr && a.lin == nullptr;
+    uint2 pf_add[VPT], pf_w[VPT], pf_b[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int v = threadIdx.x + i * THREADS;
+        pf_add[i] = make_uint2(0u, 0u); pf_w[i] = make_uint2(0u, 0u); pf_b[i] = make_uint2(0u, 0u);
+        if (v >= nvec) continue;
+        const int n = v << 2;
+        if (!PRELOADED || from_res) {
+            if (from_res || a.add_mode == ADD_RESIDUAL) pf_add[i] = __ldcg(reinterpret_cast<const uint2*>(a.res + static_cast<size_t>(t) * a.ldr + n));
+            else if (a.add_mode == ADD_POSEMB) pf_add[i] = __ldcg(reinterpret_cast<const uint2*>(a.pos + static_cast<size_t>(t % a.pos_rows) * a.N + n));
+        }
+        if (want_norm) {
+            pf_w[i] = __ldcg(reinterpret_cast<const uint2*>(a.norm_w + n));
+            if (a.norm_mode == NORM_LAYERNORM) pf_b[i] = __ldcg(reinterpret_cast<const uint2*>(a.norm_b + n));
+        }
+    }
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
         const int v = threadIdx.x + i * THREADS;
@@ -142,17 +162,16 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
                                   bf16_round(val.w * gsc.w));
             }
             if (a.add_mode == ADD_RESIDUAL) {
-                const float4 r = PRELOADED ? unpack_bf16x4(pre->add[i]) : load_bf16x4(a.res + static_cast<size_t>(t) * a.ldr + n);
+                const float4 r = PRELOADED ? unpack_bf16x4(pre->add[i]) : unpack_bf16x4(pf_add[i]);
                 val = make_float4(bf16_round(r.x + val.x), bf16_round(r.y + val.y), bf16_round(r.z + val.z),
                                   bf16_round(r.w + val.w));
             } else if (a.add_mode == ADD_POSEMB) {
-                const float4 r = PRELOADED ? unpack_bf16x4(pre->add[i])
-                                           : load_bf16x4(a.pos + static_cast<size_t>(t % a.pos_rows) * a.N + n);
+                const float4 r = PRELOADED ? unpack_bf16x4(pre->add[i]) : unpack_bf16x4(pf_add[i]);
                 val = make_float4(bf16_round(val.x + r.x), bf16_round(val.y + r.y), bf16_round(val.z + r.z),
                                   bf16_round(val.w + r.w));
             }
         } else {
-            val = load_bf16x4(a.res + static_cast<size_t>(t) * a.ldr + n);
+            val = unpack_bf16x4(pf_add[i]);
         }
         if (a.x_out != nullptr) store_bf16x4(a.x_out + static_cast<size_t>(to) * a.ldx + n, val);
         x[i] = val;
@@ -170,7 +189,7 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
             const int v = threadIdx.x + i * THREADS;
             if (v >= nvec) continue;
             const int n = v << 2;
-            const float4 w = load_bf16x4(a.norm_w + n);
+            const float4 w = unpack_bf16x4(pf_w[i]);
             // Gemma: (x * rstd) * (1 + w) in fp32, one rounding.  Llama (HF LlamaRMSNorm.forward): weight * (x * rstd).to(bf16)
             const float4 y = llama
                 ? make_float4(w.x * bf16_round(x[i].x * r), w.y * bf16_round(x[i].y * r), w.z * bf16_round(x[i].z * r),
@@ -196,7 +215,7 @@ __device__ __forceinline__ void consumer_body(const ConsumerArgs& a, const int t
             const int v = threadIdx.x + i * THREADS;
             if (v >= nvec) continue;
             const int n = v << 2;
-            const float4 w = load_bf16x4(a.norm_w + n), b = load_bf16x4(a.norm_b + n);
+            const float4 w = unpack_bf16x4(pf_w[i]), b = unpack_bf16x4(pf_b[i]);
             const float4 y = make_float4((x[i].x - mean) * rstd * w.x + b.x, (x[i].y - mean) * rstd * w.y + b.y,
                                          (x[i].z - mean) * rstd * w.z + b.z, (x[i].w - mean) * rstd * w.w + b.w);
             store_bf16x4(a.xn_out + static_cast<size_t>(to) * a.ldn + n, y);
