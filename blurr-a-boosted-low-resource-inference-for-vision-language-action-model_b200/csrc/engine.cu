@@ -1412,6 +1412,7 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_max_stages") gemm_set_max_stages(static_cast<int>(value));
     else if (n == "attn_tc") attn_set_tc(static_cast<int>(value));
     else if (n == "attn_tc_fewq") attn_set_tc_fewq(static_cast<int>(value));
+    else if (n == "gemm_x_policy") gemm_set_x_policy(static_cast<int>(value));
     else if (n == "attn_fewq_stream") attn_set_fewq_stream(static_cast<int>(value));
     else if (n == "attn_prefill_stream") attn_set_prefill_stream(static_cast<int>(value));
     else if (n == "attn_siglip_stream") attn_set_siglip_stream(static_cast<int>(value));

@@ -29,6 +29,9 @@
 #include <unordered_map>
 
 namespace blurr {
+static int g_x_normal = 0;
+void gemm_set_x_policy(int normal) { g_x_normal = normal != 0; }
+
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -598,7 +601,7 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     d.T = c.T; d.bn = bn; d.nt = 1; d.kb_total = kb_total; d.kb_per_split = kb_total;
     d.tmem_cols = 512; d.acc_bufs = 2; d.acc_stride = 256; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = nullptr;
-    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; if (c.prefetch) d.pf = *c.prefetch;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; d.x_normal = g_x_normal; if (c.prefetch) d.pf = *c.prefetch;
     d.staging_bytes = bn * (c.epi == EPI_GEGLU ? kBlockM / 2 : kBlockM) * 2;
     const int stage_bytes = kTileABytes + half * kBlockK * 2;
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
@@ -652,7 +655,7 @@ static int gemm_launch_pair_small(cudaStream_t stream, const GemmCall& c, std::s
     d.T = c.T; d.bn = bn; d.nt = 2; d.kb_total = kb_total; d.kb_per_split = kb_per_split;
     d.tmem_cols = 512; d.acc_bufs = 1; d.acc_stride = 0; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
-    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; if (c.prefetch) d.pf = *c.prefetch;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; d.x_normal = g_x_normal; if (c.prefetch) d.pf = *c.prefetch;
     d.staging_bytes = c.epi == EPI_PARTIAL ? 0 : ntok * kBlockM * 2;      // GeGLU is staged as raw gate / up values (one accumulator buffer)
     const int stage_bytes = kTileABytes + 2 * half * kBlockK * 2;
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
@@ -766,7 +769,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     d.T = c.T; d.bn = pl.bn; d.nt = pl.nt; d.stages = pl.stages; d.kb_total = pl.kb_total;
     d.kb_per_split = pl.kb_per_split; d.tmem_cols = pl.tmem_cols; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
-    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; if (c.prefetch) d.pf = *c.prefetch;
+    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; d.x_normal = g_x_normal; if (c.prefetch) d.pf = *c.prefetch;
     cudaError_t e;
     if (pl.two_cta) {
         CUtensorMap txh;

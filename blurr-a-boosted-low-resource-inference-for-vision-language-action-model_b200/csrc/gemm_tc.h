@@ -81,6 +81,7 @@ struct GemmDev {
     int staging_bytes; // persistent kernel: bf16 output staging tile behind the ring (0 = direct epilogue)
     int l2_policy;    // persistent pairs: 0 = weights evict_first / tokens evict_last, 1 = both evict_normal, 2 = weights evict_last / tokens evict_first
     int glu_act;      // EPI_GEGLU gate activation (GemmCall::glu_act)
+    int x_normal;     // experiment (gemm_set_x_policy): token tiles with the evict_normal L2 policy instead of evict_last
     GemmPrefetch pf;  // len == 0: none
     int band;         // persistent pairs: weight tile pairs per raster band (the band sweeps every token tile before the next one starts)
 };
@@ -127,6 +128,7 @@ void gemm_set_large_t_mode(int mode);
 void gemm_set_pair_band(int band);          // 0 = automatic
 void gemm_set_pair_small(int mode);         // persistent CTA pairs for 257..288 tokens: 0 never, 1 GeGLU only (default), 2 every epilogue
 void gemm_set_pair_policy(int policy);      // -1 = automatic
+void gemm_set_x_policy(int normal);         // 1: every kernel loads its token tiles with evict_normal (default 0: evict_last)
 int gemm_pair_raster(int N, int K, int T, int* band_out, int* n_pairs_out, int32_t* order, int capacity);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.
