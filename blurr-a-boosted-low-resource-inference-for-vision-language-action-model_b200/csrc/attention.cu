@@ -632,7 +632,6 @@ static int g_siglip_stream = 1;
 void attn_set_siglip_stream(int on) { g_siglip_stream = on; }
 static bool siglip_stream_applies(const AttnMmaArgs& a, int seq, int n_heads, int batch) {
     if (!g_siglip_stream || seq > kSsKeys || a.hd > 96 || (a.hd & 7)) return false;
-    if (g_siglip_stream == 2) return true;          // experiments: at any batch size
     return static_cast<long>((seq + kSsRows - 1) / kSsRows) * n_heads * batch <= 2 * 148;
 }
 static cudaError_t launch_siglip_stream(cudaStream_t stream, const AttnMmaArgs& a, int seq, int n_heads, int batch) {
@@ -675,17 +674,10 @@ cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs
 // Llama-style multi-head attention over a token-major KV cache (llm_engine.cu): head_dim 128 (or 64), one K/V head per
 // query head, causal by position.  Prefill (many query rows) and decode (one row per sequence) share the kernel.
 cudaError_t launch_mha_decode(cudaStream_t stream, const MhaAttnArgs& a);     // llm_kernels.cu
-cudaError_t launch_mha_prefill_stream(cudaStream_t stream, const MhaAttnArgs& a);
-// off: measured level with the tile kernel at 32 sequences (118-121 ms prefill either way) and slower at one (6.9 vs 5.7 ms:
-// 32 CTAs walk 9 row tiles each where the tile kernel spreads 288 tiles over the SMs); kept for experiments
-static int g_mha_prefill_stream = 0;
-void attn_set_mha_prefill_stream(int on) { g_mha_prefill_stream = on; }
 
 cudaError_t launch_mha_attention(cudaStream_t stream, const MhaAttnArgs& m) {
     if (m.n_keys > kAttnMaxBlocks * kBK || m.n_kv_heads != m.n_heads) return cudaErrorInvalidValue;
     if (m.q_per_sample == 1) return launch_mha_decode(stream, m);       // decode: K/V streaming, no tensor cores
-    if (g_mha_prefill_stream && m.head_dim == 128 && m.n_keys <= 288 && m.q_per_sample <= 288 && m.q_pos0 + m.q_per_sample == m.n_keys)
-        return launch_mha_prefill_stream(stream, m);                    // one CTA per (sequence, head): K in registers, Q / V in shared memory
     AttnMmaArgs a{};
     const int width = m.n_heads * m.head_dim;
     a.q = m.q; a.ldq = width; a.q_col0 = 0; a.q_per_sample = m.q_per_sample;

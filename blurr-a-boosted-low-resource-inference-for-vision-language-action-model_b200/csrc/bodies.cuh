@@ -321,98 +321,6 @@ __device__ __forceinline__ void rope_kv_body(const RopeKvArgs& a, const int t, c
 }
 
 
-// ---------------------------------------------------------------------------
-// Fused tails of the few-token split-K GEMM (kernels.h GemmTail; run by gemm_tcp_kernel's group finishers, 256 threads)
-// ---------------------------------------------------------------------------
-// RoPE / cache write of one 256-column group g of the q/k/v projection for every token row (T <= kTailMaxTokens):
-// g <= n_heads is a rotated head (query head g, or the key head when g == n_heads), g == n_heads + 1 the value head.
-__device__ __forceinline__ void tail_rope_group(const RopeKvArgs& a, const int g) {
-    const size_t sstride = static_cast<size_t>(a.T) * a.ldp;
-    if (g <= a.n_heads) {
-        const int t = threadIdx.x >> 5, j = (threadIdx.x & 31) << 2;
-        if (t >= a.T || (g < a.n_heads && a.q_out == nullptr)) return;
-        const int b = t / a.tokens_per_sample, i = t - b * a.tokens_per_sample;
-        long long pos = __ldcg(a.position_ids + static_cast<size_t>(b) * a.tokens_per_sample + i);
-        if (pos < 0) pos = 0;
-        if (pos >= a.n_pos) pos = a.n_pos - 1;
-        const float* prow = a.partial + static_cast<size_t>(t) * a.ldp + g * 256;
-        const float4 x1 = sum_slices(prow + j, sstride, a.splitk);
-        const float4 x2 = sum_slices(prow + 128 + j, sstride, a.splitk);
-        const float4 cs = *reinterpret_cast<const float4*>(a.cos_table + pos * 128 + j);
-        const float4 sn = *reinterpret_cast<const float4*>(a.sin_table + pos * 128 + j);
-        const float u1[4] = {bf16_round(x1.x), bf16_round(x1.y), bf16_round(x1.z), bf16_round(x1.w)};
-        const float u2[4] = {bf16_round(x2.x), bf16_round(x2.y), bf16_round(x2.z), bf16_round(x2.w)};
-        const float c[4] = {cs.x, cs.y, cs.z, cs.w}, sv[4] = {sn.x, sn.y, sn.z, sn.w};
-        float y1[4], y2[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {            // same rounding points as rope_kv_body
-            y1[e] = bf16_round(bf16_round(u1[e] * c[e]) + bf16_round(-u2[e] * sv[e]));
-            y2[e] = bf16_round(bf16_round(u2[e] * c[e]) + bf16_round(u1[e] * sv[e]));
-        }
-        const size_t cache_row = (static_cast<size_t>(b) * a.n_slots + a.slot_base + i) * 256;
-        bf16* dst = (g < a.n_heads) ? a.q_out + static_cast<size_t>(t) * (a.n_heads * 256) + g * 256 : a.k_cache + cache_row;
-        store_bf16x4(dst + j, make_float4(y1[0], y1[1], y1[2], y1[3]));
-        store_bf16x4(dst + 128 + j, make_float4(y2[0], y2[1], y2[2], y2[3]));
-    } else {
-        for (int it = threadIdx.x; it < a.T * 64; it += blockDim.x) {
-            const int t = it >> 6, j = (it & 63) << 2;
-            const int b = t / a.tokens_per_sample, i = t - b * a.tokens_per_sample;
-            const size_t cache_row = (static_cast<size_t>(b) * a.n_slots + a.slot_base + i) * 256;
-            const float4 v = sum_slices(a.partial + static_cast<size_t>(t) * a.ldp + g * 256 + j, sstride, a.splitk);
-            store_bf16x4(a.v_cache + cache_row + j,
-                         make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w)));
-        }
-    }
-}
-
-// Columns [128 * tile, +128) of the consumer for every token row: one warp per row, 4 columns per lane.  Leaves the
-// row's sum of squares over these columns in sumsq[tile * kTailMaxTokens + t] when a norm follows.
-__device__ __forceinline__ void tail_consumer_tile(const ConsumerArgs& a, const int tile, float* sumsq) {
-    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (t >= a.T) return;
-    const int n = tile * 128 + (lane << 2);
-    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < a.N) {
-        float4 acc = sum_slices(a.partial + static_cast<size_t>(t) * a.ldp + n, static_cast<size_t>(a.T) * a.ldp, a.splitk);
-        if (a.bias != nullptr) {
-            const float4 b = load_bf16x4(a.bias + n);
-            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-        }
-        val = make_float4(bf16_round(acc.x), bf16_round(acc.y), bf16_round(acc.z), bf16_round(acc.w));
-        if (a.out_scale != 1.0f)
-            val = make_float4(bf16_round(val.x * a.out_scale), bf16_round(val.y * a.out_scale),
-                              bf16_round(val.z * a.out_scale), bf16_round(val.w * a.out_scale));
-        if (a.add_mode == ADD_RESIDUAL) {
-            const float4 r = load_bf16x4(a.res + static_cast<size_t>(t) * a.ldr + n);
-            val = make_float4(bf16_round(r.x + val.x), bf16_round(r.y + val.y), bf16_round(r.z + val.z),
-                              bf16_round(r.w + val.w));
-        }
-        store_bf16x4(a.x_out + static_cast<size_t>(t) * a.ldx + n, val);
-    }
-    if (a.norm_mode == NORM_NONE || a.xn_out == nullptr) return;
-    float sq = (val.x * val.x + val.y * val.y) + (val.z * val.z + val.w * val.w);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (lane == 0) sumsq[tile * kTailMaxTokens + t] = sq;
-}
-
-// Gemma RMSNorm of every row from the tiles' sums of squares (tile order) and the rows tail_consumer_tile stored.
-__device__ __forceinline__ void tail_consumer_norm(const ConsumerArgs& a, const int n_tiles, const float* sumsq) {
-    const int nvec = a.N >> 2;
-    for (int it = threadIdx.x; it < a.T * nvec; it += blockDim.x) {
-        const int t = it / nvec, n = (it - t * nvec) << 2;
-        float ss = 0.f;
-        for (int k = 0; k < n_tiles; ++k) ss += __ldcg(sumsq + k * kTailMaxTokens + t);
-        const float r = rsqrtf(ss / static_cast<float>(a.N) + a.eps);
-        const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(a.x_out + static_cast<size_t>(t) * a.ldx + n));
-        const float4 x = unpack_bf16x4(raw);
-        const float4 w = load_bf16x4(a.norm_w + n);
-        store_bf16x4(a.xn_out + static_cast<size_t>(t) * a.ldn + n,
-                     make_float4((x.x * r) * (1.0f + w.x), (x.y * r) * (1.0f + w.y), (x.z * r) * (1.0f + w.z),
-                                 (x.w * r) * (1.0f + w.w)));
-    }
-}
-
 // ===========================================================================
 // attention
 // ===========================================================================

@@ -126,7 +126,6 @@ struct TapBuf { void* ptr; size_t bytes; };
 
 static constexpr int kNumPos = 1024;     // RoPE table rows (position ids 0..1023)
 static constexpr int kNumSMs = 148;
-static constexpr int kTailOps = 2048;        // fused tails per step before the slabs are reused (10 flow steps x 18 layers x 3 ops < 2048)
 
 struct blurr_pi0 {
     blurr_pi0_config cfg;
@@ -173,10 +172,6 @@ struct blurr_pi0 {
     // 3 = action encoder (the reference's swap skips the bare-Linear decoder and proprio encoder).  0 = off (every shipped config).
     float act_clip = 0.f; int act_clip_mask = 0;
     bf16* clip_action = nullptr;             // clamped copy of the action encoder's input (the flow state itself stays unclamped)
-    int* tail_slabs = nullptr; int tail_next = 0;       // arrival counters + scratch of the fused GEMM tails (GemmTail::slab), one per op
-    // off by default: measured slower than the PDL-chained two-kernel path (action stage 1.04 vs 0.87 ms at one episode):
-    // fence + arrival atomic + a second L2 round trip cost more than a pre-launched consumer kernel
-    bool fuse_tails = false; int fuse_tail_max_tokens = 8;
     const int *flag_gemm = nullptr, *flag_attn = nullptr;    // sticky pipeline time-out words of the kernels (NaN-poison the actions)
     // options / bookkeeping
     bool use_graph = true, debug = false;
@@ -436,10 +431,9 @@ extern "C" int blurr_pi0_create(const blurr_pi0_config* cfg, int device, int max
         ok &= ev_ok;
     }
     h->d_err = static_cast<int*>(dalloc(h, 16));
-    h->tail_slabs = static_cast<int*>(dalloc(h, static_cast<size_t>(kTailOps) * kTailSlabWords * sizeof(int)));
     h->flag_gemm = gemm_timeout_flag_ptr();
     h->flag_attn = attn_timeout_flag_ptr();
-    ok &= h->ws && h->ws2 && h->ws3 && h->d_err && h->tail_slabs && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
+    ok &= h->ws && h->ws2 && h->ws3 && h->d_err && h->vcache && h->kcache && h->A1 && h->H && h->shmid && h->patches;
     if (!ok) {
         blurr_pi0_destroy(h);
         return fail(BLURR_ERR_CUDA, "blurr_pi0_create: device allocation failed");
@@ -745,8 +739,7 @@ struct Run {
     void wait(cudaEvent_t ev) {
         if (multi && rc == 0 && cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) rc = fail(BLURR_ERR_CUDA, "cudaStreamWaitEvent failed");
     }
-    static constexpr int kFused = -2;     // gemm() return value: the consumer ran inside the GEMM kernel (GemmTail)
-    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, int alt = 0, GemmTail* tail = nullptr) {
+    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, bool bias = true, int alt = 0) {
         if (rc) return 1;
         float* ws = wsp(alt);
         const size_t ws_floats = alt ? h->ws2_floats : h->ws_floats;
@@ -772,29 +765,15 @@ struct Run {
             rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
             return 1;
         }
-        bool fused = false;
-        if (tail != nullptr && h->fuse_tails && T <= h->fuse_tail_max_tokens && !lin_mode) {
-            c.tail = tail;
-            if (gemm_tail_supported(c)) {
-                const GemmPlan pl = gemm_make_plan(T, L.Nw, L.K, c.splitk, EPI_PARTIAL, 0);
-                tail->slab = h->tail_slabs + static_cast<size_t>(h->tail_next++ % kTailOps) * kTailSlabWords;
-                if (tail->kind == TAIL_CONSUMER) { tail->consumer.partial = ws; tail->consumer.splitk = pl.splitk; tail->consumer.trace = nullptr; }
-                else { tail->rope.partial = ws; tail->rope.splitk = pl.splitk; tail->rope.trace = nullptr; }
-                fused = true;
-            } else {
-                c.tail = nullptr;
-            }
-        }
         std::string err;
         char nm[96];
-        snprintf(nm, sizeof nm, "gemm%s[epi%d T%d N%d K%d S%d]", fused ? "+tail" : "", c.epi, T, L.Nw, L.K, c.splitk);
+        snprintf(nm, sizeof nm, "gemm[epi%d T%d N%d K%d S%d]", c.epi, T, L.Nw, L.K, c.splitk);
         c.trace = trace_slot(nm);
         prof_begin(nm);
         const int s = gemm_launch(st, c, &err);
         prof_end();
         ++h->launches;
         if (s < 0) { rc = fail(BLURR_ERR_CUDA, err); return 1; }
-        if (fused) return kFused;
         return lin_mode ? 0 : s;
     }
     ConsumerArgs consumer_args(int splitk, int T, int N, int ldp, const bf16* bias, int add_mode, const bf16* res, int ldr,
@@ -820,19 +799,12 @@ struct Run {
                                        xn_out, use_partial, alt);
         { char nm[64]; snprintf(nm, sizeof nm, "consumer[T%d N%d S%d]", T, N, splitk); a.trace = trace_slot(nm); prof_begin(nm); launched(launch_consumer(st, a), "consumer"); prof_end(); }
     }
-    // Split-K GEMM + its consumer.  Few-token GEMMs (the experts: 1 or 4 tokens per episode) carry the consumer as a
-    // fused tail of the GEMM kernel (one launch instead of two); everything else launches the consumer kernel.
+    // Split-K GEMM + its consumer kernel.
     void gemm_consumer(const Lin& L, const bf16* X, int T, int alt, int N, const bf16* bias, int add_mode, const bf16* res,
                        int ldr, float out_scale, bf16* x_out, int norm_mode, const bf16* nw, const bf16* nb, float eps,
                        bf16* xn_out, bool gemm_bias = false) {
         if (rc) return;
-        GemmTail tail{};
-        tail.kind = TAIL_CONSUMER;
-        tail.consumer = consumer_args(1, T, N, L.Nw, bias, add_mode, res, ldr, out_scale, x_out, norm_mode, nw, nb, eps, xn_out,
-                                      true, alt);
-        const bool can_fuse = N == L.Nw;
-        const int s = gemm(L, X, T, EPI_PARTIAL, nullptr, 0, gemm_bias, alt, can_fuse ? &tail : nullptr);
-        if (s == kFused) return;
+        const int s = gemm(L, X, T, EPI_PARTIAL, nullptr, 0, gemm_bias, alt);
         consumer(s, T, N, L.Nw, bias, add_mode, res, ldr, out_scale, x_out, norm_mode, nw, nb, eps, xn_out, true, alt);
     }
     void bias_act(int splitk, int T, int N, int ldp, const bf16* bias, int act, float scale, bf16* out, int ldo, int alt) {
@@ -974,15 +946,12 @@ static void phase_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool k
     if (R.rc) return;
     R.rope(rope_args(R, m, l, sb, B, kv_only, s, qkv, alt));
 }
-// q/k/v projection + RoPE + cache write; for the few-token expert streams RoPE runs as the GEMM kernel's fused tail
+// q/k/v projection + RoPE + cache write
 static void phase_qkv_rope(Run& R, int m, int l, const StreamBufs& sb, int B, bool kv_only, int alt) {
     if (R.rc) return;
     const Lin qkv = qkv_lin(R.h, m, l, kv_only);
-    GemmTail tail{};
-    tail.kind = TAIL_ROPE;
-    tail.rope = rope_args(R, m, l, sb, B, kv_only, 1, qkv, alt);
-    const int s = R.gemm(qkv, sb.xn, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt, &tail);
-    if (s == Run::kFused || R.rc) return;
+    const int s = R.gemm(qkv, sb.xn, B * sb.tokens_per_sample, EPI_PARTIAL, nullptr, 0, false, alt);
+    if (R.rc) return;
     R.rope(rope_args(R, m, l, sb, B, kv_only, s, qkv, alt));
 }
 
@@ -1341,15 +1310,6 @@ extern "C" int blurr_pi0_set_option(blurr_pi0_t* h, const char* name, int64_t va
         }
         h->graphs.clear();
     }
-    else if (n == "fuse_tails") {              // 0: never; else the largest token count whose consumer rides in the GEMM kernel
-        h->fuse_tails = value != 0;
-        h->fuse_tail_max_tokens = value > 0 ? static_cast<int>(value) : 0;
-        for (auto& kv : h->graphs) {
-            cudaGraphExecDestroy(kv.second.exec);
-            cudaGraphDestroy(kv.second.graph);
-        }
-        h->graphs.clear();
-    }
     else if (n == "lin_mode") {
         h->lin_mode = value != 0;
         for (auto& kv : h->graphs) {
@@ -1412,11 +1372,9 @@ extern "C" int blurr_set_global_option(const char* name, int64_t value) {
     else if (n == "gemm_max_stages") gemm_set_max_stages(static_cast<int>(value));
     else if (n == "attn_tc") attn_set_tc(static_cast<int>(value));
     else if (n == "attn_tc_fewq") attn_set_tc_fewq(static_cast<int>(value));
-    else if (n == "gemm_x_policy") gemm_set_x_policy(static_cast<int>(value));
     else if (n == "attn_fewq_stream") attn_set_fewq_stream(static_cast<int>(value));
     else if (n == "attn_prefill_stream") attn_set_prefill_stream(static_cast<int>(value));
     else if (n == "attn_siglip_stream") attn_set_siglip_stream(static_cast<int>(value));
-    else if (n == "attn_mha_prefill_stream") attn_set_mha_prefill_stream(static_cast<int>(value));
     else if (n == "attn_cta_trace") { if (attn_set_cta_trace(reinterpret_cast<void*>(static_cast<intptr_t>(value)))) return fail(BLURR_ERR_CUDA, "attn_cta_trace: cudaMemcpyToSymbol failed"); }
     else if (n == "gemm_large_t_mode") gemm_set_large_t_mode(static_cast<int>(value));
     else if (n == "gemm_pair_band") gemm_set_pair_band(static_cast<int>(value));

@@ -120,7 +120,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDev& p, const CUtensorMap* t
     // instead of 448 below 128 tokens, and the TMA side could not issue a k-block in less than ~0.22 us.
     if (warp == 0) {
         const uint64_t pol_w = make_policy_evict_first();   // weights: streamed once
-        const uint64_t pol_x = p.x_normal ? make_policy_evict_normal() : make_policy_evict_last();    // activations: re-read by every CTA
+        const uint64_t pol_x = make_policy_evict_last();    // activations: re-read by every CTA
         // Launched with PDL: the weights do not depend on the previous kernel, so the first ring of
         // weight blocks is requested before waiting for it; only the token operand waits.
         int pre = 0;
@@ -284,7 +284,7 @@ __device__ __forceinline__ void gemm_persistent(const GemmDev& p, const CUtensor
         // few tokens: weights are streamed once, activations re-read by every CTA.  Above 1024 tokens
         // (l2_policy 1) both operands are re-read by later tiles and plain LRU does better.
         const uint64_t pol_w = p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
-        const uint64_t pol_x = (p.l2_policy == 1 || p.x_normal) ? make_policy_evict_normal() : make_policy_evict_last();
+        const uint64_t pol_x = p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_last();
         uint32_t empty_bits = 0;
         int s = 0;
         int pre = 0;
@@ -514,7 +514,7 @@ __device__ __forceinline__ void gemm_tile_2cta(const GemmDev& p, const CUtensorM
     if (warp == 0) {
         // all 32 lanes converged, operands warp-uniform, issue under elect.sync (see gemm_tile)
         const uint64_t pol_w = make_policy_evict_first();
-        const uint64_t pol_x = p.x_normal ? make_policy_evict_normal() : make_policy_evict_last();
+        const uint64_t pol_x = make_policy_evict_last();
         int s = 0;
         for (int i = 0; i < nkb; ++i) {
             if (!mbar_wait_warp(&sh.empty_bar[s], ((st.empty_bits >> s) & 1u) ^ 1u)) {
@@ -665,8 +665,7 @@ __device__ __forceinline__ void gemm_pair_persistent(const GemmDev& p, const CUt
     if (warp == 0) {
         // all 32 lanes converged, operands warp-uniform, issue under elect.sync (see gemm_tile)
         const uint64_t pol_w = p.l2_policy == 0 ? make_policy_evict_first() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_last();
-        const uint64_t pol_x = p.x_normal ? make_policy_evict_normal()
-                                          : p.l2_policy == 0 ? make_policy_evict_last() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
+        const uint64_t pol_x = p.l2_policy == 0 ? make_policy_evict_last() : p.l2_policy == 1 ? make_policy_evict_normal() : make_policy_evict_first();
         uint32_t empty_bits = 0;
         int s = 0;
         const uint32_t bar0 = map_to_cta(&sh.full_bar[0], 0u);      // the leader's full[0]; full[s] is 8 bytes further per stage

@@ -21,7 +21,6 @@
 //   EPI_PARTIAL : fp32 partial sums of one split-K slice -> workspace [z][t][n]; the consumer
 //                 kernels in norm_consumers.cu finish bias/residual/norm in a fixed order.
 #include "gemm_body.cuh"
-#include "bodies.cuh"
 #include "launch.cuh"
 
 #include <mutex>
@@ -29,8 +28,6 @@
 #include <unordered_map>
 
 namespace blurr {
-static int g_x_normal = 0;
-void gemm_set_x_policy(int normal) { g_x_normal = normal != 0; }
 
 
 template <int EPI>
@@ -66,11 +63,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 }
 
 // Persistent 1-CTA kernel: at most one CTA per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-// `tail`: optional fused consumer (kernels.h GemmTail) run by the CTA that finishes last.
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads + 128, 1)
 gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                const GemmDev p, const int gx, const int gy, const int gz, const GemmTail tail) {
+                const GemmDev p, const int gx, const int gy, const int gz) {
     extern __shared__ uint8_t smem_raw[];
     trace_stamp(p.trace, 0);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -93,53 +89,6 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     __syncthreads();
     gemm_persistent<EPI>(p, &tmap_w, &tmap_x, sh, tmem_empty_bar, gx, gy, gz, blockIdx.x, gridDim.x, true);
     __syncthreads();
-    if (p.pf.len > 0 && warp == 0 && elect_one_sync()) {
-        // this CTA has no more weights to stream: L2 prefetch rider for the next GEMM (GemmPrefetch)
-        for (int it = blockIdx.x; it < p.pf.items; it += gridDim.x) {
-            const int bx = it % p.pf.gx, bz = it / p.pf.gx;
-            const unsigned off = static_cast<unsigned>(bz) * p.pf.slice_bytes;
-            if (off >= p.pf.tile_bytes) continue;
-            const unsigned slice = min(p.pf.slice_bytes, p.pf.tile_bytes - off);
-            if (p.pf.skip >= slice) continue;
-            const unsigned len = min(p.pf.len, slice - p.pf.skip);
-            const char* src = p.pf.base + static_cast<size_t>(bx) * p.pf.tile_bytes + off + p.pf.skip;
-            for (unsigned o = 0; o < len; o += 32768u) {
-                const unsigned n = min(32768u, len - o);
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src + o), "r"(n) : "memory");
-            }
-        }
-    }
-    if (EPI == EPI_PARTIAL && tail.kind != TAIL_NONE) {
-        // one weight tile x K slice per CTA (gy == 1, gridDim.x == gx * gz): this CTA's partial stores are made visible
-        // device-wide, then it arrives at its group's counter; the group's last arrival finishes the group (GemmTail).
-        __shared__ int s_last;
-        const int bx = static_cast<int>(blockIdx.x) % gx;
-        const bool is_rope = tail.kind == TAIL_ROPE;
-        const int group = is_rope ? (bx >> 1) : bx;
-        const int expect = is_rope ? 2 * gz : gz;
-        float* sumsq = reinterpret_cast<float*>(tail.slab + 32);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(tail.slab + 1 + group, 1) == expect - 1) ? 1 : 0;
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            if (is_rope) tail_rope_group(tail.rope, group);
-            else tail_consumer_tile(tail.consumer, bx, sumsq);
-            if (threadIdx.x == 0) tail.slab[1 + group] = 0;
-            if (!is_rope && tail.consumer.norm_mode != NORM_NONE && tail.consumer.xn_out != nullptr) {
-                __threadfence();
-                __syncthreads();
-                if (threadIdx.x == 0) s_last = (atomicAdd(tail.slab, 1) == gx - 1) ? 1 : 0;
-                __syncthreads();
-                if (s_last) {
-                    __threadfence();
-                    tail_consumer_norm(tail.consumer, gx, sumsq);
-                    if (threadIdx.x == 0) tail.slab[0] = 0;
-                }
-            }
-        }
-    }
     trace_stamp(p.trace, 2);
     if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
@@ -326,7 +275,7 @@ static int next_pow2_cols(int c) {
 }
 
 static constexpr int kSmemBudget = 227 * 1024;
-static constexpr int kRingBytes = 224 * 1024;   // pipeline ring; leaves room for the kernels' static shared memory (barriers + the fused tail's scratch)
+static constexpr int kRingBytes = 225 * 1024;   // pipeline ring (the rest of the 227 KB: barriers, alignment slack)
 
 // Measured on B200 (tools/time_gemm.py, round 1): multicasting the activation tile across a cluster of
 // 2/4 CTAs is *slower* than unicast at every Pi-0 shape (the CTAs of a cluster advance in lock-step and
@@ -492,11 +441,11 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
 
 template <int EPI>
 static cudaError_t launch_epip(cudaStream_t stream, const GemmPlan& pl, const CUtensorMap& tw, const CUtensorMap& tx,
-                               const GemmDev& d, const GemmTail* tail = nullptr) {
+                               const GemmDev& d) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kSmemBudget - 1536);       // static: 1 KB of barriers + the tail's reduction scratch
+                                             kSmemBudget);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -505,10 +454,8 @@ static cudaError_t launch_epip(cudaStream_t stream, const GemmPlan& pl, const CU
     // epilogues with activation math get two warps per TMEM lane quarter so that they stay hidden under the
     // next tile's MMAs (double-buffered accumulators)
     const int threads = (d.staging_bytes > 0) ? kGemmThreads + 128 : kGemmThreads;
-    GemmTail t{};
-    if (tail != nullptr && threads == kGemmThreads) t = *tail;
     return launch_kernel(gemm_tcp_kernel<EPI>, dim3(ctas), dim3(threads), static_cast<size_t>(pl.smem_bytes), stream,
-                         tw, tx, d, pl.grid_x, pl.grid_y, pl.splitk, t);
+                         tw, tx, d, pl.grid_x, pl.grid_y, pl.splitk);
 }
 
 template <int EPI>
@@ -601,7 +548,7 @@ static int gemm_launch_pairp(cudaStream_t stream, const GemmCall& c, std::string
     d.T = c.T; d.bn = bn; d.nt = 1; d.kb_total = kb_total; d.kb_per_split = kb_total;
     d.tmem_cols = 512; d.acc_bufs = 2; d.acc_stride = 256; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = nullptr;
-    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; d.x_normal = g_x_normal; if (c.prefetch) d.pf = *c.prefetch;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act;
     d.staging_bytes = bn * (c.epi == EPI_GEGLU ? kBlockM / 2 : kBlockM) * 2;
     const int stage_bytes = kTileABytes + half * kBlockK * 2;
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
@@ -655,7 +602,7 @@ static int gemm_launch_pair_small(cudaStream_t stream, const GemmCall& c, std::s
     d.T = c.T; d.bn = bn; d.nt = 2; d.kb_total = kb_total; d.kb_per_split = kb_per_split;
     d.tmem_cols = 512; d.acc_bufs = 1; d.acc_stride = 0; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
-    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; d.x_normal = g_x_normal; if (c.prefetch) d.pf = *c.prefetch;
+    d.cluster = 1; d.slice_rows = 0; d.w_packed = 1; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act;
     d.staging_bytes = c.epi == EPI_PARTIAL ? 0 : ntok * kBlockM * 2;      // GeGLU is staged as raw gate / up values (one accumulator buffer)
     const int stage_bytes = kTileABytes + 2 * half * kBlockK * 2;
     d.stages = (kRingBytes - d.staging_bytes) / stage_bytes;
@@ -704,45 +651,7 @@ int gemm_plan_chunked_splitk(int T, int Nw, int K, size_t ws_floats, int* bn_ove
     return best_s;
 }
 
-bool gemm_make_prefetch(const GemmCall& next, size_t budget_bytes, GemmPrefetch* out) {
-    *out = GemmPrefetch{};
-    if (!next.w_packed || !next.w_static || !g_persistent || next.T > kPersistentMaxTokens || next.bn_override != 0) return false;
-    if (next.epi != EPI_PARTIAL && next.epi != EPI_GEGLU && next.epi != EPI_STORE) return false;
-    const GemmPlan pl = gemm_make_plan(next.T, next.Nw, next.K, next.splitk, next.epi, 0);
-    if (!pl.valid || pl.cluster != 1 || pl.two_cta || pl.grid_y != 1) return false;
-    const int tiles = pl.grid_x * pl.splitk;
-    const int items = tiles < kTargetCtas ? tiles : kTargetCtas;
-    const int ring = pl.stages < pl.kb_per_split ? pl.stages : pl.kb_per_split;
-    out->base = reinterpret_cast<const char*>(next.W);
-    out->tile_bytes = static_cast<unsigned>(pl.kb_total) * kTileABytes;
-    out->slice_bytes = static_cast<unsigned>(pl.kb_per_split) * kTileABytes;
-    out->skip = static_cast<unsigned>(ring) * kTileABytes;
-    out->gx = pl.grid_x;
-    out->items = items;
-    size_t len = budget_bytes / static_cast<size_t>(items);
-    len &= ~static_cast<size_t>(kTileABytes - 1);        // whole 16 KB k-blocks
-    out->len = static_cast<unsigned>(len);
-    return out->len > 0 && out->skip < out->slice_bytes;
-}
-
-bool gemm_tail_supported(const GemmCall& c) {
-    if (c.epi != EPI_PARTIAL || !g_persistent || c.T > kPersistentMaxTokens || c.bn_override != 0) return false;
-    GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, 0);
-    if (!(pl.valid && pl.cluster == 1 && !pl.two_cta && pl.nt * pl.bn <= kPersistentMaxTokens)) return false;
-    // the tails count arrivals per weight tile: one tile x slice per CTA, every token row in one chunk
-    if (c.T > kTailMaxTokens || pl.grid_y != 1 || pl.grid_x > kTailMaxGroups || pl.grid_x * pl.splitk > kTargetCtas) return false;
-    if (c.tail != nullptr) {
-        const GemmTail& t = *c.tail;
-        if (t.kind == TAIL_ROPE) return (t.rope.n_heads + 2) * 256 == c.Nw && t.rope.lin == nullptr;
-        if (t.kind == TAIL_CONSUMER)
-            return t.consumer.N == c.Nw && t.consumer.add_mode != ADD_POSEMB && t.consumer.norm_mode != NORM_LAYERNORM &&
-                   t.consumer.x_out != nullptr && t.consumer.lin == nullptr;
-    }
-    return true;
-}
-
 int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
-    if (c.tail != nullptr && (gemm_pair_small_applies(c) || gemm_pairp_applies(c))) { *err = "gemm_launch: a fused tail needs the persistent few-token kernel"; return -1; }
     if (gemm_pair_small_applies(c)) return gemm_launch_pair_small(stream, c, err);
     if (gemm_pairp_applies(c)) return gemm_launch_pairp(stream, c, err);
     GemmPlan pl = gemm_make_plan(c.T, c.Nw, c.K, c.splitk, c.epi, c.bn_override);
@@ -752,7 +661,6 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
         return -1;
     }
     if (c.epi != EPI_PARTIAL && pl.splitk != 1) { *err = "gemm_launch: split-K needs EPI_PARTIAL"; return -1; }
-    if (c.tail != nullptr && !gemm_tail_supported(c)) { *err = "gemm_launch: a fused tail needs the persistent few-token kernel"; return -1; }
     CUtensorMap tw, tx, txs;
     if (c.w_packed) {
         if (get_tmap(c.W, c.Nw * pl.kb_total, kBlockK, kBlockK, kBlockM, &tw, err)) return -1;
@@ -769,7 +677,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
     d.T = c.T; d.bn = pl.bn; d.nt = pl.nt; d.stages = pl.stages; d.kb_total = pl.kb_total;
     d.kb_per_split = pl.kb_per_split; d.tmem_cols = pl.tmem_cols; d.Nw = c.Nw;
     d.bias = c.bias; d.out = c.out; d.ldo = c.ldo; d.partial = c.partial;
-    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act; d.x_normal = g_x_normal; if (c.prefetch) d.pf = *c.prefetch;
+    d.cluster = pl.cluster; d.slice_rows = pl.slice_rows; d.w_packed = c.w_packed; d.trace = c.trace; d.w_static = c.w_static; d.glu_act = c.glu_act;
     cudaError_t e;
     if (pl.two_cta) {
         CUtensorMap txh;
@@ -804,7 +712,7 @@ int gemm_launch(cudaStream_t stream, const GemmCall& c, std::string* err) {
             case EPI_STORE:   e = launch_epip<EPI_STORE>(stream, pl, tw, tx, d); break;
             case EPI_GELU:    e = c.glu_act == 2 ? launch_epip<EPI_GELU_ERF>(stream, pl, tw, tx, d) : launch_epip<EPI_GELU>(stream, pl, tw, tx, d); break;
             case EPI_GEGLU:   e = launch_epip<EPI_GEGLU>(stream, pl, tw, tx, d); break;
-            case EPI_PARTIAL: e = launch_epip<EPI_PARTIAL>(stream, pl, tw, tx, d, c.tail); break;
+            case EPI_PARTIAL: e = launch_epip<EPI_PARTIAL>(stream, pl, tw, tx, d); break;
             default: *err = "gemm_launch: bad epilogue"; return -1;
         }
         if (e != cudaSuccess) { *err = std::string("gemm (persistent) launch failed: ") + cudaGetErrorString(e); return -1; }

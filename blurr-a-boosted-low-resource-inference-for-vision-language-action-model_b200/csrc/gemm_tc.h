@@ -9,8 +9,6 @@
 
 namespace blurr {
 
-struct GemmTail;      // kernels.h
-
 enum GemmEpilogue {
     EPI_STORE = 0,    // out[t][n] = bf16(acc + bias[n])
     EPI_GELU = 1,     // out[t][n] = bf16(gelu_tanh(bf16(acc + bias[n])))
@@ -18,19 +16,6 @@ enum GemmEpilogue {
     EPI_PARTIAL = 3,  // partial[z][t][n] = fp32 partial sum of split-K slice z
     EPI_GELU_ERF = 4, // EPI_GELU with the exact erf GELU (nn.GELU()); callers pass EPI_GELU + glu_act = 2, gemm_launch picks this
                       // instantiation - a runtime switch inside the epilogue cost the tanh flavour 3.4 us per SigLIP fc1 launch
-};
-
-// Rider of a weight-streaming GEMM: as each CTA runs out of work it asks L2 (cp.async.bulk.prefetch.L2) for the part of
-// the NEXT GEMM's weight stream that lies just past that GEMM's own shared-memory ring, so that HBM keeps streaming
-// through the small dependent kernels in between (consumer, RoPE, attention).  Filled by gemm_make_prefetch().
-struct GemmPrefetch {
-    const char* base;          // the next GEMM's tile-packed weights
-    unsigned tile_bytes;       // bytes of one 128-row weight tile (kb_total * 16 KB)
-    unsigned slice_bytes;      // bytes of one K slice of a tile
-    unsigned skip;             // leading bytes of a slice that the next GEMM fetches into shared memory before its dependency wait
-    unsigned len;              // bytes to prefetch per (tile, slice) work item
-    int gx;                    // weight tiles
-    int items;                 // first-round work items of the next GEMM (<= 148)
 };
 
 struct GemmCall {
@@ -53,8 +38,6 @@ struct GemmCall {
     int w_static;             // 1: W was written before any kernel still in flight (engine weights), so the
                               // kernel may fetch it ahead of the programmatic-dependency wait
     int glu_act;              // EPI_GEGLU: gate activation, 0 = tanh GELU (Gemma), 1 = SiLU (Llama SwiGLU)
-    const GemmPrefetch* prefetch;   // optional L2 prefetch rider for the next GEMM (few-token persistent kernel only)
-    const GemmTail* tail;     // optional consumer fused behind an EPI_PARTIAL GEMM of <= 32 tokens (gemm_tail_supported)
 };
 
 // Device-side parameters of one GEMM (filled from a GemmPlan by gemm_launch / gemm_make_step_op).
@@ -81,8 +64,6 @@ struct GemmDev {
     int staging_bytes; // persistent kernel: bf16 output staging tile behind the ring (0 = direct epilogue)
     int l2_policy;    // persistent pairs: 0 = weights evict_first / tokens evict_last, 1 = both evict_normal, 2 = weights evict_last / tokens evict_first
     int glu_act;      // EPI_GEGLU gate activation (GemmCall::glu_act)
-    int x_normal;     // experiment (gemm_set_x_policy): token tiles with the evict_normal L2 policy instead of evict_last
-    GemmPrefetch pf;  // len == 0: none
     int band;         // persistent pairs: weight tile pairs per raster band (the band sweeps every token tile before the next one starts)
 };
 
@@ -97,11 +78,6 @@ GemmPlan gemm_make_plan(int T, int Nw, int K, int splitk, int epi, int bn_overri
 // K slices (return value) and tokens per chunk (*bn_override, 0 = one CTA holds all rows) for an EPI_PARTIAL GEMM of
 // 33..288 rows, from the measured cost model (tools/sweep_splitk.py)
 int gemm_plan_chunked_splitk(int T, int Nw, int K, size_t ws_floats, int* bn_override);
-// Prefetch rider description for `next` (a few-token EPI_PARTIAL / EPI_GEGLU call with tile-packed static weights):
-// `budget_bytes` spread over its first-round work items.  Returns false (len = 0) when `next` is not such a call.
-bool gemm_make_prefetch(const GemmCall& next, size_t budget_bytes, GemmPrefetch* out);
-// true when gemm_launch would run this call on the persistent few-token kernel, which can carry a fused tail
-bool gemm_tail_supported(const GemmCall& call);
 
 // Returns the number of split-K slices actually used (>= 1), or -1 with *err set.
 int gemm_launch(cudaStream_t stream, const GemmCall& call, std::string* err);
@@ -128,7 +104,6 @@ void gemm_set_large_t_mode(int mode);
 void gemm_set_pair_band(int band);          // 0 = automatic
 void gemm_set_pair_small(int mode);         // persistent CTA pairs for 257..288 tokens: 0 never, 1 GeGLU only (default), 2 every epilogue
 void gemm_set_pair_policy(int policy);      // -1 = automatic
-void gemm_set_x_policy(int normal);         // 1: every kernel loads its token tiles with evict_normal (default 0: evict_last)
 int gemm_pair_raster(int N, int K, int T, int* band_out, int* n_pairs_out, int32_t* order, int capacity);
 
 // Largest cluster (1, 2, 4, 8) used for activation multicast; 1 disables it.

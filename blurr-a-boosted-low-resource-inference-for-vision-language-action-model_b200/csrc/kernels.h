@@ -122,7 +122,6 @@ void attn_set_tc_fewq(int mode);                 // few-query attention on the t
 bool attn_tc_fewq_applies(const JointAttnArgs& a);
 void attn_set_prefill_stream(int on);           // prefill attention of <= 2 waves of 16-row tiles as the streaming kernel (default 1)
 void attn_set_siglip_stream(int on);            // SigLIP attention of <= 2 waves of 32-row tiles as the streaming kernel (default 1)
-void attn_set_mha_prefill_stream(int on);       // Llama-shaped prefill attention: one CTA per (sequence, head); default 0 = the tile kernel
 void attn_set_fewq_stream(int on);              // few-query attention as the streaming kernel (default 1) vs the mma.sync tile kernel
 int attn_take_timeout_flag();
 int attn_set_cta_trace(void* dev_ptr);          // per-CTA timeline of the tcgen05 attention kernel (attention_tc.cu)
@@ -169,23 +168,6 @@ const int* attn_timeout_flag_ptr();
 
 cudaError_t launch_rope_table(cudaStream_t stream, const float* inv_freq, int n_pos, float* cos_t,
                               float* sin_t);
-
-// A consumer fused behind a few-token split-K GEMM (gemm_tcp_kernel, one weight tile x K slice per CTA).  Arrival counters,
-// no spinning, so no co-residency requirement: the last CTA to finish a weight tile (consumer: 128 columns) or a head
-// (RoPE: two tiles) reduces that group's partials for every token row and applies bias / residual / RoPE itself; for a
-// consumer with an RMSNorm each tile finisher also leaves its columns' sum of squares, and the last tile finisher of the
-// op normalises the rows.  Many small tails in parallel, each one L2 round trip: one kernel per op pair instead of two
-// on the experts' chains.  Sums run in a fixed order (slices, then tiles) whoever executes them.
-enum GemmTailKind { TAIL_NONE = 0, TAIL_CONSUMER = 1, TAIL_ROPE = 2 };
-static constexpr int kTailMaxTokens = 8;      // a warp per token row in the tile finisher
-static constexpr int kTailMaxGroups = 31;     // counters[0] = op level, counters[1 + g] = group g
-static constexpr int kTailSlabWords = 32 + 32 * kTailMaxTokens;    // per op: 32 counters + [tile][token] sums of squares
-struct GemmTail {
-    int kind;
-    int* slab;              // kTailSlabWords words, zero before the launch; the finishers re-arm the counters
-    ConsumerArgs consumer;  // TAIL_CONSUMER: add_mode NONE / RESIDUAL, norm NONE / RMS_GEMMA, N = the GEMM's width <= 31 tiles
-    RopeKvArgs rope;        // TAIL_ROPE: (n_heads + 2) * 256 == the GEMM's width
-};
 
 // ---------------------------------------------------------------------------
 // Llama-shaped decoder (llm_engine.cu / llm_kernels.cu): the OpenVLA-7B-shaped path

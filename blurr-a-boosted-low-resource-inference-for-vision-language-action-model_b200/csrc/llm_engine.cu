@@ -86,10 +86,6 @@ struct blurr_llm {
     struct GraphEntry { cudaGraph_t graph; cudaGraphExec_t exec; int64_t launches; };
     std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
     // in-graph timeline (option "trace"): every kernel stamps %globaltimer at entry / after its dependency wait / at exit
-    // option "l2_prefetch_mb": GemmPrefetch budget per decode GEMM.  Off by default - measured neutral (decode layer 97.0 us
-    // without, 97.1 / 98.6 us with 16 / 48 MB): the next GEMM's own pre-wait ring fetch (32 MB) already keeps HBM busy
-    // through the small kernel in front of it, and what the rider gains there the issuing GEMM loses at its tail.
-    size_t l2_prefetch_bytes = 0;
     bool trace = false;
     unsigned long long* trace_buf = nullptr;
     std::vector<std::string> trace_labels;
@@ -314,18 +310,12 @@ struct Run {
         }
         return c;
     }
-    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo, const Lin* next = nullptr) {
+    int gemm(const Lin& L, const bf16* X, int T, int epi, bf16* out, int ldo) {
         if (rc) return 0;
         GemmCall c = make_call(L, X, T, epi, out, ldo);
         if (epi == EPI_PARTIAL && static_cast<size_t>(c.splitk) * T * L.Nw > h->ws_floats) {
             rc = fail(BLURR_ERR_STATE, "split-K workspace too small");
             return 0;
-        }
-        // decode steps: as this GEMM's CTAs drain they ask L2 for the head of the next GEMM's weight stream
-        GemmPrefetch pf{};
-        if (next != nullptr && h->l2_prefetch_bytes > 0 && T <= kFewTokens) {
-            const GemmCall n = make_call(*next, nullptr, T, EPI_PARTIAL, nullptr, 0);
-            if (gemm_make_prefetch(n, h->l2_prefetch_bytes, &pf)) c.prefetch = &pf;
         }
         std::string err;
         char nm[96];
@@ -353,7 +343,7 @@ struct Run {
     }
 
     // One decoder layer over B sequences x Tq new tokens at positions pos0..pos0+Tq-1 (modeling_llama.py LlamaDecoderLayer)
-    void layer(int l, int B, int Tq, int pos0, const bf16* next_norm, const Lin* next_first) {
+    void layer(int l, int B, int Tq, int pos0, const bf16* next_norm) {
         const auto& c = h->cfg;
         Layer& L = h->layers[l];
         const int T = B * Tq, QW = c.num_heads * c.head_dim, KVW = c.num_kv_heads * c.head_dim;
@@ -361,7 +351,7 @@ struct Run {
         const bool part = few || T <= kMidTokens;       // o / down: few weight tiles, long K -> split-K partials + consumer
         const size_t cache_off = static_cast<size_t>(l) * h->max_batch * c.max_positions * KVW;
         // q/k/v projections + RoPE + cache append
-        int s = gemm(L.qkv, h->XN, T, few ? EPI_PARTIAL : EPI_STORE, h->LIN, L.qkv.Nw, &L.o);
+        int s = gemm(L.qkv, h->XN, T, few ? EPI_PARTIAL : EPI_STORE, h->LIN, L.qkv.Nw);
         RopeMhaArgs r{};
         if (few) { r.partial = h->ws; r.splitk = s; } else { r.lin = h->LIN; r.ldl = L.qkv.Nw; r.splitk = 1; }
         r.T = T; r.ldp = L.qkv.Nw; r.n_heads = c.num_heads; r.n_kv_heads = c.num_kv_heads; r.head_dim = c.head_dim;
@@ -377,16 +367,16 @@ struct Run {
         m.trace = slot(Tq == 1 ? "mha_decode" : "mha_prefill");
         if (!rc) launched(launch_mha_attention(st, m), "mha_attention");
         // o_proj + residual + post-attention norm
-        s = gemm(L.o, h->AO, T, part ? EPI_PARTIAL : EPI_STORE, h->LIN, L.o.Nw, &L.gu);
+        s = gemm(L.o, h->AO, T, part ? EPI_PARTIAL : EPI_STORE, h->LIN, L.o.Nw);
         consumer(part ? s : 0, part ? nullptr : h->LIN, T, c.hidden, L.o.Nw, h->X, h->X, L.post_ln, h->XN);
         // SwiGLU MLP
         if (few) {
-            s = gemm(L.gu, h->XN, T, EPI_PARTIAL, nullptr, 0, &L.down);
+            s = gemm(L.gu, h->XN, T, EPI_PARTIAL, nullptr, 0);
             if (!rc) launched(launch_glu_partial(st, h->ws, s, T, L.gu.Nw, 1, h->HM, c.intermediate, slot("glu")), "glu");
         } else {
             gemm(L.gu, h->XN, T, EPI_GEGLU, h->HM, c.intermediate);
         }
-        s = gemm(L.down, h->HM, T, part ? EPI_PARTIAL : EPI_STORE, h->LIN, L.down.Nw, next_first);
+        s = gemm(L.down, h->HM, T, part ? EPI_PARTIAL : EPI_STORE, h->LIN, L.down.Nw);
         consumer(part ? s : 0, part ? nullptr : h->LIN, T, c.hidden, L.down.Nw, h->X, h->X, next_norm, h->XN);
         (void)QW;
     }
@@ -394,7 +384,7 @@ struct Run {
     // final-normed rows [B][hidden] -> logits -> greedy token `step` of every sequence
     void head(const bf16* xn_rows, int B, int step, int n_new, bool keep_logits) {
         const auto& c = h->cfg;
-        const int s = gemm(h->lm_head, xn_rows, B, EPI_PARTIAL, nullptr, 0, &h->layers[0].qkv);
+        const int s = gemm(h->lm_head, xn_rows, B, EPI_PARTIAL, nullptr, 0);
         if (!rc) launched(launch_bias_act(st, h->ws, s, B, h->lm_head.Nw, h->lm_head.Nw, nullptr, ACT_NONE, 1.0f, h->LOGITS, h->lm_head.Nw), "logits");
         if (!rc) launched(launch_argmax_rows(st, h->LOGITS, B, h->lm_head.Nw, c.vocab, h->ids, h->out_ids + step, n_new), "argmax");
         if (keep_logits && !rc) {
@@ -417,17 +407,14 @@ void run_generate(Run& R, int B, int T, int n_new, bool keep_logits) {
     }
     // ---- prefill: X <- inputs_embeds, XN <- input norm of layer 0 ----
     R.consumer(0, nullptr, B * T, c.hidden, c.hidden, h->IN, h->X, h->layers[0].in_ln, h->XN);
-    for (int l = 0; l < L; ++l)
-        R.layer(l, B, T, 0, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm, l + 1 < L ? &h->layers[l + 1].qkv : &h->lm_head);
+    for (int l = 0; l < L; ++l) R.layer(l, B, T, 0, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm);
     if (!R.rc) R.launched(launch_gather_rows(R.st, h->XN, B, T, T - 1, c.hidden, h->LAST), "gather_last");
     R.head(h->LAST, B, 0, n_new, keep_logits);
     // ---- greedy decode: one token per sequence per step ----
     for (int i = 1; i < n_new; ++i) {
         if (!R.rc) R.launched(launch_embed_rows(R.st, h->ids, B, h->embed, c.vocab, c.hidden, h->X, h->d_err), "embed");
         R.consumer(0, nullptr, B, c.hidden, c.hidden, h->X, nullptr, h->layers[0].in_ln, h->XN);
-        for (int l = 0; l < L; ++l)
-            R.layer(l, B, 1, T + i - 1, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm,
-                    l + 1 < L ? &h->layers[l + 1].qkv : &h->lm_head);
+        for (int l = 0; l < L; ++l) R.layer(l, B, 1, T + i - 1, l + 1 < L ? h->layers[l + 1].in_ln : h->final_norm);
         R.head(h->XN, B, i, n_new, keep_logits);
     }
 }
@@ -498,11 +485,6 @@ extern "C" int blurr_llm_set_option(blurr_llm_t* h, const char* name, int64_t va
     if (!h || !name) return fail(BLURR_ERR_INVALID, "blurr_llm_set_option: null argument");
     const std::string n(name);
     if (n == "use_cuda_graph") h->use_graph = value != 0;
-    else if (n == "l2_prefetch_mb") {
-        h->l2_prefetch_bytes = value > 0 ? static_cast<size_t>(value) << 20 : 0;
-        for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); cudaGraphDestroy(kv.second.graph); }
-        h->graphs.clear();
-    }
     else if (n == "trace") {
         if (value != 0 && !h->trace_buf) {
             h->trace_buf = static_cast<unsigned long long*>(dalloc(h, static_cast<size_t>(kTraceMax) * 4 * sizeof(unsigned long long)));

@@ -298,209 +298,6 @@ cudaError_t launch_mha_decode(cudaStream_t stream, const MhaAttnArgs& a) {
     return cudaErrorInvalidValue;
 }
 
-// Prefill attention of the Llama-shaped decoder, head_dim 128, causal: ONE CTA per (sequence, head) keeps the head's K in
-// registers (mma.sync B fragments loaded straight from global memory in the permuted-dims order of
-// attention.cu::fewq_stream_kernel), its V and ALL of its query rows in shared memory - everything requested up front,
-// one round trip - and then walks the query rows in 32-row tiles entirely out of shared memory: logits (key tiles past the
-// tile's last position are skipped), bf16(bf16(q.k) * scale) with the positional causal mask, fp32 softmax, bf16 P, P.V.
-// K/V are read from L2 once per (sequence, head) instead of once per 64-row tile.  MEASURED: no faster than the tile kernel
-// (prefill of 32 sequences 118-121 ms either way, one sequence 6.9 vs 5.7 ms) - the tile's phases, not the K/V loads, are
-// what takes the time - so it is off by default (global option attn_mha_prefill_stream).
-static constexpr int kMsThreads = 256;
-static constexpr int kMsKeys = 288;                        // 36 key tiles of 8
-static constexpr int kMsLd = 128 + 8;                      // Q / V row stride (elements)
-static constexpr int kMsLdS = kMsKeys + 8;                 // logits / P row stride
-static constexpr int kMsRows = 32;
-static constexpr size_t kMsSmem = static_cast<size_t>(2 * kMsKeys) * kMsLd * 2 + kMsRows * kMsLdS * 4 + kMsRows * kMsLdS * 2;
-
-__global__ void __launch_bounds__(kMsThreads, 1) mha_prefill_stream_kernel(const MhaAttnArgs a) {
-    extern __shared__ __align__(16) uint8_t ms_smem[];
-    bf16* v_s = reinterpret_cast<bf16*>(ms_smem);                                  // [288][136]
-    bf16* q_s = v_s + kMsKeys * kMsLd;                                             // [288][136], permuted columns
-    float* sc = reinterpret_cast<float*>(q_s + kMsKeys * kMsLd);                   // [32][296]
-    bf16* p_s = reinterpret_cast<bf16*>(sc + kMsRows * kMsLdS);                    // [32][296]
-    trace_stamp(a.trace, 0);
-    pdl_wait();
-    pdl_trigger();
-    trace_stamp(a.trace, 1);
-    const int h = blockIdx.x, b = blockIdx.y;
-    const int Tq = a.q_per_sample, n = a.n_keys, width = a.n_heads * 128;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, c = lane & 3;
-    const bf16* kb = a.k_cache + static_cast<size_t>(b) * a.n_slots * width + h * 128;
-    const bf16* vb = a.v_cache + static_cast<size_t>(b) * a.n_slots * width + h * 128;
-    const bf16* qb = a.q + static_cast<size_t>(b) * Tq * width + h * 128;
-    // ---- everything up front: V (cp.async), K (registers), Q (registers -> permuted shared memory) ----
-    for (int i = threadIdx.x; i < kMsKeys * 16; i += kMsThreads) {
-        const int key = i >> 4, ch = i & 15;
-        const bool valid = key < n;
-        cp_async_16(v_s + key * kMsLd + ch * 8, valid ? vb + static_cast<size_t>(key) * width + ch * 8 : vb, valid);
-    }
-    cp_async_commit();
-    uint4 kr[5][4];                      // key tiles warp, warp + 8, ... (interleaved: causal skipping stays balanced)
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const int key = (warp + 8 * i) * 8 + g;
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-            kr[i][t] = (warp + 8 * i < kMsKeys / 8 && key < n)
-                           ? __ldcg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * width + 32 * t + 8 * c))
-                           : make_uint4(0u, 0u, 0u, 0u);
-    }
-    for (int i = threadIdx.x; i < kMsKeys * 16; i += kMsThreads) {
-        const int r = i >> 4, ch = i & 15;                  // dims 8 ch .. + 7 = (t, cc) = (ch >> 2, ch & 3)
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < Tq) v = *reinterpret_cast<const uint4*>(qb + static_cast<size_t>(r) * width + ch * 8);
-        const int t = ch >> 2, cc = ch & 3;
-        uint32_t* row = reinterpret_cast<uint32_t*>(q_s + r * kMsLd);
-        row[((2 * t) * 16 + 2 * cc) >> 1] = v.x;            // dims +0,1 -> k-step 2t,     k = 2cc
-        row[((2 * t) * 16 + 2 * cc + 8) >> 1] = v.y;        // dims +2,3 -> k-step 2t,     k = 2cc + 8
-        row[((2 * t + 1) * 16 + 2 * cc) >> 1] = v.z;        // dims +4,5 -> k-step 2t + 1, k = 2cc
-        row[((2 * t + 1) * 16 + 2 * cc + 8) >> 1] = v.w;    // dims +6,7 -> k-step 2t + 1, k = 2cc + 8
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-    // ---- 32-row tiles out of shared memory ----
-    for (int r0 = 0; r0 < Tq; r0 += kMsRows) {
-        const int last_row = min(r0 + kMsRows, Tq) - 1;
-        const int kmax = min(a.q_pos0 + last_row, n - 1);           // last key any row of this tile may see
-        const int ntiles = kmax / 8 + 1;                            // key tiles that matter
-        const int ncols = min(n, ntiles * 8);
-        // logits: all key tiles of this warp advance together through the 8 k-steps (5 independent accumulator chains)
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            float acc[5][4];
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                uint32_t af[4];
-                ldmatrix_x4(af, smem_u32(q_s + (r0 + mt * 16 + (lane & 15)) * kMsLd + ks * 16 + (lane >> 4) * 8));
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    if (warp + 8 * i >= ntiles) continue;           // warp-uniform
-                    const uint4 kk = kr[i][ks >> 1];
-                    if (ks & 1) mma_bf16_16816(acc[i], af, kk.z, kk.w);
-                    else mma_bf16_16816(acc[i], af, kk.x, kk.y);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int j = warp + 8 * i;
-                if (j >= ntiles) continue;
-                const int key0 = j * 8 + 2 * c;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int rl = mt * 16 + g + hh * 8;
-                    const int qpos = a.q_pos0 + r0 + rl;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int k = key0 + e;
-                        float s0 = bf16_round(bf16_round(acc[i][hh * 2 + e]) * a.scale);
-                        if (k > qpos || k >= n) s0 = -INFINITY;
-                        sc[rl * kMsLdS + k] = s0;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const int ncols16 = (ncols + 15) & ~15;
-        {
-            // softmax: the warp's 4 rows side by side (independent shuffle chains)
-            constexpr int R = kMsRows / 8, PL = kMsKeys / 32;
-            float x[R][PL], m[R], sum[R];
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                const float* row = sc + (warp * R + rr) * kMsLdS;
-                m[rr] = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < PL; ++i) {
-                    const int col = lane + i * 32;
-                    x[rr][i] = col < ncols ? row[col] : -INFINITY;
-                    m[rr] = fmaxf(m[rr], x[rr][i]);
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) m[rr] = fmaxf(m[rr], __shfl_xor_sync(0xffffffffu, m[rr], o));
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                sum[rr] = 0.f;
-#pragma unroll
-                for (int i = 0; i < PL; ++i) {
-                    const int col = lane + i * 32;
-                    x[rr][i] = col < ncols ? expf(x[rr][i] - m[rr]) : 0.f;
-                    sum[rr] += x[rr][i];
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) sum[rr] += __shfl_xor_sync(0xffffffffu, sum[rr], o);
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                const int rl = warp * R + rr;
-                const bool live = r0 + rl < Tq;                    // rows past the prompt: all-zero probabilities
-#pragma unroll
-                for (int i = 0; i < PL; ++i) {
-                    const int col = lane + i * 32;
-                    if (col < ncols16) p_s[rl * kMsLdS + col] = f2bf(live ? x[rr][i] / sum[rr] : 0.f);
-                }
-            }
-        }
-        __syncthreads();
-        {
-            float oacc[2][2][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) oacc[mt][i][e] = 0.f;
-            const int dim0 = warp * 16;
-#pragma unroll 3
-            for (int ks = 0; ks < ncols16 / 16; ++ks) {
-                uint32_t bfr[4];
-                const int mi = lane >> 3;
-                const int key = ks * 16 + (mi & 1) * 8 + (lane & 7);
-                ldmatrix_x4_trans(bfr, smem_u32(v_s + key * kMsLd + dim0 + (mi >> 1) * 8));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    uint32_t af[4];
-                    ldmatrix_x4(af, smem_u32(p_s + (mt * 16 + (lane & 15)) * kMsLdS + ks * 16 + (lane >> 4) * 8));
-                    mma_bf16_16816(oacc[mt][0], af, bfr[0], bfr[1]);
-                    mma_bf16_16816(oacc[mt][1], af, bfr[2], bfr[3]);
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int r = r0 + mt * 16 + g + hh * 8;
-                    if (r >= Tq) continue;
-                    bf16* orow = a.out + (static_cast<size_t>(b) * Tq + r) * width + h * 128 + dim0 + 2 * c;
-                    *reinterpret_cast<uint32_t*>(orow) = pack_bf16x2(oacc[mt][0][hh * 2], oacc[mt][0][hh * 2 + 1]);
-                    *reinterpret_cast<uint32_t*>(orow + 8) = pack_bf16x2(oacc[mt][1][hh * 2], oacc[mt][1][hh * 2 + 1]);
-                }
-        }
-    }
-    trace_stamp(a.trace, 2);
-}
-
-cudaError_t launch_mha_prefill_stream(cudaStream_t stream, const MhaAttnArgs& a) {
-    if (a.head_dim != 128 || a.n_keys > kMsKeys || a.q_per_sample > kMsKeys || a.n_kv_heads != a.n_heads) return cudaErrorInvalidValue;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(mha_prefill_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMsSmem));
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
-    return launch_kernel(mha_prefill_stream_kernel, dim3(a.n_heads, a.batch), dim3(kMsThreads), kMsSmem, stream, a);
-}
-
 cudaError_t launch_rope_mha(cudaStream_t stream, const RopeMhaArgs& a) {
     if ((a.head_dim & 7) || a.T <= 0) return cudaErrorInvalidValue;
     // one work item (4 rotation pairs / 4 value columns, all K slices) per thread: a decode step's single row still

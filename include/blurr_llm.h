@@ -64,8 +64,7 @@ int blurr_llm_embed(blurr_llm_t* h, void* cuda_stream, const int64_t* ids, int n
  * n_new - 1 decode steps, argmax) is replayed as one CUDA graph per (batch, prompt_len, n_new). */
 int blurr_llm_generate(blurr_llm_t* h, void* cuda_stream, int batch, int prompt_len, const void* inputs_embeds, int n_new,
                        int64_t* out_ids, void* out_logits);
-/* Options: "use_cuda_graph" (default 1), "l2_prefetch_mb" (default 0 = off; N: as a decode GEMM's CTAs drain they prefetch N MB of
- * the next GEMM's weight stream into L2 - measured neutral, kept for experiments), "trace" (default 0: every kernel stamps %globaltimer, see blurr_llm_trace_report). */
+/* Options: "use_cuda_graph" (default 1), "trace" (default 0: every kernel stamps %globaltimer, see blurr_llm_trace_report). */
 int blurr_llm_set_option(blurr_llm_t* h, const char* name, int64_t value);
 /* Synchronises the stream; reports and clears device-side sticky errors (token id outside the table, expired pipeline wait). */
 int blurr_llm_check(blurr_llm_t* h, void* cuda_stream);

@@ -133,9 +133,6 @@ int blurr_pi0_infer_action(blurr_pi0_t* h, void* cuda_stream, int batch, const b
 
 /* Options: "use_cuda_graph" (default 1; replay of the step's kernels as a CUDA graph), "debug_taps" (default 0; implies eager launches),
  * "chunked_splitk" (default 1: split-K GEMMs of 128..288 tokens also split the tokens across CTAs, chosen by a measured cost model),
- * "fuse_tails" (default 0 = separate kernels; N in 1..8: a split-K GEMM of at most N token rows - the experts' projections at one
- * or two episodes - carries its consumer (bias/residual/RMSNorm, or RoPE + cache write) as tails run by the last CTA to finish each
- * weight tile; bit-identical results, 37 fewer launches per flow step, measured SLOWER than the PDL-chained kernels),
  * "activation_clip_bits" / "activation_clip_mask" (default 0 / 0: the reference's int8 fake-quant mode, int8_linear.py:72-83 - the float32
  * bit pattern of the clamp applied to the inputs of the swapped Linears, and which modules: bit 1 proprio mixture (tied weights), bit 2
  * action mixture, bit 3 action encoder; the de-quantised weights arrive through blurr_pi0_set_weight like any others),
@@ -202,9 +199,7 @@ int blurr_op_normalize_proprio(void* cuda_stream, const double* raw, const doubl
  * "attn_tc_fewq" (1: the experts' few-query attention on the tcgen05 kernel too; default 0, measured slower at batch 1),
  * "attn_prefill_stream", "attn_fewq_stream", "attn_siglip_stream" (default 1: at one or two episodes the prefill, the experts'
  * few-query and the SigLIP attention run as the streaming mma.sync kernels of csrc/attention.cu - K straight into permuted
- * fragments, V in shared memory, every load requested up front; 0: the tile / tcgen05 kernels; attn_siglip_stream = 2 forces
- * the streaming kernel at any batch size, measured slower), "attn_mha_prefill_stream" (Llama-shaped prefill attention as one
- * CTA per (sequence, head); default 0),
+ * fragments, V in shared memory, every load requested up front; 0: the tile / tcgen05 kernels),
  * "gemm_pair_small" (257..288 tokens: 0 one CTA per weight tile, 1 persistent CTA pairs for GeGLU only, 2 (default) for every epilogue),
  * "gemm_cta_trace" / "attn_cta_trace" (device pointer to [n_cta][8] u64, 0 = off: per-CTA %globaltimer timeline), "op_gemm_bn" (token chunk
  * width used by blurr_op_gemm*, 0 = automatic),

@@ -16,8 +16,6 @@ dev = torch.device("cuda:0")
 cfg = openvla.LlamaShapedConfig(num_layers=L)
 dec = openvla.LlamaDecoder.from_state_dict(cfg, openvla.synthetic_llama_state_dict(cfg, dev, 0), dev, max_batch=B)
 dec.set_option("trace", 1)
-if "PF" in os.environ:
-    dec.set_option("l2_prefetch_mb", int(os.environ["PF"]))
 x = (torch.randn((B, 281, cfg.hidden), device=dev) * 0.5).to(torch.bfloat16)
 for _ in range(4):
     dec.generate(x, N)
