@@ -153,6 +153,7 @@ _SIGNATURES = [
     ("blurr_vit_set_weight", C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     ("blurr_vit_finalize", C.c_int, [C.c_void_p]),
     ("blurr_vit_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int]),
+    ("blurr_vit_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     ("blurr_vit_last_launch_count", C.c_int64, [C.c_void_p]),
     ("blurr_mlp_create", C.c_int, [C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ("blurr_mlp_destroy", None, [C.c_void_p]),

@@ -13,6 +13,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -134,14 +135,19 @@ struct blurr_vit {
     size_t ws_floats = 0;
     std::set<std::string> seen;
     size_t expected = 0;
-    bool finalized = false;
+    bool finalized = false, use_graph = true;
     int64_t launches = 0;
+    // blocks between the patch im2col (reads the caller's pixels) and the final row copy (writes the caller's buffer)
+    // only touch the handle's own buffers: one CUDA graph per batch size
+    struct GraphEntry { cudaGraph_t graph; cudaGraphExec_t exec; int64_t launches; };
+    std::map<int, GraphEntry> graphs;
 };
 
 extern "C" void blurr_vit_destroy(blurr_vit_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); cudaGraphDestroy(kv.second.graph); }
     for (void* p : h->allocs) cudaFree(p);
     gemm_forget_tensor_maps();
     delete h;
@@ -267,24 +273,14 @@ extern "C" int blurr_vit_finalize(blurr_vit_t* h) {
     return 0;
 }
 
-extern "C" int blurr_vit_forward(blurr_vit_t* h, void* cuda_stream, int batch, const void* pixel_values, const int64_t strides[4],
-                                 void* out, int out_ld) {
-    if (!h || !pixel_values || !strides || !out) return fail(BLURR_ERR_INVALID, "blurr_vit_forward: null argument");
-    if (!h->finalized) return fail(BLURR_ERR_STATE, "blurr_vit_forward: call blurr_vit_finalize first");
-    if (batch < 1 || batch > h->max_batch) return fail(BLURR_ERR_INVALID, "blurr_vit_forward: batch out of range");
+// patch GEMM .. last block, on the handle's own buffers (graph-capturable)
+static void vit_body(blurr_vit* h, Launcher& R, int batch) {
     const auto& c = h->cfg;
+    cudaStream_t st = R.st;
     const int H = c.hidden, P = c.num_prefix_tokens, S = h->seq, NP = h->n_patches;
-    if (out_ld < H || (out_ld & 7)) return fail(BLURR_ERR_INVALID, "blurr_vit_forward: out_ld must be >= hidden and a multiple of 8");
-    VIT_CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    h->launches = 0;
-    Launcher R{st, h->ws, h->ws_floats, h->LINB, &h->launches};
     const int T = batch * S, Tp = batch * NP;
     const int gelu = c.gelu_erf ? GELU_ERF : GELU_TANH;
-    // patch embedding + position embeddings -> the patch rows of X (behind each sample's prefix rows)
-    R.launched(launch_im2col(st, static_cast<const bf16*>(pixel_values), strides[0], strides[1], strides[2], strides[3], batch,
-                             h->patches, h->patch.K), "im2col");
-    {
+    {   // patch embedding + position embeddings -> the patch rows of X (behind each sample's prefix rows)
         ConsumerArgs a{};
         a.add_mode = ADD_POSEMB; a.pos = h->pos; a.pos_rows = NP;
         a.x_out = h->X; a.ldx = H; a.norm_mode = NORM_NONE;
@@ -324,8 +320,61 @@ extern "C" int blurr_vit_forward(blurr_vit_t* h, void* cuda_stream, int batch, c
             R.linear_consumer(L.fc2, h->HM, T, a);
         }
     }
+}
+
+extern "C" int blurr_vit_forward(blurr_vit_t* h, void* cuda_stream, int batch, const void* pixel_values, const int64_t strides[4],
+                                 void* out, int out_ld) {
+    if (!h || !pixel_values || !strides || !out) return fail(BLURR_ERR_INVALID, "blurr_vit_forward: null argument");
+    if (!h->finalized) return fail(BLURR_ERR_STATE, "blurr_vit_forward: call blurr_vit_finalize first");
+    if (batch < 1 || batch > h->max_batch) return fail(BLURR_ERR_INVALID, "blurr_vit_forward: batch out of range");
+    const auto& c = h->cfg;
+    const int H = c.hidden, P = c.num_prefix_tokens, S = h->seq, NP = h->n_patches;
+    if (out_ld < H || (out_ld & 7)) return fail(BLURR_ERR_INVALID, "blurr_vit_forward: out_ld must be >= hidden and a multiple of 8");
+    VIT_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    h->launches = 0;
+    Launcher R{st, h->ws, h->ws_floats, h->LINB, &h->launches};
+    R.launched(launch_im2col(st, static_cast<const bf16*>(pixel_values), strides[0], strides[1], strides[2], strides[3], batch,
+                             h->patches, h->patch.K), "im2col");
+    if (R.rc) return R.rc;
+    if (!h->use_graph) {
+        vit_body(h, R, batch);
+    } else {
+        auto it = h->graphs.find(batch);
+        if (it == h->graphs.end()) {
+            vit_body(h, R, batch);                                   // warm run: attribute setup, tensor maps
+            if (R.rc) return R.rc;
+            VIT_CUDA_TRY(cudaStreamSynchronize(st));
+            int64_t captured = 0;
+            cudaStream_t cs;
+            VIT_CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            Launcher C{cs, h->ws, h->ws_floats, h->LINB, &captured};
+            cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) { cudaStreamDestroy(cs); return fail(BLURR_ERR_CUDA, "graph capture begin failed"); }
+            vit_body(h, C, batch);
+            cudaGraph_t g = nullptr;
+            e = cudaStreamEndCapture(cs, &g);
+            cudaStreamDestroy(cs);
+            if (C.rc) { if (g) cudaGraphDestroy(g); return C.rc; }
+            if (e != cudaSuccess || !g) return fail(BLURR_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+            cudaGraphExec_t ex = nullptr;
+            e = cudaGraphInstantiate(&ex, g, 0);
+            if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(BLURR_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e)); }
+            it = h->graphs.emplace(batch, blurr_vit::GraphEntry{g, ex, captured}).first;
+            h->launches = 1;                                         // the im2col of this call; the replay below adds the rest
+        }
+        VIT_CUDA_TRY(cudaGraphLaunch(it->second.exec, st));
+        h->launches = 1 + it->second.launches;
+    }
     if (!R.rc) R.launched(launch_copy_rows(st, h->X, batch, S, P, NP, H, H, static_cast<bf16*>(out), out_ld), "copy_rows");
     return R.rc;
+}
+
+extern "C" int blurr_vit_set_option(blurr_vit_t* h, const char* name, int64_t value) {
+    if (!h || !name) return fail(BLURR_ERR_INVALID, "blurr_vit_set_option: null argument");
+    if (std::string(name) == "use_cuda_graph") h->use_graph = value != 0;
+    else return fail(BLURR_ERR_INVALID, std::string("blurr_vit_set_option: unknown option ") + name);
+    return 0;
 }
 
 extern "C" int64_t blurr_vit_last_launch_count(const blurr_vit_t* h) { return h ? h->launches : 0; }

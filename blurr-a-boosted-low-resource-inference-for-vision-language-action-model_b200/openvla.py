@@ -265,6 +265,9 @@ class VitEncoder:
     def finalize(self):
         capi.check(self.lib.blurr_vit_finalize(self.handle))
 
+    def set_option(self, name: str, value: int):
+        capi.check(self.lib.blurr_vit_set_option(self.handle, name.encode(), int(value)))
+
     @classmethod
     def from_hf_dinov2(cls, model, device, max_batch: int = 1, num_layers: Optional[int] = None) -> "VitEncoder":
         """From a transformers `Dinov2WithRegistersModel` (image_size 224 so that its position embeddings are native)."""
@@ -427,13 +430,26 @@ class FusedVisionBackbone:
     """DINOv2 + SigLIP towers on the same image, patch features concatenated (DINOv2 first, as in Prismatic's
     `dinosiglip` backbone) and projected to the language model's width."""
 
-    def __init__(self, dino: VitEncoder, siglip: VitEncoder, projector: MlpProjector):
+    def __init__(self, dino: VitEncoder, siglip: VitEncoder, projector: MlpProjector, concurrent: bool = True):
         self.dino, self.siglip, self.projector = dino, siglip, projector
         self.width = dino.cfg.hidden + siglip.cfg.hidden
+        # the two towers are independent chains of small, latency-bound kernels: run them side by side on two streams
+        self._side = torch.cuda.Stream(device=dino.device) if concurrent else None
 
     def forward(self, pixel_values_dino: torch.Tensor, pixel_values_siglip: torch.Tensor) -> torch.Tensor:
         B = pixel_values_dino.shape[0]
         feats = torch.empty((B, self.dino.n_patches, self.width), device=pixel_values_dino.device, dtype=torch.bfloat16)
-        self.dino.forward(pixel_values_dino, out=feats)
-        self.siglip.forward(pixel_values_siglip, out=feats[:, :, self.dino.cfg.hidden:])
+        sig_out = feats[:, :, self.dino.cfg.hidden:]
+        if self._side is None:
+            self.dino.forward(pixel_values_dino, out=feats)
+            self.siglip.forward(pixel_values_siglip, out=sig_out)
+        else:
+            cur = torch.cuda.current_stream(self.dino.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self.siglip.forward(pixel_values_siglip, out=sig_out)
+            self.dino.forward(pixel_values_dino, out=feats)
+            cur.wait_stream(self._side)
+            pixel_values_siglip.record_stream(self._side)
+            feats.record_stream(self._side)
         return self.projector.forward(feats)

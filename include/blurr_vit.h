@@ -56,6 +56,8 @@ int blurr_vit_finalize(blurr_vit_t* h);
  * halves of one concatenated feature matrix). */
 int blurr_vit_forward(blurr_vit_t* h, void* cuda_stream, int batch, const void* pixel_values, const int64_t strides[4],
                       void* out, int out_ld);
+/* Options: "use_cuda_graph" (default 1: the blocks replay as one CUDA graph per batch size). */
+int blurr_vit_set_option(blurr_vit_t* h, const char* name, int64_t value);
 int64_t blurr_vit_last_launch_count(const blurr_vit_t* h);
 
 /* Projector: y = W_n(... GELU(W_1 x + b_1) ...) + b_n, exact GELU between the layers (nn.GELU()). dims = n_layers + 1

@@ -63,6 +63,11 @@ def test_dinov2_registers_tower_matches_transformers(batch):
     got = enc.forward(px)
     torch.cuda.synchronize()
     _check_against_fp32(f"dinov2 tower B={batch} ({enc.last_launch_count} launches)", got, ref, ref32)
+    again = enc.forward(px)                        # CUDA-graph replay
+    enc.set_option("use_cuda_graph", 0)
+    eager = enc.forward(px)
+    torch.cuda.synchronize()
+    assert torch.equal(got, again) and torch.equal(got, eager)
     enc.close()
 
 
@@ -114,5 +119,8 @@ def test_projector_and_fused_backbone():
     feats = torch.cat([dino.forward(px), sig.forward(px)], dim=-1)
     assert out.shape == (2, 256, 4096) and torch.isfinite(out.float()).all()
     assert torch.equal(out, proj.forward(feats))
+    serial = openvla.FusedVisionBackbone(dino, sig, proj, concurrent=False).forward(px, px)
+    torch.cuda.synchronize()
+    assert torch.equal(out, serial)                  # two streams or one: same bits
     for m in (dino, sig, proj):
         m.close()
