@@ -673,11 +673,12 @@ cudaError_t launch_joint_attention_fewq(cudaStream_t stream, const JointAttnArgs
 
 // Llama-style multi-head attention over a token-major KV cache (llm_engine.cu): head_dim 128 (or 64), one K/V head per
 // query head, causal by position.  Prefill (many query rows) and decode (one row per sequence) share the kernel.
-cudaError_t launch_mha_decode(cudaStream_t stream, const MhaAttnArgs& a);     // llm_kernels.cu
+cudaError_t launch_mha_decode(cudaStream_t stream, const MhaAttnArgs& a, const RopeMhaArgs* rope);     // llm_kernels.cu
 
-cudaError_t launch_mha_attention(cudaStream_t stream, const MhaAttnArgs& m) {
+cudaError_t launch_mha_attention(cudaStream_t stream, const MhaAttnArgs& m, const RopeMhaArgs* fused_rope) {
     if (m.n_keys > kAttnMaxBlocks * kBK || m.n_kv_heads != m.n_heads) return cudaErrorInvalidValue;
-    if (m.q_per_sample == 1) return launch_mha_decode(stream, m);       // decode: K/V streaming, no tensor cores
+    if (m.q_per_sample == 1) return launch_mha_decode(stream, m, fused_rope);       // decode: K/V streaming, no tensor cores
+    if (fused_rope != nullptr) return cudaErrorInvalidValue;
     AttnMmaArgs a{};
     const int width = m.n_heads * m.head_dim;
     a.q = m.q; a.ldq = width; a.q_col0 = 0; a.q_per_sample = m.q_per_sample;

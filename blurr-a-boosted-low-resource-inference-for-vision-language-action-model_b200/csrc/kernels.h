@@ -183,7 +183,10 @@ struct MhaAttnArgs {
     bf16* out;                // [B * q_per_sample][n_heads * head_dim]
     unsigned long long* trace;
 };
-cudaError_t launch_mha_attention(cudaStream_t stream, const MhaAttnArgs& a);
+struct RopeMhaArgs;
+// decode steps of <= 2 waves of (sequence, head) CTAs can do the new token's RoPE + cache append themselves
+bool mha_decode_fuses_rope(const MhaAttnArgs& a);
+cudaError_t launch_mha_attention(cudaStream_t stream, const MhaAttnArgs& a, const RopeMhaArgs* fused_rope = nullptr);
 
 // q/k/v projection output -> RoPE (HF apply_rotary_pos_emb, rotate_half over head_dim / 2) -> q buffer and KV cache
 struct RopeMhaArgs {

@@ -357,15 +357,18 @@ struct Run {
         r.T = T; r.ldp = L.qkv.Nw; r.n_heads = c.num_heads; r.n_kv_heads = c.num_kv_heads; r.head_dim = c.head_dim;
         r.tokens_per_seq = Tq; r.pos0 = pos0; r.cos_table = h->cos_t; r.sin_table = h->sin_t; r.n_pos = h->n_pos;
         r.q_out = h->Q; r.k_cache = h->kcache + cache_off; r.v_cache = h->vcache + cache_off; r.n_slots = c.max_positions;
-        r.trace = slot("rope_mha");
-        if (!rc) launched(launch_rope_mha(st, r), "rope_mha");
         // causal multi-head attention over the cache
         MhaAttnArgs m{};
         m.q = h->Q; m.q_per_sample = Tq; m.q_pos0 = pos0; m.k_cache = r.k_cache; m.v_cache = r.v_cache;
         m.n_slots = c.max_positions; m.n_keys = pos0 + Tq; m.batch = B; m.n_heads = c.num_heads; m.n_kv_heads = c.num_kv_heads;
         m.head_dim = c.head_dim; m.scale = static_cast<float>(std::pow(static_cast<double>(c.head_dim), -0.5)); m.out = h->AO;
-        m.trace = slot(Tq == 1 ? "mha_decode" : "mha_prefill");
-        if (!rc) launched(launch_mha_attention(st, m), "mha_attention");
+        const bool fuse = few && Tq == 1 && mha_decode_fuses_rope(m);       // decode: RoPE + append inside the attention kernel
+        if (!fuse) {
+            r.trace = slot("rope_mha");
+            if (!rc) launched(launch_rope_mha(st, r), "rope_mha");
+        }
+        m.trace = slot(Tq == 1 ? (fuse ? "rope+mha_decode" : "mha_decode") : "mha_prefill");
+        if (!rc) launched(launch_mha_attention(st, m, fuse ? &r : nullptr), "mha_attention");
         // o_proj + residual + post-attention norm
         s = gemm(L.o, h->AO, T, part ? EPI_PARTIAL : EPI_STORE, h->LIN, L.o.Nw);
         consumer(part ? s : 0, part ? nullptr : h->LIN, T, c.hidden, L.o.Nw, h->X, h->X, L.post_ln, h->XN);

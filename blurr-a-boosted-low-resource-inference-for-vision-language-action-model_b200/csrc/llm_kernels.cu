@@ -70,13 +70,19 @@ __global__ void __launch_bounds__(256) rope_mha_kernel(const RopeMhaArgs a) {
 // head_dim * 2 bytes per CTA), so no tensor cores: a group of HD / 8 lanes owns one key (16-byte loads, 4 keys in flight
 // per group), scores and probabilities live in shared memory, the P.V sum is reduced across groups at the end.
 // Rounding chain of HF eager attention: bf16(q.k) * scale -> bf16, fp32 softmax -> bf16, fp32 accumulate -> bf16.
-template <int HD>
-__global__ void __launch_bounds__(256, 1) mha_decode_kernel(const MhaAttnArgs a) {
+// FUSED: the kernel also does the RoPE + cache append of its own head for the step's new token (rope_mha_kernel's work for
+// one (sequence, head): with multi-head attention nothing a CTA needs lives in another head), so a decode step has one
+// kernel less per layer: q, k, v of the new token come from the q/k/v GEMM's split-K partials, the new K/V row is written
+// to the cache and used from shared memory as key n - 1.
+template <int HD, bool FUSED>
+__global__ void __launch_bounds__(256, 1) mha_decode_kernel(const MhaAttnArgs a, const RopeMhaArgs r) {
     constexpr int LPK = HD / 8;                 // lanes per key
     constexpr int GROUPS = 256 / LPK;           // keys in flight per pass
     __shared__ float sc[320];
     __shared__ float red[8];
     __shared__ float part[GROUPS][HD + 4];
+    __shared__ float raw[3][HD];
+    __shared__ __align__(16) bf16 qkv_s[3][HD];
     trace_stamp(a.trace, 0);
     pdl_wait();
     pdl_trigger();
@@ -85,18 +91,11 @@ __global__ void __launch_bounds__(256, 1) mha_decode_kernel(const MhaAttnArgs a)
     const int width = a.n_heads * HD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = threadIdx.x / LPK, gl = threadIdx.x % LPK;
-    const bf16* qp = a.q + static_cast<size_t>(b) * width + h * HD + gl * 8;
-    const uint4 qraw = *reinterpret_cast<const uint4*>(qp);
-    float q[8];
-    {
-        const uint32_t w[4] = {qraw.x, qraw.y, qraw.z, qraw.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { q[2 * e] = __uint_as_float(w[e] << 16); q[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
-    }
     const size_t row0 = static_cast<size_t>(b) * a.n_slots;
     const bf16* kbase = a.k_cache + row0 * width + h * HD + gl * 8;
     const bf16* vbase = a.v_cache + row0 * width + h * HD + gl * 8;
     const int n = a.n_keys;
+    const int nload = FUSED ? n - 1 : n;        // FUSED: key n - 1 is the token this step appends
     // every K and V row of this group is requested up front (<= 320 / GROUPS keys per group, 16 bytes each per lane): the
     // kernel is two HBM round trips long instead of one per 4 keys (measured 15 -> 4 us per layer at one sequence)
     constexpr int KPG = 320 / GROUPS;
@@ -104,12 +103,63 @@ __global__ void __launch_bounds__(256, 1) mha_decode_kernel(const MhaAttnArgs a)
 #pragma unroll
     for (int u = 0; u < KPG; ++u) {
         const int k = group + u * GROUPS;
-        kr[u] = k < n ? __ldcg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(k) * width)) : make_uint4(0u, 0u, 0u, 0u);
+        kr[u] = k < nload ? __ldcg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(k) * width)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < KPG; ++u) {
         const int k = group + u * GROUPS;
-        vr[u] = k < n ? __ldcg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(k) * width)) : make_uint4(0u, 0u, 0u, 0u);
+        vr[u] = k < nload ? __ldcg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(k) * width)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint4 qraw;
+    if (FUSED) {
+        // q / k / v of the new token: sum the K slices, round to bf16 (the Linear's output), rotate q and k
+        const int half = HD >> 1;
+        const size_t sstride = static_cast<size_t>(r.T) * r.ldp;
+        for (int i = threadIdx.x; i < 3 * HD; i += 256) {
+            const int which = i / HD, d = i - which * HD;
+            const int col = (which == 0 ? 0 : which == 1 ? r.n_heads * HD : (r.n_heads + r.n_kv_heads) * HD) + h * HD + d;
+            const float* src = r.partial + static_cast<size_t>(b) * r.ldp + col;
+            float acc = 0.f;
+            for (int z = 0; z < r.splitk; ++z) acc += __ldcg(src + z * sstride);
+            raw[which][d] = bf16_round(acc);
+        }
+        __syncthreads();
+        int pos = r.pos0;
+        if (pos >= r.n_pos) pos = r.n_pos - 1;
+        const size_t cache_row = (row0 + pos) * width + h * HD;
+        for (int i = threadIdx.x; i < 2 * half + HD; i += 256) {
+            if (i < 2 * half) {                               // rotation pair j of q (i < half) or k
+                const int which = i / half, j = i - which * half;
+                const float c = r.cos_table[static_cast<size_t>(pos) * half + j], sn = r.sin_table[static_cast<size_t>(pos) * half + j];
+                const float x1 = raw[which][j], x2 = raw[which][j + half];
+                const float y1 = bf16_round(bf16_round(x1 * c) + bf16_round(-x2 * sn));
+                const float y2 = bf16_round(bf16_round(x2 * c) + bf16_round(x1 * sn));
+                qkv_s[which][j] = f2bf(y1);
+                qkv_s[which][j + half] = f2bf(y2);
+                if (which == 1) { r.k_cache[cache_row + j] = f2bf(y1); r.k_cache[cache_row + j + half] = f2bf(y2); }
+            } else {
+                const int d = i - 2 * half;
+                const bf16 v = f2bf(raw[2][d]);
+                qkv_s[2][d] = v;
+                r.v_cache[cache_row + d] = v;
+            }
+        }
+        __syncthreads();
+        qraw = *reinterpret_cast<const uint4*>(&qkv_s[0][gl * 8]);
+#pragma unroll
+        for (int u = 0; u < KPG; ++u)
+            if (group + u * GROUPS == n - 1) {
+                kr[u] = *reinterpret_cast<const uint4*>(&qkv_s[1][gl * 8]);
+                vr[u] = *reinterpret_cast<const uint4*>(&qkv_s[2][gl * 8]);
+            }
+    } else {
+        qraw = *reinterpret_cast<const uint4*>(a.q + static_cast<size_t>(b) * width + h * HD + gl * 8);
+    }
+    float q[8];
+    {
+        const uint32_t w[4] = {qraw.x, qraw.y, qraw.z, qraw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { q[2 * e] = __uint_as_float(w[e] << 16); q[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
     }
     // ---- scores ----
 #pragma unroll
@@ -286,14 +336,25 @@ __global__ void __launch_bounds__(256) mha_decode_loop_kernel(const MhaAttnArgs 
     trace_stamp(a.trace, 2);
 }
 
-cudaError_t launch_mha_decode(cudaStream_t stream, const MhaAttnArgs& a) {
+bool mha_decode_fuses_rope(const MhaAttnArgs& a) {
+    return a.q_per_sample == 1 && a.n_heads * a.batch <= 2 * 148 && (a.head_dim == 128 || a.head_dim == 64);
+}
+
+// `rope` != nullptr (only when mha_decode_fuses_rope): the kernel also rotates / appends this step's token (no rope_mha launch)
+cudaError_t launch_mha_decode(cudaStream_t stream, const MhaAttnArgs& a, const RopeMhaArgs* rope) {
     if (a.q_per_sample != 1 || a.n_keys > 320 || a.n_kv_heads != a.n_heads) return cudaErrorInvalidValue;
     const bool wide = a.n_heads * a.batch <= 2 * 148;       // few CTAs: every load of a CTA in flight at once
+    if (rope != nullptr) {
+        if (!mha_decode_fuses_rope(a) || rope->lin != nullptr || rope->tokens_per_seq != 1) return cudaErrorInvalidValue;
+        if (a.head_dim == 128) return launch_kernel(mha_decode_kernel<128, true>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a, *rope);
+        return launch_kernel(mha_decode_kernel<64, true>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a, *rope);
+    }
+    const RopeMhaArgs none{};
     if (a.head_dim == 128)
-        return wide ? launch_kernel(mha_decode_kernel<128>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a)
+        return wide ? launch_kernel(mha_decode_kernel<128, false>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a, none)
                     : launch_kernel(mha_decode_loop_kernel<128>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a);
     if (a.head_dim == 64)
-        return wide ? launch_kernel(mha_decode_kernel<64>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a)
+        return wide ? launch_kernel(mha_decode_kernel<64, false>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a, none)
                     : launch_kernel(mha_decode_loop_kernel<64>, dim3(a.n_heads, a.batch), dim3(256), 0, stream, a);
     return cudaErrorInvalidValue;
 }
