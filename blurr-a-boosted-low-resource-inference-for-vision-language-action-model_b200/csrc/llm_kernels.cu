@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(256) mha_decode_loop_kernel(const MhaAttnArgs 
     const bf16* vbase = a.v_cache + row0 * width + h * HD + gl * 8;
     const int n = a.n_keys;
     // ---- scores ----
-    for (int k0 = group; k0 < n; k0 += 4 * GROUPS) {
+    for (int kfirst = 0; kfirst < n; kfirst += 4 * GROUPS) {      // warp-uniform trip count: the groups of a warp shuffle together
+        const int k0 = kfirst + group;
         uint4 kr[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(256) mha_decode_loop_kernel(const MhaAttnArgs 
     float o8[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) o8[e] = 0.f;
-    for (int k0 = group; k0 < n; k0 += 4 * GROUPS) {
+    for (int kfirst = 0; kfirst < n; kfirst += 4 * GROUPS) {      // warp-uniform trip count: the groups of a warp shuffle together
+        const int k0 = kfirst + group;
         uint4 vr[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {

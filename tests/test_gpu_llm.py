@@ -63,6 +63,7 @@ CASES = [
     (512, 4, 128, 1408, 3, 1064, 3, 37, True),        # 111 prompt rows: bf16 hand-off path; vocab not a tile multiple
     (512, 4, 128, 1408, 2, 1064, 1, 281, True),       # OpenVLA's prompt length: the 257..288-row CTA-pair GEMMs
     (256, 4, 64, 704, 2, 520, 4, 64, False),          # head_dim 64
+    (1280, 10, 128, 2560, 2, 1000, 32, 12, False),    # 32 sequences x 10 heads: the many-CTA decode attention + separate RoPE
 ]
 
 
