@@ -64,6 +64,9 @@ CASES = [
     (512, 4, 128, 1408, 2, 1064, 1, 281, True),       # OpenVLA's prompt length: the 257..288-row CTA-pair GEMMs
     (256, 4, 64, 704, 2, 520, 4, 64, False),          # head_dim 64
     (1280, 10, 128, 2560, 2, 1000, 32, 12, False),    # 32 sequences x 10 heads: the many-CTA decode attention + separate RoPE
+    (1280, 10, 128, 2560, 1, 1000, 31, 59, False),    # odd sizes: 59 + i keys, 31 sequences
+    (256, 2, 128, 512, 1, 300, 5, 1, False),          # a one-token prompt
+    (512, 8, 64, 1024, 1, 300, 32, 3, False),         # head_dim 64, 256 decode CTAs (fused RoPE path at its upper edge)
 ]
 
 
