@@ -17,6 +17,12 @@ def pytest_collection_modifyitems(config, items):
     import torch
 
     if torch.cuda.is_available():
+        # a kernel that never returns must fail its test, not block the whole GPU run (pytest-timeout, "thread" method:
+        # a hung cudaDeviceSynchronize cannot be interrupted by a signal)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(900, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
