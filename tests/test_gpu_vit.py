@@ -39,10 +39,12 @@ def _pixels(batch, seed):
     return (torch.rand((batch, 3, 224, 224), device=DEV, generator=g) * 2 - 1).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("batch", [1, 2])
-def test_dinov2_registers_tower_matches_transformers(batch):
+# (hidden, heads, depth, batch): small towers, and DINOv2-L's real width at 5 images (1305 rows: the bf16 hand-off GEMMs and
+# the streaming consumers, with the prefix-row map and LayerScale)
+@pytest.mark.parametrize("hidden,heads,depth,batch", [(256, 4, 4, 1), (256, 4, 4, 2), (1024, 16, 3, 5)])
+def test_dinov2_registers_tower_matches_transformers(hidden, heads, depth, batch):
     from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
-    hc = Dinov2WithRegistersConfig(hidden_size=256, num_hidden_layers=4, num_attention_heads=4, mlp_ratio=4, image_size=224,
+    hc = Dinov2WithRegistersConfig(hidden_size=hidden, num_hidden_layers=depth, num_attention_heads=heads, mlp_ratio=4, image_size=224,
                                    patch_size=14, num_register_tokens=4, layerscale_value=1.0, attn_implementation="eager")
     torch.manual_seed(0)
     model = Dinov2WithRegistersModel(hc).eval()
@@ -53,7 +55,7 @@ def test_dinov2_registers_tower_matches_transformers(batch):
             elif "cls_token" in name or "register_tokens" in name or "position_embeddings" in name:
                 p.copy_(0.5 * torch.randn_like(p))
             elif name.endswith("weight") and p.dim() == 2:
-                p.mul_(3.0)                                           # attention and the MLP actually move the stream
+                p.mul_(3.0 if hidden <= 256 else 1.5)                 # attention and the MLP actually move the stream
     model = model.to(torch.bfloat16).to(DEV)
     enc = openvla.VitEncoder.from_hf_dinov2(model, DEV, max_batch=batch)
     px = _pixels(batch, 1)
@@ -71,17 +73,18 @@ def test_dinov2_registers_tower_matches_transformers(batch):
     enc.close()
 
 
-@pytest.mark.parametrize("batch", [1, 3])
-def test_siglip_tower_matches_transformers(batch):
+# small towers, and SigLIP-so400m's real widths (1152 / 4304, head_dim 72) at 5 images
+@pytest.mark.parametrize("hidden,inter,heads,depth,batch", [(256, 560, 4, 3, 1), (256, 560, 4, 3, 3), (1152, 4304, 16, 3, 5)])
+def test_siglip_tower_matches_transformers(hidden, inter, heads, depth, batch):
     from transformers import SiglipVisionConfig, SiglipVisionModel
-    hc = SiglipVisionConfig(hidden_size=256, intermediate_size=560, num_hidden_layers=3, num_attention_heads=4, image_size=224,
+    hc = SiglipVisionConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=depth, num_attention_heads=heads, image_size=224,
                             patch_size=14, attn_implementation="eager")
     torch.manual_seed(1)
     model = SiglipVisionModel(hc).eval()
     with torch.no_grad():
         for name, p in model.named_parameters():
             if name.endswith("weight") and p.dim() == 2 and "position" not in name:
-                p.mul_(2.0)
+                p.mul_(2.0 if hidden <= 256 else 1.5)
     model = model.to(torch.bfloat16).to(DEV)
     enc = openvla.VitEncoder.from_hf_siglip(model, DEV, max_batch=batch)
     px = _pixels(batch, 2)
