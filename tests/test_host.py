@@ -86,6 +86,20 @@ def test_openvla_action_detokenizer_and_rope_tables():
     assert torch.equal(cos[0, :, 64:], cos[0, :, :64])
 
 
+def test_openvla_shape_configs():
+    """The OpenVLA-7B-shaped defaults: tower depths minus one (second-to-last block), concatenated width 2176, Llama-2-7B."""
+    from blurr_b200 import openvla
+    d, s_, l = openvla.dinov2_large_reg4_config(), openvla.siglip_so400m_config(), openvla.openvla_7b_config()
+    assert (d.num_layers, d.hidden, d.num_heads, d.mlp_dim, d.num_prefix_tokens, d.use_layerscale, d.gelu_erf) == (23, 1024, 16, 4096, 5, True, True)
+    assert (s_.num_layers, s_.hidden, s_.num_heads, s_.mlp_dim, s_.num_prefix_tokens, s_.use_layerscale, s_.gelu_erf) == (26, 1152, 16, 4304, 0, False, False)
+    assert d.hidden + s_.hidden == 2176
+    assert (l.num_layers, l.hidden, l.num_heads, l.head_dim, l.intermediate, l.vocab) == (32, 4096, 32, 128, 11008, 32064)
+    assert 1 + 256 + 24 + 7 <= l.max_positions <= 320
+    # weight bytes one decode step streams: 32 x (qkv + o + gate/up + down) + the padded lm_head
+    per_layer = (3 * 4096 * 4096 + 4096 * 4096 + 2 * 11008 * 4096 + 4096 * 11008) * 2
+    assert abs(32 * per_layer + 32128 * 4096 * 2 - 13215203328) == 0
+
+
 def test_create_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
